@@ -1,0 +1,222 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle_pcl.so).
+
+TEST INFRASTRUCTURE ONLY — imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs, never by the product package.  PARITY UNPINNED: see
+oracle/pcl_oracle.h.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle_pcl.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.orc_num_threads.restype = C.c_int
+    return _LIB
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _opt(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def num_threads():
+    return lib().orc_num_threads()
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(C.c_int(int(n)))
+
+
+def _chk(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"oracle {what} failed with {rc}")
+
+
+# ------------------------------------------------------------------ search
+def radius_search(surf, q, radius, brute=False):
+    surf, q = _f32(surf), _f32(q)
+    n, nq = len(surf), len(q)
+    counts = np.zeros(nq, np.int32)
+    L = lib()
+    _chk(L.orc_radius_count(_opt(surf), n, _opt(q), nq, C.c_double(radius), _opt(counts)), "radius_count")
+    offsets = np.zeros(nq + 1, np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    idx = np.zeros(int(offsets[-1]), np.int32)
+    d2 = np.zeros(int(offsets[-1]), np.float32)
+    fn = L.orc_radius_search_brute if brute else L.orc_radius_search
+    _chk(fn(_opt(surf), n, _opt(q), nq, C.c_double(radius), _opt(offsets), _opt(idx), _opt(d2)), "radius_search")
+    return offsets, idx, d2
+
+
+def knn(surf, q, k, brute=False):
+    surf, q = _f32(surf), _f32(q)
+    idx = np.zeros((len(q), k), np.int32)
+    d2 = np.zeros((len(q), k), np.float32)
+    fn = lib().orc_knn_brute if brute else lib().orc_knn
+    _chk(fn(_opt(surf), len(surf), _opt(q), len(q), k, _opt(idx), _opt(d2)), "knn")
+    return idx, d2
+
+
+def cloud_resolution(pts):
+    pts = _f32(pts)
+    r = C.c_double(0)
+    _chk(lib().orc_cloud_resolution(_opt(pts), len(pts), C.byref(r)), "cloud_resolution")
+    return r.value
+
+
+# ------------------------------------------------------------------ normals
+def normals(surf, q=None, radius=0.0, k=0, vp=(0, 0, 0), mode=0):
+    surf = _f32(surf)
+    q = surf if q is None else _f32(q)
+    out = np.zeros((len(q), 4), np.float32)
+    cnt = np.zeros(len(q), np.int32)
+    gap = np.zeros(len(q), np.float32)
+    vpa = (C.c_float * 3)(*vp)
+    _chk(lib().orc_normals(_opt(surf), len(surf), _opt(q), len(q), C.c_double(radius), int(k), vpa,
+                           int(mode), _opt(out), _opt(cnt), _opt(gap)), "normals")
+    return out, cnt, gap
+
+
+# ------------------------------------------------------------------ keypoints
+def iss_saliency(pts, salient_radius, min_neighbors=5, g21=0.975, g32=0.975):
+    pts = _f32(pts)
+    sal = np.zeros(len(pts), np.float64)
+    _chk(lib().orc_iss_saliency(_opt(pts), len(pts), C.c_double(salient_radius), min_neighbors,
+                                C.c_double(g21), C.c_double(g32), _opt(sal)), "iss_saliency")
+    return sal
+
+
+def iss_nms(pts, saliency, nonmax_radius, min_neighbors=5):
+    pts = _f32(pts)
+    saliency = np.ascontiguousarray(saliency, np.float64)
+    kp = np.zeros(len(pts), np.int32)
+    nk = C.c_int(0)
+    _chk(lib().orc_iss_nms(_opt(pts), len(pts), _opt(saliency), C.c_double(nonmax_radius), min_neighbors,
+                           _opt(kp), C.byref(nk)), "iss_nms")
+    return kp[: nk.value].copy()
+
+
+def iss(pts, salient_radius, nonmax_radius, min_neighbors=5, g21=0.975, g32=0.975):
+    sal = iss_saliency(pts, salient_radius, min_neighbors, g21, g32)
+    return iss_nms(pts, sal, nonmax_radius, min_neighbors), sal
+
+
+def harris_response(pts, normals4, radius):
+    pts, normals4 = _f32(pts), _f32(normals4)
+    r = np.zeros(len(pts), np.float32)
+    _chk(lib().orc_harris_response(_opt(pts), _opt(normals4), len(pts), C.c_double(radius), _opt(r)), "harris_response")
+    return r
+
+
+def harris_nms(pts, response, radius, threshold):
+    pts, response = _f32(pts), _f32(response)
+    kp = np.zeros(len(pts), np.int32)
+    nk = C.c_int(0)
+    _chk(lib().orc_harris_nms(_opt(pts), _opt(response), len(pts), C.c_double(radius), C.c_float(threshold),
+                              _opt(kp), C.byref(nk)), "harris_nms")
+    return kp[: nk.value].copy()
+
+
+def harris_refine(pts, normals4, radius, corners):
+    pts, normals4 = _f32(pts), _f32(normals4)
+    c = _f32(corners).copy()
+    _chk(lib().orc_harris_refine(_opt(pts), _opt(normals4), len(pts), C.c_double(radius), _opt(c), len(c)), "harris_refine")
+    return c
+
+
+def snap_to_cloud(pts, q, max_d2=1e-4):
+    pts, q = _f32(pts), _f32(q)
+    out = np.zeros(len(q), np.int32)
+    _chk(lib().orc_snap_to_cloud(_opt(pts), len(pts), _opt(q), len(q), C.c_float(max_d2), _opt(out)), "snap")
+    return out
+
+
+# ------------------------------------------------------------------ descriptors
+def spfh(surf, normals4, pidx, radius=0.0, k=0):
+    surf, normals4 = _f32(surf), _f32(normals4)
+    pidx = np.ascontiguousarray(pidx, np.int32)
+    out = np.zeros((len(pidx), 33), np.float32)
+    _chk(lib().orc_spfh(_opt(surf), _opt(normals4), len(surf), _opt(pidx), len(pidx), C.c_double(radius), int(k),
+                        _opt(out)), "spfh")
+    return out
+
+
+def fpfh(surf, normals4, q=None, radius=0.0, k=0):
+    surf, normals4 = _f32(surf), _f32(normals4)
+    q = surf if q is None else _f32(q)
+    out = np.zeros((len(q), 33), np.float32)
+    _chk(lib().orc_fpfh(_opt(surf), _opt(normals4), len(surf), _opt(q), len(q), C.c_double(radius), int(k),
+                        _opt(out)), "fpfh")
+    return out
+
+
+def shot_lrf(surf, q, radius):
+    surf = _f32(surf)
+    q = surf if q is None else _f32(q)
+    rf = np.zeros((len(q), 9), np.float32)
+    gap = np.zeros((len(q), 2), np.float32)
+    _chk(lib().orc_shot_lrf(_opt(surf), len(surf), _opt(q), len(q), C.c_double(radius), _opt(rf), _opt(gap)), "shot_lrf")
+    return rf, gap
+
+
+def shot352(surf, normals4, q, radius, lrf_in=None):
+    surf, normals4 = _f32(surf), _f32(normals4)
+    q = surf if q is None else _f32(q)
+    out = np.zeros((len(q), 352), np.float32)
+    rf = np.zeros((len(q), 9), np.float32)
+    lrf = _f32(lrf_in) if lrf_in is not None else None
+    _chk(lib().orc_shot352(_opt(surf), _opt(normals4), len(surf), _opt(q), len(q), C.c_double(radius), _opt(lrf),
+                           _opt(out), _opt(rf)), "shot352")
+    return out, rf
+
+
+# ------------------------------------------------------------------ matching / ingest
+def match_nn(a, b):
+    a, b = _f32(a), _f32(b)
+    idx = np.zeros(len(a), np.int32)
+    d2 = np.zeros(len(a), np.float32)
+    dim = a.shape[1] if a.ndim == 2 else b.shape[1]
+    _chk(lib().orc_match_nn(_opt(a), len(a), _opt(b), len(b), dim, _opt(idx), _opt(d2)), "match_nn")
+    return idx, d2
+
+
+def match_reciprocal(a, b):
+    a, b = _f32(a), _f32(b)
+    qi = np.zeros(len(a), np.int32)
+    mi = np.zeros(len(a), np.int32)
+    dist = np.zeros(len(a), np.float32)
+    m = C.c_int(0)
+    _chk(lib().orc_match_reciprocal(_opt(a), len(a), _opt(b), len(b), a.shape[1], _opt(qi), _opt(mi), _opt(dist),
+                                    C.byref(m)), "match_reciprocal")
+    return qi[: m.value].copy(), mi[: m.value].copy(), dist[: m.value].copy()
+
+
+def voxel_grid(pts, leaf):
+    pts = _f32(pts)
+    out = np.zeros((len(pts), 3), np.float32)
+    m = C.c_int(0)
+    _chk(lib().orc_voxel_grid(_opt(pts), len(pts), C.c_float(leaf), _opt(out), len(pts), C.byref(m)), "voxel_grid")
+    return out[: m.value].copy()
