@@ -1,0 +1,153 @@
+/*
+ * pfx_b200.h — C ABI of the B200-native point-cloud feature-extraction hot path.
+ *
+ * This is the drop-in boundary for the path that the reference (srv/pcl_feature_extraction)
+ * drives through PCL: NormalEstimation -> ISS / Harris3D / NARF keypoints -> FPFH33 / SHOT352 /
+ * Narf36 descriptors -> descriptor correspondence matching.  Every entry point names the reference
+ * call site it replaces (paths are under /root/reference: include/pcl_feature_extraction/{features,keypoints,tools}.h and
+ * src/evaluation.cpp).  The header-only C++ shim in pcl_feature_extraction_b200/host/pcl_compat.hpp
+ * puts the pcl::Feature-style classes (setInputCloud / setSearchSurface / setRadiusSearch /
+ * setKSearch / compute) on top of these calls; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; `mem` says where a buffer lives (PFX_HOST or PFX_DEVICE).
+ *    Device buffers must be on the context's device.
+ *  - point buffers are arrays of records whose first three floats are x, y, z; `stride` is the
+ *    record size in bytes (16 for PointXYZ, 32 for PointXYZRGB / PointXYZI, 12 for packed xyz).
+ *  - normal buffers are records of (nx, ny, nz, pad, curvature, ...) like pcl::Normal (stride 32)
+ *    or packed (nx, ny, nz, curvature) float4 (stride 16): `curv_off` is the float offset of the
+ *    curvature inside a record (4 for pcl::Normal, 3 for float4).
+ *  - all indices are 32-bit and refer to the ORIGINAL order of the surface / query buffers.
+ *  - return value: 0 = ok; < 0 = PFX_E_* (exactly where PCL's initCompute() would print an error
+ *    and return an empty cloud); > 0 = cudaError_t.  No exceptions cross this boundary.
+ *  - a context is bound to one device and may be used by one host thread at a time.  Calls are
+ *    synchronous at return when any output is PFX_HOST; with PFX_DEVICE outputs they are enqueued
+ *    on the context's stream (pfx_set_stream) and complete in stream order (pfx_sync to wait).
+ *  - there is NO CPU fallback: every function fails with a CUDA error when no sm_100 device exists.
+ */
+#ifndef PFX_B200_H
+#define PFX_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pfx_ctx pfx_ctx;
+
+enum { PFX_HOST = 0, PFX_DEVICE = 1 };
+enum {
+  PFX_OK = 0,
+  PFX_E_INVALID = -1,  /* bad argument */
+  PFX_E_PRECOND = -2,  /* PCL initCompute() precondition (no surface, both/neither radius and k, ...) */
+  PFX_E_CAPACITY = -3, /* caller buffer too small */
+  PFX_E_STATE = -4     /* required input (normals, range image, ...) not set */
+};
+
+/* pcl::Correspondence {int index_query; int index_match; float distance} (features.h:245-249) */
+typedef struct { int32_t index_query; int32_t index_match; float distance; } pfx_correspondence;
+
+/* ------------------------------------------------------------------ context */
+int pfx_version(void);
+int pfx_create(int device, pfx_ctx** ctx);
+int pfx_destroy(pfx_ctx* ctx);
+const char* pfx_last_error(const pfx_ctx* ctx);
+int pfx_set_stream(pfx_ctx* ctx, void* cuda_stream); /* cudaStream_t; NULL = default stream */
+int pfx_sync(pfx_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t pfx_launch_count(const pfx_ctx* ctx);
+
+/* ------------------------------------------------------------------ inputs
+ * pfx_set_surface   <- Feature::setSearchSurface + search::KdTree::setInputCloud
+ *                      (features.h:190,192-193; tools.h:27,29-30; keypoints.h:185-187)
+ * pfx_set_queries   <- Feature::setInputCloud(keypoints) (features.h:191); n = 0 => queries = surface
+ * pfx_set_surface_normals <- FeatureFromNormals::setInputNormals (features.h:188)
+ * pfx_set_viewpoint <- cloud.sensor_origin_ used by flipNormalTowardsViewpoint (default 0,0,0) */
+int pfx_set_surface(pfx_ctx* ctx, const void* pts, size_t n, size_t stride, int mem);
+int pfx_set_queries(pfx_ctx* ctx, const void* pts, size_t n, size_t stride, int mem);
+int pfx_set_surface_normals(pfx_ctx* ctx, const void* normals, size_t n, size_t stride,
+                            int curv_off, int mem);
+int pfx_set_viewpoint(pfx_ctx* ctx, float vx, float vy, float vz);
+size_t pfx_num_surface(const pfx_ctx* ctx);
+size_t pfx_num_queries(const pfx_ctx* ctx);
+
+/* ------------------------------------------------------------------ neighbour search
+ * replaces pcl::KdTreeFLANN / pcl::search::KdTree radiusSearch / nearestKSearch
+ * (features.h:192-193, keypoints.h:371-386, 408-417).  d2 = ((dx*dx+dy*dy)+dz*dz) in float, no FMA;
+ * radius membership d2 < (float)(radius*radius); kNN order and tie-break ascending (d2, index). */
+int pfx_knn(pfx_ctx* ctx, int k, int32_t* idx, float* d2, int mem); /* nq x k, padded -1 / +inf */
+int pfx_radius_count(pfx_ctx* ctx, double radius, int32_t* counts, int64_t* total, int mem);
+/* offsets: nq+1 exclusive prefix of counts (int64, same `mem`); sorted != 0 => ascending (d2, index) */
+int pfx_radius_search(pfx_ctx* ctx, double radius, int sorted, const int64_t* offsets,
+                      int32_t* idx, float* d2, int mem);
+
+/* ------------------------------------------------------------------ normals
+ * pfx_normals <- NormalEstimationOMP::compute (tools.h:26-31; features.h:187; keypoints.h:302-308).
+ * Exactly one of radius / k non-zero.  Output row i belongs to query i; NaN row when the query is
+ * non-finite or has no neighbours.  out may be NULL.  When the queries are the surface the result
+ * also becomes the surface's normals (the setInputNormals that follows at features.h:188), so the
+ * pair costs no host round trip. */
+int pfx_normals(pfx_ctx* ctx, double radius, int k, void* out, size_t stride, int curv_off, int mem);
+
+/* ------------------------------------------------------------------ keypoints
+ * pfx_cloud_resolution <- Keypoints::computeCloudResolution (keypoints.h:401-428) */
+int pfx_cloud_resolution(pfx_ctx* ctx, double* resolution);
+/* pfx_iss <- ISSKeypoint3D::compute as configured at keypoints.h:184-194.  kp_idx: ascending
+ * surface indices (capacity cap); saliency (optional, n doubles, `mem`): third_eigen_value. */
+int pfx_iss(pfx_ctx* ctx, double salient_radius, double nonmax_radius, int min_neighbors,
+            double gamma21, double gamma32, int32_t* kp_idx, size_t cap, size_t* n_kp,
+            double* saliency, int mem);
+/* NMS stage alone on caller-supplied saliency (stage-wise parity) */
+int pfx_iss_nms(pfx_ctx* ctx, const double* saliency, double nonmax_radius, int min_neighbors,
+                int32_t* kp_idx, size_t cap, size_t* n_kp, int mem);
+/* pfx_harris3d <- HarrisKeypoint3D::compute as configured at keypoints.h:154-159 (radius default
+ * 0.01, internal NormalEstimation at the same radius when no normals were set) followed by the
+ * reference's snap Keypoints::getKeypointsCloud keypoints.h:360-395 (snap_max_d2 = 1e-4).
+ * Outputs (each optional): response n floats; kp_idx surface index of every NMS maximum (ascending);
+ * kp_xyz refined corner positions (cap x 3); snapped_idx cloud index after the snap or -1. */
+int pfx_harris3d(pfx_ctx* ctx, double radius, float threshold, int nonmax, int refine,
+                 float snap_max_d2, float* response, int32_t* kp_idx, float* kp_xyz,
+                 int32_t* snapped_idx, size_t cap, size_t* n_kp, int mem);
+int pfx_harris_nms(pfx_ctx* ctx, const float* response, double radius, float threshold,
+                   int32_t* kp_idx, size_t cap, size_t* n_kp, int mem);
+
+/* ------------------------------------------------------------------ descriptors
+ * pfx_fpfh <- FPFHEstimation::compute (evaluation.cpp:597-602 via features.h:190-195): SPFH over the
+ * union of the queries' neighbourhoods, then the 1/d2-weighted gather.  out: nq rows of 33 floats at
+ * `stride` bytes (132 for FPFHSignature33).  Requires surface normals. */
+int pfx_fpfh(pfx_ctx* ctx, double radius, int k, float* out, size_t stride, int mem);
+/* SPFH rows of all surface points (stage-wise parity): n x 33 floats, packed */
+int pfx_spfh(pfx_ctx* ctx, double radius, int k, float* out, int mem);
+/* pfx_shot352 <- SHOTEstimationOMP::compute incl. its internal SHOTLocalReferenceFrameEstimation
+ * (evaluation.cpp:770-775).  Radius search only (k-search is rejected like PCL does).  out: nq rows
+ * at `stride` bytes holding descriptor[352] then rf[9] (1444 for pcl::SHOT352).  lrf_in (optional,
+ * nq x 9 packed, `mem`): use these frames instead of estimating them. */
+int pfx_shot352(pfx_ctx* ctx, double radius, const float* lrf_in, float* out, size_t stride, int mem);
+int pfx_shot_lrf(pfx_ctx* ctx, double radius, float* rf9, int mem); /* nq x 9 */
+
+/* ------------------------------------------------------------------ matching
+ * pfx_match <- Features<T>::findCorrespondences / getCorrespondences (features.h:224-273) and
+ * pcl::registration::CorrespondenceEstimation::determine[Reciprocal]Correspondences.
+ * a: na x dim (source), b: nb x dim (target), row strides in bytes.  Distances are the sequential
+ * float sum of squares of FLANN's L2_Simple; ties -> lowest index; NaN rows never match.
+ * reciprocal != 0 keeps i only when nn_b(nn_a(i)) == i.  max_dist2 < 0 = no limit, else keep
+ * d2 <= max_dist2.  out capacity cap (<= na needed). */
+int pfx_match(pfx_ctx* ctx, const float* a, size_t na, size_t stride_a, const float* b, size_t nb,
+              size_t stride_b, int dim, int reciprocal, float max_dist2, pfx_correspondence* out,
+              size_t cap, size_t* n_out, int mem);
+/* one-directional exact 1-NN (nn_idx, nn_d2 sized na) */
+int pfx_match_nn(pfx_ctx* ctx, const float* a, size_t na, size_t stride_a, const float* b, size_t nb,
+                 size_t stride_b, int dim, int32_t* nn_idx, float* nn_d2, int mem);
+/* engine: 0 = exact fp32 scan, 1 = tcgen05 bf16 candidate GEMM + fp32 rescore with certificate
+ * (falls back to the exact scan per row when the certificate fails), -1 = automatic */
+int pfx_set_match_engine(pfx_ctx* ctx, int engine);
+
+/* ------------------------------------------------------------------ ingest
+ * pfx_voxel_grid <- pcl::VoxelGrid centroid filter (config C1 ingest; not in the reference code).
+ * Operates on the current surface; out: cap x 3 packed floats, ascending voxel id. */
+int pfx_voxel_grid(pfx_ctx* ctx, float leaf, float* out_xyz, size_t cap, size_t* n_out, int mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

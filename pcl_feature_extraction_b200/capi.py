@@ -1,0 +1,296 @@
+"""ctypes binding of the C ABI in include/pfx_b200.h (lib/libpfx_b200.so).
+
+The library is the product: there is no Python or CPU fallback.  Importing works without a GPU (so
+that the symbol table can be checked on a CPU box); creating a Context needs an sm_100 device and
+raises otherwise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpfx_b200.so")
+
+HOST, DEVICE = 0, 1
+E_INVALID, E_PRECOND, E_CAPACITY, E_STATE = -1, -2, -3, -4
+
+_lib = None
+
+
+class PfxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pfx error {code}: {msg}")
+        self.code = code
+
+
+class Correspondence(C.Structure):
+    _fields_ = [("index_query", C.c_int32), ("index_match", C.c_int32), ("distance", C.c_float)]
+
+
+CORR_DTYPE = np.dtype([("index_query", "<i4"), ("index_match", "<i4"), ("distance", "<f4")])
+
+# name -> (restype, argtypes); mirrors include/pfx_b200.h one to one
+_vp, _sz, _i, _d, _f = C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_float
+SIGNATURES = {
+    "pfx_version": (_i, []),
+    "pfx_create": (_i, [_i, C.POINTER(_vp)]),
+    "pfx_destroy": (_i, [_vp]),
+    "pfx_last_error": (C.c_char_p, [_vp]),
+    "pfx_set_stream": (_i, [_vp, _vp]),
+    "pfx_sync": (_i, [_vp]),
+    "pfx_launch_count": (C.c_uint64, [_vp]),
+    "pfx_set_surface": (_i, [_vp, _vp, _sz, _sz, _i]),
+    "pfx_set_queries": (_i, [_vp, _vp, _sz, _sz, _i]),
+    "pfx_set_surface_normals": (_i, [_vp, _vp, _sz, _sz, _i, _i]),
+    "pfx_set_viewpoint": (_i, [_vp, _f, _f, _f]),
+    "pfx_num_surface": (_sz, [_vp]),
+    "pfx_num_queries": (_sz, [_vp]),
+    "pfx_knn": (_i, [_vp, _i, _vp, _vp, _i]),
+    "pfx_radius_count": (_i, [_vp, _d, _vp, C.POINTER(C.c_int64), _i]),
+    "pfx_radius_search": (_i, [_vp, _d, _i, _vp, _vp, _vp, _i]),
+    "pfx_normals": (_i, [_vp, _d, _i, _vp, _sz, _i, _i]),
+    "pfx_cloud_resolution": (_i, [_vp, C.POINTER(_d)]),
+    "pfx_iss": (_i, [_vp, _d, _d, _i, _d, _d, _vp, _sz, C.POINTER(_sz), _vp, _i]),
+    "pfx_iss_nms": (_i, [_vp, _vp, _d, _i, _vp, _sz, C.POINTER(_sz), _i]),
+    "pfx_harris3d": (_i, [_vp, _d, _f, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, C.POINTER(_sz), _i]),
+    "pfx_harris_nms": (_i, [_vp, _vp, _d, _f, _vp, _sz, C.POINTER(_sz), _i]),
+    "pfx_fpfh": (_i, [_vp, _d, _i, _vp, _sz, _i]),
+    "pfx_spfh": (_i, [_vp, _d, _i, _vp, _i]),
+    "pfx_shot352": (_i, [_vp, _d, _vp, _vp, _sz, _i]),
+    "pfx_shot_lrf": (_i, [_vp, _d, _vp, _i]),
+    "pfx_match": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _f, _vp, _sz, C.POINTER(_sz), _i]),
+    "pfx_match_nn": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _vp, _vp, _i]),
+    "pfx_set_match_engine": (_i, [_vp, _i]),
+    "pfx_voxel_grid": (_i, [_vp, _f, _vp, _sz, C.POINTER(_sz), _i]),
+}
+
+
+def load():
+    """Loads lib/libpfx_b200.so; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C pcl_feature_extraction_b200/csrc). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if hasattr(a, "data_ptr"):  # torch tensor
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class Context:
+    """One device context (pfx_ctx).  Thin: every method is one C-ABI call with numpy buffers."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.pfx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise PfxError(rc, "pfx_create failed (an sm_100 CUDA device is required; there is no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pfx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise PfxError(rc, self.lib.pfx_last_error(self.h).decode())
+
+    # -- plumbing
+    def set_stream(self, stream_ptr):
+        self._chk(self.lib.pfx_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def sync(self):
+        self._chk(self.lib.pfx_sync(self.h))
+
+    @property
+    def launches(self):
+        return int(self.lib.pfx_launch_count(self.h))
+
+    # -- inputs (numpy host arrays; *_dev variants take raw device pointers)
+    def set_surface(self, pts):
+        pts = np.ascontiguousarray(pts, np.float32)
+        self._surface_keepalive = pts
+        self._chk(self.lib.pfx_set_surface(self.h, _ptr(pts), len(pts), pts.strides[0] if len(pts) else 12, HOST))
+
+    def set_surface_dev(self, ptr, n, stride):
+        self._chk(self.lib.pfx_set_surface(self.h, _ptr(ptr), n, stride, DEVICE))
+
+    def set_queries(self, pts):
+        if pts is None:
+            self._chk(self.lib.pfx_set_queries(self.h, None, 0, 0, HOST))
+            return
+        pts = np.ascontiguousarray(pts, np.float32)
+        self._chk(self.lib.pfx_set_queries(self.h, _ptr(pts), len(pts), pts.strides[0] if len(pts) else 12, HOST))
+
+    def set_queries_dev(self, ptr, n, stride):
+        self._chk(self.lib.pfx_set_queries(self.h, _ptr(ptr), n, stride, DEVICE))
+
+    def set_surface_normals(self, normals4):
+        nr = np.ascontiguousarray(normals4, np.float32)
+        assert nr.ndim == 2 and nr.shape[1] in (4, 8)
+        curv = 3 if nr.shape[1] == 4 else 4
+        self._chk(self.lib.pfx_set_surface_normals(self.h, _ptr(nr), len(nr), nr.strides[0] if len(nr) else 16, curv, HOST))
+
+    def set_viewpoint(self, x, y, z):
+        self._chk(self.lib.pfx_set_viewpoint(self.h, x, y, z))
+
+    @property
+    def num_queries(self):
+        return int(self.lib.pfx_num_queries(self.h))
+
+    @property
+    def num_surface(self):
+        return int(self.lib.pfx_num_surface(self.h))
+
+    # -- search
+    def knn(self, k):
+        nq = self.num_queries
+        idx = np.zeros((nq, k), np.int32)
+        d2 = np.zeros((nq, k), np.float32)
+        self._chk(self.lib.pfx_knn(self.h, k, _ptr(idx), _ptr(d2), HOST))
+        return idx, d2
+
+    def radius_search(self, radius, sorted=True):
+        nq = self.num_queries
+        counts = np.zeros(nq, np.int32)
+        total = C.c_int64(0)
+        self._chk(self.lib.pfx_radius_count(self.h, radius, _ptr(counts), C.byref(total), HOST))
+        offsets = np.zeros(nq + 1, np.int64)
+        np.cumsum(counts, out=offsets[1:])
+        assert offsets[-1] == total.value
+        idx = np.zeros(int(total.value), np.int32)
+        d2 = np.zeros(int(total.value), np.float32)
+        self._chk(self.lib.pfx_radius_search(self.h, radius, 1 if sorted else 0, _ptr(offsets), _ptr(idx), _ptr(d2), HOST))
+        return offsets, idx, d2
+
+    # -- normals
+    def normals(self, radius=0.0, k=0, want_output=True):
+        nq = self.num_queries
+        out = np.zeros((nq, 4), np.float32) if want_output else None
+        self._chk(self.lib.pfx_normals(self.h, radius, k, _ptr(out), 16, 3, HOST))
+        return out
+
+    def normals_dev(self, radius, k, out_ptr, stride=16, curv_off=3):
+        self._chk(self.lib.pfx_normals(self.h, radius, k, _ptr(out_ptr), stride, curv_off, DEVICE))
+
+    # -- keypoints
+    def cloud_resolution(self):
+        r = C.c_double(0)
+        self._chk(self.lib.pfx_cloud_resolution(self.h, C.byref(r)))
+        return r.value
+
+    def iss(self, salient_radius, nonmax_radius, min_neighbors=5, g21=0.975, g32=0.975):
+        n = self.num_surface
+        kp = np.zeros(n, np.int32)
+        sal = np.zeros(n, np.float64)
+        nk = C.c_size_t(0)
+        self._chk(self.lib.pfx_iss(self.h, salient_radius, nonmax_radius, min_neighbors, g21, g32, _ptr(kp), n,
+                                   C.byref(nk), _ptr(sal), HOST))
+        return kp[: nk.value].copy(), sal
+
+    def iss_nms(self, saliency, nonmax_radius, min_neighbors=5):
+        n = self.num_surface
+        sal = np.ascontiguousarray(saliency, np.float64)
+        kp = np.zeros(n, np.int32)
+        nk = C.c_size_t(0)
+        self._chk(self.lib.pfx_iss_nms(self.h, _ptr(sal), nonmax_radius, min_neighbors, _ptr(kp), n, C.byref(nk), HOST))
+        return kp[: nk.value].copy()
+
+    def harris3d(self, radius=0.01, threshold=1e-6, nonmax=True, refine=True, snap_max_d2=1e-4):
+        n = self.num_surface
+        resp = np.zeros(n, np.float32)
+        kp = np.zeros(n, np.int32)
+        xyz = np.zeros((n, 3), np.float32)
+        snap = np.zeros(n, np.int32)
+        nk = C.c_size_t(0)
+        self._chk(self.lib.pfx_harris3d(self.h, radius, threshold, int(nonmax), int(refine), snap_max_d2, _ptr(resp),
+                                        _ptr(kp), _ptr(xyz), _ptr(snap), n, C.byref(nk), HOST))
+        m = nk.value
+        return dict(response=resp, kp_idx=kp[:m].copy(), kp_xyz=xyz[:m].copy(), snapped_idx=snap[:m].copy())
+
+    def harris_nms(self, response, radius, threshold):
+        n = self.num_surface
+        resp = np.ascontiguousarray(response, np.float32)
+        kp = np.zeros(n, np.int32)
+        nk = C.c_size_t(0)
+        self._chk(self.lib.pfx_harris_nms(self.h, _ptr(resp), radius, threshold, _ptr(kp), n, C.byref(nk), HOST))
+        return kp[: nk.value].copy()
+
+    # -- descriptors
+    def fpfh(self, radius=0.0, k=0):
+        out = np.zeros((self.num_queries, 33), np.float32)
+        self._chk(self.lib.pfx_fpfh(self.h, radius, k, _ptr(out), 132, HOST))
+        return out
+
+    def fpfh_dev(self, radius, k, out_ptr, stride=132):
+        self._chk(self.lib.pfx_fpfh(self.h, radius, k, _ptr(out_ptr), stride, DEVICE))
+
+    def spfh(self, radius=0.0, k=0):
+        out = np.zeros((self.num_surface, 33), np.float32)
+        self._chk(self.lib.pfx_spfh(self.h, radius, k, _ptr(out), HOST))
+        return out
+
+    def shot_lrf(self, radius):
+        out = np.zeros((self.num_queries, 9), np.float32)
+        self._chk(self.lib.pfx_shot_lrf(self.h, radius, _ptr(out), HOST))
+        return out
+
+    def shot352(self, radius, lrf_in=None):
+        out = np.zeros((self.num_queries, 361), np.float32)
+        lrf = np.ascontiguousarray(lrf_in, np.float32) if lrf_in is not None else None
+        self._chk(self.lib.pfx_shot352(self.h, radius, _ptr(lrf), _ptr(out), 1444, HOST))
+        return out[:, :352].copy(), out[:, 352:].copy()
+
+    def shot352_dev(self, radius, out_ptr, stride=1444):
+        self._chk(self.lib.pfx_shot352(self.h, radius, None, _ptr(out_ptr), stride, DEVICE))
+
+    # -- matching
+    def match_nn(self, a, b):
+        a = np.ascontiguousarray(a, np.float32)
+        b = np.ascontiguousarray(b, np.float32)
+        dim = a.shape[1] if a.ndim == 2 and a.shape[1] else b.shape[1]
+        idx = np.zeros(len(a), np.int32)
+        d2 = np.zeros(len(a), np.float32)
+        self._chk(self.lib.pfx_match_nn(self.h, _ptr(a), len(a), dim * 4, _ptr(b), len(b), dim * 4, dim, _ptr(idx),
+                                        _ptr(d2), HOST))
+        return idx, d2
+
+    def match(self, a, b, reciprocal=True, max_dist2=-1.0):
+        a = np.ascontiguousarray(a, np.float32)
+        b = np.ascontiguousarray(b, np.float32)
+        dim = a.shape[1]
+        out = np.zeros(max(len(a), 1), CORR_DTYPE)
+        m = C.c_size_t(0)
+        self._chk(self.lib.pfx_match(self.h, _ptr(a), len(a), dim * 4, _ptr(b), len(b), dim * 4, dim, int(reciprocal),
+                                     max_dist2, _ptr(out), len(out), C.byref(m), HOST))
+        return out[: m.value].copy()
+
+    def set_match_engine(self, engine):
+        self._chk(self.lib.pfx_set_match_engine(self.h, engine))

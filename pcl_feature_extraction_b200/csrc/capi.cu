@@ -1,0 +1,742 @@
+// capi.cu — the C ABI declared in include/pfx_b200.h: context, host<->device staging, layout
+// conversion (strided AoS records <-> the float4 SoA rows the kernels use) and stage sequencing.
+#include <cstring>
+
+#include "internal.h"
+
+using namespace pfx;
+
+namespace pfx {
+
+// ------------------------------------------------------------------------------ layout kernels
+__global__ void aos_to_float4_kernel(const unsigned char* __restrict__ src, size_t stride, int n,
+                                     float4* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = reinterpret_cast<const float*>(src + (size_t)i * stride);
+  dst[i] = make_float4(p[0], p[1], p[2], __int_as_float(i));
+}
+
+__global__ void normals_in_kernel(const unsigned char* __restrict__ src, size_t stride, int curv_off, int n,
+                                  float4* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = reinterpret_cast<const float*>(src + (size_t)i * stride);
+  dst[i] = make_float4(p[0], p[1], p[2], p[curv_off]);
+}
+
+__global__ void normals_out_kernel(const float4* __restrict__ src, int n, unsigned char* __restrict__ dst,
+                                   size_t stride, int curv_off) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float* p = reinterpret_cast<float*>(dst + (size_t)i * stride);
+  float4 v = src[i];
+  p[0] = v.x;
+  p[1] = v.y;
+  p[2] = v.z;
+  p[curv_off] = v.w;
+}
+
+__global__ void permute_rows_kernel(const float4* __restrict__ src_orig, const float4* __restrict__ sorted_pts,
+                                    int n, float4* __restrict__ dst_sorted) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst_sorted[i] = src_orig[__float_as_int(sorted_pts[i].w)];
+}
+
+__global__ void gather_xyz_kernel(const float4* __restrict__ surf, const int* __restrict__ idx, int m,
+                                  float* __restrict__ xyz) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  float4 p = surf[idx[i]];
+  xyz[3 * i] = p.x;
+  xyz[3 * i + 1] = p.y;
+  xyz[3 * i + 2] = p.z;
+}
+
+// surface normals in the sorted order of grid g (cached)
+int normals_sorted_for_grid(Ctx* ctx, Grid* g, const float4** out) {
+  if (!ctx->have_normals) return ctx->fail(PFX_E_STATE, "surface normals are not set (setInputNormals)");
+  if (ctx->normals_sorted_for == g && ctx->normals_sorted_version == ctx->normals_version &&
+      g->surf_version == ctx->surf_version) {
+    *out = ctx->normals_sorted.as<float4>();
+    return 0;
+  }
+  const int n = (int)ctx->n;
+  PFX_CUDA(ctx->normals_sorted.ensure(std::max<size_t>(n, 1) * sizeof(float4)));
+  if (n > 0)
+    PFX_LAUNCH(ctx, permute_rows_kernel, div_up(n, 256), 256, 0, ctx->normals.as<float4>(), g->pts.as<float4>(), n,
+               ctx->normals_sorted.as<float4>());
+  PFX_CUDA(cudaGetLastError());
+  ctx->normals_sorted_for = g;
+  ctx->normals_sorted_version = ctx->normals_version;
+  *out = ctx->normals_sorted.as<float4>();
+  return 0;
+}
+
+static int upload_records(Ctx* ctx, const void* src, size_t n, size_t stride, int mem, DevBuf& stage,
+                          const unsigned char** dev_src) {
+  if (mem == PFX_DEVICE) {
+    *dev_src = static_cast<const unsigned char*>(src);
+    return 0;
+  }
+  PFX_CUDA(stage.ensure(std::max<size_t>(n * stride, 16)));
+  if (n) PFX_CUDA(cudaMemcpyAsync(stage.p, src, n * stride, cudaMemcpyHostToDevice, ctx->stream));
+  *dev_src = stage.as<unsigned char>();
+  return 0;
+}
+
+// copy a device result to the caller (host: synchronous at return)
+static int deliver(Ctx* ctx, void* dst, const void* dev_src, size_t bytes, int mem) {
+  if (bytes == 0) return 0;
+  if (mem == PFX_DEVICE) {
+    if (dst != dev_src)
+      PFX_CUDA(cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+  }
+  PFX_CUDA(cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static int check_ctx(pfx_ctx* ctx) {
+  if (!ctx) return PFX_E_INVALID;
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return ctx->fail_cuda(e, "cudaSetDevice", __FILE__, __LINE__);
+  return 0;
+}
+
+static int check_search_params(Ctx* ctx, double radius, int k, const char* who) {
+  // pcl::Feature::initCompute: exactly one of radius / k
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, std::string(who) + ": no surface set");
+  if (radius > 0 && k > 0) return ctx->fail(PFX_E_PRECOND, std::string(who) + ": both radius and K defined");
+  if (!(radius > 0) && k <= 0) return ctx->fail(PFX_E_PRECOND, std::string(who) + ": neither radius nor K defined");
+  if (radius < 0 || k < 0) return ctx->fail(PFX_E_INVALID, std::string(who) + ": negative search parameter");
+  return 0;
+}
+
+}  // namespace pfx
+
+// ================================================================================== context
+extern "C" int pfx_version(void) { return 100; }
+
+extern "C" int pfx_create(int device, pfx_ctx** out) {
+  if (!out) return PFX_E_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) return (int)e;
+  if (device < 0 || device >= count) return PFX_E_INVALID;
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return (int)e;
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return (int)e;
+  if (prop.major < 10) return (int)cudaErrorNoKernelImageForDevice;  // sm_100a only, no fallback
+  pfx_ctx* c = new pfx_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return 0;
+}
+
+extern "C" int pfx_destroy(pfx_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  grid_free_all(ctx);
+  for (DevBuf* b : {&ctx->surf, &ctx->normals, &ctx->normals_sorted, &ctx->qry, &ctx->knn_idx, &ctx->knn_d2,
+                    &ctx->stage, &ctx->stage2, &ctx->tmp0, &ctx->tmp1, &ctx->tmp2, &ctx->tmp3, &ctx->tmp4,
+                    &ctx->small, &ctx->scanbuf, &ctx->match_flags, &ctx->match_best, &ctx->out_stage})
+    b->release();
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  delete ctx;
+  return 0;
+}
+
+extern "C" const char* pfx_last_error(const pfx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int pfx_set_stream(pfx_ctx* ctx, void* s) {
+  if (!ctx) return PFX_E_INVALID;
+  ctx->stream = static_cast<cudaStream_t>(s);
+  return 0;
+}
+
+extern "C" int pfx_sync(pfx_ctx* ctx) {
+  PFX_TRY(check_ctx(ctx));
+  PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" uint64_t pfx_launch_count(const pfx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" size_t pfx_num_surface(const pfx_ctx* ctx) { return ctx ? ctx->n : 0; }
+extern "C" size_t pfx_num_queries(const pfx_ctx* ctx) { return ctx ? ctx->num_queries() : 0; }
+
+// ================================================================================== inputs
+extern "C" int pfx_set_surface(pfx_ctx* ctx, const void* pts, size_t n, size_t stride, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if ((n && !pts) || stride < 12 || (stride & 3) || n > 0x7fffffffull)
+    return ctx->fail(PFX_E_INVALID, "pfx_set_surface: bad pointer / stride / size");
+  const unsigned char* src = nullptr;
+  PFX_TRY(upload_records(ctx, pts, n, stride, mem, ctx->stage, &src));
+  PFX_CUDA(ctx->surf.ensure(std::max<size_t>(n, 1) * sizeof(float4)));
+  if (n) PFX_LAUNCH(ctx, aos_to_float4_kernel, div_up((long long)n, 256), 256, 0, src, stride, (int)n, ctx->surf.as<float4>());
+  PFX_CUDA(cudaGetLastError());
+  ctx->n = n;
+  ctx->surf_version = ++ctx->tick + (1ull << 32);
+  ctx->have_normals = false;
+  ctx->normals_sorted_for = nullptr;
+  ctx->knn_grid = nullptr;
+  ctx->q_is_surface = true;
+  ctx->nq = 0;
+  return 0;
+}
+
+extern "C" int pfx_set_queries(pfx_ctx* ctx, const void* pts, size_t n, size_t stride, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (n == 0 || !pts) {
+    ctx->q_is_surface = true;
+    ctx->nq = 0;
+    ctx->qry_version++;
+    return 0;
+  }
+  if (stride < 12 || (stride & 3) || n > 0x7fffffffull) return ctx->fail(PFX_E_INVALID, "pfx_set_queries: bad stride / size");
+  const unsigned char* src = nullptr;
+  PFX_TRY(upload_records(ctx, pts, n, stride, mem, ctx->stage, &src));
+  PFX_CUDA(ctx->qry.ensure(n * sizeof(float4)));
+  PFX_LAUNCH(ctx, aos_to_float4_kernel, div_up((long long)n, 256), 256, 0, src, stride, (int)n, ctx->qry.as<float4>());
+  PFX_CUDA(cudaGetLastError());
+  ctx->nq = n;
+  ctx->q_is_surface = false;
+  ctx->qry_version++;
+  return 0;
+}
+
+extern "C" int pfx_set_surface_normals(pfx_ctx* ctx, const void* normals, size_t n, size_t stride, int curv_off,
+                                       int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_set_surface_normals: no surface set");
+  // FeatureFromNormals::initCompute: normals.size() must equal surface.size()
+  if (n != ctx->n) return ctx->fail(PFX_E_PRECOND, "pfx_set_surface_normals: the number of normals differs from the surface size");
+  if (stride < 16 || (stride & 3) || curv_off < 3 || (size_t)(curv_off + 1) * 4 > stride)
+    return ctx->fail(PFX_E_INVALID, "pfx_set_surface_normals: bad stride / curvature offset");
+  const unsigned char* src = nullptr;
+  PFX_TRY(upload_records(ctx, normals, n, stride, mem, ctx->stage, &src));
+  PFX_CUDA(ctx->normals.ensure(std::max<size_t>(n, 1) * sizeof(float4)));
+  if (n) PFX_LAUNCH(ctx, normals_in_kernel, div_up((long long)n, 256), 256, 0, src, stride, curv_off, (int)n, ctx->normals.as<float4>());
+  PFX_CUDA(cudaGetLastError());
+  ctx->have_normals = true;
+  ctx->normals_version++;
+  return 0;
+}
+
+extern "C" int pfx_set_viewpoint(pfx_ctx* ctx, float vx, float vy, float vz) {
+  if (!ctx) return PFX_E_INVALID;
+  ctx->vp[0] = vx;
+  ctx->vp[1] = vy;
+  ctx->vp[2] = vz;
+  return 0;
+}
+
+// ================================================================================== search
+extern "C" int pfx_knn(pfx_ctx* ctx, int k, int32_t* idx, float* d2, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_knn: no surface set");
+  if (k < 1 || k > 32) return ctx->fail(PFX_E_INVALID, "pfx_knn: k must be in [1, 32]");
+  if (!idx || !d2) return ctx->fail(PFX_E_INVALID, "pfx_knn: null output");
+  const size_t nq = ctx->num_queries();
+  if (nq == 0) return 0;
+  Grid* g = nullptr;
+  PFX_TRY(grid_get(ctx, 0.0, k, &g));
+  PFX_TRY(knn_lists(ctx, g, k, true));
+  int32_t* didx = idx;
+  float* dd2 = d2;
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->out_stage.ensure(nq * k * (sizeof(int) + sizeof(float))));
+    didx = ctx->out_stage.as<int32_t>();
+    dd2 = reinterpret_cast<float*>(didx + nq * k);
+  }
+  PFX_TRY(knn_export(ctx, k, didx, dd2, mem));
+  if (mem == PFX_HOST) {
+    PFX_CUDA(cudaMemcpyAsync(idx, didx, nq * k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PFX_TRY(deliver(ctx, d2, dd2, nq * k * sizeof(float), mem));
+  }
+  return 0;
+}
+
+extern "C" int pfx_radius_count(pfx_ctx* ctx, double radius, int32_t* counts, int64_t* total, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_radius_count: no surface set");
+  if (!(radius > 0)) return ctx->fail(PFX_E_INVALID, "pfx_radius_count: radius must be > 0");
+  const size_t nq = ctx->num_queries();
+  if (total) *total = 0;
+  if (nq == 0) return 0;
+  Grid* g = nullptr;
+  PFX_TRY(grid_get(ctx, radius, 0, &g));
+  int* dcounts = counts;
+  if (mem == PFX_HOST || !counts) {
+    PFX_CUDA(ctx->out_stage.ensure(nq * sizeof(int)));
+    dcounts = ctx->out_stage.as<int>();
+  }
+  PFX_TRY(radius_count(ctx, g, radius, dcounts));
+  if (total) {
+    PFX_CUDA(ctx->tmp4.ensure((nq + 1) * sizeof(long long)));
+    PFX_TRY(scan_exclusive_i64(ctx, dcounts, ctx->tmp4.as<long long>(), (int)nq, ctx->scanbuf));
+    long long t = 0;
+    PFX_CUDA(cudaMemcpyAsync(&t, ctx->tmp4.as<long long>() + nq, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+    *total = t;
+  }
+  if (mem == PFX_HOST && counts) PFX_TRY(deliver(ctx, counts, dcounts, nq * sizeof(int), mem));
+  return 0;
+}
+
+extern "C" int pfx_radius_search(pfx_ctx* ctx, double radius, int sorted, const int64_t* offsets, int32_t* idx,
+                                 float* d2, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_radius_search: no surface set");
+  if (!(radius > 0) || !offsets) return ctx->fail(PFX_E_INVALID, "pfx_radius_search: bad arguments");
+  const size_t nq = ctx->num_queries();
+  if (nq == 0) return 0;
+  Grid* g = nullptr;
+  PFX_TRY(grid_get(ctx, radius, 0, &g));
+  const long long* doff = reinterpret_cast<const long long*>(offsets);
+  int* didx = idx;
+  float* dd2 = d2;
+  long long total = 0;
+  if (mem == PFX_HOST) {
+    total = offsets[nq];
+    PFX_CUDA(ctx->tmp4.ensure((nq + 1) * sizeof(long long)));
+    PFX_CUDA(cudaMemcpyAsync(ctx->tmp4.p, offsets, (nq + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    doff = ctx->tmp4.as<long long>();
+    PFX_CUDA(ctx->out_stage.ensure(std::max<size_t>((size_t)total, 1) * (sizeof(int) + sizeof(float))));
+    didx = ctx->out_stage.as<int>();
+    dd2 = reinterpret_cast<float*>(didx + total);
+  }
+  PFX_TRY(radius_fill(ctx, g, radius, sorted, doff, didx, dd2));
+  if (mem == PFX_HOST && total > 0) {
+    PFX_CUDA(cudaMemcpyAsync(idx, didx, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PFX_TRY(deliver(ctx, d2, dd2, (size_t)total * sizeof(float), mem));
+  }
+  return 0;
+}
+
+// ================================================================================== normals
+extern "C" int pfx_normals(pfx_ctx* ctx, double radius, int k, void* out, size_t stride, int curv_off, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  PFX_TRY(check_search_params(ctx, radius, k, "pfx_normals"));
+  if (k > 32) return ctx->fail(PFX_E_INVALID, "pfx_normals: k must be <= 32");
+  if (out && (stride < 16 || (stride & 3) || curv_off < 3 || (size_t)(curv_off + 1) * 4 > stride))
+    return ctx->fail(PFX_E_INVALID, "pfx_normals: bad stride / curvature offset");
+  const size_t nq = ctx->num_queries();
+  Grid* g = nullptr;
+  PFX_TRY(grid_get(ctx, radius > 0 ? radius : 0.0, k, &g));
+  float4* rows = nullptr;
+  if (out || !ctx->q_is_surface) {
+    PFX_CUDA(ctx->tmp0.ensure(std::max<size_t>(nq, 1) * sizeof(float4)));
+    rows = ctx->tmp0.as<float4>();
+  }
+  if (!out && !ctx->q_is_surface) return 0;
+  PFX_TRY(normals_compute(ctx, g, radius, k, rows));
+  if (!out || nq == 0) return 0;
+  if (mem == PFX_DEVICE) {
+    if (stride == 16 && curv_off == 3) return deliver(ctx, out, rows, nq * sizeof(float4), mem);
+    PFX_LAUNCH(ctx, normals_out_kernel, div_up((long long)nq, 256), 256, 0, rows, (int)nq, static_cast<unsigned char*>(out), stride, curv_off);
+    PFX_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (stride == 16 && curv_off == 3) return deliver(ctx, out, rows, nq * sizeof(float4), mem);
+  PFX_CUDA(ctx->out_stage.ensure(nq * stride));
+  PFX_CUDA(cudaMemsetAsync(ctx->out_stage.p, 0, nq * stride, ctx->stream));
+  PFX_LAUNCH(ctx, normals_out_kernel, div_up((long long)nq, 256), 256, 0, rows, (int)nq, ctx->out_stage.as<unsigned char>(), stride, curv_off);
+  return deliver(ctx, out, ctx->out_stage.p, nq * stride, mem);
+}
+
+// ================================================================================== keypoints
+extern "C" int pfx_cloud_resolution(pfx_ctx* ctx, double* resolution) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_cloud_resolution: no surface set");
+  if (!resolution) return ctx->fail(PFX_E_INVALID, "null output");
+  return cloud_resolution(ctx, resolution);
+}
+
+static int emit_keypoints(Ctx* ctx, const int* flags_dev, int32_t* kp_idx, size_t cap, size_t* n_kp, int mem,
+                          int** idx_dev_out) {
+  const int n = (int)ctx->n;
+  PFX_CUDA(ctx->tmp3.ensure(std::max<size_t>(n, 1) * sizeof(int)));
+  int cnt = 0;
+  PFX_TRY(compact_flags(ctx, flags_dev, n, ctx->tmp3.as<int>(), &cnt));
+  if (n_kp) *n_kp = (size_t)cnt;
+  if (idx_dev_out) *idx_dev_out = ctx->tmp3.as<int>();
+  if (kp_idx) {
+    if ((size_t)cnt > cap) return ctx->fail(PFX_E_CAPACITY, "keypoint buffer too small");
+    PFX_TRY(deliver(ctx, kp_idx, ctx->tmp3.p, (size_t)cnt * sizeof(int), mem));
+  }
+  return 0;
+}
+
+extern "C" int pfx_iss_nms(pfx_ctx* ctx, const double* saliency, double nonmax_radius, int min_neighbors,
+                           int32_t* kp_idx, size_t cap, size_t* n_kp, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_iss_nms: no surface set");
+  if (!(nonmax_radius > 0) || !saliency) return ctx->fail(PFX_E_INVALID, "pfx_iss_nms: bad arguments");
+  const size_t n = ctx->n;
+  if (n_kp) *n_kp = 0;
+  if (n == 0) return 0;
+  const double* dsal = saliency;
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->tmp1.ensure(n * sizeof(double)));
+    PFX_CUDA(cudaMemcpyAsync(ctx->tmp1.p, saliency, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    dsal = ctx->tmp1.as<double>();
+  }
+  Grid* g = nullptr;
+  PFX_TRY(grid_get(ctx, nonmax_radius, 0, &g));
+  PFX_CUDA(ctx->tmp2.ensure(n * sizeof(int)));
+  PFX_CUDA(cudaMemsetAsync(ctx->tmp2.p, 0, n * sizeof(int), ctx->stream));
+  PFX_TRY(iss_nms(ctx, g, dsal, nonmax_radius, min_neighbors, ctx->tmp2.as<int>()));
+  return emit_keypoints(ctx, ctx->tmp2.as<int>(), kp_idx, cap, n_kp, mem, nullptr);
+}
+
+extern "C" int pfx_iss(pfx_ctx* ctx, double salient_radius, double nonmax_radius, int min_neighbors, double gamma21,
+                       double gamma32, int32_t* kp_idx, size_t cap, size_t* n_kp, double* saliency, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_iss: no surface set");
+  // ISSKeypoint3D::initCompute: salient radius and non-max radius must be strictly positive
+  if (!(salient_radius > 0)) return ctx->fail(PFX_E_PRECOND, "pfx_iss: the salient radius must be strictly positive");
+  if (!(nonmax_radius > 0)) return ctx->fail(PFX_E_PRECOND, "pfx_iss: the non maxima radius must be strictly positive");
+  if (min_neighbors < 0) return ctx->fail(PFX_E_PRECOND, "pfx_iss: negative minimum neighbours");
+  const size_t n = ctx->n;
+  if (n_kp) *n_kp = 0;
+  if (n == 0) return 0;
+  PFX_CUDA(ctx->tmp1.ensure(n * sizeof(double)));
+  double* dsal = ctx->tmp1.as<double>();
+  PFX_CUDA(cudaMemsetAsync(dsal, 0, n * sizeof(double), ctx->stream));
+  Grid* gs = nullptr;
+  PFX_TRY(grid_get(ctx, salient_radius, 0, &gs));
+  PFX_TRY(iss_saliency(ctx, gs, salient_radius, min_neighbors, gamma21, gamma32, dsal));
+  Grid* gn = nullptr;
+  PFX_TRY(grid_get(ctx, nonmax_radius, 0, &gn));
+  PFX_CUDA(ctx->tmp2.ensure(n * sizeof(int)));
+  PFX_CUDA(cudaMemsetAsync(ctx->tmp2.p, 0, n * sizeof(int), ctx->stream));
+  PFX_TRY(iss_nms(ctx, gn, dsal, nonmax_radius, min_neighbors, ctx->tmp2.as<int>()));
+  if (saliency) {
+    if (mem == PFX_DEVICE) PFX_TRY(deliver(ctx, saliency, dsal, n * sizeof(double), mem));
+    else PFX_CUDA(cudaMemcpyAsync(saliency, dsal, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return emit_keypoints(ctx, ctx->tmp2.as<int>(), kp_idx, cap, n_kp, mem, nullptr);
+}
+
+extern "C" int pfx_harris_nms(pfx_ctx* ctx, const float* response, double radius, float threshold, int32_t* kp_idx,
+                              size_t cap, size_t* n_kp, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_harris_nms: no surface set");
+  if (!(radius > 0) || !response) return ctx->fail(PFX_E_INVALID, "pfx_harris_nms: bad arguments");
+  const size_t n = ctx->n;
+  if (n_kp) *n_kp = 0;
+  if (n == 0) return 0;
+  const float* dresp = response;
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->tmp1.ensure(n * sizeof(float)));
+    PFX_CUDA(cudaMemcpyAsync(ctx->tmp1.p, response, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    dresp = ctx->tmp1.as<float>();
+  }
+  Grid* g = nullptr;
+  PFX_TRY(grid_get(ctx, radius, 0, &g));
+  PFX_CUDA(ctx->tmp2.ensure(n * sizeof(int)));
+  PFX_CUDA(cudaMemsetAsync(ctx->tmp2.p, 0, n * sizeof(int), ctx->stream));
+  PFX_TRY(harris_nms(ctx, g, dresp, radius, threshold, ctx->tmp2.as<int>()));
+  return emit_keypoints(ctx, ctx->tmp2.as<int>(), kp_idx, cap, n_kp, mem, nullptr);
+}
+
+static int harris3d_impl(pfx_ctx* ctx, double radius, float threshold, int nonmax, int refine, float snap_max_d2,
+                         float* response, int32_t* kp_idx, float* kp_xyz, int32_t* snapped_idx, size_t cap,
+                         size_t* n_kp, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_harris3d: no surface set");
+  if (!(radius > 0)) return ctx->fail(PFX_E_PRECOND, "pfx_harris3d: radius must be > 0");
+  const size_t n = ctx->n;
+  if (n_kp) *n_kp = 0;
+  if (n == 0) return 0;
+  Grid* g = nullptr;
+  PFX_TRY(grid_get(ctx, radius, 0, &g));
+  // HarrisKeypoint3D::initCompute: no normals given -> NormalEstimation on the surface at the same radius
+  if (!ctx->have_normals) {
+    bool saved = ctx->q_is_surface;
+    ctx->q_is_surface = true;
+    int rc = normals_compute(ctx, g, radius, 0, nullptr);
+    ctx->q_is_surface = saved;
+    if (rc) return rc;
+  }
+  PFX_CUDA(ctx->tmp1.ensure(n * sizeof(float)));
+  float* dresp = ctx->tmp1.as<float>();
+  PFX_TRY(harris_response(ctx, g, radius, dresp));
+  if (response) {
+    if (mem == PFX_DEVICE) PFX_TRY(deliver(ctx, response, dresp, n * sizeof(float), mem));
+    else PFX_CUDA(cudaMemcpyAsync(response, dresp, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (!nonmax) {  // PCL: output = the response cloud itself (every point)
+    if (n_kp) *n_kp = n;
+    PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+  PFX_CUDA(ctx->tmp2.ensure(n * sizeof(int)));
+  PFX_CUDA(cudaMemsetAsync(ctx->tmp2.p, 0, n * sizeof(int), ctx->stream));
+  PFX_TRY(harris_nms(ctx, g, dresp, radius, threshold, ctx->tmp2.as<int>()));
+  int* didx = nullptr;
+  size_t cnt = 0;
+  PFX_TRY(emit_keypoints(ctx, ctx->tmp2.as<int>(), kp_idx, cap, &cnt, mem, &didx));
+  if (n_kp) *n_kp = cnt;
+  if (cnt == 0 || (!kp_xyz && !snapped_idx)) return 0;
+  if (cnt > cap) return ctx->fail(PFX_E_CAPACITY, "keypoint buffer too small");
+  // corner positions (refined) and the snap back onto the cloud
+  PFX_CUDA(ctx->stage2.ensure(cnt * 3 * sizeof(float) + cnt * sizeof(int)));
+  float* dxyz = ctx->stage2.as<float>();
+  int* dsnap = reinterpret_cast<int*>(dxyz + cnt * 3);
+  PFX_LAUNCH(ctx, gather_xyz_kernel, div_up((long long)cnt, 256), 256, 0, ctx->surf.as<float4>(), didx, (int)cnt, dxyz);
+  if (refine) PFX_TRY(harris_refine(ctx, g, radius, dxyz, (int)cnt));
+  if (kp_xyz) {
+    if (mem == PFX_DEVICE) PFX_TRY(deliver(ctx, kp_xyz, dxyz, cnt * 3 * sizeof(float), mem));
+    else PFX_CUDA(cudaMemcpyAsync(kp_xyz, dxyz, cnt * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (snapped_idx) {
+    PFX_TRY(snap_to_cloud(ctx, dxyz, (int)cnt, snap_max_d2, dsnap));
+    PFX_TRY(deliver(ctx, snapped_idx, dsnap, cnt * sizeof(int), mem));
+  }
+  PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int pfx_harris3d(pfx_ctx* ctx, double radius, float threshold, int nonmax, int refine, float snap_max_d2,
+                            float* response, int32_t* kp_idx, float* kp_xyz, int32_t* snapped_idx, size_t cap,
+                            size_t* n_kp, int mem) {
+  if (!ctx) return PFX_E_INVALID;
+  // normals estimated internally (HarrisKeypoint3D::initCompute) stay private to this call
+  const bool internal_normals = !ctx->have_normals;
+  int rc = harris3d_impl(ctx, radius, threshold, nonmax, refine, snap_max_d2, response, kp_idx, kp_xyz, snapped_idx,
+                         cap, n_kp, mem);
+  if (internal_normals) {
+    ctx->have_normals = false;
+    ctx->normals_sorted_for = nullptr;
+  }
+  return rc;
+}
+
+// ================================================================================== descriptors
+extern "C" int pfx_fpfh(pfx_ctx* ctx, double radius, int k, float* out, size_t stride, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  PFX_TRY(check_search_params(ctx, radius, k, "pfx_fpfh"));
+  if (k > 32) return ctx->fail(PFX_E_INVALID, "pfx_fpfh: k must be <= 32");
+  if (!ctx->have_normals) return ctx->fail(PFX_E_STATE, "pfx_fpfh: no input normals (setInputNormals)");
+  if (!out || stride < 132 || (stride & 3)) return ctx->fail(PFX_E_INVALID, "pfx_fpfh: bad output / stride");
+  const size_t nq = ctx->num_queries();
+  Grid* g = nullptr;
+  PFX_TRY(grid_get(ctx, radius > 0 ? radius : 0.0, k, &g));
+  float* dout = out;
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->out_stage.ensure(std::max<size_t>(nq * stride, 16)));
+    dout = ctx->out_stage.as<float>();
+    if (stride != 132) PFX_CUDA(cudaMemsetAsync(dout, 0, nq * stride, ctx->stream));
+  }
+  PFX_TRY(fpfh_compute(ctx, g, radius, k, dout, stride / 4, nullptr));
+  if (mem == PFX_HOST) return deliver(ctx, out, dout, nq * stride, mem);
+  return 0;
+}
+
+extern "C" int pfx_spfh(pfx_ctx* ctx, double radius, int k, float* out, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  PFX_TRY(check_search_params(ctx, radius, k, "pfx_spfh"));
+  if (k > 32) return ctx->fail(PFX_E_INVALID, "pfx_spfh: k must be <= 32");
+  if (!ctx->have_normals) return ctx->fail(PFX_E_STATE, "pfx_spfh: no input normals");
+  if (!out) return ctx->fail(PFX_E_INVALID, "pfx_spfh: null output");
+  const size_t n = ctx->n;
+  if (n == 0) return 0;
+  Grid* g = nullptr;
+  PFX_TRY(grid_get(ctx, radius > 0 ? radius : 0.0, k, &g));
+  float* dout = out;
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->out_stage.ensure(n * 33 * sizeof(float)));
+    dout = ctx->out_stage.as<float>();
+  }
+  bool saved = ctx->q_is_surface;
+  ctx->q_is_surface = true;
+  int rc = fpfh_compute(ctx, g, radius, k, nullptr, 33, dout);
+  ctx->q_is_surface = saved;
+  if (rc) return rc;
+  if (mem == PFX_HOST) return deliver(ctx, out, dout, n * 33 * sizeof(float), mem);
+  return 0;
+}
+
+extern "C" int pfx_shot_lrf(pfx_ctx* ctx, double radius, float* rf9, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_shot_lrf: no surface set");
+  if (!(radius > 0)) return ctx->fail(PFX_E_PRECOND, "pfx_shot_lrf: radius must be > 0");
+  if (!rf9) return ctx->fail(PFX_E_INVALID, "pfx_shot_lrf: null output");
+  const size_t nq = ctx->num_queries();
+  if (nq == 0) return 0;
+  Grid* g = nullptr;
+  PFX_TRY(grid_get(ctx, radius, 0, &g));
+  float* d = rf9;
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->out_stage.ensure(nq * 9 * sizeof(float)));
+    d = ctx->out_stage.as<float>();
+  }
+  PFX_TRY(shot_lrf_compute(ctx, g, radius, d, nullptr));
+  if (mem == PFX_HOST) return deliver(ctx, rf9, d, nq * 9 * sizeof(float), mem);
+  return 0;
+}
+
+extern "C" int pfx_shot352(pfx_ctx* ctx, double radius, const float* lrf_in, float* out, size_t stride, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_shot352: no surface set");
+  // SHOTEstimation::initCompute rejects k-search; the radius must be set
+  if (!(radius > 0)) return ctx->fail(PFX_E_PRECOND, "pfx_shot352: SHOT needs a radius search (setRadiusSearch)");
+  if (!ctx->have_normals) return ctx->fail(PFX_E_STATE, "pfx_shot352: no input normals (setInputNormals)");
+  if (!out || stride < 1444 || (stride & 3)) return ctx->fail(PFX_E_INVALID, "pfx_shot352: bad output / stride");
+  const size_t nq = ctx->num_queries();
+  if (nq == 0) return 0;
+  Grid* g = nullptr;
+  PFX_TRY(grid_get(ctx, radius, 0, &g));
+  PFX_CUDA(ctx->tmp2.ensure(nq * 9 * sizeof(float)));
+  float* drf = ctx->tmp2.as<float>();
+  if (lrf_in) {
+    PFX_CUDA(cudaMemcpyAsync(drf, lrf_in, nq * 9 * sizeof(float),
+                             mem == PFX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    PFX_TRY(shot_lrf_compute(ctx, g, radius, drf, nullptr));
+  }
+  float* dout = out;
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->out_stage.ensure(nq * stride));
+    dout = ctx->out_stage.as<float>();
+    if (stride != 1444) PFX_CUDA(cudaMemsetAsync(dout, 0, nq * stride, ctx->stream));
+  }
+  PFX_TRY(shot_compute(ctx, g, radius, drf, dout, stride / 4));
+  if (mem == PFX_HOST) return deliver(ctx, out, dout, nq * stride, mem);
+  return 0;
+}
+
+// ================================================================================== matching
+namespace pfx {
+__global__ void reciprocal_kernel(const int* __restrict__ s2t, const float* __restrict__ sd2,
+                                  const int* __restrict__ t2s, int na, int reciprocal, float max_d2,
+                                  int* __restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= na) return;
+  int j = s2t[i];
+  bool keep = j >= 0;
+  if (keep && reciprocal) keep = (t2s[j] == i);
+  if (keep && max_d2 >= 0.f) keep = sd2[i] <= max_d2;
+  flags[i] = keep ? 1 : 0;
+}
+__global__ void corr_emit_kernel(const int* __restrict__ flags, const int* __restrict__ pos,
+                                 const int* __restrict__ s2t, const float* __restrict__ sd2, int na,
+                                 pfx_correspondence* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= na || !flags[i]) return;
+  pfx_correspondence c;
+  c.index_query = i;
+  c.index_match = s2t[i];
+  c.distance = sd2[i];
+  out[pos[i]] = c;
+}
+}  // namespace pfx
+
+static int match_upload(Ctx* ctx, const float* m, size_t rows, size_t stride, int dim, int mem, DevBuf& buf,
+                        const float** dev, int* ld) {
+  if (stride < (size_t)dim * 4 || (stride & 3)) return ctx->fail(PFX_E_INVALID, "pfx_match: bad row stride");
+  *ld = (int)(stride / 4);
+  if (mem == PFX_DEVICE) {
+    *dev = m;
+    return 0;
+  }
+  PFX_CUDA(buf.ensure(std::max<size_t>(rows * stride, 16)));
+  if (rows) PFX_CUDA(cudaMemcpyAsync(buf.p, m, rows * stride, cudaMemcpyHostToDevice, ctx->stream));
+  *dev = buf.as<float>();
+  return 0;
+}
+
+static int match_dispatch(Ctx* ctx, const float* a, int na, int lda, const float* b, int nb, int ldb, int dim,
+                          int* idx, float* d2) {
+  return match_nn_exact(ctx, a, na, lda, b, nb, ldb, dim, idx, d2);
+}
+
+extern "C" int pfx_set_match_engine(pfx_ctx* ctx, int engine) {
+  if (!ctx || engine < -1 || engine > 1) return PFX_E_INVALID;
+  ctx->match_engine = engine;
+  return 0;
+}
+
+extern "C" int pfx_match_nn(pfx_ctx* ctx, const float* a, size_t na, size_t stride_a, const float* b, size_t nb,
+                            size_t stride_b, int dim, int32_t* nn_idx, float* nn_d2, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (dim <= 0 || !nn_idx || (na && !a) || (nb && !b)) return ctx->fail(PFX_E_INVALID, "pfx_match_nn: bad arguments");
+  if (na == 0) return 0;
+  const float *da, *db;
+  int lda, ldb;
+  PFX_TRY(match_upload(ctx, a, na, stride_a, dim, mem, ctx->stage, &da, &lda));
+  PFX_TRY(match_upload(ctx, b, nb, stride_b, dim, mem, ctx->stage2, &db, &ldb));
+  int* didx = nn_idx;
+  float* dd2 = nn_d2;
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->out_stage.ensure(na * (sizeof(int) + sizeof(float))));
+    didx = ctx->out_stage.as<int>();
+    dd2 = reinterpret_cast<float*>(didx + na);
+  } else if (!dd2) {
+    PFX_CUDA(ctx->out_stage.ensure(na * sizeof(float)));
+    dd2 = ctx->out_stage.as<float>();
+  }
+  PFX_TRY(match_dispatch(ctx, da, (int)na, lda, db, (int)nb, ldb, dim, didx, dd2));
+  if (mem == PFX_HOST) {
+    if (nn_d2) PFX_CUDA(cudaMemcpyAsync(nn_d2, dd2, na * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    return deliver(ctx, nn_idx, didx, na * sizeof(int), mem);
+  }
+  return 0;
+}
+
+extern "C" int pfx_match(pfx_ctx* ctx, const float* a, size_t na, size_t stride_a, const float* b, size_t nb,
+                         size_t stride_b, int dim, int reciprocal, float max_dist2, pfx_correspondence* out,
+                         size_t cap, size_t* n_out, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (dim <= 0 || !out || !n_out || (na && !a) || (nb && !b)) return ctx->fail(PFX_E_INVALID, "pfx_match: bad arguments");
+  *n_out = 0;
+  if (na == 0 || nb == 0) return 0;
+  const float *da, *db;
+  int lda, ldb;
+  PFX_TRY(match_upload(ctx, a, na, stride_a, dim, mem, ctx->stage, &da, &lda));
+  PFX_TRY(match_upload(ctx, b, nb, stride_b, dim, mem, ctx->stage2, &db, &ldb));
+  PFX_CUDA(ctx->tmp0.ensure(na * (sizeof(int) + sizeof(float))));
+  PFX_CUDA(ctx->tmp1.ensure(nb * (sizeof(int) + sizeof(float))));
+  int* s2t = ctx->tmp0.as<int>();
+  float* sd2 = reinterpret_cast<float*>(s2t + na);
+  int* t2s = ctx->tmp1.as<int>();
+  float* td2 = reinterpret_cast<float*>(t2s + nb);
+  PFX_TRY(match_dispatch(ctx, da, (int)na, lda, db, (int)nb, ldb, dim, s2t, sd2));
+  if (reciprocal) PFX_TRY(match_dispatch(ctx, db, (int)nb, ldb, da, (int)na, lda, dim, t2s, td2));
+  PFX_CUDA(ctx->tmp2.ensure(na * sizeof(int)));
+  PFX_CUDA(ctx->tmp3.ensure(na * sizeof(int)));
+  int* flags = ctx->tmp2.as<int>();
+  int* pos = ctx->tmp3.as<int>();
+  PFX_LAUNCH(ctx, reciprocal_kernel, div_up((long long)na, 256), 256, 0, s2t, sd2, t2s, (int)na, reciprocal, max_dist2, flags);
+  PFX_CUDA(ctx->small.ensure(256));
+  int* total = ctx->small.as<int>() + 16;
+  PFX_TRY(scan_exclusive_i32(ctx, flags, pos, (int)na, total, ctx->scanbuf));
+  int cnt = 0;
+  PFX_CUDA(cudaMemcpyAsync(&cnt, total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  *n_out = (size_t)cnt;
+  if ((size_t)cnt > cap) return ctx->fail(PFX_E_CAPACITY, "pfx_match: correspondence buffer too small");
+  pfx_correspondence* dout = out;
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->out_stage.ensure(std::max<size_t>(cnt, 1) * sizeof(pfx_correspondence)));
+    dout = ctx->out_stage.as<pfx_correspondence>();
+  }
+  PFX_LAUNCH(ctx, corr_emit_kernel, div_up((long long)na, 256), 256, 0, flags, pos, s2t, sd2, (int)na, dout);
+  PFX_CUDA(cudaGetLastError());
+  if (mem == PFX_HOST) return deliver(ctx, out, dout, (size_t)cnt * sizeof(pfx_correspondence), mem);
+  return 0;
+}
+
+// ================================================================================== ingest
+extern "C" int pfx_voxel_grid(pfx_ctx* ctx, float, float*, size_t, size_t*, int) {
+  if (!ctx) return PFX_E_INVALID;
+  return ctx->fail(PFX_E_STATE, "pfx_voxel_grid: not built yet");
+}

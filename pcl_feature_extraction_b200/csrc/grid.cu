@@ -1,0 +1,602 @@
+// grid.cu — GPU voxel hash built with sort-and-scan (replaces the kd-tree / FLANN index that the
+// reference builds at features.h:192-193, tools.h:29-30, keypoints.h:186-187,371-372,408-409).
+//
+// build: bbox -> cell edge -> 30-bit Morton keys -> hand-written LSD radix sort (8-bit digits,
+// stable) -> physically permuted float4 points -> cell heads + scan -> cell table -> open-addressing
+// hash of occupied cells -> 27-neighbour adjacency table.  Nothing synchronises with the host: the
+// grid description (GridParams) lives in device memory and every kernel that depends on a
+// data-dependent count uses a grid-stride loop over a device-side bound.
+#include "internal.h"
+
+namespace pfx {
+
+// ------------------------------------------------------------------------------------------ scan
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <typename T>
+__device__ __forceinline__ T block_excl_scan(T v, T* smem /* >= 8 */, T* block_total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  T inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    T t = __shfl_up_sync(FULL, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) smem[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    T w = (lane < (SCAN_THREADS / 32)) ? smem[lane] : T(0);
+    T winc = w;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      T t = __shfl_up_sync(FULL, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < 8) smem[lane] = winc - w;
+    if (lane == 7) smem[8] = winc;
+  }
+  __syncthreads();
+  T res = smem[wid] + inc - v;
+  if (block_total) *block_total = smem[8];
+  __syncthreads();
+  return res;
+}
+
+template <typename T>
+__global__ void scan_reduce_kernel(const int* __restrict__ in, int n, T* __restrict__ bsum) {
+  __shared__ T sm[9];
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  T s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i)
+    if (base + i < n) s += in[base + i];
+  T tot;
+  block_excl_scan<T>(s, sm, &tot);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+template <typename T>
+__global__ void scan_bsum_kernel(T* bsum, int nb, T* total_out) {
+  __shared__ T sm[9];
+  __shared__ T carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += SCAN_THREADS) {
+    int i = base + threadIdx.x;
+    T v = (i < nb) ? bsum[i] : T(0);
+    T tot;
+    T ex = block_excl_scan<T>(v, sm, &tot);
+    if (i < nb) bsum[i] = ex + carry;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+template <typename T>
+__global__ void scan_apply_kernel(const int* __restrict__ in, T* __restrict__ out, int n,
+                                  const T* __restrict__ bsum, int write_total_at_n) {
+  __shared__ T sm[9];
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  T s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    v[i] = (base + i < n) ? in[base + i] : 0;
+    s += v[i];
+  }
+  T ex = block_excl_scan<T>(s, sm, nullptr) + bsum[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    if (base + i < n) out[base + i] = ex;
+    ex += v[i];
+    if (write_total_at_n && base + i == n - 1) out[n] = ex;
+  }
+}
+
+template <typename T>
+static int scan_exclusive_impl(Ctx* ctx, const int* in, T* out, int n, T* total_dev, DevBuf& bsum,
+                               int write_total_at_n) {
+  if (n <= 0) {
+    if (write_total_at_n) PFX_CUDA(cudaMemsetAsync(out, 0, sizeof(T), ctx->stream));
+    if (total_dev) PFX_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(T), ctx->stream));
+    return 0;
+  }
+  int nb = div_up(n, SCAN_TILE);
+  PFX_CUDA(bsum.ensure((size_t)(nb + 1) * sizeof(T)));
+  PFX_LAUNCH(ctx, scan_reduce_kernel<T>, nb, SCAN_THREADS, 0, in, n, bsum.as<T>());
+  PFX_LAUNCH(ctx, scan_bsum_kernel<T>, 1, SCAN_THREADS, 0, bsum.as<T>(), nb, total_dev);
+  PFX_LAUNCH(ctx, scan_apply_kernel<T>, nb, SCAN_THREADS, 0, in, out, n, bsum.as<T>(),
+             write_total_at_n);
+  PFX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int scan_exclusive_i32(Ctx* ctx, const int* in, int* out, int n, int* total_dev, DevBuf& bsum) {
+  return scan_exclusive_impl<int>(ctx, in, out, n, total_dev, bsum, 0);
+}
+// out has n + 1 entries (CSR offsets)
+int scan_exclusive_i64(Ctx* ctx, const int* in, long long* out, int n, DevBuf& bsum) {
+  return scan_exclusive_impl<long long>(ctx, in, out, n, nullptr, bsum, 1);
+}
+
+// ------------------------------------------------------------------------------------------ bbox
+struct BuildAcc {
+  uint32_t mn[3], mx[3];
+  int n_valid;
+  int n_cells_probe;  // occupied cells counted at the trial edge (kNN density estimate)
+};
+
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void acc_init_kernel(BuildAcc* a) {
+  for (int i = 0; i < 3; ++i) {
+    a->mn[i] = 0xffffffffu;
+    a->mx[i] = 0u;
+  }
+  a->n_valid = 0;
+  a->n_cells_probe = 0;
+}
+
+__global__ void bbox_kernel(const float4* __restrict__ pts, int n, BuildAcc* acc) {
+  uint32_t mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+  int cnt = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = pts[i];
+    if (finite3(p.x, p.y, p.z)) {
+      uint32_t ox = f2ord(p.x), oy = f2ord(p.y), oz = f2ord(p.z);
+      mn[0] = min(mn[0], ox); mx[0] = max(mx[0], ox);
+      mn[1] = min(mn[1], oy); mx[1] = max(mx[1], oy);
+      mn[2] = min(mn[2], oz); mx[2] = max(mx[2], oz);
+      ++cnt;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = min(mn[a], __shfl_xor_sync(FULL, mn[a], o));
+      mx[a] = max(mx[a], __shfl_xor_sync(FULL, mx[a], o));
+    }
+    cnt += __shfl_xor_sync(FULL, cnt, o);
+  }
+  __shared__ uint32_t s_mn[3], s_mx[3];
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) {
+    for (int a = 0; a < 3; ++a) {
+      s_mn[a] = 0xffffffffu;
+      s_mx[a] = 0u;
+    }
+    s_cnt = 0;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    for (int a = 0; a < 3; ++a) {
+      atomicMin(&s_mn[a], mn[a]);
+      atomicMax(&s_mx[a], mx[a]);
+    }
+    atomicAdd(&s_cnt, cnt);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int a = 0; a < 3; ++a) {
+      atomicMin(&acc->mn[a], s_mn[a]);
+      atomicMax(&acc->mx[a], s_mx[a]);
+    }
+    atomicAdd(&acc->n_valid, s_cnt);
+  }
+}
+
+// Set the cell edge and the grid dimensions.  edge_req > 0: radius grid.  edge_req <= 0: kNN grid,
+// stage 0 picks a trial edge from the bbox (2-manifold guess), stage 1 rescales it so that an
+// occupied cell holds about `target_occ` points (occupancy measured by cell_probe_kernel).
+__global__ void params_kernel(const BuildAcc* acc, GridParams* gp, float edge_req, int stage,
+                              float target_occ) {
+  GridParams P;
+  int nv = acc->n_valid;
+  P.n_valid = nv;
+  P.ncells = 0;
+  if (nv == 0) {
+    P.mnx = P.mny = P.mnz = P.mxx = P.mxy = P.mxz = 0.f;
+  } else {
+    P.mnx = ord2f(acc->mn[0]); P.mny = ord2f(acc->mn[1]); P.mnz = ord2f(acc->mn[2]);
+    P.mxx = ord2f(acc->mx[0]); P.mxy = ord2f(acc->mx[1]); P.mxz = ord2f(acc->mx[2]);
+  }
+  float ex = P.mxx - P.mnx, ey = P.mxy - P.mny, ez = P.mxz - P.mnz;
+  float edge = edge_req;
+  if (!(edge_req > 0.f)) {
+    if (stage == 0) {
+      float a = fmaxf(ex, fmaxf(ey, ez)), c = fminf(ex, fminf(ey, ez));
+      float b = ex + ey + ez - a - c;
+      float area = fmaxf(a * b, 1e-20f);
+      edge = sqrtf(area * target_occ / fmaxf((float)nv, 1.f));
+    } else {
+      float occ = (float)nv / fmaxf((float)acc->n_cells_probe, 1.f);
+      edge = gp->edge * sqrtf(target_occ / fmaxf(occ, 1e-3f));
+    }
+    edge = fmaxf(edge, 1e-7f * fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-30f)));
+    if (!(edge > 0.f) || !isfinite(edge)) edge = 1.f;
+  }
+  for (int it = 0; it < 64; ++it) {  // keep every axis within 10 Morton bits
+    float m = fmaxf(ex, fmaxf(ey, ez)) / edge;
+    if (m < 1020.f) break;
+    edge *= 2.f;
+  }
+  P.edge = edge;
+  P.inv_e = 1.0f / edge;
+  P.ox = P.mnx; P.oy = P.mny; P.oz = P.mnz;
+  P.nx = min(1024, (int)floorf(ex * P.inv_e) + 1);
+  P.ny = min(1024, (int)floorf(ey * P.inv_e) + 1);
+  P.nz = min(1024, (int)floorf(ez * P.inv_e) + 1);
+  *gp = P;
+}
+
+__device__ __forceinline__ uint32_t point_key(const GridParams& P, float x, float y, float z) {
+  if (!finite3(x, y, z)) return KEY_INVALID;
+  return morton3(cell_coord(x, P.ox, P.inv_e, P.nx), cell_coord(y, P.oy, P.inv_e, P.ny),
+                 cell_coord(z, P.oz, P.inv_e, P.nz));
+}
+
+// count distinct occupied cells at the trial edge with a hash set (kNN density estimate)
+__global__ void cell_probe_kernel(const float4* __restrict__ pts, int n, const GridParams* gp,
+                                  uint32_t* hset, uint32_t hmask, BuildAcc* acc) {
+  const GridParams P = *gp;
+  int local = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = pts[i];
+    uint32_t key = point_key(P, p.x, p.y, p.z);
+    if (key == KEY_INVALID) continue;
+    uint32_t h = (hash_key(key) >> 7) & hmask;
+    for (;;) {
+      uint32_t prev = atomicCAS(&hset[h], KEY_INVALID, key);
+      if (prev == KEY_INVALID) { ++local; break; }
+      if (prev == key) break;
+      h = (h + 1) & hmask;
+    }
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&acc->n_cells_probe, local);
+}
+
+__global__ void keys_kernel(const float4* __restrict__ pts, int n, const GridParams* gp,
+                            uint32_t* __restrict__ keys, int* __restrict__ vals) {
+  const GridParams P = *gp;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pts[i];
+  keys[i] = point_key(P, p.x, p.y, p.z);
+  vals[i] = i;
+}
+
+// ------------------------------------------------------------------------------------ radix sort
+// LSD, 8-bit digits, stable.  Tile = 8 warps x 8 rounds x 32 lanes = 2048 keys; warp w owns the
+// contiguous chunk [w*256, w*256+256) of the tile so that (block, warp, round, lane) is the input
+// order.  Ranking inside a warp uses __match_any_sync (no shared-memory atomics on the hot path).
+constexpr int RS_THREADS = 256;
+constexpr int RS_ROUNDS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift, int nblk, int* __restrict__ ghist) {
+  __shared__ int cnt[256];
+  cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int base = blockIdx.x * RS_TILE + wid * (RS_ROUNDS * 32);
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+    int i = base + r * 32 + lane;
+    if (i < n) atomicAdd(&cnt[(keys[i] >> shift) & 255u], 1);
+  }
+  __syncthreads();
+  ghist[threadIdx.x * nblk + blockIdx.x] = cnt[threadIdx.x];
+}
+
+// exclusive scan of ghist (256 * nblk entries, digit-major) by one block
+__global__ void rs_scan_kernel(int* ghist, int total) {
+  __shared__ int sm[9];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int per = SCAN_ITEMS;
+  for (int base = 0; base < total; base += SCAN_THREADS * per) {
+    int b0 = base + threadIdx.x * per;
+    int v[per];
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < per; ++i) {
+      v[i] = (b0 + i < total) ? ghist[b0 + i] : 0;
+      s += v[i];
+    }
+    int tot;
+    int ex = block_excl_scan<int>(s, sm, &tot) + carry;
+#pragma unroll
+    for (int i = 0; i < per; ++i) {
+      if (b0 + i < total) ghist[b0 + i] = ex;
+      ex += v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ vals, int n, int shift,
+                  int nblk, const int* __restrict__ ghist, uint32_t* __restrict__ okeys,
+                  int* __restrict__ ovals) {
+  __shared__ int wcnt[8][256];
+  for (int i = threadIdx.x; i < 8 * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const int base = blockIdx.x * RS_TILE + wid * (RS_ROUNDS * 32);
+  uint32_t k[RS_ROUNDS];
+  int v[RS_ROUNDS], rk[RS_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+    int i = base + r * 32 + lane;
+    bool ok = i < n;
+    k[r] = ok ? keys[i] : 0u;
+    v[r] = ok ? vals[i] : 0;
+    int d = ok ? (int)((k[r] >> shift) & 255u) : 256;  // 256: padding lanes group together
+    unsigned m = __match_any_sync(FULL, d);
+    int old = ok ? wcnt[wid][d] : 0;
+    __syncwarp();
+    rk[r] = old + __popc(m & lt);
+    if (ok && (m & lt) == 0) wcnt[wid][d] = old + __popc(m);
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // per digit: exclusive prefix over the 8 warps, offset by the global base of (digit, block)
+    int d = threadIdx.x;
+    int run = ghist[d * nblk + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      int t = wcnt[w][d];
+      wcnt[w][d] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+    int i = base + r * 32 + lane;
+    if (i < n) {
+      int dst = wcnt[wid][(k[r] >> shift) & 255u] + rk[r];
+      okeys[dst] = k[r];
+      ovals[dst] = v[r];
+    }
+  }
+}
+
+static int radix_sort_pairs(Ctx* ctx, Grid* g, int n) {
+  int nblk = div_up(n, RS_TILE);
+  PFX_CUDA(g->ghist.ensure((size_t)256 * nblk * sizeof(int)));
+  uint32_t* k0 = g->keys.as<uint32_t>();
+  uint32_t* k1 = g->keys2.as<uint32_t>();
+  int* v0 = g->vals.as<int>();
+  int* v1 = g->vals2.as<int>();
+  for (int pass = 0; pass < 4; ++pass) {
+    int shift = pass * 8;
+    PFX_LAUNCH(ctx, rs_hist_kernel, nblk, RS_THREADS, 0, k0, n, shift, nblk, g->ghist.as<int>());
+    PFX_LAUNCH(ctx, rs_scan_kernel, 1, SCAN_THREADS, 0, g->ghist.as<int>(), 256 * nblk);
+    PFX_LAUNCH(ctx, rs_scatter_kernel, nblk, RS_THREADS, 0, k0, v0, n, shift, nblk,
+               g->ghist.as<int>(), k1, v1);
+    std::swap(k0, k1);
+    std::swap(v0, v1);
+  }
+  PFX_CUDA(cudaGetLastError());
+  return 0;  // 4 passes: result is back in keys / vals
+}
+
+// ------------------------------------------------------------------------------- post-sort stages
+__global__ void gather_kernel(const float4* __restrict__ pts, const int* __restrict__ vals, int n,
+                              float4* __restrict__ sorted, int* __restrict__ inv_perm) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int o = vals[i];
+  float4 p = pts[o];
+  p.w = __int_as_float(o);
+  sorted[i] = p;
+  inv_perm[o] = i;
+}
+
+__global__ void heads_kernel(const uint32_t* __restrict__ keys, int n, int* __restrict__ heads) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k = keys[i];
+  heads[i] = (k != KEY_INVALID && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
+}
+
+// pt_cell holds the exclusive scan of heads on entry; turn it into the cell id of every point and
+// emit the cell table
+__global__ void cells_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ heads, int n,
+                             int* __restrict__ pt_cell, uint32_t* __restrict__ cell_key,
+                             int* __restrict__ cell_start, const int* __restrict__ total_cells,
+                             GridParams* gp) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    int nc = *total_cells;
+    gp->ncells = nc;
+    cell_start[nc] = gp->n_valid;
+  }
+  if (i >= n) return;
+  int ex = pt_cell[i];
+  int h = heads[i];
+  if (h) {
+    cell_key[ex] = keys[i];
+    cell_start[ex] = i;
+  }
+  pt_cell[i] = (keys[i] == KEY_INVALID) ? -1 : (ex + h - 1);
+}
+
+__global__ void hash_insert_kernel(const uint32_t* __restrict__ cell_key, const GridParams* gp,
+                                   uint32_t* hkeys, int* hvals, uint32_t hmask) {
+  int nc = gp->ncells;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+    uint32_t key = cell_key[c];
+    uint32_t h = (hash_key(key) >> 7) & hmask;
+    for (;;) {
+      uint32_t prev = atomicCAS(&hkeys[h], KEY_INVALID, key);
+      if (prev == KEY_INVALID) {
+        hvals[h] = c;
+        break;
+      }
+      h = (h + 1) & hmask;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t compact1by2(uint32_t x) {
+  x &= 0x09249249u;
+  x = (x | (x >> 2)) & 0x030c30c3u;
+  x = (x | (x >> 4)) & 0x0300f00fu;
+  x = (x | (x >> 8)) & 0x030000ffu;
+  x = (x | (x >> 16)) & 0x3ffu;
+  return x;
+}
+
+__global__ void adjacency_kernel(GridDev g, int* __restrict__ cell_nbr) {
+  const GridParams P = *g.gp;
+  long long total = (long long)P.ncells * 27;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(t / 27), l = (int)(t % 27);
+    uint32_t key = g.cell_key[c];
+    int cx = (int)compact1by2(key), cy = (int)compact1by2(key >> 1), cz = (int)compact1by2(key >> 2);
+    int x2 = cx + l % 3 - 1, y2 = cy + (l / 3) % 3 - 1, z2 = cz + l / 9 - 1;
+    int r = -1;
+    if (l == 13)
+      r = c;
+    else if (x2 >= 0 && x2 < P.nx && y2 >= 0 && y2 < P.ny && z2 >= 0 && z2 < P.nz)
+      r = hash_lookup(g, morton3(x2, y2, z2));
+    cell_nbr[t] = r;
+  }
+}
+
+static uint32_t pow2_at_least(size_t v) {
+  uint32_t p = 1024;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static int grid_build(Ctx* ctx, Grid* g, double radius, int knn_k) {
+  const int n = (int)ctx->n;
+  g->n = n;
+  g->radius = radius;
+  g->knn_k = knn_k;
+  g->surf_version = ctx->surf_version;
+  const size_t nn = (size_t)std::max(n, 1);
+  PFX_CUDA(g->params.ensure(sizeof(GridParams)));
+  PFX_CUDA(g->misc.ensure(sizeof(BuildAcc) + 64));
+  PFX_CUDA(g->pts.ensure(nn * sizeof(float4)));
+  PFX_CUDA(g->inv_perm.ensure(nn * sizeof(int)));
+  PFX_CUDA(g->keys.ensure(nn * sizeof(uint32_t)));
+  PFX_CUDA(g->keys2.ensure(nn * sizeof(uint32_t)));
+  PFX_CUDA(g->vals.ensure(nn * sizeof(int)));
+  PFX_CUDA(g->vals2.ensure(nn * sizeof(int)));
+  PFX_CUDA(g->pt_cell.ensure(nn * sizeof(int)));
+  PFX_CUDA(g->cell_key.ensure(nn * sizeof(uint32_t)));
+  PFX_CUDA(g->cell_start.ensure((nn + 1) * sizeof(int)));
+  PFX_CUDA(g->cell_nbr.ensure(nn * 27 * sizeof(int)));
+  g->hmask = pow2_at_least(2 * nn) - 1;
+  PFX_CUDA(g->hkeys.ensure(((size_t)g->hmask + 1) * sizeof(uint32_t)));
+  PFX_CUDA(g->hvals.ensure(((size_t)g->hmask + 1) * sizeof(int)));
+
+  BuildAcc* acc = g->misc.as<BuildAcc>();
+  GridParams* gp = g->params.as<GridParams>();
+  const float4* src = ctx->surf.as<float4>();
+  const int T = 256;
+  const int wide = ctx->sm_count * 4;
+  PFX_LAUNCH(ctx, acc_init_kernel, 1, 1, 0, acc);
+  if (n > 0) PFX_LAUNCH(ctx, bbox_kernel, std::min(wide, div_up(n, T)), T, 0, src, n, acc);
+  if (radius > 0) {
+    float edge = (float)(radius * (1.0 + 1e-3));
+    PFX_LAUNCH(ctx, params_kernel, 1, 1, 0, acc, gp, edge, 0, 0.f);
+  } else {
+    float target = std::max(2.0f, 0.5f * (float)knn_k);
+    PFX_LAUNCH(ctx, params_kernel, 1, 1, 0, acc, gp, 0.f, 0, target);
+    if (n > 0) {
+      PFX_CUDA(cudaMemsetAsync(g->hkeys.p, 0xff, ((size_t)g->hmask + 1) * sizeof(uint32_t), ctx->stream));
+      PFX_LAUNCH(ctx, cell_probe_kernel, std::min(wide, div_up(n, T)), T, 0, src, n, gp,
+                 g->hkeys.as<uint32_t>(), g->hmask, acc);
+    }
+    PFX_LAUNCH(ctx, params_kernel, 1, 1, 0, acc, gp, 0.f, 1, target);
+  }
+  if (n > 0) {
+    PFX_LAUNCH(ctx, keys_kernel, div_up(n, T), T, 0, src, n, gp, g->keys.as<uint32_t>(), g->vals.as<int>());
+    PFX_TRY(radix_sort_pairs(ctx, g, n));
+    PFX_LAUNCH(ctx, gather_kernel, div_up(n, T), T, 0, src, g->vals.as<int>(), n, g->pts.as<float4>(),
+               g->inv_perm.as<int>());
+    // heads -> exclusive scan (into pt_cell) -> cell table; vals2 is free after the sort
+    int* heads = g->vals2.as<int>();
+    int* total_cells = reinterpret_cast<int*>(g->misc.as<char>() + sizeof(BuildAcc));
+    PFX_LAUNCH(ctx, heads_kernel, div_up(n, T), T, 0, g->keys.as<uint32_t>(), n, heads);
+    PFX_TRY(scan_exclusive_i32(ctx, heads, g->pt_cell.as<int>(), n, total_cells, g->bsum));
+    PFX_LAUNCH(ctx, cells_kernel, div_up(n, T), T, 0, g->keys.as<uint32_t>(), heads, n,
+               g->pt_cell.as<int>(), g->cell_key.as<uint32_t>(), g->cell_start.as<int>(), total_cells, gp);
+    PFX_CUDA(cudaMemsetAsync(g->hkeys.p, 0xff, ((size_t)g->hmask + 1) * sizeof(uint32_t), ctx->stream));
+    PFX_LAUNCH(ctx, hash_insert_kernel, std::min(wide, div_up(n, T)), T, 0, g->cell_key.as<uint32_t>(), gp,
+               g->hkeys.as<uint32_t>(), g->hvals.as<int>(), g->hmask);
+    PFX_LAUNCH(ctx, adjacency_kernel, wide * 2, T, 0, g->view(), g->cell_nbr.as<int>());
+  } else {
+    PFX_CUDA(cudaMemsetAsync(g->cell_start.p, 0, sizeof(int), ctx->stream));
+  }
+  PFX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Grids are cached per (surface version, radius | k): repeated compute() calls on the same cloud do
+// not rebuild the index (the reference rebuilds a kd-tree per Feature object, features.h:192-193).
+int grid_get(Ctx* ctx, double radius, int knn_k, Grid** out) {
+  ctx->tick++;
+  Grid* victim = nullptr;
+  for (Grid* g : ctx->grids) {
+    if (g->surf_version == ctx->surf_version &&
+        ((radius > 0 && g->radius == radius) || (!(radius > 0) && g->knn_k == knn_k && !(g->radius > 0)))) {
+      g->last_use = ctx->tick;
+      *out = g;
+      return 0;
+    }
+  }
+  if (ctx->grids.size() < 4) {
+    victim = new Grid();
+    ctx->grids.push_back(victim);
+  } else {
+    for (Grid* g : ctx->grids)  // prefer stale grids, then least recently used
+      if (!victim || (g->surf_version != ctx->surf_version && victim->surf_version == ctx->surf_version) ||
+          ((g->surf_version != ctx->surf_version) == (victim->surf_version != ctx->surf_version) &&
+           g->last_use < victim->last_use))
+        victim = g;
+  }
+  if (ctx->normals_sorted_for == victim) ctx->normals_sorted_for = nullptr;
+  if (ctx->knn_grid == victim) ctx->knn_grid = nullptr;
+  victim->last_use = ctx->tick;
+  int rc = grid_build(ctx, victim, radius, knn_k);
+  if (rc != 0) {
+    victim->surf_version = 0;
+    return rc;
+  }
+  *out = victim;
+  return 0;
+}
+
+void grid_free_all(Ctx* ctx) {
+  for (Grid* g : ctx->grids) {
+    g->release();
+    delete g;
+  }
+  ctx->grids.clear();
+}
+
+}  // namespace pfx

@@ -1,0 +1,177 @@
+// internal.h — host-side structures shared by the .cu files (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/pfx_b200.h"
+#include "common.cuh"
+
+namespace pfx {
+
+#define PFX_CUDA(call)                                                            \
+  do {                                                                            \
+    cudaError_t e__ = (call);                                                     \
+    if (e__ != cudaSuccess) return ctx->fail_cuda(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define PFX_TRY(call)          \
+  do {                         \
+    int rc__ = (call);         \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+// kernel launch + bookkeeping; every launch of ours goes through this
+#define PFX_LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
+  do {                                                                       \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);         \
+    (ctx)->launches++;                                                       \
+  } while (0)
+
+inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+struct Ctx;
+
+// One voxel hash over the current surface (sorted copy of the points + cell table).
+struct Grid {
+  // identity
+  uint64_t surf_version = 0;
+  double radius = -1;  // radius grids: cell edge = radius * (1 + 1e-3)
+  int knn_k = 0;       // kNN grids: cell edge estimated on the device from the point density
+  uint64_t last_use = 0;
+  int n = 0;
+  uint32_t hmask = 0;
+  DevBuf params, pts, inv_perm, keys, vals, keys2, vals2, ghist, cell_start, cell_key, hkeys, hvals,
+      pt_cell, cell_nbr, bsum, misc;
+  GridDev view() const {
+    GridDev g;
+    g.gp = params.as<GridParams>();
+    g.pts = pts.as<float4>();
+    g.cell_start = cell_start.as<int>();
+    g.cell_key = cell_key.as<uint32_t>();
+    g.hkeys = hkeys.as<uint32_t>();
+    g.hvals = hvals.as<int>();
+    g.hmask = hmask;
+    g.pt_cell = pt_cell.as<int>();
+    g.cell_nbr = cell_nbr.as<int>();
+    g.inv_perm = inv_perm.as<int>();
+    g.n = n;
+    return g;
+  }
+  void release() {
+    for (DevBuf* b : {&params, &pts, &inv_perm, &keys, &vals, &keys2, &vals2, &ghist, &cell_start,
+                      &cell_key, &hkeys, &hvals, &pt_cell, &cell_nbr, &bsum, &misc})
+      b->release();
+  }
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  uint64_t tick = 0;
+  int sm_count = 148;
+
+  // surface (original order): float4 (x, y, z, index bits)
+  size_t n = 0;
+  uint64_t surf_version = 0;
+  DevBuf surf;
+  float vp[3] = {0, 0, 0};
+  // surface normals, original order, float4 (nx, ny, nz, curvature)
+  DevBuf normals;
+  bool have_normals = false;
+  // normals in the sorted order of one grid (cache, avoids the re-permute on the dense path)
+  DevBuf normals_sorted;
+  const Grid* normals_sorted_for = nullptr;
+  uint64_t normals_version = 0, normals_sorted_version = 0;
+
+  // queries: float4 in caller order; q_is_surface => the surface itself
+  size_t nq = 0;
+  bool q_is_surface = true;
+  DevBuf qry;
+  uint64_t qry_version = 0;
+
+  std::vector<Grid*> grids;
+
+  // kNN list cache (sorted-position indices + d2), valid for (grid, k, query version)
+  DevBuf knn_idx, knn_d2;
+  const Grid* knn_grid = nullptr;
+  int knn_k = 0;
+  uint64_t knn_qversion = 0, knn_sversion = 0;
+  bool knn_dense = false;
+
+  // scratch
+  DevBuf stage, stage2, tmp0, tmp1, tmp2, tmp3, tmp4, small, scanbuf, match_flags, match_best, out_stage;
+  void* pinned = nullptr;
+  size_t pinned_cap = 0;
+
+  int match_engine = -1;
+
+  int fail(int code, const std::string& msg) {
+    err = msg;
+    return code;
+  }
+  int fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file,
+             line, what);
+    err = buf;
+    return (int)e;
+  }
+  size_t num_queries() const { return q_is_surface ? n : nq; }
+};
+
+// ---- grid.cu
+int grid_get(Ctx* ctx, double radius, int knn_k, Grid** out);
+void grid_free_all(Ctx* ctx);
+// device-wide exclusive scan of int32 -> int32 / int64 (total written to *total_dev when non-null)
+int scan_exclusive_i32(Ctx* ctx, const int* in, int* out, int n, int* total_dev, DevBuf& bsum);
+int scan_exclusive_i64(Ctx* ctx, const int* in, long long* out, int n, DevBuf& bsum);
+
+// ---- search.cu
+int knn_run(Ctx* ctx, Grid* g, const float4* q_dev, int nq, int k, int* idx_dev, float* d2_dev);
+int knn_lists(Ctx* ctx, Grid* g, int k, bool need_sorted_ids);  // fills ctx->knn_idx / knn_d2
+int knn_export(Ctx* ctx, int k, int32_t* idx, float* d2, int mem);
+int radius_count(Ctx* ctx, Grid* g, double radius, int* counts_dev);
+int radius_fill(Ctx* ctx, Grid* g, double radius, int sorted, const long long* offsets_dev,
+                int* idx_dev, float* d2_dev);
+
+// ---- normals.cu
+int normals_compute(Ctx* ctx, Grid* g, double radius, int k, float4* out_query_order);
+
+// ---- fpfh.cu
+int fpfh_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t stride_floats,
+                 float* spfh_out_dev);
+
+// ---- shot.cu
+int shot_lrf_compute(Ctx* ctx, Grid* g, double radius, float* rf9_dev, int* nvalid_dev);
+int shot_compute(Ctx* ctx, Grid* g, double radius, const float* rf9_dev, float* out_dev,
+                 size_t stride_floats);
+
+// ---- keypoints.cu
+int cloud_resolution(Ctx* ctx, double* res);
+int iss_saliency(Ctx* ctx, Grid* g, double radius, int min_nb, double g21, double g32,
+                 double* sal_dev_orig);
+int iss_nms(Ctx* ctx, Grid* g, const double* sal_dev_orig, double radius, int min_nb, int* flags_dev);
+int harris_response(Ctx* ctx, Grid* g, double radius, float* resp_dev_orig);
+int harris_nms(Ctx* ctx, Grid* g, const float* resp_dev_orig, double radius, float thr, int* flags_dev);
+int harris_refine(Ctx* ctx, Grid* g, double radius, float* corners_dev, int nc);
+int snap_to_cloud(Ctx* ctx, const float* q_dev, int nq, float max_d2, int* out_dev);
+int compact_flags(Ctx* ctx, const int* flags_dev, int n, int* idx_out_dev, int* count_host);
+
+// ---- match.cu
+int match_nn_exact(Ctx* ctx, const float* a, int na, int lda, const float* b, int nb, int ldb, int dim,
+                   int* nn_idx, float* nn_d2);
+int match_nn_tc(Ctx* ctx, const float* a, int na, int lda, const float* b, int nb, int ldb, int dim,
+                int* nn_idx, float* nn_d2);
+
+// ---- helpers (capi.cu)
+int normals_sorted_for_grid(Ctx* ctx, Grid* g, const float4** out);
+int ensure_pinned(Ctx* ctx, size_t bytes);
+
+}  // namespace pfx
+
+struct pfx_ctx : public pfx::Ctx {};

@@ -1,0 +1,33 @@
+"""Development timing of the C4/C5 stages on one GPU (not the contract bench; see bench.py)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import pcl_feature_extraction_b200 as pfx
+from pcl_feature_extraction_b200.synth import sheet_cloud
+
+side = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+pts = sheet_cloud(side=side)
+n = len(pts)
+p4 = np.zeros((n, 4), np.float32); p4[:, :3] = pts
+dev = torch.device("cuda:0")
+d_pts = torch.from_numpy(p4).to(dev)
+ctx = pfx.Context(0)
+ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+d_f = torch.empty((n, 33), dtype=torch.float32, device=dev)
+d_s = torch.empty((n, 361), dtype=torch.float32, device=dev)
+
+def ev():
+    e = torch.cuda.Event(enable_timing=True); e.record(); return e
+
+for it in range(4):
+    t = [ev()]
+    ctx.set_surface_dev(d_pts.data_ptr(), n, 16); t.append(ev())
+    ctx.normals_dev(0.0, 32, None); t.append(ev())
+    ctx.fpfh_dev(0.0, 32, d_f.data_ptr()); t.append(ev())
+    ctx.shot352_dev(0.0128, d_s.data_ptr()); t.append(ev())
+    torch.cuda.synchronize()
+    names = ["set_surface", "grid+knn+normals", "spfh+fpfh", "grid+lrf+shot"]
+    ms = [t[i].elapsed_time(t[i + 1]) for i in range(4)]
+    print(it, " ".join(f"{nm}={m:.3f}ms" for nm, m in zip(names, ms)), f"total={sum(ms):.3f}ms launches={ctx.launches}")
+print("fpfh sample", d_f[12345 % n, :6].cpu().numpy(), "shot norm", float(torch.linalg.norm(d_s[777 % n, :352])))
