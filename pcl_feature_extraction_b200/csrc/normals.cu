@@ -2,9 +2,9 @@
 // reference tools.h:22-32 / features.h:187 / keypoints.h:298-308).
 //
 // Per query: neighbours (kNN list or fused radius scan of the cell stencil) -> 3x3 covariance of the
-// QUERY-CENTRED coordinates in float32 (the centring is what keeps float32 at ~1e-7 of the double
-// answer; PCL's own absolute-coordinate float sums are off by ~3e-3) -> symmetric eigen solve
-// (cyclic Jacobi on the scaled matrix) -> smallest eigenvector, flipped toward the viewpoint,
+// QUERY-CENTRED coordinates, accumulated in double (12 DP ops per neighbour next to a 16-byte gather;
+// PCL's own absolute-coordinate float sums are off by ~3e-3 from the exact answer) -> symmetric eigen solve
+// (float Jacobi on the scaled matrix + one double refinement step) -> smallest eigenvector, flipped toward the viewpoint,
 // curvature = l0 / trace.  A warp accumulates one query at a time and parks the reduced moments in
 // lane t; after 32 queries every lane solves its own 3x3 problem, so the eigen solve runs at full
 // SIMT width and the float4 results are written as one coalesced 512-byte row.
@@ -15,47 +15,73 @@ namespace pfx {
 constexpr int NWPB = 8;
 
 struct Moments {
-  float s[9];  // sum d (3), sum d d^T upper triangle (6)
+  double s[9];  // sum d (3), sum d d^T upper triangle (6); d = p - q formed exactly in double
   int n;
 };
 
-__device__ __forceinline__ void mom_add(Moments& m, float dx, float dy, float dz) {
+__device__ __forceinline__ void mom_add(Moments& m, float4 p, float4 q) {
+  double dx = (double)p.x - (double)q.x, dy = (double)p.y - (double)q.y, dz = (double)p.z - (double)q.z;
   m.s[0] += dx; m.s[1] += dy; m.s[2] += dz;
   m.s[3] += dx * dx; m.s[4] += dx * dy; m.s[5] += dx * dz;
   m.s[6] += dy * dy; m.s[7] += dy * dz; m.s[8] += dz * dz;
   m.n += 1;
 }
 
+// covariance in double -> float Jacobi (cheap, ~1e-7) -> one double refinement step: Rayleigh
+// quotient for l0, then the largest cross product of two rows of (C - l0 I) (pcl::eigen33's
+// eigenvector construction) -> ~1e-12 of the double oracle unless the eigen-gap is ~1e-6 or less.
 __device__ __forceinline__ float4 solve_normal(const Moments& m, float qx, float qy, float qz, float vx,
                                                float vy, float vz) {
   const float nanv = __int_as_float(0x7fc00000);
   if (m.n == 0) return make_float4(nanv, nanv, nanv, nanv);
-  float inv = 1.0f / (float)m.n;
-  float mx = m.s[0] * inv, my = m.s[1] * inv, mz = m.s[2] * inv;
-  float c[6];
+  double inv = 1.0 / (double)m.n;
+  double mx = m.s[0] * inv, my = m.s[1] * inv, mz = m.s[2] * inv;
+  double c[6];
   c[0] = m.s[3] * inv - mx * mx;
   c[1] = m.s[4] * inv - mx * my;
   c[2] = m.s[5] * inv - mx * mz;
   c[3] = m.s[6] * inv - my * my;
   c[4] = m.s[7] * inv - my * mz;
   c[5] = m.s[8] * inv - mz * mz;
-  float tr = c[0] + c[3] + c[5];
-  float sc = fmaxf(fmaxf(fabsf(c[0]), fabsf(c[1])), fmaxf(fmaxf(fabsf(c[2]), fabsf(c[3])), fmaxf(fabsf(c[4]), fabsf(c[5]))));
-  float isc = (sc > 1e-37f) ? 1.0f / sc : 1.0f;
+  double tr = c[0] + c[3] + c[5];
+  double sc = fmax(fmax(fabs(c[0]), fabs(c[1])), fmax(fmax(fabs(c[2]), fabs(c[3])), fmax(fabs(c[4]), fabs(c[5]))));
+  double isc = (sc > 1e-300) ? 1.0 / sc : 1.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) c[i] *= isc;
   float a[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) a[i] = c[i] * isc;
+  for (int i = 0; i < 6; ++i) a[i] = (float)c[i];
   float w[3], v[3][3];
   eig_sym3<float>(a, w, v, 8);
-  float nx = v[0][0], ny = v[1][0], nz = v[2][0];
-  float trs = a[0] + a[3] + a[5];
-  float curv = (tr != 0.f && trs != 0.f) ? fabsf(w[0] / trs) : 0.f;
-  // flipNormalTowardsViewpoint
-  float dp = (vx - qx) * nx + (vy - qy) * ny + (vz - qz) * nz;
-  if (dp < 0.f) {
-    nx = -nx; ny = -ny; nz = -nz;
+  double n0 = v[0][0], n1 = v[1][0], n2 = v[2][0];
+  // Rayleigh quotient in double
+  double cx = c[0] * n0 + c[1] * n1 + c[2] * n2;
+  double cy = c[1] * n0 + c[3] * n1 + c[4] * n2;
+  double cz = c[2] * n0 + c[4] * n1 + c[5] * n2;
+  double l0 = (n0 * cx + n1 * cy + n2 * cz) / (n0 * n0 + n1 * n1 + n2 * n2);
+  // rows of (C - l0 I)
+  double r0[3] = {c[0] - l0, c[1], c[2]}, r1[3] = {c[1], c[3] - l0, c[4]}, r2[3] = {c[2], c[4], c[5] - l0};
+  double e0[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
+  double e1[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
+  double e2[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+  double l_0 = e0[0] * e0[0] + e0[1] * e0[1] + e0[2] * e0[2];
+  double l_1 = e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2];
+  double l_2 = e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2];
+  double bx = e0[0], by = e0[1], bz = e0[2], bl = l_0;
+  if (l_1 > bl) { bx = e1[0]; by = e1[1]; bz = e1[2]; bl = l_1; }
+  if (l_2 > bl) { bx = e2[0]; by = e2[1]; bz = e2[2]; bl = l_2; }
+  if (bl > 1e-280) {  // otherwise (C - l0 I) has rank < 2: keep the Jacobi vector
+    double il = rsqrt(bl);
+    bx *= il; by *= il; bz *= il;
+    if (bx * n0 + by * n1 + bz * n2 < 0) { bx = -bx; by = -by; bz = -bz; }
+    n0 = bx; n1 = by; n2 = bz;
   }
-  return make_float4(nx, ny, nz, curv);
+  double trs = c[0] + c[3] + c[5];
+  double curv = (tr != 0.0 && trs != 0.0) ? fabs(l0 / trs) : 0.0;
+  // flipNormalTowardsViewpoint
+  double dp = ((double)vx - (double)qx) * n0 + ((double)vy - (double)qy) * n1 + ((double)vz - (double)qz) * n2;
+  if (dp < 0) { n0 = -n0; n1 = -n1; n2 = -n2; }
+  return make_float4((float)n0, (float)n1, (float)n2, (float)curv);
 }
 
 // rows: DENSE -> row = sorted surface position; out_rows[row] always written (when non-null);
@@ -71,7 +97,7 @@ normals_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2,
   const int n_valid = g.gp->n_valid;
   Moments mine;
 #pragma unroll
-  for (int i = 0; i < 9; ++i) mine.s[i] = 0.f;
+  for (int i = 0; i < 9; ++i) mine.s[i] = 0.0;
   mine.n = 0;
   float4 myq = make_float4(0.f, 0.f, 0.f, 0.f);
   const int qend = min(32, nq - qbase);
@@ -80,7 +106,7 @@ normals_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2,
     float4 q = DENSE ? g.pts[qi] : queries[qi];
     Moments m;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) m.s[i] = 0.f;
+    for (int i = 0; i < 9; ++i) m.s[i] = 0.0;
     m.n = 0;
     bool ok = finite3(q.x, q.y, q.z) && (!DENSE || qi < n_valid);
     if (ok) {
@@ -89,7 +115,7 @@ normals_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2,
           int j = lists[(size_t)qi * k + c];
           if (j >= 0) {
             float4 p = g.pts[j];
-            mom_add(m, p.x - q.x, p.y - q.y, p.z - q.z);
+            mom_add(m, p, q);
           }
         }
       } else {
@@ -101,7 +127,7 @@ normals_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2,
           if (valid) {
             float4 p = g.pts[j];
             float d2 = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
-            if (d2 < r2) mom_add(m, p.x - q.x, p.y - q.y, p.z - q.z);
+            if (d2 < r2) mom_add(m, p, q);
           }
         }
       }
