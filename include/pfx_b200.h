@@ -56,6 +56,12 @@ int pfx_set_stream(pfx_ctx* ctx, void* cuda_stream); /* cudaStream_t; NULL = def
 int pfx_sync(pfx_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t pfx_launch_count(const pfx_ctx* ctx);
+/* per-kernel device timing with CUDA events on the context's stream (replaces the reference's
+ * ros::WallTime stop-watches, evaluation.cpp:278-283,596-603).  filter: substring of the kernel
+ * name to time, NULL/"" = every kernel.  pfx_profile_end waits for the stream and writes one line
+ * per kernel "<name>\t<launches>\t<total ms>\n" into buf. */
+int pfx_profile_begin(pfx_ctx* ctx, const char* filter);
+int pfx_profile_end(pfx_ctx* ctx, char* buf, size_t buflen);
 
 /* ------------------------------------------------------------------ inputs
  * pfx_set_surface   <- Feature::setSearchSurface + search::KdTree::setInputCloud

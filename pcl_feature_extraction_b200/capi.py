@@ -40,6 +40,8 @@ SIGNATURES = {
     "pfx_set_stream": (_i, [_vp, _vp]),
     "pfx_sync": (_i, [_vp]),
     "pfx_launch_count": (C.c_uint64, [_vp]),
+    "pfx_profile_begin": (_i, [_vp, C.c_char_p]),
+    "pfx_profile_end": (_i, [_vp, C.c_char_p, _sz]),
     "pfx_set_surface": (_i, [_vp, _vp, _sz, _sz, _i]),
     "pfx_set_queries": (_i, [_vp, _vp, _sz, _sz, _i]),
     "pfx_set_surface_normals": (_i, [_vp, _vp, _sz, _sz, _i, _i]),
@@ -132,6 +134,19 @@ class Context:
     @property
     def launches(self):
         return int(self.lib.pfx_launch_count(self.h))
+
+    def profile_begin(self, kernel_filter=None):
+        self._chk(self.lib.pfx_profile_begin(self.h, kernel_filter.encode() if kernel_filter else None))
+
+    def profile_end(self):
+        """-> {kernel name: (launches, total ms)} measured with CUDA events on the launching stream"""
+        buf = C.create_string_buffer(1 << 16)
+        self._chk(self.lib.pfx_profile_end(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split("\t")
+            out[name] = (int(cnt), float(ms))
+        return out
 
     # -- inputs (numpy host arrays; *_dev variants take raw device pointers)
     def set_surface(self, pts):

@@ -168,6 +168,49 @@ extern "C" int pfx_sync(pfx_ctx* ctx) {
 }
 
 extern "C" uint64_t pfx_launch_count(const pfx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int pfx_profile_begin(pfx_ctx* ctx, const char* filter) {
+  if (!ctx) return PFX_E_INVALID;
+  ctx->prof_filter = filter ? filter : "";
+  ctx->prof_used = 0;
+  ctx->prof_on = true;
+  return 0;
+}
+
+// Stops profiling, waits for the stream and writes one line per kernel: "<name>\t<launches>\t<total ms>\n"
+extern "C" int pfx_profile_end(pfx_ctx* ctx, char* buf, size_t buflen) {
+  PFX_TRY(check_ctx(ctx));
+  ctx->prof_on = false;
+  PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<std::pair<std::string, std::pair<int, double>>> agg;
+  for (size_t i = 0; i < ctx->prof_used; ++i) {
+    float ms = 0.f;
+    PFX_CUDA(cudaEventElapsedTime(&ms, ctx->prof_recs[i].e0, ctx->prof_recs[i].e1));
+    std::string nm = ctx->prof_recs[i].name;
+    bool found = false;
+    for (auto& a : agg)
+      if (a.first == nm) {
+        a.second.first++;
+        a.second.second += ms;
+        found = true;
+        break;
+      }
+    if (!found) agg.push_back({nm, {1, (double)ms}});
+  }
+  ctx->prof_used = 0;
+  std::string out;
+  for (auto& a : agg) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s\t%d\t%.6f\n", a.first.c_str(), a.second.first, a.second.second);
+    out += line;
+  }
+  if (buf && buflen) {
+    size_t m = std::min(buflen - 1, out.size());
+    memcpy(buf, out.data(), m);
+    buf[m] = 0;
+  }
+  return 0;
+}
 extern "C" size_t pfx_num_surface(const pfx_ctx* ctx) { return ctx ? ctx->n : 0; }
 extern "C" size_t pfx_num_queries(const pfx_ctx* ctx) { return ctx ? ctx->num_queries() : 0; }
 

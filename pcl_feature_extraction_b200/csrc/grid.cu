@@ -301,35 +301,6 @@ rs_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift, int nblk, in
   ghist[threadIdx.x * nblk + blockIdx.x] = cnt[threadIdx.x];
 }
 
-// exclusive scan of ghist (256 * nblk entries, digit-major) by one block
-__global__ void rs_scan_kernel(int* ghist, int total) {
-  __shared__ int sm[9];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  const int per = SCAN_ITEMS;
-  for (int base = 0; base < total; base += SCAN_THREADS * per) {
-    int b0 = base + threadIdx.x * per;
-    int v[per];
-    int s = 0;
-#pragma unroll
-    for (int i = 0; i < per; ++i) {
-      v[i] = (b0 + i < total) ? ghist[b0 + i] : 0;
-      s += v[i];
-    }
-    int tot;
-    int ex = block_excl_scan<int>(s, sm, &tot) + carry;
-#pragma unroll
-    for (int i = 0; i < per; ++i) {
-      if (b0 + i < total) ghist[b0 + i] = ex;
-      ex += v[i];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) carry += tot;
-    __syncthreads();
-  }
-}
-
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ vals, int n, int shift,
                   int nblk, const int* __restrict__ ghist, uint32_t* __restrict__ okeys,
@@ -389,7 +360,7 @@ static int radix_sort_pairs(Ctx* ctx, Grid* g, int n) {
   for (int pass = 0; pass < 4; ++pass) {
     int shift = pass * 8;
     PFX_LAUNCH(ctx, rs_hist_kernel, nblk, RS_THREADS, 0, k0, n, shift, nblk, g->ghist.as<int>());
-    PFX_LAUNCH(ctx, rs_scan_kernel, 1, SCAN_THREADS, 0, g->ghist.as<int>(), 256 * nblk);
+    PFX_TRY(scan_exclusive_i32(ctx, g->ghist.as<int>(), g->ghist.as<int>(), 256 * nblk, nullptr, g->bsum));
     PFX_LAUNCH(ctx, rs_scatter_kernel, nblk, RS_THREADS, 0, k0, v0, n, shift, nblk,
                g->ghist.as<int>(), k1, v1);
     std::swap(k0, k1);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -26,8 +27,10 @@ namespace pfx {
 // kernel launch + bookkeeping; every launch of ours goes through this
 #define PFX_LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
   do {                                                                       \
+    bool pr__ = (ctx)->prof_on && (ctx)->prof_begin(#kernel);                \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);         \
     (ctx)->launches++;                                                       \
+    if (pr__) (ctx)->prof_end();                                             \
   } while (0)
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -109,6 +112,32 @@ struct Ctx {
   size_t pinned_cap = 0;
 
   int match_engine = -1;
+
+  // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg)
+  struct ProfRec {
+    const char* name;
+    cudaEvent_t e0, e1;
+  };
+  bool prof_on = false;
+  std::string prof_filter;
+  std::vector<ProfRec> prof_recs;
+  size_t prof_used = 0;
+  bool prof_begin(const char* name) {
+    if (!prof_filter.empty() && !strstr(name, prof_filter.c_str())) return false;
+    if (prof_used == prof_recs.size()) {
+      ProfRec r;
+      r.name = name;
+      if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return false;
+      prof_recs.push_back(r);
+    }
+    prof_recs[prof_used].name = name;
+    cudaEventRecord(prof_recs[prof_used].e0, stream);
+    return true;
+  }
+  void prof_end() {
+    cudaEventRecord(prof_recs[prof_used].e1, stream);
+    prof_used++;
+  }
 
   int fail(int code, const std::string& msg) {
     err = msg;
