@@ -1,0 +1,89 @@
+// evaluation_b200.cpp — ROS-free driver with the sequencing of the reference's evaluate() loop
+// (src/evaluation.cpp:272-852): for every keypoint detector x descriptor of the B200 path, detect
+// keypoints on source and target, describe them, match reciprocally, and print one CSV row with the
+// reference's column meaning (evaluation.cpp:190-206; ICP / RANSAC columns are outside the path).
+//
+//   evaluation_b200 <source.pcd> <target.pcd> [feat_radius=0.08] [normal_radius=0.05] [dump_dir]
+//
+// With dump_dir, raw results are written (kp indices are implied by the keypoint clouds) so that
+// tests/test_host_shim.py can compare this C++ path with the Python-bound C ABI and the oracle.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
+#include "feature_pipeline.hpp"
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <typename T>
+static void dump(const std::string& dir, const std::string& name, const std::vector<T>& v) {
+  if (dir.empty()) return;
+  std::ofstream f(dir + "/" + name, std::ios::binary);
+  f.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)(v.size() * sizeof(T)));
+}
+
+template <typename FeatureT>
+static void run_descriptor(const std::string& kp_type, const std::string& desc_type,
+                           typename pcl::Feature<PointRGB, FeatureT>::Ptr extractor, const PointCloudRGB::Ptr& source,
+                           const PointCloudRGB::Ptr& target, const PointCloudRGB::Ptr& skp, const PointCloudRGB::Ptr& tkp,
+                           double feat_r, double normal_r, double kp_runtime, const std::string& dump_dir) {
+  typename pcl::PointCloud<FeatureT>::Ptr sf(new pcl::PointCloud<FeatureT>), tf(new pcl::PointCloud<FeatureT>);
+  double t0 = now_s();
+  Features<FeatureT> feat(extractor, feat_r, normal_r);
+  feat.compute(source, skp, sf);
+  feat.compute(target, tkp, tf);
+  double desc_runtime = now_s() - t0;
+  t0 = now_s();
+  pcl::CorrespondencesPtr corr(new pcl::Correspondences);
+  feat.findCorrespondences(sf, tf, corr);
+  double corr_runtime = now_s() - t0;
+  std::printf("%s, %s, %zu, %zu, %zu, %zu, %zu, %zu, %zu, %.6f, %.6f, %.6f\n", kp_type.c_str(), desc_type.c_str(),
+              source->size(), target->size(), skp->size(), tkp->size(), sf->size(), tf->size(), corr->size(), kp_runtime,
+              desc_runtime, corr_runtime);
+  dump(dump_dir, kp_type + "_" + desc_type + "_src.bin", sf->points);
+  dump(dump_dir, kp_type + "_" + desc_type + "_tgt.bin", tf->points);
+  dump(dump_dir, kp_type + "_" + desc_type + "_corr.bin", *corr);
+}
+
+int main(int argc, char** argv) {
+  if (argc < 3) {
+    std::fprintf(stderr, "usage: %s source.pcd target.pcd [feat_radius] [normal_radius] [dump_dir]\n", argv[0]);
+    return 2;
+  }
+  const double feat_r = argc > 3 ? std::atof(argv[3]) : 0.08;    // evaluation.cpp:167
+  const double normal_r = argc > 4 ? std::atof(argv[4]) : 0.05;  // evaluation.cpp:168
+  const std::string dump_dir = argc > 5 ? argv[5] : "";
+  PointCloudRGB::Ptr source(new PointCloudRGB), target(new PointCloudRGB);
+  if (loadPCDFile(argv[1], *source) != 0 || loadPCDFile(argv[2], *target) != 0) {
+    std::fprintf(stderr, "cannot read the input clouds\n");
+    return 1;
+  }
+  if (!pcl::b200::ctx()) return 3;
+  std::printf("Keypoint name, Descriptor name, Source cloud size, Target cloud size, Source keypoints size, "
+              "Target keypoints size, Source features size, Target features size, Correspondences, "
+              "Keypoints runtime, Features runtime, Correspondences runtime\n");
+  const std::string keypoints_list[] = {KP_HARRIS_3D, KP_ISS};
+  for (const std::string& kp_type : keypoints_list) {
+    PointCloudRGB::Ptr skp(new PointCloudRGB), tkp(new PointCloudRGB);
+    double t0 = now_s();
+    Keypoints kp(kp_type, normal_r);
+    kp.compute(source, skp);
+    kp.compute(target, tkp);
+    double kp_runtime = now_s() - t0;
+    if (skp->points.empty() || tkp->points.empty()) continue;  // evaluation.cpp:286-287
+    dump(dump_dir, kp_type + "_src_kp.bin", skp->points);
+    dump(dump_dir, kp_type + "_tgt_kp.bin", tkp->points);
+    {
+      pcl::Feature<PointRGB, pcl::FPFHSignature33>::Ptr ex(new pcl::FPFHEstimation<PointRGB, pcl::Normal, pcl::FPFHSignature33>);
+      run_descriptor<pcl::FPFHSignature33>(kp_type, DESC_FPFH, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime, dump_dir);
+    }
+    {
+      pcl::Feature<PointRGB, pcl::SHOT352>::Ptr ex(new pcl::SHOTEstimationOMP<PointRGB, pcl::Normal, pcl::SHOT352>);
+      run_descriptor<pcl::SHOT352>(kp_type, DESC_SHOT, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime, dump_dir);
+    }
+  }
+  pfx_destroy(pcl::b200::ctx());
+  return 0;
+}

@@ -1,0 +1,516 @@
+// pcl_compat.hpp — header-only C++ shim that puts the pcl::Feature / pcl::Keypoint style API used by
+// the reference (include/pcl_feature_extraction/{features,keypoints,tools}.h) on top of the C ABI in
+// include/pfx_b200.h.  PCL's headers are not available here, so the POD point types are defined with
+// PCL's memory layout (pcl/impl/point_types.hpp): PointXYZRGB / PointXYZI / Normal 32 B,
+// FPFHSignature33 132 B, SHOT352 1444 B, Correspondence 12 B (static_asserts below).
+//
+// Semantics kept from pcl::Feature::compute / initCompute (features/impl/feature.hpp): no exception
+// ever leaves compute(); when a precondition fails the error is printed and the output cloud is
+// emptied (width = height = 0); no surface => surface = input; exactly one of radius / k; rows of
+// non-finite queries or empty neighbourhoods are NaN and clear is_dense.
+#pragma once
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/pfx_b200.h"
+
+namespace pcl {
+
+// ------------------------------------------------------------------------------- point types
+struct alignas(16) PointXYZ { float x = 0, y = 0, z = 0, pad_ = 1.0f; };
+struct alignas(16) PointXYZRGB {
+  float x = 0, y = 0, z = 0, pad_ = 1.0f;
+  union { float rgb; uint32_t rgba; struct { uint8_t b, g, r, a; }; };
+  float pad2_[3];
+  PointXYZRGB() : rgba(0xff000000u), pad2_{0, 0, 0} {}
+};
+struct alignas(16) PointXYZI {
+  float x = 0, y = 0, z = 0, pad_ = 1.0f;
+  float intensity = 0;
+  float pad2_[3] = {0, 0, 0};
+};
+struct alignas(16) Normal {
+  float normal_x = 0, normal_y = 0, normal_z = 0, pad_ = 0;
+  float curvature = 0;
+  float pad2_[3] = {0, 0, 0};
+};
+struct FPFHSignature33 { float histogram[33]; static int descriptorSize() { return 33; } };
+struct SHOT352 { float descriptor[352]; float rf[9]; static int descriptorSize() { return 352; } };
+struct ReferenceFrame { float x_axis[3], y_axis[3], z_axis[3]; };
+struct Correspondence {
+  int index_query = 0, index_match = -1;
+  float distance = std::numeric_limits<float>::max();
+};
+static_assert(sizeof(PointXYZ) == 16 && sizeof(PointXYZRGB) == 32 && sizeof(PointXYZI) == 32, "PCL layout");
+static_assert(sizeof(Normal) == 32 && sizeof(FPFHSignature33) == 132 && sizeof(SHOT352) == 1444, "PCL layout");
+static_assert(sizeof(ReferenceFrame) == 36 && sizeof(Correspondence) == 12, "PCL layout");
+static_assert(sizeof(Correspondence) == sizeof(pfx_correspondence), "ABI layout");
+
+typedef std::vector<Correspondence> Correspondences;
+typedef std::shared_ptr<Correspondences> CorrespondencesPtr;
+struct PointIndices { std::vector<int> indices; };
+typedef std::shared_ptr<PointIndices> PointIndicesPtr;
+typedef std::shared_ptr<const PointIndices> PointIndicesConstPtr;
+
+template <typename PointT>
+struct PointCloud {
+  typedef std::shared_ptr<PointCloud<PointT>> Ptr;
+  typedef std::shared_ptr<const PointCloud<PointT>> ConstPtr;
+  std::vector<PointT> points;
+  uint32_t width = 0, height = 0;
+  bool is_dense = true;
+  float sensor_origin_[4] = {0, 0, 0, 0};
+  float sensor_orientation_[4] = {1, 0, 0, 0};  // w x y z
+  size_t size() const { return points.size(); }
+  bool empty() const { return points.empty(); }
+  void clear() { points.clear(); width = height = 0; }
+  void resize(size_t n) { points.resize(n); width = (uint32_t)n; height = 1; }
+  void push_back(const PointT& p) { points.push_back(p); width = (uint32_t)points.size(); height = 1; }
+  PointT& operator[](size_t i) { return points[i]; }
+  const PointT& operator[](size_t i) const { return points[i]; }
+};
+
+template <typename T> inline bool isFinite(const T& p) { return std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z); }
+
+// ------------------------------------------------------------------------------- context
+namespace b200 {
+inline pfx_ctx*& ctx_slot() { static pfx_ctx* c = nullptr; return c; }
+// one context per process (device 0 unless set_device() was called first); PCL objects are not
+// thread-safe either, the shim keeps that contract
+inline int& device_slot() { static int d = 0; return d; }
+inline void set_device(int d) { device_slot() = d; }
+inline pfx_ctx* ctx() {
+  pfx_ctx*& c = ctx_slot();
+  if (!c) {
+    int rc = pfx_create(device_slot(), &c);
+    if (rc != 0) {
+      std::fprintf(stderr, "[pcl::b200] pfx_create(%d) failed with %d: an sm_100 GPU is required (no CPU fallback)\n",
+                   device_slot(), rc);
+      c = nullptr;
+    }
+  }
+  return c;
+}
+inline bool ok(int rc, const char* who) {
+  if (rc == 0) return true;
+  std::fprintf(stderr, "[pcl::%s] %s (code %d)\n", who, ctx_slot() ? pfx_last_error(ctx_slot()) : "no context", rc);
+  return false;
+}
+}  // namespace b200
+
+// ------------------------------------------------------------------------------- search objects
+// The reference creates search::KdTree objects only to hand them to setSearchMethod (features.h:192,
+// tools.h:29, keypoints.h:186); the voxel hash behind pfx_set_surface replaces them, so these are tags.
+namespace search {
+template <typename PointT>
+struct KdTree {
+  typedef std::shared_ptr<KdTree<PointT>> Ptr;
+  typename PointCloud<PointT>::ConstPtr input_;
+  void setInputCloud(const typename PointCloud<PointT>::ConstPtr& c) { input_ = c; }
+  // batched form of the per-point loop at keypoints.h:411-424
+  int nearestKSearchAll(int k, std::vector<int>& idx, std::vector<float>& d2) const {
+    pfx_ctx* c = b200::ctx();
+    if (!c || !input_) return 0;
+    idx.assign(input_->size() * k, -1);
+    d2.assign(input_->size() * k, 0.f);
+    if (!b200::ok(pfx_set_surface(c, input_->points.data(), input_->size(), sizeof(PointT), PFX_HOST), "KdTree")) return 0;
+    if (!b200::ok(pfx_knn(c, k, idx.data(), d2.data(), PFX_HOST), "KdTree")) return 0;
+    return k;
+  }
+};
+}  // namespace search
+
+// KdTreeFLANN over DESCRIPTORS as used by features.h:253-273: setInputCloud(target) then
+// nearestKSearch(source, i, 1, ...) for every i.  The first call for a given source cloud runs ONE
+// batched exact 1-NN on the GPU (pfx_match_nn) and the loop then reads the cached answers.
+template <typename FeatureT>
+class KdTreeFLANN {
+ public:
+  void setInputCloud(const typename PointCloud<FeatureT>::ConstPtr& t) { target_ = t; cached_src_ = nullptr; }
+  int nearestKSearch(const PointCloud<FeatureT>& src, int index, int k, std::vector<int>& k_indices,
+                     std::vector<float>& k_sqr_distances) {
+    if (k != 1 || !target_) return 0;
+    if (cached_src_ != &src || cached_n_ != src.size()) {
+      pfx_ctx* c = b200::ctx();
+      if (!c) return 0;
+      idx_.assign(src.size(), -1);
+      d2_.assign(src.size(), 0.f);
+      const int dim = FeatureT::descriptorSize();
+      int rc = pfx_match_nn(c, reinterpret_cast<const float*>(src.points.data()), src.size(), sizeof(FeatureT),
+                            reinterpret_cast<const float*>(target_->points.data()), target_->size(), sizeof(FeatureT),
+                            dim, idx_.data(), d2_.data(), PFX_HOST);
+      if (!b200::ok(rc, "KdTreeFLANN")) return 0;
+      cached_src_ = &src;
+      cached_n_ = src.size();
+    }
+    k_indices.resize(1);
+    k_sqr_distances.resize(1);
+    k_indices[0] = idx_[index];
+    k_sqr_distances[0] = d2_[index];
+    return idx_[index] >= 0 ? 1 : 0;
+  }
+
+ private:
+  typename PointCloud<FeatureT>::ConstPtr target_;
+  const PointCloud<FeatureT>* cached_src_ = nullptr;
+  size_t cached_n_ = 0;
+  std::vector<int> idx_;
+  std::vector<float> d2_;
+};
+
+// ------------------------------------------------------------------------------- Feature base
+template <typename PointInT, typename PointOutT>
+class Feature {
+ public:
+  typedef std::shared_ptr<Feature<PointInT, PointOutT>> Ptr;
+  typedef PointCloud<PointInT> PointCloudIn;
+  typedef PointCloud<PointOutT> PointCloudOut;
+  virtual ~Feature() {}
+  void setInputCloud(const typename PointCloudIn::ConstPtr& c) { input_ = c; }
+  void setSearchSurface(const typename PointCloudIn::ConstPtr& c) { surface_ = c; }
+  template <typename Tree> void setSearchMethod(const Tree&) {}
+  void setRadiusSearch(double r) { search_radius_ = r; }
+  void setKSearch(int k) { k_ = k; }
+  double getRadiusSearch() const { return search_radius_; }
+  int getKSearch() const { return k_; }
+  void setNumberOfThreads(unsigned) {}  // OMP variants: the GPU path has no thread knob
+
+  void compute(PointCloudOut& output) {
+    if (!initCompute()) {
+      output.width = output.height = 0;
+      output.points.clear();
+      return;
+    }
+    output.points.resize(input_->size());
+    if (input_->width * input_->height == input_->size() && input_->size() > 0) {
+      output.width = input_->width;
+      output.height = input_->height;
+    } else {
+      output.width = (uint32_t)input_->size();
+      output.height = 1;
+    }
+    output.is_dense = input_->is_dense;
+    if (!computeFeature(output)) {
+      output.width = output.height = 0;
+      output.points.clear();
+    }
+  }
+
+ protected:
+  virtual const char* name() const = 0;
+  virtual bool computeFeature(PointCloudOut& output) = 0;
+  virtual bool initCompute() {
+    if (!input_) {
+      std::fprintf(stderr, "[pcl::%s::compute] no input dataset given!\n", name());
+      return false;
+    }
+    if (!surface_) surface_ = input_;  // "fake surface"
+    if (search_radius_ != 0.0 && k_ != 0) {
+      std::fprintf(stderr, "[pcl::%s::compute] Both radius (%f) and K (%d) defined! Set one of them to zero first.\n",
+                   name(), search_radius_, k_);
+      return false;
+    }
+    if (search_radius_ == 0.0 && k_ == 0) {
+      std::fprintf(stderr, "[pcl::%s::compute] Neither radius nor K defined!\n", name());
+      return false;
+    }
+    return b200::ctx() != nullptr;
+  }
+  // surface + queries to the device; dense when input and surface are the same cloud
+  bool upload() {
+    pfx_ctx* c = b200::ctx();
+    if (!b200::ok(pfx_set_surface(c, surface_->points.data(), surface_->size(), sizeof(PointInT), PFX_HOST), name())) return false;
+    pfx_set_viewpoint(c, surface_->sensor_origin_[0], surface_->sensor_origin_[1], surface_->sensor_origin_[2]);
+    if (input_.get() == surface_.get()) return b200::ok(pfx_set_queries(c, nullptr, 0, 0, PFX_HOST), name());
+    return b200::ok(pfx_set_queries(c, input_->points.data(), input_->size(), sizeof(PointInT), PFX_HOST), name());
+  }
+  typename PointCloudIn::ConstPtr input_, surface_;
+  double search_radius_ = 0.0;
+  int k_ = 0;
+};
+
+template <typename PointInT, typename PointNT, typename PointOutT>
+class FeatureFromNormals : public Feature<PointInT, PointOutT> {
+ public:
+  typedef std::shared_ptr<FeatureFromNormals<PointInT, PointNT, PointOutT>> Ptr;
+  void setInputNormals(const typename PointCloud<PointNT>::ConstPtr& n) { normals_ = n; }
+
+ protected:
+  bool initCompute() override {
+    if (!Feature<PointInT, PointOutT>::initCompute()) return false;
+    if (!normals_) {
+      std::fprintf(stderr, "[pcl::%s::initCompute] No input dataset containing normals was given!\n", this->name());
+      return false;
+    }
+    if (normals_->size() != this->surface_->size()) {
+      std::fprintf(stderr, "[pcl::%s::initCompute] The number of points in the surface differs from the number of normals!\n", this->name());
+      return false;
+    }
+    return true;
+  }
+  bool uploadWithNormals() {
+    if (!this->upload()) return false;
+    return b200::ok(pfx_set_surface_normals(b200::ctx(), normals_->points.data(), normals_->size(), sizeof(PointNT), 4, PFX_HOST),
+                    this->name());
+  }
+  typename PointCloud<PointNT>::ConstPtr normals_;
+};
+
+// ------------------------------------------------------------------------------- NormalEstimation
+template <typename PointInT, typename PointOutT>
+class NormalEstimation : public Feature<PointInT, PointOutT> {
+ public:
+  void setViewPoint(float x, float y, float z) { vp_[0] = x; vp_[1] = y; vp_[2] = z; use_origin_ = false; }
+
+ protected:
+  const char* name() const override { return "NormalEstimation"; }
+  bool computeFeature(PointCloud<PointOutT>& output) override {
+    if (!this->upload()) return false;
+    pfx_ctx* c = b200::ctx();
+    if (!use_origin_) pfx_set_viewpoint(c, vp_[0], vp_[1], vp_[2]);
+    for (auto& p : output.points) p = PointOutT();
+    int rc = pfx_normals(c, this->search_radius_, this->k_, output.points.data(), sizeof(PointOutT), 4, PFX_HOST);
+    if (!b200::ok(rc, name())) return false;
+    for (const auto& p : output.points)
+      if (!std::isfinite(p.normal_x)) { output.is_dense = false; break; }
+    return true;
+  }
+  float vp_[3] = {0, 0, 0};
+  bool use_origin_ = true;
+};
+template <typename PointInT, typename PointOutT>
+class NormalEstimationOMP : public NormalEstimation<PointInT, PointOutT> {
+ public:
+  explicit NormalEstimationOMP(unsigned = 0) {}
+};
+
+// ------------------------------------------------------------------------------- FPFH
+template <typename PointInT, typename PointNT, typename PointOutT = FPFHSignature33>
+class FPFHEstimation : public FeatureFromNormals<PointInT, PointNT, PointOutT> {
+ protected:
+  const char* name() const override { return "FPFHEstimation"; }
+  bool computeFeature(PointCloud<PointOutT>& output) override {
+    if (!this->uploadWithNormals()) return false;
+    int rc = pfx_fpfh(b200::ctx(), this->search_radius_, this->k_, reinterpret_cast<float*>(output.points.data()),
+                      sizeof(PointOutT), PFX_HOST);
+    if (!b200::ok(rc, name())) return false;
+    for (const auto& p : output.points)
+      if (!std::isfinite(p.histogram[0])) { output.is_dense = false; break; }
+    return true;
+  }
+};
+template <typename PointInT, typename PointNT, typename PointOutT = FPFHSignature33>
+class FPFHEstimationOMP : public FPFHEstimation<PointInT, PointNT, PointOutT> {};
+
+// ------------------------------------------------------------------------------- SHOT
+template <typename PointInT, typename PointNT, typename PointOutT = SHOT352, typename PointRFT = ReferenceFrame>
+class SHOTEstimation : public FeatureFromNormals<PointInT, PointNT, PointOutT> {
+ public:
+  void setInputReferenceFrames(const typename PointCloud<PointRFT>::ConstPtr& f) { frames_ = f; }
+  void setLRFRadius(float r) { lrf_radius_ = r; }
+
+ protected:
+  const char* name() const override { return "SHOTEstimation"; }
+  bool initCompute() override {
+    if (!FeatureFromNormals<PointInT, PointNT, PointOutT>::initCompute()) return false;
+    if (this->k_ != 0) {  // SHOT cannot work with k-search
+      std::fprintf(stderr, "[pcl::%s::initCompute] Error! Search method set to k-neighborhood. Call setKSearch(0) and setRadiusSearch( radius ) to use this class.\n", name());
+      return false;
+    }
+    if (frames_ && frames_->size() != this->input_->size()) {
+      std::fprintf(stderr, "[pcl::%s::initCompute] The number of reference frames differs from the number of input points!\n", name());
+      return false;
+    }
+    return true;
+  }
+  bool computeFeature(PointCloud<PointOutT>& output) override {
+    if (!this->uploadWithNormals()) return false;
+    pfx_ctx* c = b200::ctx();
+    std::vector<float> lrf;
+    const float* lrf_in = nullptr;
+    if (frames_) {
+      lrf_in = reinterpret_cast<const float*>(frames_->points.data());
+    } else if (lrf_radius_ > 0 && (double)lrf_radius_ != this->search_radius_) {
+      lrf.resize(output.points.size() * 9);
+      if (!b200::ok(pfx_shot_lrf(c, lrf_radius_, lrf.data(), PFX_HOST), name())) return false;
+      lrf_in = lrf.data();
+    }
+    int rc = pfx_shot352(c, this->search_radius_, lrf_in, reinterpret_cast<float*>(output.points.data()),
+                         sizeof(PointOutT), PFX_HOST);
+    if (!b200::ok(rc, name())) return false;
+    for (const auto& p : output.points)
+      if (!std::isfinite(p.descriptor[0])) { output.is_dense = false; break; }
+    return true;
+  }
+  typename PointCloud<PointRFT>::ConstPtr frames_;
+  float lrf_radius_ = 0;
+};
+template <typename PointInT, typename PointNT, typename PointOutT = SHOT352, typename PointRFT = ReferenceFrame>
+class SHOTEstimationOMP : public SHOTEstimation<PointInT, PointNT, PointOutT, PointRFT> {};
+
+// ------------------------------------------------------------------------------- keypoints
+template <typename PointInT, typename PointOutT>
+class Keypoint {
+ public:
+  virtual ~Keypoint() {}
+  void setInputCloud(const typename PointCloud<PointInT>::ConstPtr& c) { input_ = c; }
+  void setSearchSurface(const typename PointCloud<PointInT>::ConstPtr& c) { surface_ = c; }
+  template <typename Tree> void setSearchMethod(const Tree&) {}
+  void setRadiusSearch(double r) { search_radius_ = r; }
+  void setKSearch(int k) { k_ = k; }
+  PointIndicesConstPtr getKeypointsIndices() const { return keypoints_indices_; }
+  void compute(PointCloud<PointOutT>& output) {
+    keypoints_indices_.reset(new PointIndices);
+    output.points.clear();
+    output.width = output.height = 0;
+    if (!input_) {
+      std::fprintf(stderr, "[pcl::Keypoint::compute] no input dataset given!\n");
+      return;
+    }
+    if (!b200::ctx()) return;
+    detectKeypoints(output);
+    output.width = (uint32_t)output.points.size();
+    output.height = 1;
+    output.is_dense = true;
+  }
+
+ protected:
+  virtual void detectKeypoints(PointCloud<PointOutT>& output) = 0;
+  typename PointCloud<PointInT>::ConstPtr input_, surface_;
+  double search_radius_ = 0.0;
+  int k_ = 0;
+  PointIndicesPtr keypoints_indices_;
+};
+
+template <typename PointInT, typename PointOutT, typename NormalT = Normal>
+class ISSKeypoint3D : public Keypoint<PointInT, PointOutT> {
+ public:
+  explicit ISSKeypoint3D(double salient_radius = 0.0001) : salient_radius_(salient_radius) {}
+  void setSalientRadius(double r) { salient_radius_ = r; }
+  void setNonMaxRadius(double r) { non_max_radius_ = r; }
+  void setMinNeighbors(int n) { min_neighbors_ = n; }
+  void setThreshold21(double g) { gamma_21_ = g; }
+  void setThreshold32(double g) { gamma_32_ = g; }
+  void setNormalRadius(double) {}
+  void setBorderRadius(double r) { border_radius_ = r; }
+  void setNumberOfThreads(unsigned) {}
+
+ protected:
+  void detectKeypoints(PointCloud<PointOutT>& output) override {
+    pfx_ctx* c = b200::ctx();
+    if (border_radius_ > 0) {
+      std::fprintf(stderr, "[pcl::ISSKeypoint3D] border estimation (border_radius > 0) is outside the reference's path\n");
+      return;
+    }
+    const auto& in = *this->input_;
+    if (!b200::ok(pfx_set_surface(c, in.points.data(), in.size(), sizeof(PointInT), PFX_HOST), "ISSKeypoint3D")) return;
+    std::vector<int> idx(in.size());
+    size_t n = 0;
+    int rc = pfx_iss(c, salient_radius_, non_max_radius_, min_neighbors_, gamma_21_, gamma_32_, idx.data(), idx.size(), &n,
+                     nullptr, PFX_HOST);
+    if (!b200::ok(rc, "ISSKeypoint3D")) return;
+    output.points.resize(n);
+    this->keypoints_indices_->indices.assign(idx.begin(), idx.begin() + n);
+    for (size_t i = 0; i < n; ++i) {  // upstream copies xyz only; other fields stay default-constructed
+      output.points[i] = PointOutT();
+      output.points[i].x = in.points[idx[i]].x;
+      output.points[i].y = in.points[idx[i]].y;
+      output.points[i].z = in.points[idx[i]].z;
+    }
+  }
+  double salient_radius_, non_max_radius_ = 0.0, gamma_21_ = 0.975, gamma_32_ = 0.975, border_radius_ = 0.0;
+  int min_neighbors_ = 5;
+};
+
+template <typename PointInT, typename PointOutT, typename NormalT = Normal>
+class HarrisKeypoint3D : public Keypoint<PointInT, PointOutT> {
+ public:
+  enum ResponseMethod { HARRIS = 1 };
+  explicit HarrisKeypoint3D(ResponseMethod = HARRIS, float radius = 0.01f, float threshold = 0.0f)
+      : threshold_(threshold) { this->search_radius_ = radius; }
+  void setRadius(float r) { this->search_radius_ = r; }
+  void setThreshold(float t) { threshold_ = t; }
+  void setNonMaxSupression(bool b) { nonmax_ = b; }
+  void setRefine(bool b) { refine_ = b; }
+  void setNormals(const typename PointCloud<NormalT>::ConstPtr& n) { normals_ = n; }
+  void setNumberOfThreads(unsigned) {}
+  // cloud indices of the corners after the reference's 1 cm snap (keypoints.h:360-395), -1 = dropped
+  const std::vector<int>& getSnappedIndices() const { return snapped_; }
+
+ protected:
+  void detectKeypoints(PointCloud<PointOutT>& output) override {
+    pfx_ctx* c = b200::ctx();
+    const auto& in = *this->input_;
+    if (!b200::ok(pfx_set_surface(c, in.points.data(), in.size(), sizeof(PointInT), PFX_HOST), "HarrisKeypoint3D")) return;
+    pfx_set_viewpoint(c, in.sensor_origin_[0], in.sensor_origin_[1], in.sensor_origin_[2]);
+    if (normals_ && !b200::ok(pfx_set_surface_normals(c, normals_->points.data(), normals_->size(), sizeof(NormalT), 4, PFX_HOST),
+                              "HarrisKeypoint3D")) return;
+    const size_t cap = in.size();
+    std::vector<float> resp(cap), xyz(cap * 3);
+    std::vector<int> idx(cap);
+    snapped_.assign(cap, -1);
+    size_t n = 0;
+    int rc = pfx_harris3d(c, this->search_radius_, threshold_, nonmax_ ? 1 : 0, refine_ ? 1 : 0, 1e-4f, resp.data(),
+                          idx.data(), xyz.data(), snapped_.data(), cap, &n, PFX_HOST);
+    if (!b200::ok(rc, "HarrisKeypoint3D")) return;
+    if (!nonmax_) {
+      output.points.resize(in.size());
+      for (size_t i = 0; i < in.size(); ++i) {
+        output.points[i].x = in.points[i].x; output.points[i].y = in.points[i].y; output.points[i].z = in.points[i].z;
+        output.points[i].intensity = resp[i];
+      }
+      snapped_.clear();
+      return;
+    }
+    output.points.resize(n);
+    snapped_.resize(n);
+    this->keypoints_indices_->indices.assign(idx.begin(), idx.begin() + n);
+    for (size_t i = 0; i < n; ++i) {
+      output.points[i].x = xyz[3 * i]; output.points[i].y = xyz[3 * i + 1]; output.points[i].z = xyz[3 * i + 2];
+      output.points[i].intensity = resp[idx[i]];
+    }
+  }
+  float threshold_;
+  bool nonmax_ = true, refine_ = true;
+  typename PointCloud<NormalT>::ConstPtr normals_;
+  std::vector<int> snapped_;
+};
+
+// ------------------------------------------------------------------------------- registration
+namespace registration {
+// pcl::registration::CorrespondenceEstimation (included at evaluation.cpp:20; named by north_star)
+template <typename FeatureT>
+class CorrespondenceEstimation {
+ public:
+  void setInputSource(const typename PointCloud<FeatureT>::ConstPtr& s) { source_ = s; }
+  void setInputTarget(const typename PointCloud<FeatureT>::ConstPtr& t) { target_ = t; }
+  void determineCorrespondences(Correspondences& out, double max_distance = std::numeric_limits<double>::max()) { run(out, max_distance, 0); }
+  void determineReciprocalCorrespondences(Correspondences& out, double max_distance = std::numeric_limits<double>::max()) { run(out, max_distance, 1); }
+
+ private:
+  void run(Correspondences& out, double max_distance, int reciprocal) {
+    out.clear();
+    pfx_ctx* c = b200::ctx();
+    if (!c || !source_ || !target_) return;
+    out.resize(source_->size());
+    size_t n = 0;
+    float md2 = (max_distance >= 1e18) ? -1.f : (float)(max_distance * max_distance);
+    int rc = pfx_match(c, reinterpret_cast<const float*>(source_->points.data()), source_->size(), sizeof(FeatureT),
+                       reinterpret_cast<const float*>(target_->points.data()), target_->size(), sizeof(FeatureT),
+                       FeatureT::descriptorSize(), reciprocal, md2, reinterpret_cast<pfx_correspondence*>(out.data()),
+                       out.size(), &n, PFX_HOST);
+    if (!b200::ok(rc, "CorrespondenceEstimation")) n = 0;
+    out.resize(n);
+  }
+  typename PointCloud<FeatureT>::ConstPtr source_, target_;
+};
+}  // namespace registration
+
+}  // namespace pcl

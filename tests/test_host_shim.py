@@ -1,0 +1,68 @@
+"""The C++ host side (pcl_compat.hpp + feature_pipeline.hpp + evaluation_b200.cpp): the reference's
+evaluate() sequencing through the pcl::Feature-style shim, compared with the Python-bound C ABI and
+the oracle.  Needs a GPU (the driver calls the CUDA library; there is no CPU path)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "pcl_feature_extraction_b200", "lib", "evaluation_b200")
+
+
+def test_shim_compiles_against_the_c_abi():
+    """CPU: the driver binary is built by __graft_entry__.build() and links the C-ABI library."""
+    assert os.path.exists(BIN), "run __graft_entry__.build()"
+    out = subprocess.run(["ldd", BIN], capture_output=True, text=True).stdout
+    assert "libpfx_b200.so" in out
+
+
+@pytest.mark.gpu
+def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
+    from pcl_feature_extraction_b200.pcd import write_pcd
+    src = np.ascontiguousarray(clouds["underwater_source"][:30000])
+    tgt = np.ascontiguousarray(clouds["underwater_target"][:30000])
+    write_pcd(tmp_path / "s.pcd", src)
+    write_pcd(tmp_path / "t.pcd", tgt)
+    r = subprocess.run([BIN, str(tmp_path / "s.pcd"), str(tmp_path / "t.pcd"), "0.05", "0.03", str(tmp_path)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    rows = [l.split(", ") for l in r.stdout.strip().splitlines()[1:]]
+    assert [(x[0], x[1]) for x in rows] == [("Harris3D", "FPFH"), ("Harris3D", "SHOT"), ("Iss", "FPFH"), ("Iss", "SHOT")]
+
+    def kp_xyz(name):
+        a = np.fromfile(tmp_path / name, dtype=np.float32).reshape(-1, 8)
+        return np.ascontiguousarray(a[:, :3])
+
+    # ISS keypoints: same as the C ABI called from Python, and as the oracle NMS on the GPU saliency
+    ctx.set_surface(src)
+    res = ctx.cloud_resolution()
+    kp, sal = ctx.iss(6 * res, 4 * res)
+    assert np.array_equal(kp_xyz("Iss_src_kp.bin"), src[kp])
+    assert np.array_equal(kp, orc.iss_nms(src, sal, 4 * res))
+    # Harris keypoints after the snap
+    h = ctx.harris3d(0.01, 1e-6)
+    snapped = h["snapped_idx"][h["snapped_idx"] >= 0]
+    assert np.array_equal(kp_xyz("Harris3D_src_kp.bin"), src[snapped])
+    # FPFH at the ISS keypoints: shim == C ABI bit for bit; vs oracle within the FPFH tolerance
+    f_shim = np.fromfile(tmp_path / "Iss_FPFH_src.bin", dtype=np.float32).reshape(-1, 33)
+    ctx.set_surface(src)
+    ctx.set_queries(None)
+    nr = ctx.normals(radius=0.03)
+    ctx.set_queries(src[kp])
+    f_abi = ctx.fpfh(radius=0.05)
+    assert np.array_equal(f_shim, f_abi)
+    f_or = orc.fpfh(src, nr, src[kp], radius=0.05)
+    assert (np.abs(f_shim - f_or).max(1) <= 1e-2).mean() > 0.97
+    # SHOT rows carry descriptor[352] + rf[9]
+    s_shim = np.fromfile(tmp_path / "Iss_SHOT_src.bin", dtype=np.float32).reshape(-1, 361)
+    s_abi, rf_abi = ctx.shot352(0.05)
+    assert np.array_equal(s_shim[:, :352], s_abi, equal_nan=True) and np.array_equal(s_shim[:, 352:], rf_abi, equal_nan=True)
+    # correspondences: reciprocal exact matching of the dumped descriptors == oracle, bit-exact indices
+    f_tgt = np.fromfile(tmp_path / "Iss_FPFH_tgt.bin", dtype=np.float32).reshape(-1, 33)
+    corr = np.fromfile(tmp_path / "Iss_FPFH_corr.bin", dtype=np.int32).reshape(-1, 3)
+    q, m, d = orc.match_reciprocal(f_shim, f_tgt)
+    assert np.array_equal(corr[:, 0], q) and np.array_equal(corr[:, 1], m)
+    assert np.array_equal(corr[:, 2].view(np.float32), d)
+    assert int(rows[2][8]) == len(q)
