@@ -40,6 +40,8 @@ SIGNATURES = {
     "pfx_set_stream": (_i, [_vp, _vp]),
     "pfx_sync": (_i, [_vp]),
     "pfx_launch_count": (C.c_uint64, [_vp]),
+    "pfx_grid_info": (_i, [_vp, C.POINTER(_d)]),
+    "pfx_set_knn_occupancy": (_i, [_vp, _f]),
     "pfx_profile_begin": (_i, [_vp, C.c_char_p]),
     "pfx_profile_end": (_i, [_vp, C.c_char_p, _sz]),
     "pfx_set_surface": (_i, [_vp, _vp, _sz, _sz, _i]),
@@ -134,6 +136,15 @@ class Context:
     @property
     def launches(self):
         return int(self.lib.pfx_launch_count(self.h))
+
+    def grid_info(self):
+        out = (C.c_double * 8)()
+        self._chk(self.lib.pfx_grid_info(self.h, out))
+        return dict(edge=out[0], dims=(int(out[1]), int(out[2]), int(out[3])), ncells=int(out[4]), n_valid=int(out[5]),
+                    tile_flagged=int(out[6]))
+
+    def set_knn_occupancy(self, frac):
+        self._chk(self.lib.pfx_set_knn_occupancy(self.h, frac))
 
     def profile_begin(self, kernel_filter=None):
         self._chk(self.lib.pfx_profile_begin(self.h, kernel_filter.encode() if kernel_filter else None))

@@ -169,6 +169,37 @@ extern "C" int pfx_sync(pfx_ctx* ctx) {
 
 extern "C" uint64_t pfx_launch_count(const pfx_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+// Diagnostics of the voxel hash used by the last call: out[0] cell edge, out[1..3] cells per axis,
+// out[4] occupied cells, out[5] finite points, out[6] queries the cell-tile path handed to the generic
+// kernels (-1 when no tile pass ran on that grid), out[7] reserved.
+extern "C" int pfx_grid_info(pfx_ctx* ctx, double* out8) {
+  PFX_TRY(check_ctx(ctx));
+  if (!out8) return ctx->fail(PFX_E_INVALID, "pfx_grid_info: null output");
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
+  Grid* g = ctx->last_grid;
+  if (!g || g->surf_version != ctx->surf_version) return ctx->fail(PFX_E_STATE, "pfx_grid_info: no grid built yet");
+  GridParams P;
+  PFX_CUDA(cudaMemcpyAsync(&P, g->params.p, sizeof(P), cudaMemcpyDeviceToHost, ctx->stream));
+  PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  out8[0] = P.edge; out8[1] = P.nx; out8[2] = P.ny; out8[3] = P.nz; out8[4] = P.ncells; out8[5] = P.n_valid;
+  out8[6] = -1;
+  if (ctx->knn_grid == g && ctx->knn_sversion == ctx->surf_version && ctx->knn_dense && !ctx->knn_sorted && ctx->n > 0) {
+    std::vector<unsigned char> f(ctx->n);
+    PFX_CUDA(cudaMemcpy(f.data(), ctx->qflag.p, ctx->n, cudaMemcpyDeviceToHost));
+    long long c = 0;
+    for (unsigned char v : f) c += v ? 1 : 0;
+    out8[6] = (double)c;
+  }
+  return 0;
+}
+
+// target points per occupied cell of kNN grids, as a fraction of k (default 0.3)
+extern "C" int pfx_set_knn_occupancy(pfx_ctx* ctx, float fraction_of_k) {
+  if (!ctx || !(fraction_of_k > 0.f)) return PFX_E_INVALID;
+  ctx->knn_occupancy = fraction_of_k;
+  return 0;
+}
+
 extern "C" int pfx_profile_begin(pfx_ctx* ctx, const char* filter) {
   if (!ctx) return PFX_E_INVALID;
   ctx->prof_filter = filter ? filter : "";

@@ -495,7 +495,9 @@ static int grid_build(Ctx* ctx, Grid* g, double radius, int knn_k) {
     float edge = (float)(radius * (1.0 + 1e-3));
     PFX_LAUNCH(ctx, params_kernel, 1, 1, 0, acc, gp, edge, 0, 0.f);
   } else {
-    float target = std::max(2.0f, 0.5f * (float)knn_k);
+    // points per occupied cell: ~k/3 keeps the 3x3x3 stencil of a surface at 100-200 candidates while
+    // the k-th neighbour still falls inside it (cell-tile kNN, knn_tile.cu)
+    float target = std::max(2.0f, ctx->knn_occupancy * (float)knn_k);
     PFX_LAUNCH(ctx, params_kernel, 1, 1, 0, acc, gp, 0.f, 0, target);
     if (n > 0) {
       PFX_CUDA(cudaMemsetAsync(g->hkeys.p, 0xff, ((size_t)g->hmask + 1) * sizeof(uint32_t), ctx->stream));
@@ -537,6 +539,7 @@ int grid_get(Ctx* ctx, double radius, int knn_k, Grid** out) {
         ((radius > 0 && g->radius == radius) || (!(radius > 0) && g->knn_k == knn_k && !(g->radius > 0)))) {
       g->last_use = ctx->tick;
       *out = g;
+      ctx->last_grid = g;
       return 0;
     }
   }
@@ -559,6 +562,7 @@ int grid_get(Ctx* ctx, double radius, int knn_k, Grid** out) {
     return rc;
   }
   *out = victim;
+  ctx->last_grid = victim;
   return 0;
 }
 

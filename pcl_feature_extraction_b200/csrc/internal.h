@@ -106,12 +106,19 @@ struct Ctx {
   uint64_t knn_qversion = 0, knn_sversion = 0;
   bool knn_dense = false;
 
+  bool knn_sorted = false;  // rows ascending (d2, index)? (the cell-tile path writes unsorted sets)
+  // qflag[i] != 0: dense query i was handed from the cell-tile path to the generic kernels
+  DevBuf qflag;
+  bool tile_has_normals = false;
+
   // scratch
   DevBuf stage, stage2, tmp0, tmp1, tmp2, tmp3, tmp4, small, scanbuf, match_flags, match_best, out_stage;
   void* pinned = nullptr;
   size_t pinned_cap = 0;
 
   int match_engine = -1;
+  float knn_occupancy = 0.3f;  // target points per occupied cell of a kNN grid, as a fraction of k
+  Grid* last_grid = nullptr;
 
   // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg)
   struct ProfRec {
@@ -163,6 +170,9 @@ int scan_exclusive_i64(Ctx* ctx, const int* in, long long* out, int n, DevBuf& b
 // ---- search.cu
 int knn_run(Ctx* ctx, Grid* g, const float4* q_dev, int nq, int k, int* idx_dev, float* d2_dev);
 int knn_lists(Ctx* ctx, Grid* g, int k, bool need_sorted_ids);  // fills ctx->knn_idx / knn_d2
+int knn_run_flagged(Ctx* ctx, Grid* g, int nq, int k, int* idx_dev, float* d2_dev, const unsigned char* only);
+// ---- knn_tile.cu
+int knn_tile_lists(Ctx* ctx, Grid* g, int k, bool with_normals);
 int knn_export(Ctx* ctx, int k, int32_t* idx, float* d2, int mem);
 int radius_count(Ctx* ctx, Grid* g, double radius, int* counts_dev);
 int radius_fill(Ctx* ctx, Grid* g, double radius, int sorted, const long long* offsets_dev,

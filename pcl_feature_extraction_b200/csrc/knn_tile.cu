@@ -1,0 +1,265 @@
+// knn_tile.cu — dense kNN neighbour SETS (+ fused normals) on cell tiles.
+//
+// One warp per occupied cell: the <= TCAP candidate points of the 3x3x3 stencil are staged in shared
+// memory once; queries of the cell are processed four at a time, eight lanes per query.  A lane keeps
+// the squared distances of its share of the candidates in registers; the k nearest are found by
+// SELECTION, not sorting: a bracketing search on the distance threshold tau (interpolation while the
+// bracket is wide - count(d2 <= tau) is nearly linear in tau on a surface - then bisection) until
+// exactly k candidates satisfy d2 <= tau.  Each step is one compare-and-count pass over registers.
+// Rows are written as global sorted positions + d2 (same layout as the generic kernel, search.cu),
+// unsorted inside a row.  With NORMALS the covariance moments of the selected neighbours are
+// accumulated in the same pass (NormalEstimation with the same k: tools.h:26-31 / features.h:187) and
+// solved 32 queries at a time (normals_solve.cuh).
+//
+// Anything the tile path cannot certify - a stencil with more than TCAP points, fewer than k
+// candidates, a k-th distance that reaches beyond the 3x3x3 block, exact distance ties across the
+// k-th rank (the set then depends on the index tie-break) - is flagged per query and redone by the
+// generic ring-expanding kernel, which implements the full ascending (d2, index) rule.
+#include "internal.h"
+#include "normals_solve.cuh"
+#include "tile.cuh"
+
+namespace pfx {
+
+constexpr int TCAP = 256;
+constexpr int TR = TCAP / 8;
+constexpr int TWPB = 8;
+
+struct KnnTileSmem {
+  float4 pts[TCAP];
+  int gidx[TCAP];
+  double mom[32][10];
+  TileTab tab;
+};
+
+__device__ __forceinline__ int group_sum8(int v) {
+  v += __shfl_xor_sync(FULL, v, 1);
+  v += __shfl_xor_sync(FULL, v, 2);
+  v += __shfl_xor_sync(FULL, v, 4);
+  return v;
+}
+__device__ __forceinline__ double group_sum8(double v) {
+  v += __shfl_xor_sync(FULL, v, 1);
+  v += __shfl_xor_sync(FULL, v, 2);
+  v += __shfl_xor_sync(FULL, v, 4);
+  return v;
+}
+__device__ __forceinline__ int group_excl_scan8(int v, int sl) {
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    int t = __shfl_up_sync(FULL, inc, o, 8);
+    if (sl >= o) inc += t;
+  }
+  return inc - v;
+}
+
+template <bool NORMALS>
+__global__ void __launch_bounds__(TWPB * 32)
+knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__ out_d2,
+                unsigned char* __restrict__ qflag, float vx, float vy, float vz, float4* __restrict__ nrm_sorted,
+                float4* __restrict__ nrm_orig) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int sub = lane >> 3, sl = lane & 7;
+  KnnTileSmem* S = reinterpret_cast<KnnTileSmem*>(smem_raw) + wid;
+  const GridParams P = *g.gp;
+  const int total_warps = gridDim.x * TWPB;
+  const float INF = CUDART_INF_F;
+  // non-finite points sit after n_valid in sorted order and belong to no cell: the generic kernels
+  // give them their rows
+  if (blockIdx.x == 0)
+    for (int i = P.n_valid + threadIdx.x; i < g.n; i += blockDim.x) qflag[i] = 1;
+  for (int cell = blockIdx.x * TWPB + wid; cell < P.ncells; cell += total_warps) {
+    __syncwarp();
+    const int M = tile_setup(g, cell, lane, &S->tab);
+    const int q0 = S->tab.start[13];
+    const int nqc = S->tab.prefix[14] - S->tab.prefix[13];
+    const int own = S->tab.prefix[13];
+    if (M > TCAP || M < k) {  // generic kernel: bigger stencil / ring expansion
+      for (int t = lane; t < nqc; t += 32) qflag[q0 + t] = 1;
+      continue;
+    }
+    for (int t = lane; t < M; t += 32) {
+      int j = tile_global_index(&S->tab, t);
+      S->gidx[t] = j;
+      S->pts[t] = g.pts[j];
+    }
+    __syncwarp();
+    int cx, cy, cz;
+    {
+      float4 p0 = S->pts[own];
+      cx = cell_coord(p0.x, P.ox, P.inv_e, P.nx);
+      cy = cell_coord(p0.y, P.oy, P.inv_e, P.ny);
+      cz = cell_coord(p0.z, P.oz, P.inv_e, P.nz);
+    }
+    const float tau0 = 2.865f * P.edge * P.edge * (float)k / (float)M;
+    for (int c0 = 0; c0 < nqc; c0 += 32) {
+      const int cend = min(c0 + 32, nqc);
+      for (int qb = c0; qb < cend; qb += 4) {
+        const bool active = (qb + sub) < cend;
+        const float4 q = S->pts[own + min(qb + sub, nqc - 1)];
+        float d2[TR];
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+          if (r * 8 >= M) break;
+          int c = r * 8 + sl;
+          float4 p = S->pts[min(c, M - 1)];
+          float d = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
+          d2[r] = (c < M) ? d : INF;
+        }
+        // ---- bracketing search: find tau with count(d2 <= tau) == k
+        float lo = -1.f, hi = INF, tau = tau0;
+        int clo = 0, chi = M;
+        bool done = !active, fail = false;
+        for (int it = 0; it < 40; ++it) {
+          if (__all_sync(FULL, done || fail)) break;
+          int c = 0;
+#pragma unroll
+          for (int r = 0; r < TR; ++r) {
+            if (r * 8 >= M) break;
+            c += (d2[r] <= tau) ? 1 : 0;
+          }
+          c = group_sum8(c);
+          if (!(done || fail)) {
+            if (c == k) {
+              done = true;
+            } else {
+              if (c < k) { lo = tau; clo = c; } else { hi = tau; chi = c; }
+              float t;
+              if (hi == INF) {
+                t = lo * fmaxf(1.25f, ((float)k + 1.f) / ((float)clo + 0.5f));
+              } else if (lo < 0.f) {
+                t = hi * ((float)k / ((float)chi + 0.5f));
+              } else if (chi - clo > 4 && (it & 3) != 3) {
+                t = lo + (hi - lo) * (((float)(k - clo) + 0.5f) / (float)(chi - clo + 1));
+              } else {
+                t = 0.5f * lo + 0.5f * hi;
+              }
+              const float lo_next = (lo < 0.f) ? 0.f : __uint_as_float(__float_as_uint(lo) + 1u);
+              if (!(t > lo)) t = lo_next;
+              if (!(t < hi)) t = __uint_as_float(__float_as_uint(hi) - 1u);
+              if (!(t > lo) || !(t < hi)) fail = true;  // adjacent floats: a distance tie straddles rank k
+              tau = t;
+            }
+          }
+        }
+        if (!done) fail = true;
+        // ---- certificate: the k-th distance must lie inside the scanned 3x3x3 block
+        if (active && !fail) {
+          const float ux = __fmul_rn(__fsub_rn(q.x, P.ox), P.inv_e), uy = __fmul_rn(__fsub_rn(q.y, P.oy), P.inv_e),
+                      uz = __fmul_rn(__fsub_rn(q.z, P.oz), P.inv_e);
+          float safe = INF;
+          if (cx - 1 > 0) safe = fminf(safe, ux - (float)(cx - 1));
+          if (cx + 1 < P.nx - 1) safe = fminf(safe, (float)(cx + 2) - ux);
+          if (cy - 1 > 0) safe = fminf(safe, uy - (float)(cy - 1));
+          if (cy + 1 < P.ny - 1) safe = fminf(safe, (float)(cy + 2) - uy);
+          if (cz - 1 > 0) safe = fminf(safe, uz - (float)(cz - 1));
+          if (cz + 1 < P.nz - 1) safe = fminf(safe, (float)(cz + 2) - uz);
+          if (safe != INF) {
+            safe = (safe - 1e-3f) * P.edge;
+            if (!(safe > 0.f && tau < safe * safe)) fail = true;  // tau >= k-th distance
+          }
+        }
+        // ---- emit the set (+ moments)
+        const bool good = active && !fail;
+        unsigned selmask = 0;  // bit r: my r-th candidate belongs to the set
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+          if (r * 8 >= M) break;
+          if (d2[r] <= tau) selmask |= 1u << r;
+        }
+        if (!good) selmask = 0;
+        int pos = group_excl_scan8(__popc(selmask), sl);
+        const int qi = q0 + qb + sub;
+        double m9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        while (selmask) {
+          const int c = (__ffs(selmask) - 1) * 8 + sl;
+          selmask &= selmask - 1;
+          const float4 p = S->pts[c];
+          out_idx[(size_t)qi * k + pos] = S->gidx[c];
+          out_d2[(size_t)qi * k + pos] = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
+          ++pos;
+          if (NORMALS) {
+            double dx = (double)p.x - (double)q.x, dy = (double)p.y - (double)q.y, dz = (double)p.z - (double)q.z;
+            m9[0] += dx; m9[1] += dy; m9[2] += dz;
+            m9[3] += dx * dx; m9[4] += dx * dy; m9[5] += dx * dz;
+            m9[6] += dy * dy; m9[7] += dy * dz; m9[8] += dz * dz;
+          }
+        }
+        if (active && !good && sl == 0) qflag[qi] = 1;
+        if (NORMALS) {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) m9[i] = group_sum8(m9[i]);
+          if (active && sl == 0) {
+            double* dst = S->mom[qb - c0 + sub];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) dst[i] = m9[i];
+            dst[9] = good ? (double)k : -1.0;
+          }
+        }
+      }
+      if (NORMALS) {
+        __syncwarp();
+        const int t = c0 + lane;
+        if (t < cend) {
+          const double* mm = S->mom[lane];
+          if (mm[9] > 0) {
+            float4 q = S->pts[own + t];
+            float4 r = solve_normal_m9(mm, (int)mm[9], q.x, q.y, q.z, vx, vy, vz);
+            nrm_sorted[q0 + t] = r;
+            nrm_orig[__float_as_int(q.w)] = r;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// Dense kNN sets (+ normals) of the surface: fills ctx->knn_idx / knn_d2 (rows in sorted query
+// order, global sorted positions, UNSORTED inside a row except for the rows redone generically) and
+// ctx->qflag (which queries were redone).
+int knn_tile_lists(Ctx* ctx, Grid* g, int k, bool with_normals) {
+  const int n = (int)ctx->n;
+  if (ctx->knn_grid == g && ctx->knn_k == k && ctx->knn_sversion == ctx->surf_version && ctx->knn_dense &&
+      (!with_normals || ctx->tile_has_normals))
+    return 0;
+  PFX_CUDA(ctx->qflag.ensure((size_t)std::max(n, 1)));
+  PFX_CUDA(ctx->knn_idx.ensure((size_t)std::max(n, 1) * k * sizeof(int)));
+  PFX_CUDA(ctx->knn_d2.ensure((size_t)std::max(n, 1) * k * sizeof(float)));
+  if (with_normals) {
+    PFX_CUDA(ctx->normals.ensure(std::max<size_t>(n, 1) * sizeof(float4)));
+    PFX_CUDA(ctx->normals_sorted.ensure(std::max<size_t>(n, 1) * sizeof(float4)));
+  }
+  if (n == 0) return 0;
+  PFX_CUDA(cudaMemsetAsync(ctx->qflag.p, 0, (size_t)n, ctx->stream));
+  const size_t smem = sizeof(KnnTileSmem) * TWPB;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PFX_CUDA(cudaFuncSetAttribute(knn_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PFX_CUDA(cudaFuncSetAttribute(knn_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int blocks = ctx->sm_count * 3;
+  if (with_normals)
+    PFX_LAUNCH(ctx, knn_tile_kernel<true>, blocks, TWPB * 32, smem, g->view(), k, ctx->knn_idx.as<int>(),
+               ctx->knn_d2.as<float>(), ctx->qflag.as<unsigned char>(), ctx->vp[0], ctx->vp[1], ctx->vp[2],
+               ctx->normals_sorted.as<float4>(), ctx->normals.as<float4>());
+  else
+    PFX_LAUNCH(ctx, knn_tile_kernel<false>, blocks, TWPB * 32, smem, g->view(), k, ctx->knn_idx.as<int>(),
+               ctx->knn_d2.as<float>(), ctx->qflag.as<unsigned char>(), 0.f, 0.f, 0.f, nullptr, nullptr);
+  PFX_CUDA(cudaGetLastError());
+  // generic completion of the flagged queries (early exit elsewhere)
+  PFX_TRY(knn_run_flagged(ctx, g, n, k, ctx->knn_idx.as<int>(), ctx->knn_d2.as<float>(), ctx->qflag.as<unsigned char>()));
+  ctx->knn_grid = g;
+  ctx->knn_k = k;
+  ctx->knn_sversion = ctx->surf_version;
+  ctx->knn_qversion = ctx->qry_version;
+  ctx->knn_dense = true;
+  ctx->knn_sorted = false;
+  ctx->tile_has_normals = with_normals;
+  return 0;
+}
+
+}  // namespace pfx

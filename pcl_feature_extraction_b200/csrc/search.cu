@@ -105,11 +105,12 @@ __device__ __forceinline__ void knn_scan_block(const GridDev& g, const CellBlock
 template <bool DENSE>
 __global__ void __launch_bounds__(WPB * 32)
 knn_kernel(GridDev g, const float4* __restrict__ queries, int nq, int k, int* __restrict__ out_idx,
-           float* __restrict__ out_d2) {
+           float* __restrict__ out_d2, const unsigned char* __restrict__ only) {
   __shared__ unsigned long long sbuf[WPB][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int qi = blockIdx.x * WPB + wid;
   if (qi >= nq) return;
+  if (only && !only[qi]) return;
   const GridParams P = *g.gp;
   unsigned long long* buf = sbuf[wid];
   float4 q = DENSE ? g.pts[qi] : queries[qi];
@@ -197,19 +198,28 @@ int knn_run(Ctx* ctx, Grid* g, const float4* q_dev, int nq, int k, int* idx_dev,
   if (k < 1 || k > 32) return ctx->fail(PFX_E_INVALID, "k must be in [1, 32]");
   if (nq <= 0) return 0;
   if (!q_dev)
-    PFX_LAUNCH(ctx, knn_kernel<true>, div_up(nq, WPB), WPB * 32, 0, g->view(), nullptr, nq, k, idx_dev, d2_dev);
+    PFX_LAUNCH(ctx, knn_kernel<true>, div_up(nq, WPB), WPB * 32, 0, g->view(), nullptr, nq, k, idx_dev, d2_dev, nullptr);
   else
-    PFX_LAUNCH(ctx, knn_kernel<false>, div_up(nq, WPB), WPB * 32, 0, g->view(), q_dev, nq, k, idx_dev, d2_dev);
+    PFX_LAUNCH(ctx, knn_kernel<false>, div_up(nq, WPB), WPB * 32, 0, g->view(), q_dev, nq, k, idx_dev, d2_dev, nullptr);
+  PFX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// dense rows of the queries flagged by the tile path only (everything else exits at once)
+int knn_run_flagged(Ctx* ctx, Grid* g, int nq, int k, int* idx_dev, float* d2_dev, const unsigned char* only) {
+  if (nq <= 0) return 0;
+  PFX_LAUNCH(ctx, knn_kernel<true>, div_up(nq, WPB), WPB * 32, 0, g->view(), nullptr, nq, k, idx_dev, d2_dev, only);
   PFX_CUDA(cudaGetLastError());
   return 0;
 }
 
 // Fills ctx->knn_idx / knn_d2 for the current queries (cached per grid, k, query version).
-int knn_lists(Ctx* ctx, Grid* g, int k, bool) {
+int knn_lists(Ctx* ctx, Grid* g, int k, bool need_sorted) {
   if (k < 1 || k > 32) return ctx->fail(PFX_E_INVALID, "k must be in [1, 32]");
   const bool dense = ctx->q_is_surface;
   if (ctx->knn_grid == g && ctx->knn_k == k && ctx->knn_sversion == ctx->surf_version &&
-      ctx->knn_dense == dense && (dense || ctx->knn_qversion == ctx->qry_version))
+      ctx->knn_dense == dense && (dense || ctx->knn_qversion == ctx->qry_version) &&
+      (!need_sorted || ctx->knn_sorted))
     return 0;
   const int nq = (int)ctx->num_queries();
   PFX_CUDA(ctx->knn_idx.ensure((size_t)std::max(nq, 1) * k * sizeof(int)));
@@ -221,6 +231,8 @@ int knn_lists(Ctx* ctx, Grid* g, int k, bool) {
   ctx->knn_sversion = ctx->surf_version;
   ctx->knn_qversion = ctx->qry_version;
   ctx->knn_dense = dense;
+  ctx->knn_sorted = true;
+  ctx->tile_has_normals = false;
   return 0;
 }
 

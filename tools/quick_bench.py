@@ -30,4 +30,15 @@ for it in range(4):
     names = ["set_surface", "grid+knn+normals", "spfh+fpfh", "grid+lrf+shot"]
     ms = [t[i].elapsed_time(t[i + 1]) for i in range(4)]
     print(it, " ".join(f"{nm}={m:.3f}ms" for nm, m in zip(names, ms)), f"total={sum(ms):.3f}ms launches={ctx.launches}")
+ctx.profile_begin(None)
+ctx.set_surface_dev(d_pts.data_ptr(), n, 16)
+ctx.normals_dev(0.0, 32, None)
+ctx.fpfh_dev(0.0, 32, d_f.data_ptr())
+ctx.shot352_dev(0.0128, d_s.data_ptr())
+prof = ctx.profile_end()
+ctx.normals_dev(0.0, 32, None)
+print("grid info (kNN grid):", ctx.grid_info())
+for nm, (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:14]:
+    print(f"  {nm:45s} x{c:2d} {ms:8.3f} ms")
+print("  sum", sum(ms for _, ms in prof.values()))
 print("fpfh sample", d_f[12345 % n, :6].cpu().numpy(), "shot norm", float(torch.linalg.norm(d_s[777 % n, :352])))
