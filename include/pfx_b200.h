@@ -63,7 +63,7 @@ uint64_t pfx_launch_count(const pfx_ctx* ctx);
 /* diagnostics of the voxel hash used by the last call: out8 = {cell edge, nx, ny, nz, occupied cells,
  * finite points, queries handed from the cell-tile path to the generic kernels (-1: no tile pass), 0} */
 int pfx_grid_info(pfx_ctx* ctx, double* out8);
-/* tuning: target points per occupied cell of kNN grids as a fraction of k (default 0.3) */
+/* tuning: target points per occupied cell of kNN grids as a fraction of k (default 0.4) */
 int pfx_set_knn_occupancy(pfx_ctx* ctx, float fraction_of_k);
 int pfx_profile_begin(pfx_ctx* ctx, const char* filter);
 int pfx_profile_end(pfx_ctx* ctx, char* buf, size_t buflen);

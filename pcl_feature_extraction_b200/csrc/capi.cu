@@ -146,7 +146,8 @@ extern "C" int pfx_destroy(pfx_ctx* ctx) {
   grid_free_all(ctx);
   for (DevBuf* b : {&ctx->surf, &ctx->normals, &ctx->normals_sorted, &ctx->qry, &ctx->knn_idx, &ctx->knn_d2,
                     &ctx->stage, &ctx->stage2, &ctx->tmp0, &ctx->tmp1, &ctx->tmp2, &ctx->tmp3, &ctx->tmp4,
-                    &ctx->small, &ctx->scanbuf, &ctx->match_flags, &ctx->match_best, &ctx->out_stage})
+                    &ctx->small, &ctx->scanbuf, &ctx->match_flags, &ctx->match_best, &ctx->out_stage, &ctx->qflag,
+                    &ctx->worklist, &ctx->worklist2})
     b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   delete ctx;
@@ -193,7 +194,7 @@ extern "C" int pfx_grid_info(pfx_ctx* ctx, double* out8) {
   return 0;
 }
 
-// target points per occupied cell of kNN grids, as a fraction of k (default 0.3)
+// target points per occupied cell of kNN grids, as a fraction of k (default 0.4)
 extern "C" int pfx_set_knn_occupancy(pfx_ctx* ctx, float fraction_of_k) {
   if (!ctx || !(fraction_of_k > 0.f)) return PFX_E_INVALID;
   ctx->knn_occupancy = fraction_of_k;
@@ -669,21 +670,21 @@ extern "C" int pfx_shot352(pfx_ctx* ctx, double radius, const float* lrf_in, flo
   if (nq == 0) return 0;
   Grid* g = nullptr;
   PFX_TRY(grid_get(ctx, radius, 0, &g));
-  PFX_CUDA(ctx->tmp2.ensure(nq * 9 * sizeof(float)));
-  float* drf = ctx->tmp2.as<float>();
-  if (lrf_in) {
-    PFX_CUDA(cudaMemcpyAsync(drf, lrf_in, nq * 9 * sizeof(float),
-                             mem == PFX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
-  } else {
-    PFX_TRY(shot_lrf_compute(ctx, g, radius, drf, nullptr));
-  }
   float* dout = out;
   if (mem == PFX_HOST) {
     PFX_CUDA(ctx->out_stage.ensure(nq * stride));
     dout = ctx->out_stage.as<float>();
     if (stride != 1444) PFX_CUDA(cudaMemsetAsync(dout, 0, nq * stride, ctx->stream));
   }
-  PFX_TRY(shot_compute(ctx, g, radius, drf, dout, stride / 4));
+  if (lrf_in) {  // caller-supplied frames (setInputReferenceFrames)
+    PFX_CUDA(ctx->tmp2.ensure(nq * 9 * sizeof(float)));
+    float* drf = ctx->tmp2.as<float>();
+    PFX_CUDA(cudaMemcpyAsync(drf, lrf_in, nq * 9 * sizeof(float),
+                             mem == PFX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+    PFX_TRY(shot_compute(ctx, g, radius, drf, dout, stride / 4));
+  } else {  // frames estimated at the same radius: one fused kernel
+    PFX_TRY(shot_fused_compute(ctx, g, radius, dout, stride / 4));
+  }
   if (mem == PFX_HOST) return deliver(ctx, out, dout, nq * stride, mem);
   return 0;
 }

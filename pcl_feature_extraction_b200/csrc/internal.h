@@ -108,7 +108,8 @@ struct Ctx {
 
   bool knn_sorted = false;  // rows ascending (d2, index)? (the cell-tile path writes unsorted sets)
   // qflag[i] != 0: dense query i was handed from the cell-tile path to the generic kernels
-  DevBuf qflag;
+  DevBuf worklist2;  // work list of the fused SHOT kernel (same layout)
+  DevBuf qflag, worklist;  // worklist: [0] = count, [16..] = sorted positions of the flagged queries
   bool tile_has_normals = false;
 
   // scratch
@@ -117,7 +118,7 @@ struct Ctx {
   size_t pinned_cap = 0;
 
   int match_engine = -1;
-  float knn_occupancy = 0.3f;  // target points per occupied cell of a kNN grid, as a fraction of k
+  float knn_occupancy = 0.4f;  // target points per occupied cell of a kNN grid, as a fraction of k
   Grid* last_grid = nullptr;
 
   // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg)
@@ -170,7 +171,7 @@ int scan_exclusive_i64(Ctx* ctx, const int* in, long long* out, int n, DevBuf& b
 // ---- search.cu
 int knn_run(Ctx* ctx, Grid* g, const float4* q_dev, int nq, int k, int* idx_dev, float* d2_dev);
 int knn_lists(Ctx* ctx, Grid* g, int k, bool need_sorted_ids);  // fills ctx->knn_idx / knn_d2
-int knn_run_flagged(Ctx* ctx, Grid* g, int nq, int k, int* idx_dev, float* d2_dev, const unsigned char* only);
+int knn_run_worklist(Ctx* ctx, Grid* g, int k, int* idx_dev, float* d2_dev, const int* worklist, const int* wl_count);
 // ---- knn_tile.cu
 int knn_tile_lists(Ctx* ctx, Grid* g, int k, bool with_normals);
 int knn_export(Ctx* ctx, int k, int32_t* idx, float* d2, int mem);
@@ -189,6 +190,8 @@ int fpfh_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t
 int shot_lrf_compute(Ctx* ctx, Grid* g, double radius, float* rf9_dev, int* nvalid_dev);
 int shot_compute(Ctx* ctx, Grid* g, double radius, const float* rf9_dev, float* out_dev,
                  size_t stride_floats);
+// ---- shot_fused.cu
+int shot_fused_compute(Ctx* ctx, Grid* g, double radius, float* out_dev, size_t stride_floats);
 
 // ---- keypoints.cu
 int cloud_resolution(Ctx* ctx, double* res);

@@ -28,7 +28,6 @@ constexpr int TWPB = 8;
 struct KnnTileSmem {
   float4 pts[TCAP];
   int gidx[TCAP];
-  double mom[32][10];
   TileTab tab;
 };
 
@@ -57,8 +56,8 @@ __device__ __forceinline__ int group_excl_scan8(int v, int sl) {
 template <bool NORMALS>
 __global__ void __launch_bounds__(TWPB * 32)
 knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__ out_d2,
-                unsigned char* __restrict__ qflag, float vx, float vy, float vz, float4* __restrict__ nrm_sorted,
-                float4* __restrict__ nrm_orig) {
+                unsigned char* __restrict__ qflag, int* __restrict__ wl_count, int* __restrict__ wl,
+                double* __restrict__ mom_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int sub = lane >> 3, sl = lane & 7;
@@ -69,7 +68,10 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
   // non-finite points sit after n_valid in sorted order and belong to no cell: the generic kernels
   // give them their rows
   if (blockIdx.x == 0)
-    for (int i = P.n_valid + threadIdx.x; i < g.n; i += blockDim.x) qflag[i] = 1;
+    for (int i = P.n_valid + threadIdx.x; i < g.n; i += blockDim.x) {
+      qflag[i] = 1;
+      wl[atomicAdd(wl_count, 1)] = i;
+    }
   for (int cell = blockIdx.x * TWPB + wid; cell < P.ncells; cell += total_warps) {
     __syncwarp();
     const int M = tile_setup(g, cell, lane, &S->tab);
@@ -77,7 +79,10 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
     const int nqc = S->tab.prefix[14] - S->tab.prefix[13];
     const int own = S->tab.prefix[13];
     if (M > TCAP || M < k) {  // generic kernel: bigger stencil / ring expansion
-      for (int t = lane; t < nqc; t += 32) qflag[q0 + t] = 1;
+      for (int t = lane; t < nqc; t += 32) {
+        qflag[q0 + t] = 1;
+        wl[atomicAdd(wl_count, 1)] = q0 + t;
+      }
       continue;
     }
     for (int t = lane; t < M; t += 32) {
@@ -94,15 +99,15 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
       cz = cell_coord(p0.z, P.oz, P.inv_e, P.nz);
     }
     const float tau0 = 2.865f * P.edge * P.edge * (float)k / (float)M;
-    for (int c0 = 0; c0 < nqc; c0 += 32) {
-      const int cend = min(c0 + 32, nqc);
-      for (int qb = c0; qb < cend; qb += 4) {
+    {
+      const int cend = nqc;
+      for (int qb = 0; qb < cend; qb += 4) {
         const bool active = (qb + sub) < cend;
         const float4 q = S->pts[own + min(qb + sub, nqc - 1)];
         float d2[TR];
 #pragma unroll
         for (int r = 0; r < TR; ++r) {
-          if (r * 8 >= M) break;
+          if ((r & 3) == 0 && r * 8 >= M) break;
           int c = r * 8 + sl;
           float4 p = S->pts[min(c, M - 1)];
           float d = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
@@ -117,7 +122,7 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
           int c = 0;
 #pragma unroll
           for (int r = 0; r < TR; ++r) {
-            if (r * 8 >= M) break;
+            if ((r & 3) == 0 && r * 8 >= M) break;
             c += (d2[r] <= tau) ? 1 : 0;
           }
           c = group_sum8(c);
@@ -166,7 +171,7 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
         unsigned selmask = 0;  // bit r: my r-th candidate belongs to the set
 #pragma unroll
         for (int r = 0; r < TR; ++r) {
-          if (r * 8 >= M) break;
+          if ((r & 3) == 0 && r * 8 >= M) break;
           if (d2[r] <= tau) selmask |= 1u << r;
         }
         if (!good) selmask = 0;
@@ -187,34 +192,39 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
             m9[6] += dy * dy; m9[7] += dy * dz; m9[8] += dz * dz;
           }
         }
-        if (active && !good && sl == 0) qflag[qi] = 1;
+        if (active && !good && sl == 0) {
+          qflag[qi] = 1;
+          wl[atomicAdd(wl_count, 1)] = qi;
+        }
         if (NORMALS) {
+          // the 3x3 eigen problems are solved by normals_from_moments_kernel at full SIMT width
+          // (a cell holds ~10 queries: solving here would leave 2/3 of the lanes idle)
 #pragma unroll
           for (int i = 0; i < 9; ++i) m9[i] = group_sum8(m9[i]);
-          if (active && sl == 0) {
-            double* dst = S->mom[qb - c0 + sub];
+          if (good && sl == 0) {
+            double* dst = mom_out + (size_t)qi * 9;
 #pragma unroll
             for (int i = 0; i < 9; ++i) dst[i] = m9[i];
-            dst[9] = good ? (double)k : -1.0;
           }
         }
-      }
-      if (NORMALS) {
-        __syncwarp();
-        const int t = c0 + lane;
-        if (t < cend) {
-          const double* mm = S->mom[lane];
-          if (mm[9] > 0) {
-            float4 q = S->pts[own + t];
-            float4 r = solve_normal_m9(mm, (int)mm[9], q.x, q.y, q.z, vx, vy, vz);
-            nrm_sorted[q0 + t] = r;
-            nrm_orig[__float_as_int(q.w)] = r;
-          }
-        }
-        __syncwarp();
       }
     }
   }
+}
+
+// one thread per query: moments -> normal (rows flagged for the generic path are skipped)
+__global__ void normals_from_moments_kernel(GridDev g, const double* __restrict__ mom, int k,
+                                            const unsigned char* __restrict__ qflag, float vx, float vy, float vz,
+                                            float4* __restrict__ nrm_sorted, float4* __restrict__ nrm_orig) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.gp->n_valid || qflag[i]) return;
+  double s[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) s[t] = mom[(size_t)i * 9 + t];
+  const float4 q = g.pts[i];
+  const float4 r = solve_normal_m9(s, k, q.x, q.y, q.z, vx, vy, vz);
+  nrm_sorted[i] = r;
+  nrm_orig[__float_as_int(q.w)] = r;
 }
 
 // Dense kNN sets (+ normals) of the surface: fills ctx->knn_idx / knn_d2 (rows in sorted query
@@ -233,7 +243,11 @@ int knn_tile_lists(Ctx* ctx, Grid* g, int k, bool with_normals) {
     PFX_CUDA(ctx->normals_sorted.ensure(std::max<size_t>(n, 1) * sizeof(float4)));
   }
   if (n == 0) return 0;
+  PFX_CUDA(ctx->worklist.ensure(((size_t)n + 16) * sizeof(int)));
   PFX_CUDA(cudaMemsetAsync(ctx->qflag.p, 0, (size_t)n, ctx->stream));
+  PFX_CUDA(cudaMemsetAsync(ctx->worklist.p, 0, 16 * sizeof(int), ctx->stream));
+  int* wl_count = ctx->worklist.as<int>();
+  int* wl = wl_count + 16;
   const size_t smem = sizeof(KnnTileSmem) * TWPB;
   static bool attr_set = false;
   if (!attr_set) {
@@ -242,16 +256,20 @@ int knn_tile_lists(Ctx* ctx, Grid* g, int k, bool with_normals) {
     attr_set = true;
   }
   const int blocks = ctx->sm_count * 3;
-  if (with_normals)
+  if (with_normals) {
+    PFX_CUDA(ctx->tmp4.ensure((size_t)n * 9 * sizeof(double)));
     PFX_LAUNCH(ctx, knn_tile_kernel<true>, blocks, TWPB * 32, smem, g->view(), k, ctx->knn_idx.as<int>(),
-               ctx->knn_d2.as<float>(), ctx->qflag.as<unsigned char>(), ctx->vp[0], ctx->vp[1], ctx->vp[2],
-               ctx->normals_sorted.as<float4>(), ctx->normals.as<float4>());
-  else
+               ctx->knn_d2.as<float>(), ctx->qflag.as<unsigned char>(), wl_count, wl, ctx->tmp4.as<double>());
+    PFX_LAUNCH(ctx, normals_from_moments_kernel, div_up(n, 128), 128, 0, g->view(), ctx->tmp4.as<double>(), k,
+               ctx->qflag.as<unsigned char>(), ctx->vp[0], ctx->vp[1], ctx->vp[2], ctx->normals_sorted.as<float4>(),
+               ctx->normals.as<float4>());
+  } else {
     PFX_LAUNCH(ctx, knn_tile_kernel<false>, blocks, TWPB * 32, smem, g->view(), k, ctx->knn_idx.as<int>(),
-               ctx->knn_d2.as<float>(), ctx->qflag.as<unsigned char>(), 0.f, 0.f, 0.f, nullptr, nullptr);
+               ctx->knn_d2.as<float>(), ctx->qflag.as<unsigned char>(), wl_count, wl, nullptr);
+  }
   PFX_CUDA(cudaGetLastError());
-  // generic completion of the flagged queries (early exit elsewhere)
-  PFX_TRY(knn_run_flagged(ctx, g, n, k, ctx->knn_idx.as<int>(), ctx->knn_d2.as<float>(), ctx->qflag.as<unsigned char>()));
+  // generic completion of the queries handed back (persistent kernel over the device-side work list)
+  PFX_TRY(knn_run_worklist(ctx, g, k, ctx->knn_idx.as<int>(), ctx->knn_d2.as<float>(), wl, wl_count));
   ctx->knn_grid = g;
   ctx->knn_k = k;
   ctx->knn_sversion = ctx->surf_version;

@@ -10,7 +10,7 @@
 // Dense kNN normals take the cell-tile path (knn_tile.cu: selection and moments in one pass over
 // shared memory).  This file holds the generic kernel: one warp per query, the reduced moments of
 // query t parked in lane t, and after 32 queries every lane solves its own 3x3 problem so the eigen
-// solve runs at full SIMT width.  `only` (optional) restricts it to the queries the tile path flagged.
+// solve runs at full SIMT width.  With a work list it runs persistently over the queries the tile path handed back.
 #include "internal.h"
 #include "normals_solve.cuh"
 
@@ -24,65 +24,60 @@ template <bool DENSE, bool USE_LIST>
 __global__ void __launch_bounds__(NWPB * 32)
 normals_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2, const int* __restrict__ lists, int k,
                float vx, float vy, float vz, float4* __restrict__ out_rows, float4* __restrict__ out_orig,
-               const unsigned char* __restrict__ only) {
+               const int* __restrict__ worklist, const int* __restrict__ wl_count) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int qbase = (blockIdx.x * NWPB + wid) * 32;
-  if (qbase >= nq) return;
-  const int qend = min(32, nq - qbase);
-  bool mine_on = true;
-  if (only) {
-    mine_on = (lane < qend) && only[qbase + lane];
-    if (!__any_sync(FULL, mine_on)) return;
-  }
-  const unsigned on_mask = __ballot_sync(FULL, mine_on);
+  const int limit = worklist ? *wl_count : nq;
   const int n_valid = g.gp->n_valid;
-  Moments mine;
+  for (int qbase = (blockIdx.x * NWPB + wid) * 32; qbase < limit; qbase += gridDim.x * NWPB * 32) {
+    const int qend = min(32, limit - qbase);
+    Moments mine;
 #pragma unroll
-  for (int i = 0; i < 9; ++i) mine.s[i] = 0.0;
-  mine.n = 0;
-  float4 myq = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int t = 0; t < qend; ++t) {
-    if (!((on_mask >> t) & 1u)) continue;
-    const int qi = qbase + t;
-    float4 q = DENSE ? g.pts[qi] : queries[qi];
-    Moments m;
+    for (int i = 0; i < 9; ++i) mine.s[i] = 0.0;
+    mine.n = 0;
+    float4 myq = make_float4(0.f, 0.f, 0.f, 0.f);
+    int myqi = 0;
+    for (int t = 0; t < qend; ++t) {
+      const int qi = worklist ? worklist[qbase + t] : qbase + t;
+      float4 q = DENSE ? g.pts[qi] : queries[qi];
+      Moments m;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) m.s[i] = 0.0;
-    m.n = 0;
-    bool ok = finite3(q.x, q.y, q.z) && (!DENSE || qi < n_valid);
-    if (ok) {
-      if (USE_LIST) {
-        for (int c = lane; c < k; c += 32) {
-          int j = lists[(size_t)qi * k + c];
-          if (j >= 0) mom_add(m, g.pts[j], q);
-        }
-      } else {
-        CellBlock blk = DENSE ? stencil_of_point(g, qi, lane) : stencil_of_pos(g, q.x, q.y, q.z, lane);
-        for (int base = 0; base < blk.total; base += 32) {
-          int c = base + lane;
-          bool valid = c < blk.total;
-          int j = block_candidate(blk, valid ? c : 0);
-          if (valid) {
-            float4 p = g.pts[j];
-            float d2 = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
-            if (d2 < r2) mom_add(m, p, q);
+      for (int i = 0; i < 9; ++i) m.s[i] = 0.0;
+      m.n = 0;
+      bool ok = finite3(q.x, q.y, q.z) && (!DENSE || qi < n_valid);
+      if (ok) {
+        if (USE_LIST) {
+          for (int c = lane; c < k; c += 32) {
+            int j = lists[(size_t)qi * k + c];
+            if (j >= 0) mom_add(m, g.pts[j], q);
+          }
+        } else {
+          CellBlock blk = DENSE ? stencil_of_point(g, qi, lane) : stencil_of_pos(g, q.x, q.y, q.z, lane);
+          for (int base = 0; base < blk.total; base += 32) {
+            int c = base + lane;
+            bool valid = c < blk.total;
+            int j = block_candidate(blk, valid ? c : 0);
+            if (valid) {
+              float4 p = g.pts[j];
+              float d2 = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
+              if (d2 < r2) mom_add(m, p, q);
+            }
           }
         }
-      }
 #pragma unroll
-      for (int i = 0; i < 9; ++i) m.s[i] = warp_sum(m.s[i]);
-      m.n = warp_sum(m.n);
+        for (int i = 0; i < 9; ++i) m.s[i] = warp_sum(m.s[i]);
+        m.n = warp_sum(m.n);
+      }
+      if (lane == t) {
+        mine = m;
+        myq = q;
+        myqi = qi;
+      }
     }
-    if (lane == t) {
-      mine = m;
-      myq = q;
+    if (lane < qend) {
+      float4 r = solve_normal_m9(mine.s, mine.n, myq.x, myq.y, myq.z, vx, vy, vz);
+      if (out_rows) out_rows[myqi] = r;
+      if (DENSE && out_orig) out_orig[__float_as_int(myq.w)] = r;
     }
-  }
-  if (lane < qend && mine_on) {
-    const int qi = qbase + lane;
-    float4 r = solve_normal_m9(mine.s, mine.n, myq.x, myq.y, myq.z, vx, vy, vz);
-    if (out_rows) out_rows[qi] = r;
-    if (DENSE && out_orig) out_orig[__float_as_int(myq.w)] = r;
   }
 }
 
@@ -104,12 +99,12 @@ int normals_compute(Ctx* ctx, Grid* g, double radius, int k, float4* out_query_o
     if (k > 0) {
       // tile path: selection + moments fused; the generic kernel only redoes flagged queries
       PFX_TRY(knn_tile_lists(ctx, g, k, true));
-      PFX_LAUNCH(ctx, (normals_kernel<true, true>), blocks, NWPB * 32, 0, g->view(), nullptr, nq, r2,
+      PFX_LAUNCH(ctx, (normals_kernel<true, true>), ctx->sm_count, NWPB * 32, 0, g->view(), nullptr, nq, r2,
                  ctx->knn_idx.as<int>(), k, ctx->vp[0], ctx->vp[1], ctx->vp[2], sorted, orig,
-                 ctx->qflag.as<unsigned char>());
+                 ctx->worklist.as<int>() + 16, ctx->worklist.as<int>());
     } else {
       PFX_LAUNCH(ctx, (normals_kernel<true, false>), blocks, NWPB * 32, 0, g->view(), nullptr, nq, r2, nullptr, 0,
-                 ctx->vp[0], ctx->vp[1], ctx->vp[2], sorted, orig, nullptr);
+                 ctx->vp[0], ctx->vp[1], ctx->vp[2], sorted, orig, nullptr, nullptr);
     }
     ctx->have_normals = true;
     ctx->normals_version++;
@@ -125,10 +120,10 @@ int normals_compute(Ctx* ctx, Grid* g, double radius, int k, float4* out_query_o
       PFX_TRY(knn_lists(ctx, g, k, false));
       lists = ctx->knn_idx.as<int>();
       PFX_LAUNCH(ctx, (normals_kernel<false, true>), blocks, NWPB * 32, 0, g->view(), ctx->qry.as<float4>(), nq, r2,
-                 lists, k, ctx->vp[0], ctx->vp[1], ctx->vp[2], out_query_order, nullptr, nullptr);
+                 lists, k, ctx->vp[0], ctx->vp[1], ctx->vp[2], out_query_order, nullptr, nullptr, nullptr);
     } else {
       PFX_LAUNCH(ctx, (normals_kernel<false, false>), blocks, NWPB * 32, 0, g->view(), ctx->qry.as<float4>(), nq, r2,
-                 nullptr, 0, ctx->vp[0], ctx->vp[1], ctx->vp[2], out_query_order, nullptr, nullptr);
+                 nullptr, 0, ctx->vp[0], ctx->vp[1], ctx->vp[2], out_query_order, nullptr, nullptr, nullptr);
     }
   }
   PFX_CUDA(cudaGetLastError());

@@ -103,16 +103,10 @@ __device__ __forceinline__ void knn_scan_block(const GridDev& g, const CellBlock
 // rows: DENSE -> row i = sorted surface point i; else row q = query q (caller order).
 // out_idx holds SORTED positions of the neighbours (-1 padding), out_d2 the squared distances.
 template <bool DENSE>
-__global__ void __launch_bounds__(WPB * 32)
-knn_kernel(GridDev g, const float4* __restrict__ queries, int nq, int k, int* __restrict__ out_idx,
-           float* __restrict__ out_d2, const unsigned char* __restrict__ only) {
-  __shared__ unsigned long long sbuf[WPB][32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int qi = blockIdx.x * WPB + wid;
-  if (qi >= nq) return;
-  if (only && !only[qi]) return;
+__device__ __forceinline__ void knn_one_query(const GridDev& g, const float4* __restrict__ queries, int qi, int k,
+                                              int* __restrict__ out_idx, float* __restrict__ out_d2,
+                                              unsigned long long* buf, int lane) {
   const GridParams P = *g.gp;
-  unsigned long long* buf = sbuf[wid];
   float4 q = DENSE ? g.pts[qi] : queries[qi];
   KnnState s;
   s.best = KMAX;
@@ -192,23 +186,46 @@ knn_kernel(GridDev g, const float4* __restrict__ queries, int nq, int k, int* __
   }
 }
 
+template <bool DENSE>
+__global__ void __launch_bounds__(WPB * 32)
+knn_kernel(GridDev g, const float4* __restrict__ queries, int nq, int k, int* __restrict__ out_idx,
+           float* __restrict__ out_d2) {
+  __shared__ unsigned long long sbuf[WPB][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int qi = blockIdx.x * WPB + wid;
+  if (qi >= nq) return;
+  knn_one_query<DENSE>(g, queries, qi, k, out_idx, out_d2, sbuf[wid], lane);
+}
+
+// persistent variant over a device-side work list (the queries the cell-tile path handed back)
+__global__ void __launch_bounds__(WPB * 32)
+knn_worklist_kernel(GridDev g, const int* __restrict__ worklist, const int* __restrict__ wl_count, int k,
+                    int* __restrict__ out_idx, float* __restrict__ out_d2) {
+  __shared__ unsigned long long sbuf[WPB][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int count = *wl_count;
+  for (int w = blockIdx.x * WPB + wid; w < count; w += gridDim.x * WPB) {
+    knn_one_query<true>(g, nullptr, worklist[w], k, out_idx, out_d2, sbuf[wid], lane);
+    __syncwarp();
+  }
+}
+
 // kNN of `nq` rows: q_dev == nullptr -> rows are the sorted surface points (dense), else float4
 // positions.  idx receives SORTED positions (-1 padding).
 int knn_run(Ctx* ctx, Grid* g, const float4* q_dev, int nq, int k, int* idx_dev, float* d2_dev) {
   if (k < 1 || k > 32) return ctx->fail(PFX_E_INVALID, "k must be in [1, 32]");
   if (nq <= 0) return 0;
   if (!q_dev)
-    PFX_LAUNCH(ctx, knn_kernel<true>, div_up(nq, WPB), WPB * 32, 0, g->view(), nullptr, nq, k, idx_dev, d2_dev, nullptr);
+    PFX_LAUNCH(ctx, knn_kernel<true>, div_up(nq, WPB), WPB * 32, 0, g->view(), nullptr, nq, k, idx_dev, d2_dev);
   else
-    PFX_LAUNCH(ctx, knn_kernel<false>, div_up(nq, WPB), WPB * 32, 0, g->view(), q_dev, nq, k, idx_dev, d2_dev, nullptr);
+    PFX_LAUNCH(ctx, knn_kernel<false>, div_up(nq, WPB), WPB * 32, 0, g->view(), q_dev, nq, k, idx_dev, d2_dev);
   PFX_CUDA(cudaGetLastError());
   return 0;
 }
 
-// dense rows of the queries flagged by the tile path only (everything else exits at once)
-int knn_run_flagged(Ctx* ctx, Grid* g, int nq, int k, int* idx_dev, float* d2_dev, const unsigned char* only) {
-  if (nq <= 0) return 0;
-  PFX_LAUNCH(ctx, knn_kernel<true>, div_up(nq, WPB), WPB * 32, 0, g->view(), nullptr, nq, k, idx_dev, d2_dev, only);
+// dense rows of the queries the tile path handed back (device-side work list, persistent grid)
+int knn_run_worklist(Ctx* ctx, Grid* g, int k, int* idx_dev, float* d2_dev, const int* worklist, const int* wl_count) {
+  PFX_LAUNCH(ctx, knn_worklist_kernel, ctx->sm_count * 2, WPB * 32, 0, g->view(), worklist, wl_count, k, idx_dev, d2_dev);
   PFX_CUDA(cudaGetLastError());
   return 0;
 }

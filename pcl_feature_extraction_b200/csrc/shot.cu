@@ -116,20 +116,22 @@ struct TieItem {  // a query whose tie must be resolved by the block-level kerne
 template <bool DENSE>
 __global__ void __launch_bounds__(SWPB * 32)
 lrf_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2, double R, float* __restrict__ rf9,
-           TieItem* __restrict__ tie_list, int* __restrict__ tie_count, int tie_cap) {
+           TieItem* __restrict__ tie_list, int* __restrict__ tie_count, int tie_cap, const int* __restrict__ qmap,
+           const int* __restrict__ qcount) {
   __shared__ unsigned long long skeys[SWPB][WTIE_CAP];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int qbase = (blockIdx.x * SWPB + wid) * 32;
-  if (qbase >= nq) return;
+  const int limit = qmap ? min(*qcount, nq) : nq;  // qmap: work list of query numbers (optional)
+  if (qbase >= limit) return;
   const int n_valid = g.gp->n_valid;
-  const int qend = min(32, nq - qbase);
+  const int qend = min(32, limit - qbase);
   LrfAcc mine;
 #pragma unroll
   for (int i = 0; i < 6; ++i) mine.m[i] = 0.0;
   mine.sw = 0.0;
   mine.nvalid = 0;
   for (int t = 0; t < qend; ++t) {
-    const int qi = qbase + t;
+    const int qi = qmap ? qmap[qbase + t] : qbase + t;
     float4 q = DENSE ? g.pts[qi] : queries[qi];
     LrfAcc a;
 #pragma unroll
@@ -162,7 +164,7 @@ lrf_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2, doub
   // pass 2: sign votes (+ PCL's median fallback on ties)
   bool flip_x = false, flip_z = false;
   for (int t = 0; t < qend; ++t) {
-    const int qi = qbase + t;
+    const int qi = qmap ? qmap[qbase + t] : qbase + t;
     bool gd = __shfl_sync(FULL, (int)good, t);
     if (!gd) continue;
     const int nv = __shfl_sync(FULL, mine.nvalid, t);
@@ -221,7 +223,7 @@ lrf_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2, doub
     }
   }
   if (lane < qend) {
-    const int qi = qbase + lane;
+    const int qi = qmap ? qmap[qbase + lane] : qbase + lane;
     float4 q = DENSE ? g.pts[qi] : queries[qi];
     const size_t row = DENSE ? (size_t)__float_as_int(q.w) : (size_t)qi;
     float* o = rf9 + row * 9;
@@ -308,7 +310,18 @@ lrf_tie_kernel(GridDev g, const float4* __restrict__ queries, float r2, float* _
   }
 }
 
+static int lrf_run(Ctx* ctx, Grid* g, double radius, float* rf9_dev, const int* qmap, const int* qcount);
+
 int shot_lrf_compute(Ctx* ctx, Grid* g, double radius, float* rf9_dev, int*) {
+  return lrf_run(ctx, g, radius, rf9_dev, nullptr, nullptr);
+}
+
+// frames of the queries on a device-side work list only (rows of the others are left untouched)
+int shot_lrf_worklist(Ctx* ctx, Grid* g, double radius, float* rf9_dev, const int* wl, const int* wl_count) {
+  return lrf_run(ctx, g, radius, rf9_dev, wl, wl_count);
+}
+
+static int lrf_run(Ctx* ctx, Grid* g, double radius, float* rf9_dev, const int* qmap, const int* qcount) {
   const int nq = (int)ctx->num_queries();
   if (nq == 0) return 0;
   const bool dense = ctx->q_is_surface;
@@ -317,17 +330,17 @@ int shot_lrf_compute(Ctx* ctx, Grid* g, double radius, float* rf9_dev, int*) {
   PFX_CUDA(ctx->tmp1.ensure((size_t)tie_cap * sizeof(TieItem)));
   PFX_CUDA(ctx->small.ensure(256));
   TieItem* tl = ctx->tmp1.as<TieItem>();
-  int* flags = ctx->small.as<int>();  // [0] tie count, [1] overflow
+  int* flags = ctx->small.as<int>() + 32;  // [0] tie count, [1] overflow
   PFX_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int), ctx->stream));
   const int blocks = div_up(nq, SWPB * 32);
   if (dense) {
     PFX_LAUNCH(ctx, lrf_kernel<true>, blocks, SWPB * 32, 0, g->view(), nullptr, nq, r2, radius, rf9_dev, tl, flags,
-               tie_cap);
+               tie_cap, qmap, qcount);
     PFX_LAUNCH(ctx, lrf_tie_kernel<true>, ctx->sm_count, 128, 0, g->view(), nullptr, r2, rf9_dev, tl, flags, tie_cap,
                flags + 1);
   } else {
     PFX_LAUNCH(ctx, lrf_kernel<false>, blocks, SWPB * 32, 0, g->view(), ctx->qry.as<float4>(), nq, r2, radius,
-               rf9_dev, tl, flags, tie_cap);
+               rf9_dev, tl, flags, tie_cap, qmap, qcount);
     PFX_LAUNCH(ctx, lrf_tie_kernel<false>, ctx->sm_count, 128, 0, g->view(), ctx->qry.as<float4>(), r2, rf9_dev, tl,
                flags, tie_cap, flags + 1);
   }
@@ -341,15 +354,11 @@ __device__ __forceinline__ void shot_add(int* h, int slot, double v, float scale
 }
 
 template <bool DENSE>
-__global__ void __launch_bounds__(SWPB * 32)
-shot_kernel(GridDev g, const float4* __restrict__ queries, int nq, const float4* __restrict__ nrm, float r2,
-            double R, const float* __restrict__ rf9, float* __restrict__ out, size_t stride) {
-  __shared__ int hist[SWPB][352];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int qi = blockIdx.x * SWPB + wid;
-  if (qi >= nq) return;
+__device__ __forceinline__ void shot_one_query(const GridDev& g, const float4* __restrict__ queries, int qi,
+                                               const float4* __restrict__ nrm, float r2, double R,
+                                               const float* __restrict__ rf9, float* __restrict__ out, size_t stride,
+                                               int* h, int lane) {
   const int n_valid = g.gp->n_valid;
-  int* h = hist[wid];
   for (int c = lane; c < 352; c += 32) h[c] = 0;
   __syncwarp();
   float4 q = DENSE ? g.pts[qi] : queries[qi];
@@ -495,6 +504,47 @@ shot_kernel(GridDev g, const float4* __restrict__ queries, int nq, const float4*
   acc = warp_sum(acc);
   float nrmv = (float)sqrt(acc);
   for (int c = lane; c < 352; c += 32) o[c] = __fdiv_rn((float)h[c] * inv_scale, nrmv);
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(SWPB * 32)
+shot_kernel(GridDev g, const float4* __restrict__ queries, int nq, const float4* __restrict__ nrm, float r2,
+            double R, const float* __restrict__ rf9, float* __restrict__ out, size_t stride) {
+  __shared__ int hist[SWPB][352];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int qi = blockIdx.x * SWPB + wid;
+  if (qi >= nq) return;
+  shot_one_query<DENSE>(g, queries, qi, nrm, r2, R, rf9, out, stride, hist[wid], lane);
+}
+
+// persistent variant over a device-side work list (queries the fused kernel handed back)
+template <bool DENSE>
+__global__ void __launch_bounds__(SWPB * 32)
+shot_worklist_kernel(GridDev g, const float4* __restrict__ queries, const int* __restrict__ wl,
+                     const int* __restrict__ wl_count, const float4* __restrict__ nrm, float r2, double R,
+                     const float* __restrict__ rf9, float* __restrict__ out, size_t stride) {
+  __shared__ int hist[SWPB][352];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int count = *wl_count;
+  for (int w = blockIdx.x * SWPB + wid; w < count; w += gridDim.x * SWPB) {
+    shot_one_query<DENSE>(g, queries, wl[w], nrm, r2, R, rf9, out, stride, hist[wid], lane);
+    __syncwarp();
+  }
+}
+
+int shot_worklist(Ctx* ctx, Grid* g, double radius, const float* rf9_dev, float* out_dev, size_t stride_floats,
+                  const int* wl, const int* wl_count) {
+  const float r2 = (float)(radius * radius);
+  const float4* nrm = nullptr;
+  PFX_TRY(normals_sorted_for_grid(ctx, g, &nrm));
+  if (ctx->q_is_surface)
+    PFX_LAUNCH(ctx, shot_worklist_kernel<true>, ctx->sm_count * 4, SWPB * 32, 0, g->view(), nullptr, wl, wl_count, nrm,
+               r2, radius, rf9_dev, out_dev, stride_floats);
+  else
+    PFX_LAUNCH(ctx, shot_worklist_kernel<false>, ctx->sm_count * 4, SWPB * 32, 0, g->view(), ctx->qry.as<float4>(), wl,
+               wl_count, nrm, r2, radius, rf9_dev, out_dev, stride_floats);
+  PFX_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int shot_compute(Ctx* ctx, Grid* g, double radius, const float* rf9_dev, float* out_dev, size_t stride_floats) {

@@ -14,13 +14,15 @@ dev = torch.device("cuda:0")
 d_pts = torch.from_numpy(p4).to(dev)
 ctx = pfx.Context(0)
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+if os.environ.get("PFX_OCC"):
+    ctx.set_knn_occupancy(float(os.environ["PFX_OCC"]))
 d_f = torch.empty((n, 33), dtype=torch.float32, device=dev)
 d_s = torch.empty((n, 361), dtype=torch.float32, device=dev)
 
 def ev():
     e = torch.cuda.Event(enable_timing=True); e.record(); return e
 
-for it in range(4):
+for it in range(3):
     t = [ev()]
     ctx.set_surface_dev(d_pts.data_ptr(), n, 16); t.append(ev())
     ctx.normals_dev(0.0, 32, None); t.append(ev())
