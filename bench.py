@@ -43,6 +43,10 @@ ALG_BYTES = {
     "fpfh_kernel": lambda nb: 264 + 8 * nb,
     "lrf_kernel": lambda nb: 52 + 8 * nb,
     "shot_kernel": lambda nb: 1512 + 8 * nb,
+    # fused frame + descriptor kernel: S5 + S6 of SURVEY.md §8d
+    "shot_fused_kernel": lambda nb: (52 + 8 * nb) + (1512 + 8 * nb),
+    "knn_tile_kernel": lambda nb: (16 + 8 * nb) + (32 + 4 * nb),  # kNN sets + fused normals (S1 + S2)
+    "fpfh_list_kernel": lambda nb: 264 + 8 * nb,
 }
 
 
@@ -216,7 +220,7 @@ def main():
 
     # mean neighbour count of the radius stages (for their algorithmic bytes), outside the timed region
     nbar = float(K_NN)
-    if dom_key in ("lrf_kernel", "shot_kernel"):
+    if dom_key in ("lrf_kernel", "shot_kernel", "shot_fused_kernel"):
         cnt = torch.empty(n, dtype=torch.int32, device=dev)
         ctx._chk(ctx.lib.pfx_radius_count(ctx.h, SHOT_RADIUS, pfx.capi._ptr(cnt), None, pfx.capi.DEVICE))
         torch.cuda.synchronize()
