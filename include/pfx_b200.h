@@ -152,6 +152,9 @@ int pfx_match_nn(pfx_ctx* ctx, const float* a, size_t na, size_t stride_a, const
 /* engine: 0 = exact fp32 scan, 1 = tcgen05 bf16 candidate GEMM + fp32 rescore with certificate
  * (falls back to the exact scan per row when the certificate fails), -1 = automatic */
 int pfx_set_match_engine(pfx_ctx* ctx, int engine);
+/* statistics of the tensor-core matcher: out4[0] 1-NN passes run on the tensor cores, out4[1] query rows
+ * they processed, out4[2] rows whose exactness certificate failed and were redone by the exact scan */
+int pfx_match_info(pfx_ctx* ctx, double* out4);
 
 /* ------------------------------------------------------------------ ingest
  * pfx_voxel_grid <- pcl::VoxelGrid centroid filter (config C1 ingest; not in the reference code).

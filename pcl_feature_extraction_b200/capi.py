@@ -66,6 +66,7 @@ SIGNATURES = {
     "pfx_match": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _f, _vp, _sz, C.POINTER(_sz), _i]),
     "pfx_match_nn": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _vp, _vp, _i]),
     "pfx_set_match_engine": (_i, [_vp, _i]),
+    "pfx_match_info": (_i, [_vp, _vp]),
     "pfx_voxel_grid": (_i, [_vp, _f, _vp, _sz, C.POINTER(_sz), _i]),
 }
 
@@ -308,6 +309,11 @@ class Context:
                                         _ptr(d2), HOST))
         return idx, d2
 
+    def match_nn_dev(self, a_ptr, na, b_ptr, nb, dim, idx_ptr, d2_ptr, stride_a=None, stride_b=None):
+        """device-resident rows (row stride in bytes, default dim * 4); idx / d2: device buffers of na entries"""
+        self._chk(self.lib.pfx_match_nn(self.h, _ptr(a_ptr), na, stride_a or dim * 4, _ptr(b_ptr), nb,
+                                        stride_b or dim * 4, dim, _ptr(idx_ptr), _ptr(d2_ptr), DEVICE))
+
     def match(self, a, b, reciprocal=True, max_dist2=-1.0):
         a = np.ascontiguousarray(a, np.float32)
         b = np.ascontiguousarray(b, np.float32)
@@ -320,3 +326,8 @@ class Context:
 
     def set_match_engine(self, engine):
         self._chk(self.lib.pfx_set_match_engine(self.h, engine))
+
+    def match_info(self):
+        out = np.zeros(4, np.float64)
+        self._chk(self.lib.pfx_match_info(self.h, _ptr(out)))
+        return {"tc_passes": int(out[0]), "rows": int(out[1]), "redone_exact": int(out[2])}

@@ -144,6 +144,7 @@ extern "C" int pfx_destroy(pfx_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   grid_free_all(ctx);
+  match_tc_release(ctx);
   for (DevBuf* b : {&ctx->surf, &ctx->normals, &ctx->normals_sorted, &ctx->qry, &ctx->knn_idx, &ctx->knn_d2,
                     &ctx->stage, &ctx->stage2, &ctx->tmp0, &ctx->tmp1, &ctx->tmp2, &ctx->tmp3, &ctx->tmp4,
                     &ctx->small, &ctx->scanbuf, &ctx->match_flags, &ctx->match_best, &ctx->out_stage, &ctx->qflag,
@@ -729,9 +730,29 @@ static int match_upload(Ctx* ctx, const float* m, size_t rows, size_t stride, in
   return 0;
 }
 
+// engine: 1 = tcgen05 candidate GEMM + exact fp32 rescore (match_tc.cu), 0 = exact fp32 all-pairs scan.
+// Both return bit-identical results; auto picks the tensor cores once the all-pairs work is large.
+static bool match_use_tc(const Ctx* ctx, size_t na, size_t nb, int dim) {
+  if (nb == 0 || dim > 2048) return false;
+  if (ctx->match_engine >= 0) return ctx->match_engine == 1;
+  return (double)na * (double)nb * (double)dim >= 1.5e9;
+}
+
 static int match_dispatch(Ctx* ctx, const float* a, int na, int lda, const float* b, int nb, int ldb, int dim,
                           int* idx, float* d2) {
+  if (match_use_tc(ctx, na, nb, dim)) return match_nn_tc(ctx, a, na, lda, b, nb, ldb, dim, idx, d2);
   return match_nn_exact(ctx, a, na, lda, b, nb, ldb, dim, idx, d2);
+}
+
+// statistics of the tensor-core matcher since the context was created: out[0] 1-NN passes run on the
+// tensor cores, out[1] query rows they processed, out[2] rows whose certificate failed (redone exactly)
+extern "C" int pfx_match_info(pfx_ctx* ctx, double* out4) {
+  if (!ctx || !out4) return PFX_E_INVALID;
+  out4[0] = (double)ctx->match_tc_calls;
+  out4[1] = (double)ctx->match_rows;
+  out4[2] = (double)ctx->match_redo;
+  out4[3] = 0;
+  return 0;
 }
 
 extern "C" int pfx_set_match_engine(pfx_ctx* ctx, int engine) {
@@ -784,8 +805,12 @@ extern "C" int pfx_match(pfx_ctx* ctx, const float* a, size_t na, size_t stride_
   float* sd2 = reinterpret_cast<float*>(s2t + na);
   int* t2s = ctx->tmp1.as<int>();
   float* td2 = reinterpret_cast<float*>(t2s + nb);
-  PFX_TRY(match_dispatch(ctx, da, (int)na, lda, db, (int)nb, ldb, dim, s2t, sd2));
-  if (reciprocal) PFX_TRY(match_dispatch(ctx, db, (int)nb, ldb, da, (int)na, lda, dim, t2s, td2));
+  if (match_use_tc(ctx, na, nb, dim)) {
+    PFX_TRY(match_pair_tc(ctx, da, (int)na, lda, db, (int)nb, ldb, dim, s2t, sd2, reciprocal ? t2s : nullptr, td2));
+  } else {
+    PFX_TRY(match_nn_exact(ctx, da, (int)na, lda, db, (int)nb, ldb, dim, s2t, sd2));
+    if (reciprocal) PFX_TRY(match_nn_exact(ctx, db, (int)nb, ldb, da, (int)na, lda, dim, t2s, td2));
+  }
   PFX_CUDA(ctx->tmp2.ensure(na * sizeof(int)));
   PFX_CUDA(ctx->tmp3.ensure(na * sizeof(int)));
   int* flags = ctx->tmp2.as<int>();

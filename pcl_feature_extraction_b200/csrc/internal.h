@@ -70,6 +70,12 @@ struct Grid {
   }
 };
 
+// one matrix prepared for the tensor-core matcher (match_tc.cu): bf16 core-matrix tiles + row statistics
+struct TcOperand {
+  DevBuf tiles, norm, err, maxima;
+  int n = 0, npad = 0, dpad = 0;
+};
+
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -117,7 +123,10 @@ struct Ctx {
   void* pinned = nullptr;
   size_t pinned_cap = 0;
 
-  int match_engine = -1;
+  int match_engine = -1;  // -1 auto, 0 exact fp32 scan, 1 tcgen05 candidates + fp32 rescore
+  TcOperand tc_ops[2];
+  DevBuf tc_cand_d, tc_cand_j, tc_redo, tc_rows, tc_res;
+  long long match_rows = 0, match_redo = 0, match_tc_calls = 0;  // statistics of the tensor-core matcher
   float knn_occupancy = 0.4f;  // target points per occupied cell of a kNN grid, as a fraction of k
   Grid* last_grid = nullptr;
 
@@ -207,8 +216,12 @@ int compact_flags(Ctx* ctx, const int* flags_dev, int n, int* idx_out_dev, int* 
 // ---- match.cu
 int match_nn_exact(Ctx* ctx, const float* a, int na, int lda, const float* b, int nb, int ldb, int dim,
                    int* nn_idx, float* nn_d2);
+// ---- match_tc.cu
 int match_nn_tc(Ctx* ctx, const float* a, int na, int lda, const float* b, int nb, int ldb, int dim,
                 int* nn_idx, float* nn_d2);
+int match_pair_tc(Ctx* ctx, const float* a, int na, int lda, const float* b, int nb, int ldb, int dim, int* s2t,
+                  float* sd2, int* t2s, float* td2);
+void match_tc_release(Ctx* ctx);
 
 // ---- helpers (capi.cu)
 int normals_sorted_for_grid(Ctx* ctx, Grid* g, const float4** out);

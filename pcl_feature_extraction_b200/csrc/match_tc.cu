@@ -1,0 +1,578 @@
+// match_tc.cu — descriptor 1-NN through the 5th-generation tensor cores (replaces the same reference
+// code as match.cu: Features<T>::getCorrespondences, features.h:253-273, KdTreeFLANN<FeatureT> 1-NN in
+// 33 / 36 / 352 dimensions, i.e. a linear scan).  The one dense contraction of the path.
+//
+//   d~2(i, j) = |a~_i|^2 + |b~_j|^2 - 2 a~_i . b~_j        (a~, b~ = operands rounded to bf16)
+//
+// Pipeline (all on the context's stream):
+//  1. tc_prep_kernel      fp32 rows -> bf16 in the UMMA "core matrix" order (8 rows x 16 bytes, K-major,
+//                         no swizzle), 128-row tiles, so that a tile (or a K-slab of it) is ONE contiguous
+//                         block of global memory; per-row |x~|^2 and the rounding error |x - x~|.
+//  2. tc_candidates_kernel warp-specialised: warp 0 streams B K-slabs with cp.async.bulk (TMA bulk copies,
+//                         mbarrier complete_tx) through an N-stage ring, warp 1 issues tcgen05.mma
+//                         (cta_group::1, kind::f16, M = 128, N = 128 per half tile, fp32 accumulators in
+//                         TMEM, two 256-column accumulator buffers), warps 4-7 read the accumulators back
+//                         with tcgen05.ld (one thread = one A row) and keep a running top-K of d~2 in
+//                         registers while the next tile's MMAs run.
+//  3. tc_rescore_kernel   exact fp32 distance (FLANN L2_Simple: sequential sum of (a-b)^2, no FMA) of the
+//                         candidates, argmin with the (d2, index) rule, and a CERTIFICATE that no
+//                         non-candidate can beat it: sqrt(d2*) < sqrt(kth d~2 - delta) - (|a-a~| + max|b-b~|).
+//  4. rows that fail the certificate are redone by the exact all-pairs kernel (match.cu).
+// Result: indices and distances are bit-identical to the exact path.
+#include <cuda_bf16.h>
+
+#include "internal.h"
+
+namespace pfx {
+
+constexpr int TC_TILE = 128;              // rows per operand tile (= UMMA M, and N of one half tile)
+constexpr int TC_K = 8;                   // candidates kept per (row, column split)
+constexpr int TC_SLAB = TC_TILE * 16;     // bytes of one K-slab (8 bf16 of K for 128 rows)
+constexpr int TC_STAGE = 2 * 4 * TC_SLAB; // a stage = 2 half tiles x 4 slabs (K = 32)
+constexpr int TC_EPI_WARPS = 8;           // epilogue warps: (TMEM lane quarter) x (half of the 256 columns)
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_THREADS = 128 + TC_EPI_THREADS;
+constexpr int TC_LISTS = 2;               // top-K lists per (row, split): one per column half
+constexpr int TC_KS = TC_K + 1;           // list stride in the candidate arrays: K entries + the bound slot
+constexpr float TC_BIG = 1e30f;           // |x~|^2 of a row that must never match (non-finite / padding)
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor: core matrices of 8 rows x 16 bytes stored as 128
+// contiguous bytes; LBO = byte step between the two 16-byte K chunks of one MMA (one slab), SBO = byte
+// step between 8-row groups; version 1 (Blackwell) in bits 46-47.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((TC_SLAB >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((128u >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TILE >> 3) << 17) |
+                              ((uint32_t)(TC_TILE >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------ prep
+// one warp per (padded) row: bf16 tile order + |x~|^2 + |x - x~| (+ max of the latter two over the rows)
+__global__ void tc_prep_kernel(const float* __restrict__ X, int n, int ld, int dim, int dpad, int npad,
+                               __nv_bfloat16* __restrict__ Xt, float* __restrict__ norm, float* __restrict__ err,
+                               unsigned* __restrict__ maxima /* [0] max err bits, [1] max finite norm bits */) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= npad) return;
+  bool fin = r < n;
+  if (fin) {
+    bool good = true;
+    for (int k = lane; k < dim; k += 32) good = good && isfinite(X[(size_t)r * ld + k]);
+    fin = __all_sync(FULL, good);
+  }
+  const size_t tile_base = (size_t)(r >> 7) * (size_t)(dpad >> 3) * (TC_SLAB / 2);
+  const int rr = r & 127;
+  const size_t row_off = (size_t)(rr >> 3) * 64 + (size_t)(rr & 7) * 8;
+  float s2 = 0.f, e2 = 0.f;
+  for (int k = lane; k < dpad; k += 32) {
+    float v = (fin && k < dim) ? X[(size_t)r * ld + k] : 0.f;
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    float vr = __bfloat162float(h);
+    s2 = fmaf(vr, vr, s2);
+    float dv = v - vr;
+    e2 = fmaf(dv, dv, e2);
+    Xt[tile_base + (size_t)(k >> 3) * (TC_SLAB / 2) + row_off + (k & 7)] = h;
+  }
+  s2 = warp_sum(s2);
+  e2 = warp_sum(e2);
+  if (lane == 0) {
+    float e = fin ? sqrtf(e2) * 1.001f + 1e-30f : 0.f;
+    norm[r] = fin ? s2 : TC_BIG;
+    err[r] = e;
+    if (fin) {
+      atomicMax(&maxima[0], __float_as_uint(e));
+      atomicMax(&maxima[1], __float_as_uint(s2));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ GEMM + top-K
+// Cold path of the epilogue: insert (d, j) into the calling thread's ascending top-K list, which lives in
+// shared memory ([slot][thread], conflict-free) so that the hot loop carries only the K-th value in a
+// register and stays small enough for the instruction cache.  Returns the new K-th value.
+__device__ __noinline__ float tc_topk_insert(float* sd, int* sj, float d, int j) {
+  int i = TC_K - 1;
+  while (i > 0) {
+    const float prev = sd[(i - 1) * TC_EPI_THREADS];
+    if (!(d < prev)) break;
+    sd[i * TC_EPI_THREADS] = prev;
+    sj[i * TC_EPI_THREADS] = sj[(i - 1) * TC_EPI_THREADS];
+    --i;
+  }
+  sd[i * TC_EPI_THREADS] = d;
+  sj[i * TC_EPI_THREADS] = j;
+  return sd[(TC_K - 1) * TC_EPI_THREADS];
+}
+
+struct TcArgs {
+  const __nv_bfloat16* At;
+  const __nv_bfloat16* Bt;
+  const float* na;
+  const float* nb;
+  int n_btiles;         // 128-row tiles of B
+  int dpad;
+  int nsplit;           // column splits (units per A tile)
+  int pairs_per_split;  // 256-column tile pairs per unit
+  int nstage;
+  float* cand_d;        // [A rows padded][nsplit][TC_LISTS][TC_KS]; slot TC_K of a list = its bound
+  int* cand_j;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a_tile = blockIdx.x / P.nsplit, split = blockIdx.x % P.nsplit;
+  const int nslab = P.dpad >> 3;
+  const int nchunk = (nslab + 3) >> 2;
+  const int npairs_all = (P.n_btiles + 1) >> 1;
+  const int p0 = split * P.pairs_per_split, p1 = min(npairs_all, p0 + P.pairs_per_split);
+
+  unsigned char* sA = smem;
+  unsigned char* sB = sA + (size_t)nslab * TC_SLAB;
+  float* nbs = reinterpret_cast<float*>(sB + (size_t)P.nstage * TC_STAGE);  // [2][256]
+  float* list_d = nbs + 512;                                               // [TC_K][epilogue threads]
+  int* list_j = reinterpret_cast<int*>(list_d + TC_K * TC_EPI_THREADS);    // [TC_K][epilogue threads]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(list_j + TC_K * TC_EPI_THREADS);
+  // bars: [0, nstage) full, [nstage, 2 nstage) empty, then afull, tfull[2], tempty[2]
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + P.nstage),
+                 bar_afull = smem_u32(bars + 2 * P.nstage), bar_tfull = smem_u32(bars + 2 * P.nstage + 1),
+                 bar_tempty = smem_u32(bars + 2 * P.nstage + 3);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P.nstage + 5);
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < P.nstage; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_afull, 1);
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tfull + 8, 1);
+    mbar_init(bar_tempty, TC_EPI_WARPS);
+    mbar_init(bar_tempty + 8, TC_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== producer: A once, then the B slabs of every tile pair through the ring
+    if (lane == 0) {
+      const unsigned char* srcA = reinterpret_cast<const unsigned char*>(P.At) + (size_t)a_tile * nslab * TC_SLAB;
+      const uint32_t a_bytes = (uint32_t)nslab * TC_SLAB;
+      mbar_expect_tx(bar_afull, a_bytes);
+      for (uint32_t off = 0; off < a_bytes; off += 16384u)
+        bulk_g2s(smem_u32(sA + off), srcA + off, min(16384u, a_bytes - off), bar_afull);
+      int it = 0;
+      for (int p = p0; p < p1; ++p) {
+        const int nh = min(2, P.n_btiles - 2 * p);
+        for (int c = 0; c < nchunk; ++c, ++it) {
+          const int s = it % P.nstage;
+          const uint32_t ph = (uint32_t)((it / P.nstage) & 1);
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          const int ns = min(4, nslab - 4 * c);
+          const uint32_t bytes = (uint32_t)ns * TC_SLAB;
+          mbar_expect_tx(bar_full + 8 * s, bytes * nh);
+          for (int h = 0; h < nh; ++h) {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(P.Bt) +
+                                       ((size_t)(2 * p + h) * nslab + (size_t)4 * c) * TC_SLAB;
+            bulk_g2s(smem_u32(sB + (size_t)s * TC_STAGE + (size_t)h * 4 * TC_SLAB), src, bytes, bar_full + 8 * s);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread)
+    if (lane == 0) {
+      mbar_wait(bar_afull, 0);
+      int it = 0;
+      for (int p = p0; p < p1; ++p) {
+        const int lp = p - p0, buf = lp & 1;
+        const int nh = min(2, P.n_btiles - 2 * p);
+        mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((lp >> 1) & 1) ^ 1));
+        tc_fence_after();
+        for (int c = 0; c < nchunk; ++c, ++it) {
+          const int s = it % P.nstage;
+          const uint32_t ph = (uint32_t)((it / P.nstage) & 1);
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const int nm = min(4, nslab - 4 * c) >> 1;  // K = 16 steps in this chunk
+          for (int m = 0; m < nm; ++m) {
+            const uint64_t ad = umma_desc(smem_u32(sA + (size_t)(4 * c + 2 * m) * TC_SLAB));
+            for (int h = 0; h < nh; ++h) {
+              const uint64_t bd = umma_desc(smem_u32(sB + (size_t)s * TC_STAGE + (size_t)(h * 4 + 2 * m) * TC_SLAB));
+              umma_bf16(tmem_base + (uint32_t)(buf * 256 + h * 128), ad, bd, TC_IDESC, (c | m) ? 1u : 0u);
+            }
+          }
+          umma_commit(bar_empty + 8 * s);  // frees the stage when these MMAs have read it
+        }
+        umma_commit(bar_tfull + 8 * buf);  // accumulators of this pair are complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: thread = (A row, column half).  Per 256-column pair the three smallest
+    // keys of the thread's 128 columns come out of a branch-free min/max network (the column number rides
+    // in the 7 low mantissa bits of d~2, a 2^-16 relative perturbation that the certificate's slack covers);
+    // the two smallest are offered to the thread's running top-K list, the third lower-bounds everything
+    // that was never offered.
+    const int q = warp & 3, hsel = (warp - 4) >> 2;
+    const int row = a_tile * TC_TILE + q * 32 + lane;
+    const float na = P.na[row];
+    const int et = threadIdx.x - 128;
+    float* sd = list_d + et;
+    int* sj = list_j + et;
+#pragma unroll
+    for (int i = 0; i < TC_K; ++i) {
+      sd[i * TC_EPI_THREADS] = CUDART_INF_F;
+      sj[i * TC_EPI_THREADS] = -1;
+    }
+    float worst = CUDART_INF_F;  // K-th smallest key offered so far
+    float bound = CUDART_INF_F;  // lower bound of every key never offered
+    for (int p = p0; p < p1; ++p) {
+      const int lp = p - p0, buf = lp & 1;
+      const int nh = min(2, P.n_btiles - 2 * p);
+      float* nbuf = nbs + buf * 256;
+      nbuf[et] = (et < nh * 128) ? P.nb[(size_t)p * 256 + et] : TC_BIG;
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+      mbar_wait(bar_tfull + 8 * buf, (uint32_t)((lp >> 1) & 1));
+      tc_fence_after();
+      if (hsel < nh) {
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + hsel * 128);
+        const float* nh_buf = nbuf + hsel * 128;
+        float m1 = 3e38f, m2 = 3e38f, m3 = 3e38f;
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tbase + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const float4 n4 = *reinterpret_cast<const float4*>(nh_buf + c0 + c);
+            const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float d = fmaf(-2.f, __uint_as_float(v[c + u]), na + nn[u]);
+              const float x = __uint_as_float((__float_as_uint(d) & 0xFFFFFF80u) | (uint32_t)(c0 + c + u));
+              const float t1 = fmaxf(m1, x);
+              m1 = fminf(m1, x);
+              const float t2 = fmaxf(m2, t1);
+              m2 = fminf(m2, t1);
+              m3 = fminf(m3, t2);
+            }
+          }
+        }
+        bound = fminf(bound, m3);
+        const int jbase = p * 256 + hsel * 128;
+        if (m1 < worst) worst = tc_topk_insert(sd, sj, m1, jbase + (int)(__float_as_uint(m1) & 0x7Fu));
+        if (m2 < worst) worst = tc_topk_insert(sd, sj, m2, jbase + (int)(__float_as_uint(m2) & 0x7Fu));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+    }
+    float* od = P.cand_d + (((size_t)row * P.nsplit + split) * TC_LISTS + hsel) * TC_KS;
+    int* oj = P.cand_j + (((size_t)row * P.nsplit + split) * TC_LISTS + hsel) * TC_KS;
+#pragma unroll
+    for (int i = 0; i < TC_K; ++i) {
+      od[i] = sd[i * TC_EPI_THREADS];
+      oj[i] = sj[i * TC_EPI_THREADS];
+    }
+    od[TC_K] = bound;
+    oj[TC_K] = -1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ rescore
+// one warp per A row: exact distances of the candidates that can still win, argmin by (d2, j), certificate
+__global__ void __launch_bounds__(256)
+tc_rescore_kernel(const float* __restrict__ A, int na, int lda, const float* __restrict__ B, int nb, int ldb, int dim,
+                  const float* __restrict__ cand_d, const int* __restrict__ cand_j, int nlists /* nsplit * TC_LISTS */,
+                  const float* __restrict__ norm_a, const float* __restrict__ err_a,
+                  const unsigned* __restrict__ maxima_b, int* __restrict__ nn_idx, float* __restrict__ nn_d2,
+                  int* __restrict__ redo_list, int* __restrict__ redo_count) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= na) return;
+  const float nai = norm_a[i];
+  if (!(nai < 0.5f * TC_BIG)) {  // non-finite query row: never matched
+    if (lane == 0) {
+      nn_idx[i] = -1;
+      if (nn_d2) nn_d2[i] = CUDART_INF_F;
+    }
+    return;
+  }
+  const float eb_max = __uint_as_float(maxima_b[0]), nb_max = __uint_as_float(maxima_b[1]);
+  const float eps = err_a[i] + eb_max;
+  // slack of the approximate squared distances themselves: fp32 accumulation of `dim` exact bf16 products,
+  // the cancellation in na + nb - 2 dot, and the column number stored in the 7 low mantissa bits of a key
+  const float delta2 = 2.4e-7f * (float)dim * sqrtf(nai * nb_max) + 2e-6f * (nai + nb_max);
+  const float REL = 2e-5f;
+  const int ncand = nlists * TC_KS;
+  const float* cd = cand_d + (size_t)i * ncand;
+  const int* cj = cand_j + (size_t)i * ncand;
+  // outside bound: per list, the bound slot (keys never offered) and, when the list is full, its last entry
+  // (keys offered but rejected or evicted are >= it)
+  float kth = CUDART_INF_F, dmin = CUDART_INF_F;
+  for (int c = lane; c < ncand; c += 32) {
+    const int slot = c % TC_KS;
+    const float d = cd[c];
+    if (slot == TC_K) kth = fminf(kth, d);
+    else if (cj[c] >= 0) {
+      if (slot == TC_K - 1) kth = fminf(kth, d);
+      dmin = fminf(dmin, d);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kth = fminf(kth, __shfl_xor_sync(FULL, kth, o));
+    dmin = fminf(dmin, __shfl_xor_sync(FULL, dmin, o));
+  }
+  // a candidate can only win if its lower bound is below the upper bound of the approximate best
+  const float win_hi = sqrtf(fmaxf(dmin + delta2 + REL * fabsf(dmin), 0.f)) + eps;
+  unsigned long long best = 0xffffffffffffffffull;
+  for (int c0 = 0; c0 < ncand; c0 += 32) {
+    const int c = c0 + lane;
+    unsigned long long key = 0xffffffffffffffffull;
+    if (c < ncand && (c % TC_KS) != TC_K) {
+      const int j = cj[c];
+      const float dc = cd[c];
+      if (j >= 0 && j < nb && dc < 0.5f * TC_BIG) {
+        const float lo = sqrtf(fmaxf(dc - delta2 - REL * fabsf(dc), 0.f)) - eps;
+        if (lo <= win_hi) {
+          const float* a = A + (size_t)i * lda;
+          const float* b = B + (size_t)j * ldb;
+          float acc = 0.f;
+          for (int d = 0; d < dim; ++d) {
+            float df = __fsub_rn(a[d], b[d]);
+            acc = __fadd_rn(acc, __fmul_rn(df, df));
+          }
+          key = ((unsigned long long)__float_as_uint(acc) << 32) | (unsigned)j;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long other = __shfl_xor_sync(FULL, key, o);
+      key = other < key ? other : key;
+    }
+    best = key < best ? key : best;
+  }
+  if (lane == 0) {
+    bool certified = false;
+    int j = -1;
+    float d2 = CUDART_INF_F;
+    const bool outside_any = kth < 0.5f * TC_BIG;  // some valid column is not in the lists
+    if (best != 0xffffffffffffffffull) {
+      j = (int)(unsigned)(best & 0xffffffffull);
+      d2 = __uint_as_float((unsigned)(best >> 32));
+      // every column outside the lists has true distance >= sqrt(kth - slack) - eps
+      const float outside_lo =
+          outside_any ? sqrtf(fmaxf(kth - delta2 - REL * fabsf(kth), 0.f)) - eps : CUDART_INF_F;
+      certified = sqrtf(d2) * 1.000001f < outside_lo;
+    } else {
+      certified = !outside_any;  // no finite target at all
+    }
+    nn_idx[i] = j;
+    if (nn_d2) nn_d2[i] = d2;
+    if (!certified) redo_list[atomicAdd(redo_count, 1)] = i;
+  }
+}
+
+__global__ void tc_gather_rows_kernel(const float* __restrict__ A, int lda, int dim, const int* __restrict__ rows,
+                                      int nrows, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= nrows) return;
+  const float* src = A + (size_t)rows[r] * lda;
+  for (int d = lane; d < dim; d += 32) out[(size_t)r * dim + d] = src[d];
+}
+__global__ void tc_scatter_kernel(const int* __restrict__ rows, int nrows, const int* __restrict__ idx,
+                                  const float* __restrict__ d2, int* __restrict__ nn_idx, float* __restrict__ nn_d2) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  nn_idx[rows[r]] = idx[r];
+  if (nn_d2) nn_d2[rows[r]] = d2[r];
+}
+
+// ------------------------------------------------------------------------------------------ host
+static int tc_prepare(Ctx* ctx, TcOperand& op, const float* x, int n, int ld, int dim) {
+  op.n = n;
+  op.dpad = (dim + 15) & ~15;
+  op.npad = std::max(1, div_up(n, TC_TILE)) * TC_TILE;
+  PFX_CUDA(op.tiles.ensure((size_t)op.npad * op.dpad * sizeof(__nv_bfloat16)));
+  PFX_CUDA(op.norm.ensure((size_t)(op.npad + 256) * sizeof(float)));
+  PFX_CUDA(op.err.ensure((size_t)op.npad * sizeof(float)));
+  PFX_CUDA(op.maxima.ensure(16));
+  PFX_CUDA(cudaMemsetAsync(op.maxima.p, 0, 16, ctx->stream));
+  PFX_LAUNCH(ctx, tc_prep_kernel, div_up(op.npad, 8), 256, 0, x, n, ld, dim, op.dpad, op.npad,
+             op.tiles.as<__nv_bfloat16>(), op.norm.as<float>(), op.err.as<float>(), op.maxima.as<unsigned>());
+  PFX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// 1-NN of every row of a among the rows of b.  prepared: bit 0 / bit 1 = operand slot 0 / 1 already holds
+// a / b (reciprocal matching prepares each matrix once).  slot_a selects which slot plays the A role.
+static int tc_run(Ctx* ctx, int slot_a, const float* a, int na, int lda, const float* b, int nb, int ldb, int dim,
+                  int* nn_idx, float* nn_d2) {
+  TcOperand& A = ctx->tc_ops[slot_a];
+  TcOperand& B = ctx->tc_ops[slot_a ^ 1];
+  const int n_at = A.npad / TC_TILE, n_bt = B.npad / TC_TILE;
+  const int npairs = (n_bt + 1) / 2;
+  // Long units: the running top-K settles after a few hundred columns (insertions decay like K / n), so a
+  // unit should own as many columns as possible; B is split only to give idle SMs work (n_at < #SMs).
+  int nsplit = std::max(1, std::min(npairs, ctx->sm_count / std::max(n_at, 1)));
+  int pps = div_up(npairs, nsplit);
+  nsplit = div_up(npairs, pps);
+  const size_t a_bytes = (size_t)(A.dpad / 8) * TC_SLAB;
+  const size_t fixed = a_bytes + 512 * sizeof(float) + 2 * TC_K * TC_EPI_THREADS * 4 + 32 * 8 + 64;
+  int nstage = (int)std::min<size_t>(8, (225 * 1024 - fixed) / TC_STAGE);
+  if (nstage < 2) return ctx->fail(PFX_E_INVALID, "tensor-core matching: descriptor dimension too large for one A tile");
+  const size_t smem = std::max<size_t>(fixed + (size_t)nstage * TC_STAGE, 120 * 1024);
+  const int nlists = nsplit * TC_LISTS;
+  const int ncand = nlists * TC_KS;
+  PFX_CUDA(ctx->tc_cand_d.ensure((size_t)A.npad * ncand * sizeof(float)));
+  PFX_CUDA(ctx->tc_cand_j.ensure((size_t)A.npad * ncand * sizeof(int)));
+  PFX_CUDA(ctx->tc_redo.ensure(((size_t)na + 16) * sizeof(int)));
+  int* redo_count = ctx->tc_redo.as<int>();
+  int* redo_list = redo_count + 16;
+  PFX_CUDA(cudaMemsetAsync(redo_count, 0, 16 * sizeof(int), ctx->stream));
+  static bool attr_set = false;
+  if (!attr_set) {
+    PFX_CUDA(cudaFuncSetAttribute(tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  TcArgs P;
+  P.At = A.tiles.as<__nv_bfloat16>();
+  P.Bt = B.tiles.as<__nv_bfloat16>();
+  P.na = A.norm.as<float>();
+  P.nb = B.norm.as<float>();
+  P.n_btiles = n_bt;
+  P.dpad = A.dpad;
+  P.nsplit = nsplit;
+  P.pairs_per_split = pps;
+  P.nstage = nstage;
+  P.cand_d = ctx->tc_cand_d.as<float>();
+  P.cand_j = ctx->tc_cand_j.as<int>();
+  PFX_LAUNCH(ctx, tc_candidates_kernel, n_at * nsplit, TC_THREADS, smem, P);
+  PFX_LAUNCH(ctx, tc_rescore_kernel, div_up(na, 8), 256, 0, a, na, lda, b, nb, ldb, dim, P.cand_d, P.cand_j, nlists,
+             A.norm.as<float>(), A.err.as<float>(), B.maxima.as<unsigned>(), nn_idx, nn_d2, redo_list, redo_count);
+  PFX_CUDA(cudaGetLastError());
+  int redo = 0;
+  PFX_CUDA(cudaMemcpyAsync(&redo, redo_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->match_rows += na;
+  ctx->match_redo += redo;
+  ctx->match_tc_calls++;
+  if (redo > 0) {  // exact all-pairs scan of the rows without a certificate
+    PFX_CUDA(ctx->tc_rows.ensure((size_t)redo * dim * sizeof(float)));
+    PFX_CUDA(ctx->tc_res.ensure((size_t)redo * (sizeof(int) + sizeof(float))));
+    float* ga = ctx->tc_rows.as<float>();
+    int* ridx = ctx->tc_res.as<int>();
+    float* rd2 = reinterpret_cast<float*>(ridx + redo);
+    PFX_LAUNCH(ctx, tc_gather_rows_kernel, div_up(redo, 8), 256, 0, a, lda, dim, redo_list, redo, ga);
+    PFX_TRY(match_nn_exact(ctx, ga, redo, dim, b, nb, ldb, dim, ridx, rd2));
+    PFX_LAUNCH(ctx, tc_scatter_kernel, div_up(redo, 256), 256, 0, redo_list, redo, ridx, rd2, nn_idx, nn_d2);
+    PFX_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int match_nn_tc(Ctx* ctx, const float* a, int na, int lda, const float* b, int nb, int ldb, int dim, int* nn_idx,
+                float* nn_d2) {
+  if (na == 0) return 0;
+  PFX_TRY(tc_prepare(ctx, ctx->tc_ops[0], a, na, lda, dim));
+  PFX_TRY(tc_prepare(ctx, ctx->tc_ops[1], b, nb, ldb, dim));
+  return tc_run(ctx, 0, a, na, lda, b, nb, ldb, dim, nn_idx, nn_d2);
+}
+
+// both directions with one preparation of each matrix (Features<T>::findCorrespondences, features.h:232-237)
+int match_pair_tc(Ctx* ctx, const float* a, int na, int lda, const float* b, int nb, int ldb, int dim, int* s2t,
+                  float* sd2, int* t2s, float* td2) {
+  PFX_TRY(tc_prepare(ctx, ctx->tc_ops[0], a, na, lda, dim));
+  PFX_TRY(tc_prepare(ctx, ctx->tc_ops[1], b, nb, ldb, dim));
+  PFX_TRY(tc_run(ctx, 0, a, na, lda, b, nb, ldb, dim, s2t, sd2));
+  if (t2s) PFX_TRY(tc_run(ctx, 1, b, nb, ldb, a, na, lda, dim, t2s, td2));
+  return 0;
+}
+
+void match_tc_release(Ctx* ctx) {
+  for (TcOperand& o : ctx->tc_ops) {
+    o.tiles.release();
+    o.norm.release();
+    o.err.release();
+    o.maxima.release();
+  }
+  for (DevBuf* b : {&ctx->tc_cand_d, &ctx->tc_cand_j, &ctx->tc_redo, &ctx->tc_rows, &ctx->tc_res}) b->release();
+}
+
+}  // namespace pfx

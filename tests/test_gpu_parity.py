@@ -476,6 +476,85 @@ def test_match_ties_and_nan_rows(ctx, orc):
     assert np.array_equal(c["index_query"], q) and np.array_equal(c["index_match"], mm)
 
 
+# ---- tensor-core engine (match_tc.cu): bf16 tcgen05 candidates + exact fp32 rescore + certificate.
+# The bar is the same as for the exact scan: indices AND distances bit-identical to the oracle.
+@pytest.mark.parametrize("dim,na,nb", [(33, 799, 747), (352, 500, 613), (36, 65, 130), (33, 1, 1), (352, 1300, 2100),
+                                       (33, 4097, 3000), (352, 129, 257)])
+def test_match_tensor_core_bit_exact(ctx, orc, dim, na, nb):
+    rng = np.random.default_rng(1000 + dim + na)
+    a = rng.uniform(0, 100, (na, dim)).astype(np.float32)
+    b = rng.uniform(0, 100, (nb, dim)).astype(np.float32)
+    m = min(na, nb) // 2
+    b[:m] = a[:m] + rng.normal(0, 1.0, (m, dim)).astype(np.float32)
+    ctx.set_match_engine(1)
+    try:
+        before = ctx.match_info()
+        idx, d2 = ctx.match_nn(a, b)
+        c = ctx.match(a, b, reciprocal=True)
+        after = ctx.match_info()
+    finally:
+        ctx.set_match_engine(-1)
+    assert after["tc_passes"] == before["tc_passes"] + 3  # the tensor-core path really ran
+    oidx, od2 = orc.match_nn(a, b)
+    assert np.array_equal(idx, oidx)
+    assert np.array_equal(d2.view(np.uint32), od2.view(np.uint32))
+    q, mm, dist = orc.match_reciprocal(a, b)
+    assert np.array_equal(c["index_query"], q) and np.array_equal(c["index_match"], mm)
+    assert np.array_equal(c["distance"].view(np.uint32), dist.view(np.uint32))
+    # well separated data: the certificate must hold for (almost) every row, not fall back wholesale
+    redone = after["redone_exact"] - before["redone_exact"]
+    assert redone <= 0.05 * (after["rows"] - before["rows"]) + 2, (redone, after["rows"] - before["rows"])
+
+
+def test_match_tensor_core_ties_nan_and_near_duplicates(ctx, orc):
+    rng = np.random.default_rng(12)
+    a = rng.integers(0, 3, (300, 33)).astype(np.float32)  # many exact ties -> certificate fails -> exact redo
+    b = rng.integers(0, 3, (280, 33)).astype(np.float32)
+    b[17] = b[5]
+    a[4, 3] = np.nan
+    b[9, 0] = np.nan
+    # near-duplicate targets closer together than bf16 can resolve
+    a2 = rng.uniform(0, 100, (200, 352)).astype(np.float32)
+    b2 = np.repeat(a2[:50], 6, axis=0) + rng.normal(0, 1e-3, (300, 352)).astype(np.float32)
+    ctx.set_match_engine(1)
+    try:
+        idx, d2 = ctx.match_nn(a, b)
+        c = ctx.match(a, b, reciprocal=True)
+        idx2, d22 = ctx.match_nn(a2, b2)
+        e_idx, _ = ctx.match_nn(a[:0], b)          # empty query set
+        z_idx, _ = ctx.match_nn(a, b[:0])          # empty target set
+    finally:
+        ctx.set_match_engine(-1)
+    oidx, od2 = orc.match_nn(a, b)
+    assert np.array_equal(idx, oidx) and idx[4] == -1 and (idx != 9).all()
+    assert np.array_equal(d2[idx >= 0], od2[oidx >= 0])
+    q, mm, dist = orc.match_reciprocal(a, b)
+    assert np.array_equal(c["index_query"], q) and np.array_equal(c["index_match"], mm)
+    oidx2, od22 = orc.match_nn(a2, b2)
+    assert np.array_equal(idx2, oidx2) and np.array_equal(d22.view(np.uint32), od22.view(np.uint32))
+    assert len(e_idx) == 0 and (z_idx == -1).all()
+
+
+def test_match_tensor_core_on_real_descriptors(ctx, orc, sheet):
+    """FPFH33 rows of a dense cloud: neighbouring points have nearly identical descriptors, the hard case
+    for the bf16 candidate pass.  Results must still be bit-identical; the redo rate is reported."""
+    pts = sheet[:20000]
+    nr, _, _ = orc.normals(pts, k=16)
+    f = orc.fpfh(pts, nr, k=16)
+    a, b = f[:6000], f[6000:14000]
+    ctx.set_match_engine(1)
+    try:
+        before = ctx.match_info()
+        idx, d2 = ctx.match_nn(a, b)
+        after = ctx.match_info()
+    finally:
+        ctx.set_match_engine(-1)
+    oidx, od2 = orc.match_nn(a, b)
+    assert np.array_equal(idx, oidx)
+    assert np.array_equal(d2.view(np.uint32), od2.view(np.uint32))
+    print("tensor-core matcher on FPFH rows: redone exactly", after["redone_exact"] - before["redone_exact"], "of", len(a))
+
+
 def test_golden_kat(ctx):
     """the committed oracle fixtures (tests/golden/oracle_kat.npz) replayed on the GPU"""
     import os
