@@ -107,6 +107,146 @@ __device__ __forceinline__ void shot_accumulate_neighbor(int* h, float scale, fl
   shot_add(h, vol + step, w, scale);
 }
 
+// Float variant of the above for the fused dense kernel.  The three frame projections keep the CPU's
+// float arithmetic (separate multiply / add); everything else is single precision.  SHOT's quadrilinear
+// interpolation is continuous across every discrete boundary (cosine step, radial shell, elevation and
+// azimuth sector: the weight that leaves one bin enters its neighbour), so a decision that flips within
+// float round-off of a boundary moves O(1e-7) of weight, far inside the 1e-4 tolerance.
+__device__ __forceinline__ void shot_accumulate_neighbor_f(int* h, float scale, float4 q, float4 p, float d2, float4 nj,
+                                                           const float* rf, float R) {
+  if (!finite3(nj.x, nj.y, nj.z)) return;
+  const float r12 = 0.5f * R, r14 = 0.25f * R, r34 = 0.75f * R, inv_r12 = 2.0f / R;
+  const float RAD45 = 0.78539816339744830962f, RAD135 = 2.35619449019234492885f, RAD_PI_7_8 = 2.7488935718910690836f,
+              INV_RAD90 = 0.63661977236758134308f, INV_RAD45 = 1.27323954473516268615f;
+  float cosd = __fadd_rn(__fadd_rn(__fmul_rn(nj.x, rf[6]), __fmul_rn(nj.y, rf[7])), __fmul_rn(nj.z, rf[8]));
+  cosd = fminf(1.0f, fmaxf(-1.0f, cosd));
+  float bd = (1.0f + cosd) * 5.0f;
+  const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+  const float dist = sqrtf(d2);
+  if (dist < 1e-15f) return;
+  float x = __fadd_rn(__fadd_rn(__fmul_rn(dx, rf[0]), __fmul_rn(dy, rf[1])), __fmul_rn(dz, rf[2]));
+  float y = __fadd_rn(__fadd_rn(__fmul_rn(dx, rf[3]), __fmul_rn(dy, rf[4])), __fmul_rn(dz, rf[5]));
+  float z = __fadd_rn(__fadd_rn(__fmul_rn(dx, rf[6]), __fmul_rn(dy, rf[7])), __fmul_rn(dz, rf[8]));
+  if (fabsf(y) < 1e-30f) y = 0.f;
+  if (fabsf(x) < 1e-30f) x = 0.f;
+  if (fabsf(z) < 1e-30f) z = 0.f;
+  const int bit4 = ((y > 0.f) || ((y == 0.f) && (x < 0.f))) ? 1 : 0;
+  const int bit3 = ((x > 0.f) || ((x == 0.f) && (y > 0.f))) ? !bit4 : bit4;
+  int di = ((bit4 << 3) + (bit3 << 2)) << 1;
+  const bool same_sign = (x > 0.f && y > 0.f) || (x < 0.f && y < 0.f);  // x * y > 0 without underflow
+  if (same_sign || (x == 0.f))
+    di += (fabsf(x) >= fabsf(y)) ? 0 : 4;
+  else
+    di += (fabsf(x) > fabsf(y)) ? 4 : 0;
+  di += z > 0.f ? 1 : 0;
+  di += (dist > r12) ? 2 : 0;
+  const int step = __float2int_rd(bd + 0.5f);
+  const int vol = di * 11;
+  bd -= (float)step;
+  float w = 1.0f - fabsf(bd);
+  {
+    const int nb_step = (bd > 0.f) ? ((step + 1) % 10) : ((step + 9) % 10);
+    atomicAdd(&h[vol + nb_step], __float2int_rn(fabsf(bd) * scale));
+  }
+  if (dist > r12) {
+    const float rd = (dist - r34) * inv_r12;
+    if (dist > r34)
+      w += 1.0f - rd;
+    else {
+      w += 1.0f + rd;
+      atomicAdd(&h[(di - 2) * 11 + step], __float2int_rn(-rd * scale));
+    }
+  } else {
+    const float rd = (dist - r14) * inv_r12;
+    if (dist < r14)
+      w += 1.0f + rd;
+    else {
+      w += 1.0f - rd;
+      atomicAdd(&h[(di + 2) * 11 + step], __float2int_rn(rd * scale));
+    }
+  }
+  const float inc = acosf(fminf(1.0f, fmaxf(-1.0f, z / dist)));
+  if (z <= 0.f) {
+    const float e = (inc - RAD135) * INV_RAD90;
+    if (inc > RAD135)
+      w += 1.0f - e;
+    else {
+      w += 1.0f + e;
+      atomicAdd(&h[(di + 1) * 11 + step], __float2int_rn(-e * scale));
+    }
+  } else {
+    const float e = (inc - RAD45) * INV_RAD90;
+    if (inc < RAD45)
+      w += 1.0f + e;
+    else {
+      w += 1.0f - e;
+      atomicAdd(&h[(di - 1) * 11 + step], __float2int_rn(e * scale));
+    }
+  }
+  if (y != 0.f || x != 0.f) {
+    const float az = atan2f(y, x);
+    const int sel = di >> 2;
+    float ad = (az - (-RAD_PI_7_8 + RAD45 * (float)sel)) * INV_RAD45;
+    ad = fmaxf(-0.5f, fminf(ad, 0.5f));
+    if (ad > 0.f) {
+      w += 1.0f - ad;
+      atomicAdd(&h[((di + 4) & 31) * 11 + step], __float2int_rn(ad * scale));
+    } else {
+      w += 1.0f + ad;
+      atomicAdd(&h[((di + 28) & 31) * 11 + step], __float2int_rn(-ad * scale));
+    }
+  }
+  atomicAdd(&h[vol + step], __float2int_rn(w * scale));
+}
+
+// Eigenvectors of the largest (x) and smallest (z) eigenvalue of a symmetric 3x3 matrix given in double
+// (a = xx xy xz yy yz zz).  Float Jacobi on the max-scaled matrix finds the vectors to ~1e-7; one double
+// refinement step per vector (Rayleigh quotient, then the largest cross product of two rows of A - l I,
+// pcl::eigen33's construction) brings them to ~1e-12 unless the eigenvalue is (nearly) repeated, where no
+// two implementations agree anyway.  Returns false when the matrix is not finite.
+__device__ __forceinline__ void refine_eigvec(const double c[6], double v[3]) {
+  const double cx = c[0] * v[0] + c[1] * v[1] + c[2] * v[2];
+  const double cy = c[1] * v[0] + c[3] * v[1] + c[4] * v[2];
+  const double cz = c[2] * v[0] + c[4] * v[1] + c[5] * v[2];
+  const double l = (v[0] * cx + v[1] * cy + v[2] * cz) / (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  const double r0[3] = {c[0] - l, c[1], c[2]}, r1[3] = {c[1], c[3] - l, c[4]}, r2[3] = {c[2], c[4], c[5] - l};
+  const double e0[3] = {r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]};
+  const double e1[3] = {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]};
+  const double e2[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+  const double l0 = e0[0] * e0[0] + e0[1] * e0[1] + e0[2] * e0[2];
+  const double l1 = e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2];
+  const double l2 = e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2];
+  double bx = e0[0], by = e0[1], bz = e0[2], bl = l0;
+  if (l1 > bl) { bx = e1[0]; by = e1[1]; bz = e1[2]; bl = l1; }
+  if (l2 > bl) { bx = e2[0]; by = e2[1]; bz = e2[2]; bl = l2; }
+  if (bl > 1e-24) {  // (c is scaled to unit max-abs) otherwise rank < 2: keep the Jacobi vector
+    const double il = rsqrt(bl);
+    bx *= il; by *= il; bz *= il;
+    if (bx * v[0] + by * v[1] + bz * v[2] < 0) { bx = -bx; by = -by; bz = -bz; }
+    v[0] = bx; v[1] = by; v[2] = bz;
+  }
+}
+
+__device__ __forceinline__ bool eig_extreme_refined(const double a[6], double x[3], double z[3]) {
+  double sc = fmax(fmax(fabs(a[0]), fabs(a[1])), fmax(fmax(fabs(a[2]), fabs(a[3])), fmax(fabs(a[4]), fabs(a[5]))));
+  if (!isfinite(sc)) return false;
+  const double isc = (sc > 1e-300) ? 1.0 / sc : 1.0;
+  double c[6];
+  float af[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    c[i] = a[i] * isc;
+    af[i] = (float)c[i];
+  }
+  float w[3], v[3][3];
+  eig_sym3<float>(af, w, v, 8);
+  x[0] = v[0][2]; x[1] = v[1][2]; x[2] = v[2][2];
+  z[0] = v[0][0]; z[1] = v[1][0]; z[2] = v[2][0];
+  refine_eigvec(c, x);
+  refine_eigvec(c, z);
+  return true;
+}
+
 // y = z x x in float (rf.row(1) = rf.row(2).cross(rf.row(0)))
 __device__ __forceinline__ void lrf_to_float9(const double x[3], const double z[3], float* o) {
   float fx[3] = {(float)x[0], (float)x[1], (float)x[2]};

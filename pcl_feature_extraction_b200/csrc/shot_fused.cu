@@ -2,15 +2,15 @@
 // points (replaces SHOTEstimationOMP::compute incl. its internal SHOTLocalReferenceFrameEstimation,
 // reference evaluation.cpp:770-775).
 //
-// A warp owns 32 queries.  Phase A scans the cell stencil of each query ONCE and compacts the
-// neighbours that pass d2 < r^2 into a per-query list in shared memory; the (R - d)-weighted scatter
-// matrix is accumulated from that dense list (all lanes busy) and parked in lane t.  Phase B solves
-// the 32 3x3 eigen problems together (double Jacobi, one per lane).  Phase C, per query: sign votes
-// and PCL's median tie fallback from the cached list, then the 352-bin histogram (int32 fixed point
-// in shared memory), L2 normalisation and the 1444-byte row.  The generic kernels in shot.cu scan the
-// stencil four times per query with ~20 % of the lanes doing the per-neighbour work; this one scans
-// once and runs the heavy code on compact lists.  Queries with more than NCAP neighbours are put on
-// a work list for the generic kernels.
+// A warp owns 32 queries.  Phases A-C run one query per LANE (no shuffles, no warp reductions): A walks the
+// 27 cells of the query's stencil once, writes the neighbours that pass d2 < r^2 into a [position][lane]
+// table in shared memory and accumulates the (R - d)-weighted scatter matrix in double; B solves the 32
+// eigen problems together (float Jacobi + one double refinement step per axis); C takes the sign votes
+// from the cached list (vote ties: the warp ranks that query's list for PCL's median fallback).  Phase D
+// runs one query per WARP, one neighbour per lane: the 352-bin histogram (int32 fixed point in shared
+// memory, order-independent => bit-reproducible), L2 normalisation and the coalesced 1444-byte row.
+// Neighbouring queries read the same cells at the same time, so phase A's loads are warp broadcasts or
+// L1 hits.  Queries with more than NCAP neighbours go to the generic kernels (shot.cu) over a work list.
 #include "internal.h"
 #include "shot_common.cuh"
 
@@ -18,12 +18,23 @@ namespace pfx {
 
 constexpr int NCAP = 64;
 constexpr int FS_WPB = 4;
+constexpr int NPAD = 33;  // row pitch of the neighbour table: [position][query lane], conflict-free both ways
 
 struct FusedSmem {
-  int nbr[32][NCAP];
+  int nbr[NCAP][NPAD];
   int hist[352];
   unsigned long long keys[NCAP];
 };
+
+// cell id of stencil slot l (0..26) of a query: adjacency row for surface points, hash probe otherwise
+template <bool DENSE>
+__device__ __forceinline__ int stencil_cell(const GridDev& g, const GridParams& P, const int* __restrict__ adj, int cx,
+                                            int cy, int cz, int l) {
+  if (DENSE) return adj[l];
+  const int x2 = cx + l % 3 - 1, y2 = cy + (l / 3) % 3 - 1, z2 = cz + l / 9 - 1;
+  if (x2 < 0 || x2 >= P.nx || y2 < 0 || y2 >= P.ny || z2 < 0 || z2 >= P.nz) return -1;
+  return hash_lookup(g, morton3(x2, y2, z2));
+}
 
 template <bool DENSE>
 __global__ void __launch_bounds__(FS_WPB * 32)
@@ -32,190 +43,197 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   FusedSmem* S = reinterpret_cast<FusedSmem*>(smem_raw) + wid;
-  const int n_valid = g.gp->n_valid;
+  const GridParams P = *g.gp;
+  const int n_valid = P.n_valid;
   const float nanv = __int_as_float(0x7fc00000);
+  const float Rf = (float)R;
   const unsigned lt = (1u << lane) - 1u;
   for (int qbase = (blockIdx.x * FS_WPB + wid) * 32; qbase < nq; qbase += gridDim.x * FS_WPB * 32) {
-    const int qend = min(32, nq - qbase);
-    // ---------------- phase A: neighbour lists + weighted scatter
+    // ---------------- phase A (lane = query): one pass over the 3x3x3 stencil builds the neighbour list
+    // in shared memory and the (R - d)-weighted scatter matrix of getLocalRF in double
+    const int qi = qbase + lane;
+    const bool have_q = qi < nq;
+    const float4 q = have_q ? (DENSE ? g.pts[qi] : queries[qi]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool q_ok = have_q && finite3(q.x, q.y, q.z) && (!DENSE || qi < n_valid) && n_valid > 0;
     double m6[6] = {0, 0, 0, 0, 0, 0};
     double msw = 0.0;
-    int mvalid = 0, mn = 0;  // valid (p != q) neighbours, all neighbours; -1: overflow / no query
-    for (int t = 0; t < qend; ++t) {
-      const int qi = qbase + t;
-      const float4 q = DENSE ? g.pts[qi] : queries[qi];
-      int n_t = -1;
-      double a6[6] = {0, 0, 0, 0, 0, 0};
-      double asw = 0.0;
-      int avalid = 0;
-      if (finite3(q.x, q.y, q.z) && (!DENSE || qi < n_valid)) {
-        CellBlock blk = DENSE ? stencil_of_point(g, qi, lane) : stencil_of_pos(g, q.x, q.y, q.z, lane);
-        n_t = 0;
-        for (int base = 0; base < blk.total; base += 32) {
-          int c = base + lane;
-          bool valid = c < blk.total;
-          int j = block_candidate(blk, valid ? c : 0);
-          if (valid) {
-            float4 p = g.pts[j];
-            valid = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z) < r2;
-          }
-          unsigned m = __ballot_sync(FULL, valid);
-          int pos = n_t + __popc(m & lt);
-          if (valid && pos < NCAP) S->nbr[t][pos] = j;
-          n_t += __popc(m);
-        }
-        __syncwarp();
-        if (n_t > NCAP) {
-          n_t = -2;  // generic kernels
-        } else {
-          for (int c = lane; c < n_t; c += 32) {
-            float4 p = g.pts[S->nbr[t][c]];
+    int n_all = 0, n_val = 0;
+    if (q_ok) {
+      const int* adj = nullptr;
+      int cx = 0, cy = 0, cz = 0;
+      if (DENSE) {
+        adj = g.cell_nbr + (size_t)g.pt_cell[qi] * 27;
+      } else {
+        cx = cell_coord(q.x, P.ox, P.inv_e, P.nx);
+        cy = cell_coord(q.y, P.oy, P.inv_e, P.ny);
+        cz = cell_coord(q.z, P.oz, P.inv_e, P.nz);
+      }
+      for (int l = 0; l < 27; ++l) {
+        const int c = stencil_cell<DENSE>(g, P, adj, cx, cy, cz, l);
+        if (c < 0) continue;
+        const int j1 = g.cell_start[c + 1];
+        for (int j = g.cell_start[c]; j < j1; ++j) {
+          const float4 p = g.pts[j];
+          const float d2 = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
+          if (d2 < r2) {
+            if (n_all < NCAP) S->nbr[n_all][lane] = j;
+            ++n_all;
             if (!(p.x == q.x && p.y == q.y && p.z == q.z)) {
-              float d2 = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
-              double vx = (double)__fsub_rn(p.x, q.x), vy = (double)__fsub_rn(p.y, q.y), vz = (double)__fsub_rn(p.z, q.z);
-              double w = R - sqrt((double)d2);
-              a6[0] += w * (vx * vx); a6[1] += w * (vx * vy); a6[2] += w * (vx * vz);
-              a6[3] += w * (vy * vy); a6[4] += w * (vy * vz); a6[5] += w * (vz * vz);
-              asw += w;
-              avalid += 1;
+              const double vx = (double)__fsub_rn(p.x, q.x), vy = (double)__fsub_rn(p.y, q.y),
+                           vz = (double)__fsub_rn(p.z, q.z);
+              const double w = R - sqrt((double)d2);
+              m6[0] += w * (vx * vx); m6[1] += w * (vx * vy); m6[2] += w * (vx * vz);
+              m6[3] += w * (vy * vy); m6[4] += w * (vy * vz); m6[5] += w * (vz * vz);
+              msw += w;
+              ++n_val;
             }
           }
-#pragma unroll
-          for (int i = 0; i < 6; ++i) a6[i] = warp_sum(a6[i]);
-          asw = warp_sum(asw);
-          avalid = warp_sum(avalid);
         }
       }
-      if (lane == t) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) m6[i] = a6[i];
-        msw = asw;
-        mvalid = avalid;
-        mn = n_t;
-      }
     }
-    if (lane >= qend) mn = -1;
-    // ---------------- phase B: every lane solves its own query
+    const bool overflow = n_all > NCAP;  // handed to the generic kernels
+    // ---------------- phase B: every lane solves its own 3x3 eigen problem
     double x[3] = {0, 0, 0}, z[3] = {0, 0, 0};
     bool good = false;
-    if (mn >= 0 && mvalid >= 5) {
+    if (q_ok && !overflow && n_val >= 5) {
       double a[6];
+      const double inv = 1.0 / msw;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) a[i] = m6[i] / msw;
-      double w[3], v[3][3];
-      eig_sym3<double>(a, w, v, 12);
-      good = isfinite(w[0]) && isfinite(w[1]) && isfinite(w[2]);
-      x[0] = v[0][2]; x[1] = v[1][2]; x[2] = v[2][2];
-      z[0] = v[0][0]; z[1] = v[1][0]; z[2] = v[2][0];
+      for (int i = 0; i < 6; ++i) a[i] = m6[i] * inv;
+      good = eig_extreme_refined(a, x, z);
     }
-    // ---------------- phase C: votes, frame, histogram, row
-    for (int t = 0; t < qend; ++t) {
-      const int qi = qbase + t;
-      const int n_t = __shfl_sync(FULL, mn, t);
-      const float4 q = DENSE ? g.pts[qi] : queries[qi];
-      const size_t row = DENSE ? (size_t)__float_as_int(q.w) : (size_t)qi;
-      float* o = out + row * stride;
-      if (n_t == -2) {  // hand over to the generic kernels
-        if (lane == 0) wl[atomicAdd(wl_count, 1)] = qi;
-        continue;
+    // ---------------- phase C (lane = query): sign votes over the cached list
+    int votex = 1, votez = 1;
+    if (good) {
+      int px = 0, pz = 0;
+      for (int c = 0; c < n_all; ++c) {
+        const float4 p = g.pts[S->nbr[c][lane]];
+        if (!(p.x == q.x && p.y == q.y && p.z == q.z)) {
+          const double vx = (double)__fsub_rn(p.x, q.x), vy = (double)__fsub_rn(p.y, q.y),
+                       vz = (double)__fsub_rn(p.z, q.z);
+          if (vx * x[0] + vy * x[1] + vz * x[2] >= 0) ++px;
+          if (vx * z[0] + vy * z[1] + vz * z[2] >= 0) ++pz;
+        }
       }
-      const bool gd = __shfl_sync(FULL, (int)good, t);
-      if (n_t <= 0 || !gd) {  // non-finite query, no neighbours, or NaN frame: all-NaN row
-        for (int c = lane; c < 361; c += 32) o[c] = nanv;
-        continue;
-      }
-      const int nv = __shfl_sync(FULL, mvalid, t);
+      votex = 2 * px - n_val;
+      votez = 2 * pz - n_val;
+    }
+    bool fx = votex < 0, fz = votez < 0;
+    // vote ties: PCL's fallback needs the neighbours' ranks in (d2, index) order -> the warp ranks the list of
+    // each tied query together
+    unsigned ties = __ballot_sync(FULL, good && (votex == 0 || votez == 0));
+    while (ties) {
+      const int t = __ffs(ties) - 1;
+      ties &= ties - 1;
+      const int n_t = __shfl_sync(FULL, n_all, t);
+      const float qx = __shfl_sync(FULL, q.x, t), qy = __shfl_sync(FULL, q.y, t), qz = __shfl_sync(FULL, q.z, t);
       double xs[3], zs[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         xs[i] = __shfl_sync(FULL, x[i], t);
         zs[i] = __shfl_sync(FULL, z[i], t);
       }
-      // sign votes over the cached list
-      int px = 0, pz = 0;
-      for (int c = lane; c < n_t; c += 32) {
-        float4 p = g.pts[S->nbr[t][c]];
-        if (!(p.x == q.x && p.y == q.y && p.z == q.z)) {
-          double vx = (double)__fsub_rn(p.x, q.x), vy = (double)__fsub_rn(p.y, q.y), vz = (double)__fsub_rn(p.z, q.z);
-          if (vx * xs[0] + vy * xs[1] + vz * xs[2] >= 0) ++px;
-          if (vx * zs[0] + vy * zs[1] + vz * zs[2] >= 0) ++pz;
+      int cntv = 0;
+      for (int c0 = 0; c0 < n_t; c0 += 32) {
+        const int c = c0 + lane;
+        bool v = false;
+        unsigned long long key = 0;
+        if (c < n_t) {
+          const float4 p = g.pts[S->nbr[c][t]];
+          v = !(p.x == qx && p.y == qy && p.z == qz);
+          const float d2 = dist2_flann(qx, qy, qz, p.x, p.y, p.z);
+          key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(p.w);
+        }
+        const unsigned m = __ballot_sync(FULL, v);
+        if (v) S->keys[cntv + __popc(m & lt)] = key;
+        cntv += __popc(m);
+      }
+      __syncwarp();
+      const int med = cntv / 2;
+      int plx = 0, plz = 0;
+      for (int a = lane; a < cntv; a += 32) {
+        const unsigned long long ka = S->keys[a];
+        int rank = 0;
+        for (int b = 0; b < cntv; ++b) rank += (S->keys[b] < ka) ? 1 : 0;
+        if (rank >= med - 2 && rank <= med + 2) {
+          const float4 p = g.pts[g.inv_perm[(int)(unsigned)(ka & 0xffffffffull)]];
+          const double vx = (double)__fsub_rn(p.x, qx), vy = (double)__fsub_rn(p.y, qy), vz = (double)__fsub_rn(p.z, qz);
+          if (vx * xs[0] + vy * xs[1] + vz * xs[2] > 0) ++plx;
+          if (vx * zs[0] + vy * zs[1] + vz * zs[2] > 0) ++plz;
         }
       }
-      px = warp_sum(px);
-      pz = warp_sum(pz);
-      const int votex = 2 * px - nv, votez = 2 * pz - nv;
-      bool fx = votex < 0, fz = votez < 0;
-      if (votex == 0 || votez == 0) {
-        // PCL's fallback: valid neighbours in (d2, index) order, ranks nv/2-2 .. nv/2+2, strictly positive
-        int cntv = 0;
-        for (int c0 = 0; c0 < n_t; c0 += 32) {
-          int c = c0 + lane;
-          bool v = false;
-          unsigned long long key = 0;
-          if (c < n_t) {
-            float4 p = g.pts[S->nbr[t][c]];
-            v = !(p.x == q.x && p.y == q.y && p.z == q.z);
-            float d2 = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
-            key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(p.w);
-          }
-          unsigned m = __ballot_sync(FULL, v);
-          if (v) S->keys[cntv + __popc(m & lt)] = key;
-          cntv += __popc(m);
-        }
-        __syncwarp();
-        const int med = cntv / 2;
-        int plx = 0, plz = 0;
-        for (int a = lane; a < cntv; a += 32) {
-          unsigned long long ka = S->keys[a];
-          int rank = 0;
-          for (int b = 0; b < cntv; ++b) rank += (S->keys[b] < ka) ? 1 : 0;
-          if (rank >= med - 2 && rank <= med + 2) {
-            float4 p = g.pts[g.inv_perm[(int)(unsigned)(ka & 0xffffffffull)]];
-            double vx = (double)__fsub_rn(p.x, q.x), vy = (double)__fsub_rn(p.y, q.y), vz = (double)__fsub_rn(p.z, q.z);
-            if (vx * xs[0] + vy * xs[1] + vz * xs[2] > 0) ++plx;
-            if (vx * zs[0] + vy * zs[1] + vz * zs[2] > 0) ++plz;
-          }
-        }
-        plx = warp_sum(plx);
-        plz = warp_sum(plz);
+      plx = warp_sum(plx);
+      plz = warp_sum(plz);
+      if (lane == t) {
         if (votex == 0) fx = plx < 3;
         if (votez == 0) fz = plz < 3;
-        __syncwarp();
       }
-      if (fx) { xs[0] = -xs[0]; xs[1] = -xs[1]; xs[2] = -xs[2]; }
-      if (fz) { zs[0] = -zs[0]; zs[1] = -zs[1]; zs[2] = -zs[2]; }
-      float rf[9];
-      lrf_to_float9(xs, zs, rf);
-      if (lane < 9) o[352 + lane] = rf[lane];
+      __syncwarp();
+    }
+    float rf[9];
+    {
+      if (fx) { x[0] = -x[0]; x[1] = -x[1]; x[2] = -x[2]; }
+      if (fz) { z[0] = -z[0]; z[1] = -z[1]; z[2] = -z[2]; }
+      lrf_to_float9(x, z, rf);
+    }
+    // ---------------- phase D (warp per query, lane = neighbour): 352-bin histogram, normalise, write the row
+    const int qend = min(32, nq - qbase);
+    for (int t = 0; t < qend; ++t) {
+      const int n_t = __shfl_sync(FULL, n_all, t);
+      const bool ok_t = __shfl_sync(FULL, (int)q_ok, t);
+      const bool of_t = __shfl_sync(FULL, (int)overflow, t);
+      const bool gd = __shfl_sync(FULL, (int)good, t);
+      const float4 qt = make_float4(__shfl_sync(FULL, q.x, t), __shfl_sync(FULL, q.y, t), __shfl_sync(FULL, q.z, t),
+                                    __shfl_sync(FULL, q.w, t));
+      const size_t row = DENSE ? (size_t)__float_as_int(qt.w) : (size_t)(qbase + t);
+      float* o = out + row * stride;
+      if (of_t) {
+        if (lane == 0) wl[atomicAdd(wl_count, 1)] = qbase + t;
+        continue;
+      }
+      if (!ok_t || n_t <= 0 || !gd) {  // non-finite query, no neighbours, or NaN frame: all-NaN row
+        for (int c = lane; c < 361; c += 32) o[c] = nanv;
+        continue;
+      }
+      float rft[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) rft[i] = __shfl_sync(FULL, rf[i], t);
+      if (lane < 9) {
+        float v = rft[0];
+#pragma unroll
+        for (int i = 1; i < 9; ++i) v = (lane == i) ? rft[i] : v;
+        o[352 + lane] = v;
+      }
       if (n_t < 5) {  // computePointSHOT: too few neighbours -> NaN descriptor, frame kept
         for (int c = lane; c < 352; c += 32) o[c] = nanv;
         continue;
       }
-      // histogram
-      for (int c = lane; c < 352; c += 32) S->hist[c] = 0;
+#pragma unroll
+      for (int i = 0; i < 11; ++i) S->hist[lane + 32 * i] = 0;
       __syncwarp();
       const float scale = shot_scale(n_t);
       for (int c = lane; c < n_t; c += 32) {
-        const int j = S->nbr[t][c];
+        const int j = S->nbr[c][t];
         const float4 p = g.pts[j];
-        const float d2 = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
-        shot_accumulate_neighbor(S->hist, scale, q, p, d2, nrm[j], rf, R);
+        const float d2 = dist2_flann(qt.x, qt.y, qt.z, p.x, p.y, p.z);
+        shot_accumulate_neighbor_f(S->hist, scale, qt, p, d2, nrm[j], rft, Rf);
       }
       __syncwarp();
       const float inv_scale = 1.0f / scale;
-      double acc = 0.0;
+      float acc = 0.f;
       float hv[11];
 #pragma unroll
       for (int i = 0; i < 11; ++i) {
         hv[i] = (float)S->hist[lane + 32 * i] * inv_scale;
-        acc += (double)__fmul_rn(hv[i], hv[i]);
+        acc = fmaf(hv[i], hv[i], acc);
       }
       acc = warp_sum(acc);
-      const float nrmv = (float)sqrt(acc);
+      const float inv_n = 1.0f / sqrtf(acc);
 #pragma unroll
-      for (int i = 0; i < 11; ++i) o[lane + 32 * i] = __fdiv_rn(hv[i], nrmv);
+      for (int i = 0; i < 11; ++i) o[lane + 32 * i] = hv[i] * inv_n;
       __syncwarp();
     }
+    __syncwarp();
   }
 }
 
