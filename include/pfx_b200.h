@@ -156,6 +156,43 @@ int pfx_set_match_engine(pfx_ctx* ctx, int engine);
  * they processed, out4[2] rows whose exactness certificate failed and were redone by the exact scan */
 int pfx_match_info(pfx_ctx* ctx, double* out4);
 
+/* ------------------------------------------------------------------ range image, NARF keypoints, Narf36
+ * pfx_range_image_planar <- RangeImagePlanar::createFromPointCloudWithFixedSize (keypoints.h:204-216,
+ * tools.h:65-76); pfx_range_image_spherical <- RangeImage::createFromPointCloud (config C3).  Both project
+ * the current surface with the sensor at the origin of the cloud frame (CAMERA_FRAME, identity pose: what
+ * the reference passes for the bundled clouds), noise_level 0.  The image (height x width pixels of
+ * x, y, z, range = pcl::PointWithRange without padding; unobserved: NaN xyz, range -inf) stays in the
+ * context; desc_out receives its geometry (the spherical image is cropped to the observed box + border). */
+typedef struct {
+  int32_t width, height, planar;
+  float cx, cy, fx, fy; /* planar */
+  float ang_res;        /* spherical: radians per pixel, both axes */
+  int32_t off_x, off_y; /* spherical: offset of the image inside the full 360 x 180 degree grid */
+} pfx_range_image_desc;
+int pfx_range_image_planar(pfx_ctx* ctx, int width, int height, float cx, float cy, float fx, float fy,
+                           float min_range, pfx_range_image_desc* desc_out);
+int pfx_range_image_spherical(pfx_ctx* ctx, float ang_res, float max_angle_width, float max_angle_height,
+                              float min_range, int border, pfx_range_image_desc* desc_out);
+/* use a caller-supplied image (height*width*4 floats) / read the current one back */
+int pfx_range_image_set(pfx_ctx* ctx, const pfx_range_image_desc* desc, const float* img, int mem);
+int pfx_range_image_get(pfx_ctx* ctx, pfx_range_image_desc* desc_out, float* img, int mem);
+/* stage outputs of RangeImageBorderExtractor, each optional: traits (h*w int32 bit sets: 1 obstacle border,
+ * 2 shadow border, 4 veil point, then per-direction bits), border scores (4*h*w: left, right, top,
+ * bottom), surface-change score (h*w) and direction (h*w*3) */
+int pfx_narf_borders(pfx_ctx* ctx, int32_t* traits, float* border_scores, float* change_score,
+                     float* change_dir, int mem);
+/* pfx_narf_keypoints <- NarfKeypoint::compute (keypoints.h:218-224) with PCL's default parameters except
+ * support_size.  kp_px: range-image pixel indices y * width + x, ascending; kp_xyz (optional, 3 floats
+ * each) the pixels' 3-D points; interest_image (optional, h*w). */
+int pfx_narf_keypoints(pfx_ctx* ctx, float support_size, int32_t* kp_px, float* kp_xyz, float* kp_interest,
+                       size_t cap, size_t* n_kp, float* interest_image, int mem);
+/* pfx_narf36 <- NarfDescriptor::compute (evaluation.cpp:629-637): one row per (keypoint, dominant
+ * rotation) when rotation_invariant, rows in keypoint order; row = pcl::Narf36 {x, y, z, roll, pitch, yaw,
+ * descriptor[36]} (168 bytes) at `stride` bytes.  Keypoints whose pixel is unobserved or whose
+ * neighbourhood cannot support a normal produce no row. */
+int pfx_narf36(pfx_ctx* ctx, const int32_t* kp_px, size_t n_kp, float support_size, int rotation_invariant,
+               void* out, size_t stride, size_t cap, size_t* n_out, int mem);
+
 /* ------------------------------------------------------------------ ingest
  * pfx_voxel_grid <- pcl::VoxelGrid centroid filter (config C1 ingest; not in the reference code).
  * Operates on the current surface; out: cap x 3 packed floats, ascending voxel id. */

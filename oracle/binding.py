@@ -220,3 +220,64 @@ def voxel_grid(pts, leaf):
     m = C.c_int(0)
     _chk(lib().orc_voxel_grid(_opt(pts), len(pts), C.c_float(leaf), _opt(out), len(pts), C.byref(m)), "voxel_grid")
     return out[: m.value].copy()
+
+
+# ------------------------------------------------------------------ range image / NARF
+class RiDesc(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("planar", C.c_int), ("cx", C.c_float), ("cy", C.c_float),
+                ("fx", C.c_float), ("fy", C.c_float), ("ang_res", C.c_float), ("off_x", C.c_int), ("off_y", C.c_int)]
+
+
+def range_image_planar(pts, width, height, cx, cy, fx, fy, min_range=0.0):
+    """-> (img [h, w, 4] = x, y, z, range; RiDesc)"""
+    pts = _f32(pts)
+    img = np.zeros((height, width, 4), np.float32)
+    _chk(lib().orc_range_image_planar(_opt(pts), len(pts), width, height, C.c_float(cx), C.c_float(cy), C.c_float(fx),
+                                      C.c_float(fy), C.c_float(min_range), _opt(img)), "range_image_planar")
+    return img, RiDesc(width, height, 1, cx, cy, fx, fy, 0.0, 0, 0)
+
+
+def range_image_spherical(pts, ang_res, max_angle_w=2 * np.pi, max_angle_h=np.pi, min_range=0.0, border=0):
+    pts = _f32(pts)
+    cap = int(np.floor(max_angle_w / ang_res)) * int(np.floor(max_angle_h / ang_res)) + 16
+    buf = np.zeros(cap * 4, np.float32)
+    w, h, ox, oy = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    _chk(lib().orc_range_image_spherical(_opt(pts), len(pts), C.c_float(ang_res), C.c_float(max_angle_w),
+                                         C.c_float(max_angle_h), C.c_float(min_range), int(border), _opt(buf), cap,
+                                         C.byref(w), C.byref(h), C.byref(ox), C.byref(oy)), "range_image_spherical")
+    img = buf[: w.value * h.value * 4].reshape(h.value, w.value, 4).copy()
+    return img, RiDesc(w.value, h.value, 0, 0.0, 0.0, 1.0, 1.0, ang_res, ox.value, oy.value)
+
+
+def narf_borders(img, desc):
+    img = _f32(img)
+    n = desc.width * desc.height
+    traits = np.zeros(n, np.int32)
+    scores = np.zeros((4, n), np.float32)
+    sc = np.zeros(n, np.float32)
+    sd = np.zeros((n, 3), np.float32)
+    _chk(lib().orc_narf_borders(_opt(img), C.byref(desc), _opt(traits), _opt(scores), _opt(sc), _opt(sd)), "narf_borders")
+    return traits, scores, sc, sd
+
+
+def narf_keypoints(img, desc, support_size):
+    img = _f32(img)
+    n = desc.width * desc.height
+    kp = np.zeros(n, np.int32)
+    val = np.zeros(n, np.float32)
+    interest = np.zeros(n, np.float32)
+    m = C.c_int(0)
+    _chk(lib().orc_narf_keypoints(_opt(img), C.byref(desc), C.c_float(support_size), _opt(kp), _opt(val), n, C.byref(m),
+                                  _opt(interest)), "narf_keypoints")
+    return kp[: m.value].copy(), val[: m.value].copy(), interest
+
+
+def narf36(img, desc, kp_px, support_size, rotation_invariant=True):
+    img = _f32(img)
+    kp_px = np.ascontiguousarray(kp_px, np.int32)
+    cap = max(1, 8 * len(kp_px))
+    out = np.zeros((cap, 42), np.float32)
+    m = C.c_int(0)
+    _chk(lib().orc_narf36(_opt(img), C.byref(desc), _opt(kp_px), len(kp_px), C.c_float(support_size),
+                          int(bool(rotation_invariant)), _opt(out), cap, C.byref(m)), "narf36")
+    return out[: m.value].copy()

@@ -113,6 +113,10 @@ typedef struct {
   float cx, cy, fx, fy;      /* planar */
   float ang_res; int off_x, off_y; /* spherical */
 } orc_ri_desc;
+/* stage outputs of RangeImageBorderExtractor (each optional): traits h*w (bit set, see narf.cpp),
+ * border scores 4*h*w (left, right, top, bottom), surface-change score h*w and direction h*w*3 */
+int orc_narf_borders(const float* img, const orc_ri_desc* d, int* traits, float* border_scores,
+                     float* sc_score, float* sc_dir);
 int orc_narf_keypoints(const float* img, const orc_ri_desc* d, float support_size,
                        int* kp_px, float* kp_interest, int cap, int* n_kp,
                        float* interest_image /* optional h*w */);

@@ -28,6 +28,12 @@ class Correspondence(C.Structure):
     _fields_ = [("index_query", C.c_int32), ("index_match", C.c_int32), ("distance", C.c_float)]
 
 
+class RangeImageDesc(C.Structure):
+    """pfx_range_image_desc (include/pfx_b200.h)"""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("planar", C.c_int32), ("cx", C.c_float), ("cy", C.c_float),
+                ("fx", C.c_float), ("fy", C.c_float), ("ang_res", C.c_float), ("off_x", C.c_int32), ("off_y", C.c_int32)]
+
+
 CORR_DTYPE = np.dtype([("index_query", "<i4"), ("index_match", "<i4"), ("distance", "<f4")])
 
 # name -> (restype, argtypes); mirrors include/pfx_b200.h one to one
@@ -65,6 +71,13 @@ SIGNATURES = {
     "pfx_shot_lrf": (_i, [_vp, _d, _vp, _i]),
     "pfx_match": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _f, _vp, _sz, C.POINTER(_sz), _i]),
     "pfx_match_nn": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _vp, _vp, _i]),
+    "pfx_range_image_planar": (_i, [_vp, _i, _i, _f, _f, _f, _f, _f, _vp]),
+    "pfx_range_image_spherical": (_i, [_vp, _f, _f, _f, _f, _i, _vp]),
+    "pfx_range_image_set": (_i, [_vp, _vp, _vp, _i]),
+    "pfx_range_image_get": (_i, [_vp, _vp, _vp, _i]),
+    "pfx_narf_borders": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
+    "pfx_narf_keypoints": (_i, [_vp, _f, _vp, _vp, _vp, _sz, C.POINTER(_sz), _vp, _i]),
+    "pfx_narf36": (_i, [_vp, _vp, _sz, _f, _i, _vp, _sz, _sz, C.POINTER(_sz), _i]),
     "pfx_set_match_engine": (_i, [_vp, _i]),
     "pfx_match_info": (_i, [_vp, _vp]),
     "pfx_voxel_grid": (_i, [_vp, _f, _vp, _sz, C.POINTER(_sz), _i]),
@@ -297,6 +310,62 @@ class Context:
 
     def shot352_dev(self, radius, out_ptr, stride=1444):
         self._chk(self.lib.pfx_shot352(self.h, radius, None, _ptr(out_ptr), stride, DEVICE))
+
+    # -- range image / NARF
+    def range_image_planar(self, width, height, cx, cy, fx, fy, min_range=0.0):
+        d = RangeImageDesc()
+        self._chk(self.lib.pfx_range_image_planar(self.h, width, height, cx, cy, fx, fy, min_range, C.byref(d)))
+        return d
+
+    def range_image_spherical(self, ang_res, max_angle_w=2 * np.pi, max_angle_h=np.pi, min_range=0.0, border=0):
+        d = RangeImageDesc()
+        self._chk(self.lib.pfx_range_image_spherical(self.h, ang_res, max_angle_w, max_angle_h, min_range, border, C.byref(d)))
+        return d
+
+    def range_image_set(self, desc, img):
+        img = np.ascontiguousarray(img, np.float32)
+        self._chk(self.lib.pfx_range_image_set(self.h, C.byref(desc), _ptr(img), HOST))
+
+    def range_image_get(self):
+        d = RangeImageDesc()
+        self._chk(self.lib.pfx_range_image_get(self.h, C.byref(d), None, HOST))
+        img = np.zeros((d.height, d.width, 4), np.float32)
+        if img.size:
+            self._chk(self.lib.pfx_range_image_get(self.h, C.byref(d), _ptr(img), HOST))
+        return d, img
+
+    def narf_borders(self):
+        d, _ = RangeImageDesc(), None
+        self._chk(self.lib.pfx_range_image_get(self.h, C.byref(d), None, HOST))
+        n = d.width * d.height
+        traits = np.zeros(n, np.int32)
+        scores = np.zeros((4, n), np.float32)
+        cs = np.zeros(n, np.float32)
+        cd = np.zeros((n, 3), np.float32)
+        self._chk(self.lib.pfx_narf_borders(self.h, _ptr(traits), _ptr(scores), _ptr(cs), _ptr(cd), HOST))
+        return traits, scores, cs, cd
+
+    def narf_keypoints(self, support_size):
+        d = RangeImageDesc()
+        self._chk(self.lib.pfx_range_image_get(self.h, C.byref(d), None, HOST))
+        n = max(d.width * d.height, 1)
+        kp = np.zeros(n, np.int32)
+        xyz = np.zeros((n, 3), np.float32)
+        val = np.zeros(n, np.float32)
+        interest = np.zeros(n, np.float32)
+        m = C.c_size_t(0)
+        self._chk(self.lib.pfx_narf_keypoints(self.h, support_size, _ptr(kp), _ptr(xyz), _ptr(val), n, C.byref(m),
+                                              _ptr(interest), HOST))
+        return kp[: m.value].copy(), xyz[: m.value].copy(), val[: m.value].copy(), interest
+
+    def narf36(self, kp_px, support_size, rotation_invariant=True):
+        kp_px = np.ascontiguousarray(kp_px, np.int32)
+        cap = max(1, 8 * len(kp_px))
+        out = np.zeros((cap, 42), np.float32)
+        m = C.c_size_t(0)
+        self._chk(self.lib.pfx_narf36(self.h, _ptr(kp_px), len(kp_px), support_size, int(bool(rotation_invariant)),
+                                      _ptr(out), 168, cap, C.byref(m), HOST))
+        return out[: m.value].copy()
 
     # -- matching
     def match_nn(self, a, b):

@@ -148,7 +148,8 @@ extern "C" int pfx_destroy(pfx_ctx* ctx) {
   for (DevBuf* b : {&ctx->surf, &ctx->normals, &ctx->normals_sorted, &ctx->qry, &ctx->knn_idx, &ctx->knn_d2,
                     &ctx->stage, &ctx->stage2, &ctx->tmp0, &ctx->tmp1, &ctx->tmp2, &ctx->tmp3, &ctx->tmp4,
                     &ctx->small, &ctx->scanbuf, &ctx->match_flags, &ctx->match_best, &ctx->out_stage, &ctx->qflag,
-                    &ctx->worklist, &ctx->worklist2})
+                    &ctx->worklist, &ctx->worklist2, &ctx->ri_img, &ctx->nb_surf, &ctx->nb_scores, &ctx->nb_shadow,
+                    &ctx->nb_traits, &ctx->nb_dir, &ctx->nb_change, &ctx->nk_interest})
     b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   delete ctx;
@@ -832,6 +833,143 @@ extern "C" int pfx_match(pfx_ctx* ctx, const float* a, size_t na, size_t stride_
   PFX_LAUNCH(ctx, corr_emit_kernel, div_up((long long)na, 256), 256, 0, flags, pos, s2t, sd2, (int)na, dout);
   PFX_CUDA(cudaGetLastError());
   if (mem == PFX_HOST) return deliver(ctx, out, dout, (size_t)cnt * sizeof(pfx_correspondence), mem);
+  return 0;
+}
+
+// ================================================================================== range image / NARF
+extern "C" int pfx_range_image_planar(pfx_ctx* ctx, int width, int height, float cx, float cy, float fx, float fy,
+                                      float min_range, pfx_range_image_desc* desc_out) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_range_image_planar: no surface set");
+  if (width <= 0 || height <= 0 || !(fx > 0) || !(fy > 0)) return ctx->fail(PFX_E_INVALID, "pfx_range_image_planar: bad geometry");
+  pfx_range_image_desc d = {};
+  d.width = width; d.height = height; d.planar = 1;
+  d.cx = cx; d.cy = cy; d.fx = fx; d.fy = fy;
+  PFX_TRY(range_image_build(ctx, &d, 0.f, 0.f, min_range, 0));
+  if (desc_out) *desc_out = ctx->ri;
+  return 0;
+}
+
+extern "C" int pfx_range_image_spherical(pfx_ctx* ctx, float ang_res, float max_angle_width, float max_angle_height,
+                                         float min_range, int border, pfx_range_image_desc* desc_out) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_range_image_spherical: no surface set");
+  if (!(ang_res > 0) || !(max_angle_width > 0) || !(max_angle_height > 0) || border < 0)
+    return ctx->fail(PFX_E_INVALID, "pfx_range_image_spherical: bad geometry");
+  pfx_range_image_desc d = {};
+  d.planar = 0;
+  d.ang_res = ang_res;
+  d.fx = d.fy = 1.f;
+  PFX_TRY(range_image_build(ctx, &d, max_angle_width, max_angle_height, min_range, border));
+  if (desc_out) *desc_out = ctx->ri;
+  return 0;
+}
+
+extern "C" int pfx_range_image_set(pfx_ctx* ctx, const pfx_range_image_desc* desc, const float* img, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (!desc || desc->width < 0 || desc->height < 0 || (desc->width * desc->height > 0 && !img))
+    return ctx->fail(PFX_E_INVALID, "pfx_range_image_set: bad arguments");
+  const size_t bytes = (size_t)desc->width * desc->height * sizeof(float4);
+  PFX_CUDA(ctx->ri_img.ensure(std::max<size_t>(bytes, 16)));
+  if (bytes)
+    PFX_CUDA(cudaMemcpyAsync(ctx->ri_img.p, img, bytes, mem == PFX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                             ctx->stream));
+  ctx->ri = *desc;
+  ctx->ri_valid = true;
+  ctx->ri_stage = 0;
+  return 0;
+}
+
+extern "C" int pfx_range_image_get(pfx_ctx* ctx, pfx_range_image_desc* desc_out, float* img, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (!ctx->ri_valid) return ctx->fail(PFX_E_STATE, "pfx_range_image_get: no range image");
+  if (desc_out) *desc_out = ctx->ri;
+  if (img) return deliver(ctx, img, ctx->ri_img.p, (size_t)ctx->ri.width * ctx->ri.height * sizeof(float4), mem);
+  return 0;
+}
+
+namespace pfx {
+__global__ void narf_export_kernel(const float4* __restrict__ change, int np, float* __restrict__ score,
+                                   float* __restrict__ dir) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  float4 c = change[i];
+  if (score) score[i] = c.w;
+  if (dir) {
+    dir[3 * i] = c.x; dir[3 * i + 1] = c.y; dir[3 * i + 2] = c.z;
+  }
+}
+}  // namespace pfx
+
+extern "C" int pfx_narf_borders(pfx_ctx* ctx, int32_t* traits, float* border_scores, float* change_score,
+                                float* change_dir, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  PFX_TRY(narf_prepare(ctx, 1, 0.f));
+  const size_t np = (size_t)ctx->ri.width * ctx->ri.height;
+  if (np == 0) return 0;
+  if (traits) PFX_TRY(deliver(ctx, traits, ctx->nb_traits.p, np * sizeof(int), mem));
+  if (border_scores) PFX_TRY(deliver(ctx, border_scores, ctx->nb_scores.p, np * 4 * sizeof(float), mem));
+  if (change_score || change_dir) {
+    float* ds = change_score;
+    float* dd = change_dir;
+    if (mem == PFX_HOST) {
+      PFX_CUDA(ctx->out_stage.ensure(np * 4 * sizeof(float)));
+      ds = ctx->out_stage.as<float>();
+      dd = ds + np;
+    }
+    PFX_LAUNCH(ctx, narf_export_kernel, div_up((long long)np, 256), 256, 0, ctx->nb_change.as<float4>(), (int)np,
+               change_score ? ds : nullptr, change_dir ? dd : nullptr);
+    PFX_CUDA(cudaGetLastError());
+    if (mem == PFX_HOST) {
+      if (change_score) PFX_TRY(deliver(ctx, change_score, ds, np * sizeof(float), mem));
+      if (change_dir) PFX_TRY(deliver(ctx, change_dir, dd, np * 3 * sizeof(float), mem));
+    }
+  }
+  return 0;
+}
+
+extern "C" int pfx_narf_keypoints(pfx_ctx* ctx, float support_size, int32_t* kp_px, float* kp_xyz, float* kp_interest,
+                                  size_t cap, size_t* n_kp, float* interest_image, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (!(support_size > 0)) return ctx->fail(PFX_E_PRECOND, "pfx_narf_keypoints: support_size must be > 0");
+  if (n_kp) *n_kp = 0;
+  int* dkp = nullptr;
+  int cnt = 0;
+  PFX_TRY(narf_keypoints(ctx, support_size, &dkp, &cnt));
+  if (n_kp) *n_kp = (size_t)cnt;
+  const size_t np = (size_t)ctx->ri.width * ctx->ri.height;
+  if (interest_image && np) PFX_TRY(deliver(ctx, interest_image, ctx->nk_interest.p, np * sizeof(float), mem));
+  if (cnt == 0) return 0;
+  if ((size_t)cnt > cap && (kp_px || kp_xyz || kp_interest)) return ctx->fail(PFX_E_CAPACITY, "pfx_narf_keypoints: keypoint buffer too small");
+  if (kp_px) PFX_TRY(deliver(ctx, kp_px, dkp, (size_t)cnt * sizeof(int), mem));
+  if (kp_xyz || kp_interest) PFX_TRY(narf_keypoint_attrs(ctx, dkp, cnt, kp_xyz, kp_interest, mem));
+  return 0;
+}
+
+extern "C" int pfx_narf36(pfx_ctx* ctx, const int32_t* kp_px, size_t n_kp, float support_size, int rotation_invariant,
+                          void* out, size_t stride, size_t cap, size_t* n_out, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (!(support_size > 0)) return ctx->fail(PFX_E_PRECOND, "pfx_narf36: support_size must be > 0");
+  if (!n_out || (n_kp && !kp_px) || stride < 168 || (stride & 3) || (cap && !out))
+    return ctx->fail(PFX_E_INVALID, "pfx_narf36: bad arguments");
+  *n_out = 0;
+  if (n_kp == 0) return 0;
+  const int* dkp = kp_px;
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->stage.ensure(n_kp * sizeof(int)));
+    PFX_CUDA(cudaMemcpyAsync(ctx->stage.p, kp_px, n_kp * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    dkp = ctx->stage.as<int>();
+  }
+  unsigned char* dout = static_cast<unsigned char*>(out);
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->out_stage.ensure(std::max<size_t>(cap * stride, 16)));
+    dout = ctx->out_stage.as<unsigned char>();
+    if (stride != 168 && cap) PFX_CUDA(cudaMemsetAsync(dout, 0, cap * stride, ctx->stream));
+  }
+  int cnt = 0;
+  PFX_TRY(narf36_compute(ctx, dkp, (int)n_kp, support_size, rotation_invariant, dout, stride, (int)cap, &cnt));
+  *n_out = (size_t)cnt;
+  if (mem == PFX_HOST && cnt > 0) return deliver(ctx, out, dout, (size_t)cnt * stride, mem);
   return 0;
 }
 

@@ -123,6 +123,13 @@ struct Ctx {
   void* pinned = nullptr;
   size_t pinned_cap = 0;
 
+  // range image + NARF state (narf.cu)
+  pfx_range_image_desc ri = {};
+  DevBuf ri_img, nb_surf, nb_scores, nb_shadow, nb_traits, nb_dir, nb_change, nk_interest;
+  bool ri_valid = false;
+  int ri_stage = 0;  // 0 image only, 1 borders extracted, 2 interest image for ri_support
+  float ri_support = 0.f;
+
   int match_engine = -1;  // -1 auto, 0 exact fp32 scan, 1 tcgen05 candidates + fp32 rescore
   TcOperand tc_ops[2];
   DevBuf tc_cand_d, tc_cand_j, tc_redo, tc_rows, tc_res;
@@ -222,6 +229,15 @@ int match_nn_tc(Ctx* ctx, const float* a, int na, int lda, const float* b, int n
 int match_pair_tc(Ctx* ctx, const float* a, int na, int lda, const float* b, int nb, int ldb, int dim, int* s2t,
                   float* sd2, int* t2s, float* td2);
 void match_tc_release(Ctx* ctx);
+
+// ---- narf.cu
+int range_image_build(Ctx* ctx, const pfx_range_image_desc* want, float max_angle_w, float max_angle_h, float min_range,
+                      int border);
+int narf_prepare(Ctx* ctx, int stage, float support_size);
+int narf_keypoints(Ctx* ctx, float support_size, int** kp_dev, int* n_kp);
+int narf_keypoint_attrs(Ctx* ctx, const int* kp_dev, int n, float* xyz, float* val, int mem);
+int narf36_compute(Ctx* ctx, const int* kp_dev, int n_kp, float support_size, int rotation_invariant,
+                   unsigned char* out_dev, size_t stride, int cap, int* n_out);
 
 // ---- helpers (capi.cu)
 int normals_sorted_for_grid(Ctx* ctx, Grid* g, const float4** out);

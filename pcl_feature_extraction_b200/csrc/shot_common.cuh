@@ -107,6 +107,28 @@ __device__ __forceinline__ void shot_accumulate_neighbor(int* h, float scale, fl
   shot_add(h, vol + step, w, scale);
 }
 
+// atan2 for the interpolation weights: octant reduction + the 9-term odd minimax polynomial of Abramowitz &
+// Stegun 4.4.49 (|error| <= 2e-8 on [0, 1]); about half the instructions of atan2f.  Not used for any
+// discrete decision.  (0, 0) -> 0.
+__device__ __forceinline__ float fast_atan2f(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float t = (mx > 0.f) ? __fdividef(mn, mx) : 0.f;
+  const float s = t * t;
+  float r = 0.0028662257f;
+  r = fmaf(r, s, -0.0161657367f);
+  r = fmaf(r, s, 0.0429096138f);
+  r = fmaf(r, s, -0.0752896400f);
+  r = fmaf(r, s, 0.1065626393f);
+  r = fmaf(r, s, -0.1420889944f);
+  r = fmaf(r, s, 0.1999355085f);
+  r = fmaf(r, s, -0.3333314528f);
+  r = fmaf(r * s, t, t);
+  if (ay > ax) r = 1.57079632679489661923f - r;
+  if (x < 0.f) r = 3.14159265358979323846f - r;
+  return copysignf(r, y);
+}
+
 // Float variant of the above for the fused dense kernel.  The three frame projections keep the CPU's
 // float arithmetic (separate multiply / add); everything else is single precision.  SHOT's quadrilinear
 // interpolation is continuous across every discrete boundary (cosine step, radial shell, elevation and
@@ -165,7 +187,8 @@ __device__ __forceinline__ void shot_accumulate_neighbor_f(int* h, float scale, 
       atomicAdd(&h[(di + 2) * 11 + step], __float2int_rn(rd * scale));
     }
   }
-  const float inc = acosf(fminf(1.0f, fmaxf(-1.0f, z / dist)));
+  const float rho = sqrtf(fmaf(x, x, y * y));  // inc = acos(z / dist) = atan2(|(x, y)|, z), in [0, pi]
+  const float inc = fast_atan2f(rho, z);
   if (z <= 0.f) {
     const float e = (inc - RAD135) * INV_RAD90;
     if (inc > RAD135)
@@ -184,7 +207,7 @@ __device__ __forceinline__ void shot_accumulate_neighbor_f(int* h, float scale, 
     }
   }
   if (y != 0.f || x != 0.f) {
-    const float az = atan2f(y, x);
+    const float az = fast_atan2f(y, x);
     const int sel = di >> 2;
     float ad = (az - (-RAD_PI_7_8 + RAD45 * (float)sel)) * INV_RAD45;
     ad = fmaxf(-0.5f, fminf(ad, 0.5f));

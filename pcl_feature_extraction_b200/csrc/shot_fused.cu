@@ -78,16 +78,26 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
           if (d2 < r2) {
             if (n_all < NCAP) S->nbr[n_all][lane] = j;
             ++n_all;
-            if (!(p.x == q.x && p.y == q.y && p.z == q.z)) {
-              const double vx = (double)__fsub_rn(p.x, q.x), vy = (double)__fsub_rn(p.y, q.y),
-                           vz = (double)__fsub_rn(p.z, q.z);
-              const double w = R - sqrt((double)d2);
-              m6[0] += w * (vx * vx); m6[1] += w * (vx * vy); m6[2] += w * (vx * vz);
-              m6[3] += w * (vy * vy); m6[4] += w * (vy * vz); m6[5] += w * (vz * vz);
-              msw += w;
-              ++n_val;
-            }
           }
+        }
+      }
+      // scatter matrix from the compact list (uniform trip counts: no lanes idle on rejected candidates)
+      const int n_list = min(n_all, NCAP);
+      for (int c = 0; c < n_list; ++c) {
+        const float4 p = g.pts[S->nbr[c][lane]];
+        if (!(p.x == q.x && p.y == q.y && p.z == q.z)) {
+          const float d2 = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
+          const double vx = (double)__fsub_rn(p.x, q.x), vy = (double)__fsub_rn(p.y, q.y),
+                       vz = (double)__fsub_rn(p.z, q.z);
+          // sqrt((double)d2): float rsqrt seed + one Newton step in double (error ~1e-14 relative)
+          const double xd = (double)d2, rs = (d2 > 0.f) ? (double)rsqrtf(d2) : 0.0;
+          double sq = xd * rs;
+          sq = fma(0.5 * rs, fma(-sq, sq, xd), sq);
+          const double w = R - sq;
+          m6[0] += w * (vx * vx); m6[1] += w * (vx * vy); m6[2] += w * (vx * vz);
+          m6[3] += w * (vy * vy); m6[4] += w * (vy * vz); m6[5] += w * (vz * vz);
+          msw += w;
+          ++n_val;
         }
       }
     }
