@@ -311,6 +311,15 @@ class Context:
     def shot352_dev(self, radius, out_ptr, stride=1444):
         self._chk(self.lib.pfx_shot352(self.h, radius, None, _ptr(out_ptr), stride, DEVICE))
 
+    # -- ingest
+    def voxel_grid(self, leaf):
+        """pcl::VoxelGrid centroids of the current surface, ascending voxel id"""
+        n = max(self.num_surface, 1)
+        out = np.zeros((n, 3), np.float32)
+        m = C.c_size_t(0)
+        self._chk(self.lib.pfx_voxel_grid(self.h, leaf, _ptr(out), n, C.byref(m), HOST))
+        return out[: m.value].copy()
+
     # -- range image / NARF
     def range_image_planar(self, width, height, cx, cy, fx, fy, min_range=0.0):
         d = RangeImageDesc()

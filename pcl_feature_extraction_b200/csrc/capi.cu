@@ -974,7 +974,17 @@ extern "C" int pfx_narf36(pfx_ctx* ctx, const int32_t* kp_px, size_t n_kp, float
 }
 
 // ================================================================================== ingest
-extern "C" int pfx_voxel_grid(pfx_ctx* ctx, float, float*, size_t, size_t*, int) {
-  if (!ctx) return PFX_E_INVALID;
-  return ctx->fail(PFX_E_STATE, "pfx_voxel_grid: not built yet");
+extern "C" int pfx_voxel_grid(pfx_ctx* ctx, float leaf, float* out_xyz, size_t cap, size_t* n_out, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_voxel_grid: no surface set");
+  if (!(leaf > 0) || !n_out || (cap && !out_xyz)) return ctx->fail(PFX_E_INVALID, "pfx_voxel_grid: bad arguments");
+  float* dout = out_xyz;
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->out_stage.ensure(std::max<size_t>(cap * 3 * sizeof(float), 16)));
+    dout = ctx->out_stage.as<float>();
+  }
+  PFX_TRY(voxel_grid_run(ctx, leaf, dout, cap, n_out));
+  if (*n_out > cap) return ctx->fail(PFX_E_CAPACITY, "pfx_voxel_grid: output buffer too small");
+  if (mem == PFX_HOST) return deliver(ctx, out_xyz, dout, *n_out * 3 * sizeof(float), mem);
+  return 0;
 }

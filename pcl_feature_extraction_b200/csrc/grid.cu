@@ -566,6 +566,115 @@ int grid_get(Ctx* ctx, double radius, int knn_k, Grid** out) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------- VoxelGrid
+// pcl::VoxelGrid centroid filter (config C1 ingest): voxel id = (ix - min_bx) + (iy - min_by) * div_bx +
+// (iz - min_bz) * div_bx * div_by with ix = floor(x * inv_leaf) in float; output = one centroid per occupied
+// voxel in ascending id order.  Sort-and-scan like the voxel hash; the centroid of a voxel is summed by ONE
+// thread in ascending point-index order, which is the order PCL's sorted index vector yields, so the float
+// sums are bit-identical to the CPU.
+__global__ void vg_keys_kernel(const float4* __restrict__ pts, int n, float inv, float minbx, float minby, float minbz,
+                               int divx, int divxy, uint32_t* __restrict__ keys, int* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pts[i];
+  uint32_t key = KEY_INVALID;
+  if (finite3(p.x, p.y, p.z)) {
+    int a = (int)(floorf(__fmul_rn(p.x, inv)) - minbx), b = (int)(floorf(__fmul_rn(p.y, inv)) - minby),
+        c = (int)(floorf(__fmul_rn(p.z, inv)) - minbz);
+    key = (uint32_t)(a + b * divx + c * divxy);
+  }
+  keys[i] = key;
+  vals[i] = i;
+}
+
+__global__ void vg_starts_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ heads,
+                                 const int* __restrict__ excl, int n, int* __restrict__ starts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (heads[i]) starts[excl[i]] = i;
+}
+
+__global__ void vg_centroid_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ keys,
+                                   const int* __restrict__ vals, const int* __restrict__ starts,
+                                   const int* __restrict__ nvox_dev, int n, int cap, float* __restrict__ out) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nvox = *nvox_dev;
+  if (v >= nvox || v >= cap) return;
+  const int s = starts[v];
+  const uint32_t key = keys[s];
+  float cx = 0.f, cy = 0.f, cz = 0.f;
+  int e = s;
+  for (; e < n && keys[e] == key; ++e) {
+    float4 p = pts[vals[e]];
+    cx = __fadd_rn(cx, p.x);
+    cy = __fadd_rn(cy, p.y);
+    cz = __fadd_rn(cz, p.z);
+  }
+  const float cnt = (float)(e - s);
+  out[3 * (size_t)v] = __fdiv_rn(cx, cnt);
+  out[3 * (size_t)v + 1] = __fdiv_rn(cy, cnt);
+  out[3 * (size_t)v + 2] = __fdiv_rn(cz, cnt);
+}
+
+// out_dev: cap x 3 floats (device).  *n_out = number of occupied voxels (may exceed cap: nothing beyond cap is
+// written and the caller reports PFX_E_CAPACITY).
+int voxel_grid_run(Ctx* ctx, float leaf, float* out_dev, size_t cap, size_t* n_out) {
+  const int n = (int)ctx->n;
+  *n_out = 0;
+  if (n == 0) return 0;
+  static Grid scratch;  // sort buffers only
+  Grid* g = &scratch;
+  PFX_CUDA(g->misc.ensure(sizeof(BuildAcc) + 64));
+  PFX_CUDA(g->keys.ensure((size_t)n * sizeof(uint32_t)));
+  PFX_CUDA(g->keys2.ensure((size_t)n * sizeof(uint32_t)));
+  PFX_CUDA(g->vals.ensure((size_t)n * sizeof(int)));
+  PFX_CUDA(g->vals2.ensure((size_t)n * sizeof(int)));
+  PFX_CUDA(g->pt_cell.ensure((size_t)n * sizeof(int)));
+  PFX_CUDA(g->cell_start.ensure(((size_t)n + 1) * sizeof(int)));
+  BuildAcc* acc = g->misc.as<BuildAcc>();
+  const float4* src = ctx->surf.as<float4>();
+  const int T = 256;
+  PFX_LAUNCH(ctx, acc_init_kernel, 1, 1, 0, acc);
+  PFX_LAUNCH(ctx, bbox_kernel, std::min(ctx->sm_count * 4, div_up(n, T)), T, 0, src, n, acc);
+  BuildAcc h;
+  PFX_CUDA(cudaMemcpyAsync(&h, acc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h.n_valid == 0) return 0;
+  auto ord2f_host = [](uint32_t u) {
+    uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+  };
+  const float inv = 1.0f / leaf;
+  long long minb[3], divb[3];
+  for (int a = 0; a < 3; ++a) {
+    float mn = ord2f_host(h.mn[a]), mx = ord2f_host(h.mx[a]);
+    minb[a] = (long long)floorf(mn * inv);
+    divb[a] = (long long)floorf(mx * inv) - minb[a] + 1;
+  }
+  // PCL: "Leaf size is too small for the input dataset. Integer indices would overflow."
+  if (divb[0] * divb[1] * divb[2] > 0x7fffffffll) return ctx->fail(PFX_E_PRECOND, "pfx_voxel_grid: leaf size too small for the dataset (voxel index overflows int32)");
+  PFX_LAUNCH(ctx, vg_keys_kernel, div_up(n, T), T, 0, src, n, inv, (float)minb[0], (float)minb[1], (float)minb[2],
+             (int)divb[0], (int)(divb[0] * divb[1]), g->keys.as<uint32_t>(), g->vals.as<int>());
+  PFX_TRY(radix_sort_pairs(ctx, g, n));
+  int* heads = g->vals2.as<int>();
+  int* total = reinterpret_cast<int*>(g->misc.as<char>() + sizeof(BuildAcc));
+  PFX_LAUNCH(ctx, heads_kernel, div_up(n, T), T, 0, g->keys.as<uint32_t>(), n, heads);
+  PFX_TRY(scan_exclusive_i32(ctx, heads, g->pt_cell.as<int>(), n, total, g->bsum));
+  PFX_LAUNCH(ctx, vg_starts_kernel, div_up(n, T), T, 0, g->keys.as<uint32_t>(), heads, g->pt_cell.as<int>(), n,
+             g->cell_start.as<int>());
+  int nvox = 0;
+  PFX_CUDA(cudaMemcpyAsync(&nvox, total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  *n_out = (size_t)nvox;
+  if (nvox > 0 && cap > 0)
+    PFX_LAUNCH(ctx, vg_centroid_kernel, div_up(std::min<long long>(nvox, (long long)cap), T), T, 0, src, g->keys.as<uint32_t>(),
+               g->vals.as<int>(), g->cell_start.as<int>(), total, n, (int)std::min<size_t>(cap, 0x7fffffff), out_dev);
+  PFX_CUDA(cudaGetLastError());
+  return 0;
+}
+
 void grid_free_all(Ctx* ctx) {
   for (Grid* g : ctx->grids) {
     g->release();

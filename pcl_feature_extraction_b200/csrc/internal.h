@@ -180,6 +180,7 @@ struct Ctx {
 // ---- grid.cu
 int grid_get(Ctx* ctx, double radius, int knn_k, Grid** out);
 void grid_free_all(Ctx* ctx);
+int voxel_grid_run(Ctx* ctx, float leaf, float* out_dev, size_t cap, size_t* n_out);
 // device-wide exclusive scan of int32 -> int32 / int64 (total written to *total_dev when non-null)
 int scan_exclusive_i32(Ctx* ctx, const int* in, int* out, int n, int* total_dev, DevBuf& bsum);
 int scan_exclusive_i64(Ctx* ctx, const int* in, long long* out, int n, DevBuf& bsum);

@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "feature_pipeline.hpp"
 
@@ -82,6 +83,49 @@ int main(int argc, char** argv) {
     {
       pcl::Feature<PointRGB, pcl::SHOT352>::Ptr ex(new pcl::SHOTEstimationOMP<PointRGB, pcl::Normal, pcl::SHOT352>);
       run_descriptor<pcl::SHOT352>(kp_type, DESC_SHOT, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime, dump_dir);
+    }
+  }
+  {
+    // NARF keypoints + Narf36 (keypoints.h:199-231, evaluation.cpp:613-648).  Each cloud is described on ITS
+    // OWN range image (the reference builds the target descriptors on the source image, evaluation.cpp:630).
+    double t0 = now_s();
+    PointCloudRGB::Ptr skp(new PointCloudRGB), tkp(new PointCloudRGB);
+    Keypoints skd(KP_NARF, normal_r), tkd(KP_NARF, normal_r);
+    skd.compute(source, skp);
+    tkd.compute(target, tkp);
+    double kp_runtime = now_s() - t0;
+    if (!skp->points.empty() && !tkp->points.empty()) {
+      t0 = now_s();
+      pcl::PointCloud<pcl::Narf36>::Ptr sf(new pcl::PointCloud<pcl::Narf36>), tf(new pcl::PointCloud<pcl::Narf36>);
+      pcl::RangeImagePlanar sri, tri;
+      Tools::convertToRangeImage(source, sri);
+      Tools::convertToRangeImage(target, tri);
+      pcl::NarfDescriptor sd(&sri, &skd.getNarfPixelIndices()), td(&tri, &tkd.getNarfPixelIndices());
+      sd.getParameters().support_size = 0.2f;
+      sd.getParameters().rotation_invariant = true;
+      td.getParameters().support_size = 0.2f;
+      td.getParameters().rotation_invariant = true;
+      sd.compute(*sf);
+      td.compute(*tf);
+      double desc_runtime = now_s() - t0;
+      t0 = now_s();
+      // only descriptor[36] is the point representation (not the pose): match on packed copies
+      std::vector<float> a(sf->size() * 36), b(tf->size() * 36);
+      for (size_t i = 0; i < sf->size(); ++i) std::memcpy(&a[36 * i], sf->points[i].descriptor, 144);
+      for (size_t i = 0; i < tf->size(); ++i) std::memcpy(&b[36 * i], tf->points[i].descriptor, 144);
+      pcl::Correspondences corr(sf->size());
+      size_t nc = 0;
+      if (!sf->points.empty() && !tf->points.empty())
+        pcl::b200::ok(pfx_match(pcl::b200::ctx(), a.data(), sf->size(), 144, b.data(), tf->size(), 144, 36, 1, -1.f,
+                                reinterpret_cast<pfx_correspondence*>(corr.data()), corr.size(), &nc, PFX_HOST), "match");
+      corr.resize(nc);
+      double corr_runtime = now_s() - t0;
+      std::printf("%s, %s, %zu, %zu, %zu, %zu, %zu, %zu, %zu, %.6f, %.6f, %.6f\n", KP_NARF.c_str(), DESC_NARF.c_str(),
+                  source->size(), target->size(), skp->size(), tkp->size(), sf->size(), tf->size(), corr.size(), kp_runtime,
+                  desc_runtime, corr_runtime);
+      dump(dump_dir, "Narf_src_px.bin", skd.getNarfPixelIndices());
+      dump(dump_dir, "Narf_NARF_src.bin", sf->points);
+      dump(dump_dir, "Narf_NARF_corr.bin", corr);
     }
   }
   pfx_destroy(pcl::b200::ctx());

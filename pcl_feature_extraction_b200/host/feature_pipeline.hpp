@@ -19,6 +19,8 @@ typedef pcl::PointCloud<pcl::PointXYZI> PointCloudXYZI;
 
 static const std::string KP_HARRIS_3D = "Harris3D";
 static const std::string KP_ISS = "Iss";
+static const std::string KP_NARF = "Narf";
+static const std::string DESC_NARF = "NARF";
 static const std::string DESC_FPFH = "FPFH";
 static const std::string DESC_SHOT = "SHOT";
 
@@ -33,6 +35,18 @@ class Tools {
     pcl::search::KdTree<PointRGB>::Ptr tree(new pcl::search::KdTree<PointRGB>);
     ne.setSearchMethod(tree);
     ne.compute(*normals);
+  }
+
+  // tools.h:61-77
+  static void convertToRangeImage(const PointCloudRGB::Ptr& cloud, pcl::RangeImagePlanar& range_image) {
+    int image_size_x = 640, image_size_y = 480;
+    float center_x = (640.0f / 2.0f), center_y = (480.0f / 2.0f);
+    float focal_length_x = 525.0f;
+    float noise_level = 0.0f, minimum_range = 0.0f;
+    const int sensor_pose_identity = 0;  // translation(sensor_origin) * rotation(sensor_orientation) = identity here
+    range_image.createFromPointCloudWithFixedSize(*cloud, image_size_x, image_size_y, center_x, center_y, focal_length_x,
+                                                  focal_length_x, sensor_pose_identity, pcl::RangeImage::CAMERA_FRAME,
+                                                  noise_level, minimum_range);
   }
 };
 
@@ -72,6 +86,28 @@ class Keypoints {
       detector.compute(*cloud_keypoints);
       return;
     }
+    if (kp_type_ == KP_NARF) {
+      // keypoints.h:199-231.  The reference indexes the UNORGANISED cloud with range-image pixel indices
+      // (keypoints.h:228-229, out of bounds for 640 x 480 = 307 200 > cloud size); here a keypoint is the
+      // range-image point of its pixel, and the pixel indices are kept for the descriptor stage.
+      pcl::RangeImagePlanar range_image;
+      Tools::convertToRangeImage(cloud, range_image);
+      pcl::PointCloud<int> keypoints;
+      pcl::RangeImageBorderExtractor border_extractor;
+      pcl::NarfKeypoint detector(&border_extractor);
+      detector.setRangeImage(&range_image);
+      detector.getParameters().support_size = 0.2f;
+      detector.compute(keypoints);
+      cloud_keypoints.reset(new PointCloudRGB);
+      narf_pixel_indices_.assign(keypoints.points.begin(), keypoints.points.end());
+      for (int px : keypoints.points) {
+        const pcl::PointWithRange& p = range_image.getPoint(px);
+        PointRGB q;
+        q.x = p.x; q.y = p.y; q.z = p.z;
+        cloud_keypoints->push_back(q);
+      }
+      return;
+    }
     std::fprintf(stderr, "[Keypoints::compute] keypoint type %s is outside the B200 path\n", kp_type_.c_str());
   }
 
@@ -85,9 +121,14 @@ class Keypoints {
     return res;
   }
 
+  // range-image pixel indices of the last NARF detection (what NarfDescriptor needs; the reference recovers
+  // indices with the O(K N) Tools::getIndices, tools.h:91-102, which yields cloud indices instead)
+  const std::vector<int>& getNarfPixelIndices() const { return narf_pixel_indices_; }
+
  private:
   std::string kp_type_;
   double normal_radius_search_;
+  std::vector<int> narf_pixel_indices_;
 };
 
 template <typename FeatureType>

@@ -44,6 +44,9 @@ struct alignas(16) Normal {
 struct FPFHSignature33 { float histogram[33]; static int descriptorSize() { return 33; } };
 struct SHOT352 { float descriptor[352]; float rf[9]; static int descriptorSize() { return 352; } };
 struct ReferenceFrame { float x_axis[3], y_axis[3], z_axis[3]; };
+// pcl::Narf36: 168 bytes; the representation used for matching is the 36 descriptor floats only
+struct Narf36 { float x, y, z, roll, pitch, yaw; float descriptor[36]; static int descriptorSize() { return 36; } };
+struct alignas(16) PointWithRange { float x = 0, y = 0, z = 0, pad_ = 1.0f; float range = 0; float pad2_[3] = {0, 0, 0}; };
 struct Correspondence {
   int index_query = 0, index_match = -1;
   float distance = std::numeric_limits<float>::max();
@@ -52,6 +55,7 @@ static_assert(sizeof(PointXYZ) == 16 && sizeof(PointXYZRGB) == 32 && sizeof(Poin
 static_assert(sizeof(Normal) == 32 && sizeof(FPFHSignature33) == 132 && sizeof(SHOT352) == 1444, "PCL layout");
 static_assert(sizeof(ReferenceFrame) == 36 && sizeof(Correspondence) == 12, "PCL layout");
 static_assert(sizeof(Correspondence) == sizeof(pfx_correspondence), "ABI layout");
+static_assert(sizeof(Narf36) == 168 && sizeof(PointWithRange) == 32, "PCL layout");
 
 typedef std::vector<Correspondence> Correspondences;
 typedef std::shared_ptr<Correspondences> CorrespondencesPtr;
@@ -481,6 +485,203 @@ class HarrisKeypoint3D : public Keypoint<PointInT, PointOutT> {
   bool nonmax_ = true, refine_ = true;
   typename PointCloud<NormalT>::ConstPtr normals_;
   std::vector<int> snapped_;
+};
+
+// ------------------------------------------------------------------------------- filters
+// pcl::VoxelGrid (config C1 ingest): setInputCloud / setLeafSize / filter.  Centroids of xyz in ascending
+// voxel-index order; colour is not carried (downsample_all_data for rgb is outside the path).
+template <typename PointT>
+class VoxelGrid {
+ public:
+  void setInputCloud(const typename PointCloud<PointT>::ConstPtr& c) { input_ = c; }
+  void setLeafSize(float lx, float ly, float lz) { leaf_ = lx; uniform_ = (lx == ly && ly == lz); }
+  void filter(PointCloud<PointT>& output) {
+    output.points.clear();
+    output.width = output.height = 0;
+    pfx_ctx* c = b200::ctx();
+    if (!c || !input_) return;
+    if (!uniform_) {
+      std::fprintf(stderr, "[pcl::VoxelGrid] only cubic leaves are implemented\n");
+      return;
+    }
+    if (!b200::ok(pfx_set_surface(c, input_->points.data(), input_->size(), sizeof(PointT), PFX_HOST), "VoxelGrid")) return;
+    std::vector<float> xyz(3 * std::max<size_t>(input_->size(), 1));
+    size_t n = 0;
+    int rc = pfx_voxel_grid(c, leaf_, xyz.data(), input_->size(), &n, PFX_HOST);
+    if (rc == PFX_E_PRECOND) {  // PCL: warns and returns the input unchanged when the index would overflow
+      std::fprintf(stderr, "[pcl::VoxelGrid::applyFilter] Leaf size is too small for the input dataset. Integer indices would overflow.\n");
+      output = *input_;
+      return;
+    }
+    if (!b200::ok(rc, "VoxelGrid")) return;
+    output.points.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      output.points[i].x = xyz[3 * i];
+      output.points[i].y = xyz[3 * i + 1];
+      output.points[i].z = xyz[3 * i + 2];
+    }
+    output.width = (uint32_t)n;
+    output.height = 1;
+    output.is_dense = true;
+    output.sensor_origin_ = input_->sensor_origin_;
+  }
+
+ private:
+  typename PointCloud<PointT>::ConstPtr input_;
+  float leaf_ = 0.01f;
+  bool uniform_ = true;
+};
+
+// ------------------------------------------------------------------------------- range image / NARF
+// The subset of pcl::RangeImage(Planar), RangeImageBorderExtractor, NarfKeypoint and NarfDescriptor that
+// the reference drives (keypoints.h:204-224, tools.h:65-76, evaluation.cpp:629-637).  The image itself
+// lives in the library's context; these objects hold its geometry and re-install it before use, so several
+// RangeImage objects may coexist like in the reference.
+class RangeImage {
+ public:
+  enum CoordinateFrame { CAMERA_FRAME = 0, LASER_FRAME = 1 };
+  virtual ~RangeImage() {}
+  uint32_t width = 0, height = 0;
+  std::vector<PointWithRange> points;
+  // RangeImage::createFromPointCloud (config C3): spherical projection, cropped.  sensor pose: identity.
+  template <typename CloudT>
+  void createFromPointCloud(const CloudT& cloud, float angular_resolution, float max_angle_width, float max_angle_height,
+                            const std::array<float, 16>* /*sensor_pose: identity*/ = nullptr,
+                            CoordinateFrame frame = CAMERA_FRAME, float noise_level = 0.0f, float min_range = 0.0f,
+                            int border_size = 0) {
+    pfx_ctx* c = b200::ctx();
+    valid_ = false;
+    if (!c || frame != CAMERA_FRAME || noise_level != 0.0f) {
+      std::fprintf(stderr, "[pcl::RangeImage] only CAMERA_FRAME with noise_level 0 is implemented\n");
+      return;
+    }
+    if (!b200::ok(pfx_set_surface(c, cloud.points.data(), cloud.size(), sizeof(cloud.points[0]), PFX_HOST), "RangeImage")) return;
+    if (!b200::ok(pfx_range_image_spherical(c, angular_resolution, max_angle_width, max_angle_height, min_range, border_size, &desc_), "RangeImage")) return;
+    fetch(c);
+  }
+  bool isValid(int index) const { return index >= 0 && (size_t)index < points.size() && std::isfinite(points[index].range); }
+  const PointWithRange& getPoint(int index) const { return points[index]; }
+  // make this image the current one of the context (no-op cost when it already is)
+  bool install() const {
+    pfx_ctx* c = b200::ctx();
+    if (!c || !valid_) return false;
+    return b200::ok(pfx_range_image_set(c, &desc_, raw_.data(), PFX_HOST), "RangeImage");
+  }
+  const pfx_range_image_desc& desc() const { return desc_; }
+
+ protected:
+  void fetch(pfx_ctx* c) {
+    raw_.assign((size_t)4 * desc_.width * desc_.height, 0.f);
+    if (!b200::ok(pfx_range_image_get(c, &desc_, raw_.data(), PFX_HOST), "RangeImage")) return;
+    width = (uint32_t)desc_.width;
+    height = (uint32_t)desc_.height;
+    points.resize((size_t)width * height);
+    for (size_t i = 0; i < points.size(); ++i) {
+      points[i].x = raw_[4 * i]; points[i].y = raw_[4 * i + 1]; points[i].z = raw_[4 * i + 2]; points[i].range = raw_[4 * i + 3];
+    }
+    valid_ = true;
+  }
+  pfx_range_image_desc desc_ = {};
+  std::vector<float> raw_;
+  bool valid_ = false;
+};
+
+class RangeImagePlanar : public RangeImage {
+ public:
+  // keypoints.h:212-216, tools.h:72-76
+  template <typename CloudT, typename PoseT>
+  void createFromPointCloudWithFixedSize(const CloudT& cloud, int di_width, int di_height, float di_center_x,
+                                         float di_center_y, float di_focal_length_x, float di_focal_length_y,
+                                         const PoseT& /*sensor_pose: identity for the bundled clouds*/,
+                                         CoordinateFrame frame = CAMERA_FRAME, float noise_level = 0.0f,
+                                         float min_range = 0.0f) {
+    pfx_ctx* c = b200::ctx();
+    valid_ = false;
+    if (!c || frame != CAMERA_FRAME || noise_level != 0.0f) {
+      std::fprintf(stderr, "[pcl::RangeImagePlanar] only CAMERA_FRAME with noise_level 0 is implemented\n");
+      return;
+    }
+    if (!b200::ok(pfx_set_surface(c, cloud.points.data(), cloud.size(), sizeof(cloud.points[0]), PFX_HOST), "RangeImagePlanar")) return;
+    if (!b200::ok(pfx_range_image_planar(c, di_width, di_height, di_center_x, di_center_y, di_focal_length_x, di_focal_length_y, min_range, &desc_), "RangeImagePlanar")) return;
+    fetch(c);
+  }
+};
+
+class RangeImageBorderExtractor {
+ public:
+  explicit RangeImageBorderExtractor(const RangeImage* range_image = nullptr) : range_image_(range_image) {}
+  void setRangeImage(const RangeImage* range_image) { range_image_ = range_image; }
+  const RangeImage* getRangeImagePtr() const { return range_image_; }
+
+ private:
+  const RangeImage* range_image_;
+};
+
+class NarfKeypoint {
+ public:
+  struct Parameters { float support_size = -1.0f; };
+  explicit NarfKeypoint(RangeImageBorderExtractor* border_extractor = nullptr, float support_size = -1.0f)
+      : border_extractor_(border_extractor) { parameters_.support_size = support_size; }
+  void setRangeImageBorderExtractor(RangeImageBorderExtractor* b) { border_extractor_ = b; }
+  void setRangeImage(const RangeImage* range_image) { if (border_extractor_) border_extractor_->setRangeImage(range_image); }
+  Parameters& getParameters() { return parameters_; }
+  // output: range-image pixel indices (y * width + x), ascending
+  void compute(PointCloud<int>& output) {
+    output.points.clear();
+    output.width = output.height = 0;
+    pfx_ctx* c = b200::ctx();
+    const RangeImage* ri = border_extractor_ ? border_extractor_->getRangeImagePtr() : nullptr;
+    if (!c || !ri) {
+      std::fprintf(stderr, "[pcl::NarfKeypoint::detectKeypoints] RangeImageBorderExtractor member is NULL or has no range image\n");
+      return;
+    }
+    if (!ri->install()) return;
+    std::vector<int32_t> kp((size_t)ri->width * ri->height + 1);
+    size_t n = 0;
+    if (!b200::ok(pfx_narf_keypoints(c, parameters_.support_size, kp.data(), nullptr, nullptr, kp.size(), &n, nullptr, PFX_HOST), "NarfKeypoint")) return;
+    output.points.assign(kp.begin(), kp.begin() + n);
+    output.width = (uint32_t)n;
+    output.height = 1;
+  }
+
+ private:
+  RangeImageBorderExtractor* border_extractor_;
+  Parameters parameters_;
+};
+
+class NarfDescriptor {
+ public:
+  struct Parameters { float support_size = -1.0f; bool rotation_invariant = true; };
+  explicit NarfDescriptor(const RangeImage* range_image = nullptr, const std::vector<int>* indices = nullptr)
+      : range_image_(range_image), indices_(indices) {}
+  void setRangeImage(const RangeImage* range_image, const std::vector<int>* indices = nullptr) { range_image_ = range_image; indices_ = indices; }
+  Parameters& getParameters() { return parameters_; }
+  void compute(PointCloud<Narf36>& output) {
+    output.points.clear();
+    output.width = output.height = 0;
+    pfx_ctx* c = b200::ctx();
+    if (!c || !range_image_) {
+      std::fprintf(stderr, "[pcl::NarfDescriptor::computeFeature] no range image given\n");
+      return;
+    }
+    if (parameters_.support_size <= 0.0f) {
+      std::fprintf(stderr, "[pcl::NarfDescriptor::computeFeature] support size is not set!\n");
+      return;
+    }
+    if (!indices_ || indices_->empty() || !range_image_->install()) return;
+    output.points.resize(indices_->size() * 8);
+    size_t n = 0;
+    if (!b200::ok(pfx_narf36(c, indices_->data(), indices_->size(), parameters_.support_size, parameters_.rotation_invariant ? 1 : 0,
+                             output.points.data(), sizeof(Narf36), output.points.size(), &n, PFX_HOST), "NarfDescriptor")) n = 0;
+    output.points.resize(n);
+    output.width = (uint32_t)n;
+    output.height = 1;
+  }
+
+ private:
+  const RangeImage* range_image_;
+  const std::vector<int>* indices_;
+  Parameters parameters_;
 };
 
 // ------------------------------------------------------------------------------- registration

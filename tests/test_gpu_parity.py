@@ -577,3 +577,58 @@ def test_golden_kat(ctx):
     assert np.abs(s[ok] - z["shot"][ok]).max() <= 1e-4
     c = ctx.match(z["match_a"], z["match_b"])
     assert np.array_equal(c["index_query"], z["match_q"]) and np.array_equal(c["index_match"], z["match_m"])
+
+
+# ------------------------------------------------------------------------------------ ingest (config C1)
+@pytest.mark.parametrize("name,leaf,expect", [("indoor_source", 0.01, 41884), ("indoor_target", 0.01, 33116),
+                                              ("underwater_source", 0.02, None)])
+def test_voxel_grid_bit_exact(ctx, orc, clouds, name, leaf, expect):
+    """pcl::VoxelGrid centroids: same voxels in the same (ascending id) order, float sums bit-identical"""
+    pts = clouds[name]
+    ctx.set_surface(pts)
+    g = ctx.voxel_grid(leaf)
+    o = orc.voxel_grid(pts, leaf)
+    if expect is not None:
+        assert len(o) == expect  # SURVEY.md §6
+    assert g.shape == o.shape
+    assert np.array_equal(g.view(np.uint32), o.view(np.uint32))
+
+
+def test_voxel_grid_edge_cases(ctx, orc):
+    pts = np.array([[0, 0, 0], [0.001, 0.002, 0.003], [np.nan, 0, 0], [5, 5, 5], [-3.2, 0.4, 9.9]], np.float32)
+    ctx.set_surface(pts)
+    g = ctx.voxel_grid(0.5)
+    o = orc.voxel_grid(pts, 0.5)
+    assert np.array_equal(g, o) and len(g) == 3
+    ctx.set_surface(np.zeros((0, 3), np.float32))
+    assert len(ctx.voxel_grid(0.5)) == 0
+    ctx.set_surface(np.array([[0, 0, 0], [1000, 1000, 1000]], np.float32))
+    with pytest.raises(RuntimeError):  # PCL: "leaf size is too small ... integer indices would overflow"
+        ctx.voxel_grid(1e-4)
+
+
+def test_config_c1_pipeline(ctx, orc, clouds):
+    """BASELINE config C1 on the GPU, stage by stage against the oracle fed the same inputs:
+    VoxelGrid 1 cm -> normals r = 3 cm -> ISS -> FPFH33 r = 5 cm at the keypoints -> reciprocal matching"""
+    feats = []
+    for name in ("indoor_source", "indoor_target"):
+        ctx.set_surface(clouds[name])
+        xyz = ctx.voxel_grid(0.01)
+        assert np.array_equal(xyz, orc.voxel_grid(clouds[name], 0.01))
+        ctx.set_surface(xyz)
+        ctx.set_viewpoint(0, 0, 0)
+        nr = ctx.normals(radius=0.03)
+        res = ctx.cloud_resolution()
+        kp, _ = ctx.iss(6 * res, 4 * res)
+        okp, _ = orc.iss(xyz, 6 * res, 4 * res)
+        assert np.array_equal(kp, okp) and 600 < len(kp) < 1000
+        ctx.set_queries(xyz[kp])
+        f = ctx.fpfh(radius=0.05)
+        of = orc.fpfh(xyz, nr, q=xyz[okp], radius=0.05)
+        assert (np.abs(f - of).max(1) <= 1e-2).mean() > 0.97
+        ctx.set_queries(None)
+        feats.append(f)
+    c = ctx.match(feats[0], feats[1], reciprocal=True)
+    q, m, dist = orc.match_reciprocal(feats[0], feats[1])
+    assert np.array_equal(c["index_query"], q) and np.array_equal(c["index_match"], m)
+    assert len(c) > 50

@@ -29,7 +29,19 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     rows = [l.split(", ") for l in r.stdout.strip().splitlines()[1:]]
-    assert [(x[0], x[1]) for x in rows] == [("Harris3D", "FPFH"), ("Harris3D", "SHOT"), ("Iss", "FPFH"), ("Iss", "SHOT")]
+    assert [(x[0], x[1]) for x in rows][:4] == [("Harris3D", "FPFH"), ("Harris3D", "SHOT"), ("Iss", "FPFH"), ("Iss", "SHOT")]
+    # NARF row (present when both clouds yield keypoints): the shim's RangeImagePlanar / NarfKeypoint /
+    # NarfDescriptor objects against the C ABI called from Python on the same cloud
+    ctx.set_surface(src)
+    ctx.range_image_planar(640, 480, 320.0, 240.0, 525.0, 525.0)
+    kp_px, kp_xyz_abi, _, _ = ctx.narf_keypoints(0.2)
+    if len(rows) > 4:
+        assert (rows[4][0], rows[4][1]) == ("Narf", "NARF")
+        px = np.fromfile(tmp_path / "Narf_src_px.bin", dtype=np.int32)
+        assert np.array_equal(px, kp_px)
+        f36 = np.fromfile(tmp_path / "Narf_NARF_src.bin", dtype=np.float32).reshape(-1, 42)
+        assert np.array_equal(f36, ctx.narf36(kp_px, 0.2, True))
+        assert int(rows[4][6]) == len(f36)
 
     def kp_xyz(name):
         a = np.fromfile(tmp_path / name, dtype=np.float32).reshape(-1, 8)
