@@ -1,0 +1,168 @@
+"""Multi-GPU partitioning of the feature-extraction path: one process per GPU (torch.distributed), no
+collective on the data path except the one-off halo exchange.
+
+The reference has nothing distributed; every stage of the path is per-point with a bounded
+spatial support, so it shards two ways:
+
+* cloud-level  - independent clouds are dealt round-robin to the ranks (`assign_clouds`); no communication.
+  This is what `bench.py --gpus N` measures (config C5's 64-cloud batch).
+* slab-level   - ONE cloud is cut into `world` slabs along its longest axis at equal-count quantiles
+  (`slab_cuts`).  A rank owns the points of its slab and receives, once, the points of its two neighbours
+  that lie within `halo` of the cut (`exchange_halo`: pairwise isend / irecv, NCCL on GPUs, gloo on CPUs).
+  Every stage then runs unchanged on (owned + halo) points and only the owned rows are kept: with
+  halo >= the support of the stage chain, each owned point sees exactly the neighbourhood it sees on one GPU.
+  Support of a chain = sum of its radii: normals r_n; SPFH needs normals of points within r_f -> r_f + r_n;
+  FPFH needs SPFH rows of points within r_f -> 2 r_f + r_n; SHOT (frame + descriptor at r_s on normals) ->
+  r_s + r_n.  For k-searches the radius is data dependent: `knn_support_radius` takes the largest k-th
+  neighbour distance over all ranks (all-reduce MAX).
+
+Host-side logic only (numpy + torch.distributed): the CUDA library is called by the caller on the returned
+arrays, so this module is exercised on CPU with the gloo backend in tests/test_sharding_gloo.py.
+"""
+import numpy as np
+
+try:  # torch is plumbing here (process groups); the pure partitioning functions work without it
+    import torch
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    torch = None
+    dist = None
+
+
+def assign_clouds(n_clouds, world, rank):
+    """cloud ids of `rank` (round-robin), e.g. 64 clouds on 8 ranks -> 8 each"""
+    return list(range(rank, n_clouds, world))
+
+
+def longest_axis(lo, hi):
+    return int(np.argmax(np.asarray(hi, np.float64) - np.asarray(lo, np.float64)))
+
+
+def slab_cuts(coord, world):
+    """world-1 cut positions at equal-count quantiles of the 1-D coordinates (finite values only)"""
+    c = np.sort(coord[np.isfinite(coord)].astype(np.float64))
+    if world <= 1 or len(c) == 0:
+        return np.zeros(0, np.float64)
+    idx = (np.arange(1, world) * len(c)) // world
+    return c[np.minimum(idx, len(c) - 1)]
+
+
+def slab_of(coord, cuts):
+    """slab index of every coordinate: slab r = [cuts[r-1], cuts[r]) (non-finite points go to slab 0)"""
+    s = np.searchsorted(cuts, coord, side="right").astype(np.int32)
+    s[~np.isfinite(coord)] = 0
+    return s
+
+
+def chain_support(normal_radius=0.0, feature_radius=0.0, descriptor="fpfh"):
+    """halo width that makes a sharded run see the single-GPU neighbourhoods (see the module docstring)"""
+    if descriptor == "normals":
+        return normal_radius
+    if descriptor == "fpfh":
+        return 2.0 * feature_radius + normal_radius
+    if descriptor == "shot":
+        return feature_radius + normal_radius
+    if descriptor == "fpfh+shot":
+        return max(2.0 * feature_radius + normal_radius, feature_radius + normal_radius)
+    raise ValueError(descriptor)
+
+
+def halo_masks(coord, cuts, rank, halo):
+    """(to_left, to_right): which of THIS rank's owned points its left / right neighbour needs"""
+    world = len(cuts) + 1
+    to_left = np.zeros(len(coord), bool)
+    to_right = np.zeros(len(coord), bool)
+    if rank > 0:
+        to_left = coord < cuts[rank - 1] + halo
+    if rank < world - 1:
+        to_right = coord >= cuts[rank] - halo
+    return to_left, to_right
+
+
+def exchange_halo(owned, axis, cuts, rank, world, halo, device=None, group=None):
+    """One-off halo exchange with the two neighbouring slabs.
+
+    owned: [n, C] float32 rows of this rank (xyz first).  Returns (local, n_owned): local = owned rows followed
+    by the halo rows received from the left and right neighbours.  Works on any backend: sizes travel first,
+    then the payload, as pairwise isend / irecv (NCCL P2P over NVLink when the tensors are on GPUs)."""
+    owned = np.ascontiguousarray(owned, np.float32)
+    if world == 1:
+        return owned, len(owned)
+    to_left, to_right = halo_masks(owned[:, axis].astype(np.float64), cuts, rank, halo)
+    dev = device if device is not None else torch.device("cpu")
+    send = {rank - 1: owned[to_left], rank + 1: owned[to_right]}
+    peers = [p for p in (rank - 1, rank + 1) if 0 <= p < world]
+    width = owned.shape[1]
+    # sizes
+    size_out = {p: torch.tensor([len(send[p])], dtype=torch.int64, device=dev) for p in peers}
+    size_in = {p: torch.zeros(1, dtype=torch.int64, device=dev) for p in peers}
+    ops = []
+    for p in peers:
+        ops.append(dist.P2POp(dist.isend, size_out[p], p, group))
+        ops.append(dist.P2POp(dist.irecv, size_in[p], p, group))
+    for r in dist.batch_isend_irecv(ops):
+        r.wait()
+    # payload
+    bufs_out = {p: torch.from_numpy(np.ascontiguousarray(send[p])).to(dev) for p in peers}
+    bufs_in = {p: torch.empty((int(size_in[p].item()), width), dtype=torch.float32, device=dev) for p in peers}
+    ops = []
+    for p in peers:
+        if bufs_out[p].numel():
+            ops.append(dist.P2POp(dist.isend, bufs_out[p], p, group))
+        if bufs_in[p].numel():
+            ops.append(dist.P2POp(dist.irecv, bufs_in[p], p, group))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    parts = [owned] + [bufs_in[p].cpu().numpy() for p in peers]
+    return np.concatenate(parts, 0), len(owned)
+
+
+def knn_support_radius(kth_dist_local_max, chain_len, device=None, group=None):
+    """support of a chain of `chain_len` k-searches: chain_len x the largest k-th neighbour distance over all
+    ranks (all-reduce MAX of one float)"""
+    t = torch.tensor([float(kth_dist_local_max)], dtype=torch.float64, device=device or torch.device("cpu"))
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return chain_len * float(t.item())
+
+
+def max_over_ranks(seconds, device=None, group=None):
+    """the time every multi-GPU number is quoted with: MAX over ranks of a device-measured duration"""
+    t = torch.tensor([float(seconds)], dtype=torch.float64, device=device or torch.device("cpu"))
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
+
+
+def gather_rows(rows, n_total, owner_index, rank, world, device=None, group=None):
+    """collect the owned rows of every rank on rank 0 into an [n_total, C] array in the ORIGINAL point order.
+    rows: [n_owned, C] float32; owner_index: [n_owned] original indices.  (verification / output assembly; the
+    sharded compute itself never needs it)"""
+    rows = np.ascontiguousarray(rows, np.float32)
+    owner_index = np.ascontiguousarray(owner_index, np.int64)
+    if world == 1:
+        out = np.zeros((n_total, rows.shape[1]), np.float32)
+        out[owner_index] = rows
+        return out
+    dev = device or torch.device("cpu")
+    n_local = torch.tensor([len(rows)], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, n_local, group=group)
+    m = int(max(int(s.item()) for s in sizes))
+    pad_rows = torch.zeros((m, rows.shape[1]), dtype=torch.float32, device=dev)
+    pad_idx = torch.full((m,), -1, dtype=torch.int64, device=dev)
+    pad_rows[: len(rows)] = torch.from_numpy(rows).to(dev)
+    pad_idx[: len(rows)] = torch.from_numpy(owner_index).to(dev)
+    all_rows = [torch.empty_like(pad_rows) for _ in range(world)]
+    all_idx = [torch.empty_like(pad_idx) for _ in range(world)]
+    dist.all_gather(all_rows, pad_rows, group=group)
+    dist.all_gather(all_idx, pad_idx, group=group)
+    if rank != 0:
+        return None
+    out = np.zeros((n_total, rows.shape[1]), np.float32)
+    for r, i in zip(all_rows, all_idx):
+        i = i.cpu().numpy()
+        keep = i >= 0
+        out[i[keep]] = r.cpu().numpy()[keep]
+    return out

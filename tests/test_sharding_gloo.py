@@ -1,0 +1,104 @@
+"""Host-side logic of the multi-GPU path (pcl_feature_extraction_b200/sharding.py) on CPU: two processes, gloo
+backend.  Each rank owns one slab of a cloud, exchanges halos with its neighbour, runs the CPU ORACLE on
+(owned + halo) and keeps its owned rows; gathered on rank 0 they must equal the single-process result bit for
+bit - the halo makes every owned point's neighbourhood identical.  (On GPUs the same partitioning feeds the
+CUDA library; that path is exercised by tools/slab_bench.py under torchrun.)"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from pcl_feature_extraction_b200 import sharding  # noqa: E402
+
+
+def test_assign_clouds_and_cuts():
+    assert sharding.assign_clouds(64, 8, 3) == [3, 11, 19, 27, 35, 43, 51, 59]
+    assert sum(len(sharding.assign_clouds(10, 4, r)) for r in range(4)) == 10
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=10001)
+    cuts = sharding.slab_cuts(x, 4)
+    s = sharding.slab_of(x, cuts)
+    counts = np.bincount(s, minlength=4)
+    assert len(cuts) == 3 and counts.min() >= 2499 and counts.max() <= 2502
+    x[5] = np.nan
+    assert sharding.slab_of(x, cuts)[5] == 0
+    assert sharding.chain_support(0.03, 0.05, "fpfh") == pytest.approx(0.13)
+    assert sharding.chain_support(0.03, 0.05, "shot") == pytest.approx(0.08)
+    tl, tr = sharding.halo_masks(np.array([0.0, 0.5, 0.9]), np.array([1.0]), 0, 0.15)  # rank 0 owns x < 1.0
+    assert not tl.any() and tr.tolist() == [False, False, True]                         # 0.9 is within the halo
+    tl, tr = sharding.halo_masks(np.array([1.0, 1.1, 2.0]), np.array([1.0]), 1, 0.15)
+    assert tl.tolist() == [True, True, False] and not tr.any()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, cloud_path, out_path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import binding as orc
+        orc.set_num_threads(2)
+        pts = np.load(cloud_path)
+        n = len(pts)
+        r_n, r_f = 0.03, 0.05
+        lo, hi = pts.min(0), pts.max(0)
+        axis = sharding.longest_axis(lo, hi)
+        cuts = sharding.slab_cuts(pts[:, axis], world)
+        slab = sharding.slab_of(pts[:, axis], cuts)
+        mine = np.where(slab == rank)[0]
+        # rows carry (x, y, z, original index) so that results can be put back in order
+        owned = np.concatenate([pts[mine], mine[:, None].astype(np.float32)], 1).astype(np.float32)
+        halo = sharding.chain_support(r_n, r_f, "fpfh+shot")
+        local, n_owned = sharding.exchange_halo(owned, axis, cuts, rank, world, halo)
+        xyz = np.ascontiguousarray(local[:, :3])
+        # every point within `halo` of an owned point must be present locally
+        d_cut = np.minimum(np.abs(pts[:, axis] - cuts[0]), np.inf)
+        need = (slab == rank) | (d_cut <= halo * 0.999)
+        have = np.zeros(n, bool)
+        have[local[:, 3].astype(np.int64)] = True
+        assert have[need].all()
+        # the path on (owned + halo): normals everywhere, FPFH + SHOT for the owned points only
+        nr, _, _ = orc.normals(xyz, radius=r_n)
+        f = orc.fpfh(xyz, nr, q=xyz[:n_owned], radius=r_f)
+        s, rf = orc.shot352(xyz, nr, xyz[:n_owned], r_f)
+        rows = np.concatenate([nr[:n_owned], f, s, rf], 1).astype(np.float32)
+        full = sharding.gather_rows(rows, n, mine, rank, world)
+        t = sharding.max_over_ranks(1.0 + rank)
+        assert t == 2.0
+        assert sharding.knn_support_radius(0.01 * (rank + 1), 3) == pytest.approx(0.06)
+        if rank == 0:
+            np.save(out_path, full)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_sharded_equals_single_process(tmp_path, orc, clouds):
+    import torch.multiprocessing as mp
+    pts = np.ascontiguousarray(clouds["underwater_source"][:6000])
+    cloud_path, out_path = str(tmp_path / "cloud.npy"), str(tmp_path / "out.npy")
+    np.save(cloud_path, pts)
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), cloud_path, out_path), nprocs=world, join=True)
+    got = np.load(out_path)
+    r_n, r_f = 0.03, 0.05
+    nr, _, _ = orc.normals(pts, radius=r_n)
+    f = orc.fpfh(pts, nr, radius=r_f)
+    s, rf = orc.shot352(pts, nr, None, r_f)
+    want = np.concatenate([nr, f, s, rf], 1).astype(np.float32)
+    assert got.shape == want.shape
+    # identical neighbourhoods, identical arithmetic: bit for bit (NaN rows included)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
