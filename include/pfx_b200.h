@@ -35,7 +35,11 @@ extern "C" {
 
 typedef struct pfx_ctx pfx_ctx;
 
-enum { PFX_HOST = 0, PFX_DEVICE = 1 };
+/* PFX_HOST_ASYNC (accepted for the OUTPUT of pfx_fpfh and pfx_shot352): like PFX_HOST, but the device-to-host
+ * copy is enqueued on the context's copy stream behind the producing kernels and the call returns at once;
+ * the rows are valid after pfx_sync().  Lets the PCIe transfer of one result overlap the compute of the next
+ * call / the next cloud (the buffer should be page-locked, otherwise the copy is staged by the driver). */
+enum { PFX_HOST = 0, PFX_DEVICE = 1, PFX_HOST_ASYNC = 2 };
 enum {
   PFX_OK = 0,
   PFX_E_INVALID = -1,  /* bad argument */

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpfx_b200.so")
 
-HOST, DEVICE = 0, 1
+HOST, DEVICE, HOST_ASYNC = 0, 1, 2
 E_INVALID, E_PRECOND, E_CAPACITY, E_STATE = -1, -2, -3, -4
 
 _lib = None

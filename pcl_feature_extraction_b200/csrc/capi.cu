@@ -98,6 +98,37 @@ static int deliver(Ctx* ctx, void* dst, const void* dev_src, size_t bytes, int m
   return 0;
 }
 
+// ---- PFX_HOST_ASYNC plumbing
+static int async_init(Ctx* ctx) {
+  if (ctx->copy_stream) return 0;
+  PFX_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int s = 0; s < 2; ++s) {
+    PFX_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[s], cudaEventDisableTiming));
+    PFX_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[s], cudaEventDisableTiming));
+  }
+  return 0;
+}
+// staging buffer of slot s, safe to overwrite: the compute stream first waits for the slot's previous copy
+static int async_stage_acquire(Ctx* ctx, int s, size_t bytes, void** out) {
+  PFX_TRY(async_init(ctx));
+  if (ctx->copy_pending[s]) {
+    if (bytes > ctx->async_stage[s].cap) PFX_CUDA(cudaEventSynchronize(ctx->ev_copied[s]));  // about to be reallocated
+    PFX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[s], 0));
+  }
+  PFX_CUDA(ctx->async_stage[s].ensure(std::max<size_t>(bytes, 16)));
+  *out = ctx->async_stage[s].p;
+  return 0;
+}
+// enqueue the device-to-host copy of slot s behind everything issued so far on the compute stream
+static int async_deliver(Ctx* ctx, int s, void* dst, size_t bytes) {
+  PFX_CUDA(cudaEventRecord(ctx->ev_ready[s], ctx->stream));
+  PFX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready[s], 0));
+  if (bytes) PFX_CUDA(cudaMemcpyAsync(dst, ctx->async_stage[s].p, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  PFX_CUDA(cudaEventRecord(ctx->ev_copied[s], ctx->copy_stream));
+  ctx->copy_pending[s] = true;
+  return 0;
+}
+
 static int check_ctx(pfx_ctx* ctx) {
   if (!ctx) return PFX_E_INVALID;
   cudaError_t e = cudaSetDevice(ctx->device);
@@ -143,6 +174,15 @@ extern "C" int pfx_destroy(pfx_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    for (int s = 0; s < 2; ++s) {
+      cudaEventDestroy(ctx->ev_ready[s]);
+      cudaEventDestroy(ctx->ev_copied[s]);
+      ctx->async_stage[s].release();
+    }
+  }
   grid_free_all(ctx);
   match_tc_release(ctx);
   for (DevBuf* b : {&ctx->surf, &ctx->normals, &ctx->normals_sorted, &ctx->qry, &ctx->knn_idx, &ctx->knn_d2,
@@ -167,6 +207,10 @@ extern "C" int pfx_set_stream(pfx_ctx* ctx, void* s) {
 extern "C" int pfx_sync(pfx_ctx* ctx) {
   PFX_TRY(check_ctx(ctx));
   PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->copy_stream) {
+    PFX_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->copy_pending[0] = ctx->copy_pending[1] = false;
+  }
   return 0;
 }
 
@@ -608,12 +652,18 @@ extern "C" int pfx_fpfh(pfx_ctx* ctx, double radius, int k, float* out, size_t s
   Grid* g = nullptr;
   PFX_TRY(grid_get(ctx, radius > 0 ? radius : 0.0, k, &g));
   float* dout = out;
-  if (mem == PFX_HOST) {
+  if (mem == PFX_HOST_ASYNC) {
+    void* st = nullptr;
+    PFX_TRY(async_stage_acquire(ctx, 0, nq * stride, &st));
+    dout = static_cast<float*>(st);
+    if (stride != 132) PFX_CUDA(cudaMemsetAsync(dout, 0, nq * stride, ctx->stream));
+  } else if (mem == PFX_HOST) {
     PFX_CUDA(ctx->out_stage.ensure(std::max<size_t>(nq * stride, 16)));
     dout = ctx->out_stage.as<float>();
     if (stride != 132) PFX_CUDA(cudaMemsetAsync(dout, 0, nq * stride, ctx->stream));
   }
   PFX_TRY(fpfh_compute(ctx, g, radius, k, dout, stride / 4, nullptr));
+  if (mem == PFX_HOST_ASYNC) return async_deliver(ctx, 0, out, nq * stride);
   if (mem == PFX_HOST) return deliver(ctx, out, dout, nq * stride, mem);
   return 0;
 }
@@ -673,7 +723,13 @@ extern "C" int pfx_shot352(pfx_ctx* ctx, double radius, const float* lrf_in, flo
   Grid* g = nullptr;
   PFX_TRY(grid_get(ctx, radius, 0, &g));
   float* dout = out;
-  if (mem == PFX_HOST) {
+  if (mem == PFX_HOST_ASYNC) {
+    if (lrf_in) return ctx->fail(PFX_E_INVALID, "pfx_shot352: PFX_HOST_ASYNC output with caller-supplied frames is not supported");
+    void* st = nullptr;
+    PFX_TRY(async_stage_acquire(ctx, 1, nq * stride, &st));
+    dout = static_cast<float*>(st);
+    if (stride != 1444) PFX_CUDA(cudaMemsetAsync(dout, 0, nq * stride, ctx->stream));
+  } else if (mem == PFX_HOST) {
     PFX_CUDA(ctx->out_stage.ensure(nq * stride));
     dout = ctx->out_stage.as<float>();
     if (stride != 1444) PFX_CUDA(cudaMemsetAsync(dout, 0, nq * stride, ctx->stream));
@@ -687,6 +743,7 @@ extern "C" int pfx_shot352(pfx_ctx* ctx, double radius, const float* lrf_in, flo
   } else {  // frames estimated at the same radius: one fused kernel
     PFX_TRY(shot_fused_compute(ctx, g, radius, dout, stride / 4));
   }
+  if (mem == PFX_HOST_ASYNC) return async_deliver(ctx, 1, out, nq * stride);
   if (mem == PFX_HOST) return deliver(ctx, out, dout, nq * stride, mem);
   return 0;
 }

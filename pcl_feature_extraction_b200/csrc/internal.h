@@ -118,6 +118,13 @@ struct Ctx {
   DevBuf qflag, worklist;  // worklist: [0] = count, [16..] = sorted positions of the flagged queries
   bool tile_has_normals = false;
 
+  // asynchronous result delivery (PFX_HOST_ASYNC): a copy stream and one staging slot per descriptor type;
+  // ev_ready[s] = slot s has been produced (compute stream), ev_copied[s] = slot s has been copied out
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  bool copy_pending[2] = {false, false};
+  DevBuf async_stage[2];
+
   // scratch
   DevBuf stage, stage2, tmp0, tmp1, tmp2, tmp3, tmp4, small, scanbuf, match_flags, match_best, out_stage;
   void* pinned = nullptr;

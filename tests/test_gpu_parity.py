@@ -632,3 +632,25 @@ def test_config_c1_pipeline(ctx, orc, clouds):
     q, m, dist = orc.match_reciprocal(feats[0], feats[1])
     assert np.array_equal(c["index_query"], q) and np.array_equal(c["index_match"], m)
     assert len(c) > 50
+
+
+def test_async_host_delivery_equals_synchronous(ctx, sheet):
+    """PFX_HOST_ASYNC: same rows as PFX_HOST once pfx_sync() returns, also when results of consecutive calls are
+    in flight together and a staging slot is reused"""
+    import ctypes as C
+    import pcl_feature_extraction_b200 as pfx
+    n = len(sheet)
+    ctx.set_surface(sheet)
+    ctx.set_queries(None)
+    ctx.normals(k=16, want_output=False)
+    f_sync = ctx.fpfh(k=16)
+    s_sync, rf_sync = ctx.shot352(0.0128)
+    fa = [np.zeros((n, 33), np.float32) for _ in range(2)]
+    sa = [np.zeros((n, 361), np.float32) for _ in range(2)]
+    for rep in range(2):  # second round reuses both staging slots while the first copies may still be running
+        ctx._chk(ctx.lib.pfx_fpfh(ctx.h, 0.0, 16, pfx.capi._ptr(fa[rep]), 132, pfx.capi.HOST_ASYNC))
+        ctx._chk(ctx.lib.pfx_shot352(ctx.h, 0.0128, None, pfx.capi._ptr(sa[rep]), 1444, pfx.capi.HOST_ASYNC))
+    ctx._chk(ctx.lib.pfx_sync(ctx.h))
+    for rep in range(2):
+        assert np.array_equal(fa[rep], f_sync, equal_nan=True)
+        assert np.array_equal(sa[rep][:, :352], s_sync, equal_nan=True) and np.array_equal(sa[rep][:, 352:], rf_sync, equal_nan=True)
