@@ -166,3 +166,39 @@ def gather_rows(rows, n_total, owner_index, rank, world, device=None, group=None
         keep = i >= 0
         out[i[keep]] = r.cpu().numpy()[keep]
     return out
+
+
+# ------------------------------------------------------------------ descriptor matching over ranks
+def pack_nn(d2, idx, offset=0):
+    """(d2 float32 >= 0, idx int32 >= 0 or -1) -> int64 keys whose integer order is (d2, global index) order.
+    d2 >= 0, so the float's bit pattern orders like its value; a missing match (-1) packs to the largest key."""
+    d2 = np.ascontiguousarray(d2, np.float32)
+    idx = np.ascontiguousarray(idx, np.int64)
+    key = (d2.view(np.uint32).astype(np.int64) << 32) | (idx + offset)
+    key[idx < 0] = np.iinfo(np.int64).max
+    return key
+
+
+def unpack_nn(key):
+    key = np.asarray(key, np.int64)
+    none = key == np.iinfo(np.int64).max
+    idx = (key & 0xFFFFFFFF).astype(np.int32)
+    d2 = (key >> 32).astype(np.uint32).view(np.float32).copy()
+    idx[none] = -1
+    d2[none] = np.inf
+    return idx, d2
+
+
+def sharded_match_nn(match_fn, a, b_local, b_offset, device=None, group=None):
+    """Exact 1-NN of every row of `a` among target rows that are SHARDED over the ranks.
+
+    Every rank holds all query rows `a` and its block `b_local` of the targets (global index of its first row:
+    b_offset).  match_fn(a, b_local) -> (idx int32, d2 float32) is the single-GPU matcher (Context.match_nn).  The
+    one collective of the path: an all-reduce MIN over packed (d2, global index) keys, which is exactly the
+    "smallest distance, then lowest index" rule of the single-GPU result.  Returns (idx, d2) on every rank."""
+    idx, d2 = match_fn(a, b_local) if len(b_local) else (np.full(len(a), -1, np.int32), np.full(len(a), np.inf, np.float32))
+    key = pack_nn(d2, idx, b_offset)
+    t = torch.from_numpy(key).to(device or torch.device("cpu"))
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return unpack_nn(t.cpu().numpy())

@@ -86,6 +86,51 @@ def _worker(rank, world, port, cloud_path, out_path):
         dist.destroy_process_group()
 
 
+def _match_worker(rank, world, port, path, out_path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import binding as orc
+        orc.set_num_threads(2)
+        z = np.load(path)
+        a, b = z["a"], z["b"]
+        bounds = np.linspace(0, len(b), world + 1).astype(int)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        idx, d2 = sharding.sharded_match_nn(orc.match_nn, a, np.ascontiguousarray(b[lo:hi]), lo)
+        if rank == 0:
+            np.savez(out_path, idx=idx, d2=d2)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pack_nn_orders_like_distance_then_index():
+    d2 = np.array([0.5, 0.5, 0.25, 3.0, 0.0], np.float32)
+    idx = np.array([7, 3, 9, -1, 2], np.int32)
+    key = sharding.pack_nn(d2, idx, offset=100)
+    order = np.argsort(key, kind="stable")
+    assert order.tolist() == [4, 2, 1, 0, 3]  # smaller d2 first, ties by lower index, missing last
+    i2, dd = sharding.unpack_nn(key)
+    assert i2.tolist() == [107, 103, 109, -1, 102] and dd[3] == np.inf and np.array_equal(dd[[0, 1, 2, 4]], d2[[0, 1, 2, 4]])
+
+
+def test_target_sharded_matching_equals_single_process(tmp_path, orc):
+    """descriptor matching with the targets sharded over 2 ranks and a packed-MIN all-reduce (gloo)"""
+    import torch.multiprocessing as mp
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 4, (700, 33)).astype(np.float32)   # coarse values: many exact distance ties across shards
+    b = rng.integers(0, 4, (901, 33)).astype(np.float32)
+    a[3, 0] = np.nan
+    path, out_path = str(tmp_path / "ab.npz"), str(tmp_path / "out.npz")
+    np.savez(path, a=a, b=b)
+    mp.spawn(_match_worker, args=(2, _free_port(), path, out_path), nprocs=2, join=True)
+    got = np.load(out_path)
+    idx, d2 = orc.match_nn(a, b)
+    assert np.array_equal(got["idx"], idx) and got["idx"][3] == -1
+    assert np.array_equal(got["d2"][idx >= 0], d2[idx >= 0])
+
+
 def test_slab_sharded_equals_single_process(tmp_path, orc, clouds):
     import torch.multiprocessing as mp
     pts = np.ascontiguousarray(clouds["underwater_source"][:6000])
