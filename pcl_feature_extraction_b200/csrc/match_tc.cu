@@ -227,48 +227,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
       mbar_expect_tx(bar_afull, a_bytes);
       for (uint32_t off = 0; off < a_bytes; off += 16384u)
         bulk_g2s(smem_u32(sA + off), srcA + off, min(16384u, a_bytes - off), bar_afull);
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      const unsigned char* srcB = reinterpret_cast<const unsigned char*>(P.Bt);
       for (int p = p0; p < p1; ++p) {
         const int nh = min(2, P.n_btiles - 2 * p);
-        for (int c = 0; c < nchunk; ++c, ++it) {
-          const int s = it % P.nstage;
-          const uint32_t ph = (uint32_t)((it / P.nstage) & 1);
+        for (int c = 0; c < nchunk; ++c) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1u);
           const int ns = min(4, nslab - 4 * c);
           const uint32_t bytes = (uint32_t)ns * TC_SLAB;
           mbar_expect_tx(bar_full + 8 * s, bytes * nh);
-          for (int h = 0; h < nh; ++h) {
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(P.Bt) +
-                                       ((size_t)(2 * p + h) * nslab + (size_t)4 * c) * TC_SLAB;
-            bulk_g2s(smem_u32(sB + (size_t)s * TC_STAGE + (size_t)h * 4 * TC_SLAB), src, bytes, bar_full + 8 * s);
+          const uint32_t dst = smem_u32(sB) + (uint32_t)s * TC_STAGE;
+          const unsigned char* src = srcB + ((size_t)(2 * p) * nslab + (size_t)4 * c) * TC_SLAB;
+          bulk_g2s(dst, src, bytes, bar_full + 8 * s);
+          if (nh == 2) bulk_g2s(dst + 4 * TC_SLAB, src + (size_t)nslab * TC_SLAB, bytes, bar_full + 8 * s);
+          if (++s == P.nstage) {
+            s = 0;
+            ph ^= 1u;
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread)
+    // ===================== MMA issuer (one thread).  The loop must stay far below the tensor pipe's 64 cycles per
+    // MMA, so descriptors are one 32-bit add away from a precomputed base (only the 14-bit start-address field
+    // changes) and the ring position is a counter, not a division.
     if (lane == 0) {
       mbar_wait(bar_afull, 0);
-      int it = 0;
+      const uint64_t desc_hi = (uint64_t)(((128u >> 4) & 0x3FFFu) | (1u << 14)) << 32;  // SBO = 128 B, version 1
+      const uint32_t lbo = (uint32_t)((TC_SLAB >> 4) & 0x3FFF) << 16;
+      const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFFu) | lbo;
+      const uint32_t b_lo0 = ((smem_u32(sB) >> 4) & 0x3FFFu) | lbo;
+      constexpr uint32_t SLAB16 = TC_SLAB >> 4, STAGE16 = TC_STAGE >> 4;
+      const int last_nm = (nslab - 4 * (nchunk - 1)) >> 1;  // K = 16 steps of the last chunk (1 or 2)
+      int s = 0;
+      uint32_t ph = 0;
       for (int p = p0; p < p1; ++p) {
         const int lp = p - p0, buf = lp & 1;
-        const int nh = min(2, P.n_btiles - 2 * p);
+        const bool two = (P.n_btiles - 2 * p) >= 2;
         mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((lp >> 1) & 1) ^ 1));
         tc_fence_after();
-        for (int c = 0; c < nchunk; ++c, ++it) {
-          const int s = it % P.nstage;
-          const uint32_t ph = (uint32_t)((it / P.nstage) & 1);
+        const uint32_t d0 = tmem_base + (uint32_t)(buf * 256), d1 = d0 + 128;
+        for (int c = 0; c < nchunk; ++c) {
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          const int nm = min(4, nslab - 4 * c) >> 1;  // K = 16 steps in this chunk
-          for (int m = 0; m < nm; ++m) {
-            const uint64_t ad = umma_desc(smem_u32(sA + (size_t)(4 * c + 2 * m) * TC_SLAB));
-            for (int h = 0; h < nh; ++h) {
-              const uint64_t bd = umma_desc(smem_u32(sB + (size_t)s * TC_STAGE + (size_t)(h * 4 + 2 * m) * TC_SLAB));
-              umma_bf16(tmem_base + (uint32_t)(buf * 256 + h * 128), ad, bd, TC_IDESC, (c | m) ? 1u : 0u);
-            }
+          const uint32_t a_lo = a_lo0 + (uint32_t)c * (4 * SLAB16);
+          const uint32_t b_lo = b_lo0 + (uint32_t)s * STAGE16;
+          const uint32_t acc0 = c ? 1u : 0u;
+          umma_bf16(d0, desc_hi | a_lo, desc_hi | b_lo, TC_IDESC, acc0);
+          if (two) umma_bf16(d1, desc_hi | a_lo, desc_hi | (b_lo + 4 * SLAB16), TC_IDESC, acc0);
+          if (c + 1 < nchunk || last_nm == 2) {
+            umma_bf16(d0, desc_hi | (a_lo + 2 * SLAB16), desc_hi | (b_lo + 2 * SLAB16), TC_IDESC, 1u);
+            if (two) umma_bf16(d1, desc_hi | (a_lo + 2 * SLAB16), desc_hi | (b_lo + 6 * SLAB16), TC_IDESC, 1u);
           }
           umma_commit(bar_empty + 8 * s);  // frees the stage when these MMAs have read it
+          if (++s == P.nstage) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
         umma_commit(bar_tfull + 8 * buf);  // accumulators of this pair are complete
       }
