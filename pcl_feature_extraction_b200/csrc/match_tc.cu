@@ -308,11 +308,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
     }
     float worst = CUDART_INF_F;  // K-th smallest key offered so far
     float bound = CUDART_INF_F;  // lower bound of every key never offered
+    // |b~|^2 of the pair's 256 columns: one value per epilogue thread, fetched one pair ahead so that the global
+    // load's latency is hidden behind the previous pair's min/max network
+    auto load_nb = [&](int p) -> float {
+      const int nh = min(2, P.n_btiles - 2 * p);
+      return (p < p1 && et < nh * 128) ? P.nb[(size_t)p * 256 + et] : TC_BIG;
+    };
+    float nb_next = load_nb(p0);
     for (int p = p0; p < p1; ++p) {
       const int lp = p - p0, buf = lp & 1;
       const int nh = min(2, P.n_btiles - 2 * p);
       float* nbuf = nbs + buf * 256;
-      nbuf[et] = (et < nh * 128) ? P.nb[(size_t)p * 256 + et] : TC_BIG;
+      nbuf[et] = nb_next;
+      nb_next = load_nb(p + 1);
       asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
       mbar_wait(bar_tfull + 8 * buf, (uint32_t)((lp >> 1) & 1));
       tc_fence_after();
@@ -320,11 +328,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + hsel * 128);
         const float* nh_buf = nbuf + hsel * 128;
         float m1 = 3e38f, m2 = 3e38f, m3 = 3e38f;
-#pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tbase + (uint32_t)c0, v);
-          tmem_ld_wait();
+        // sorted insertion of the 32 keys of one accumulator slab into (m1 <= m2 <= m3)
+        auto consume = [&](const uint32_t (&v)[32], int c0) {
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
             const float4 n4 = *reinterpret_cast<const float4*>(nh_buf + c0 + c);
@@ -333,18 +338,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
             for (int u = 0; u < 4; ++u) {
               const float d = fmaf(-2.f, __uint_as_float(v[c + u]), na + nn[u]);
               const float x = __uint_as_float((__float_as_uint(d) & 0xFFFFFF80u) | (uint32_t)(c0 + c + u));
-              const float t1 = fmaxf(m1, x);
+              const float n3 = fminf(m3, fmaxf(m2, x));  // the three updates only read the old values
+              const float n2 = fminf(m2, fmaxf(m1, x));
               m1 = fminf(m1, x);
-              const float t2 = fmaxf(m2, t1);
-              m2 = fminf(m2, t1);
-              m3 = fminf(m3, t2);
+              m2 = n2;
+              m3 = n3;
             }
           }
-        }
+        };
+        // two register buffers: the tcgen05.ld of slab i + 1 is in flight while slab i goes through the network
+        uint32_t va[32], vb[32];
+        tmem_ld32(tbase, va);
+        tmem_ld_wait();
+        tmem_ld32(tbase + 32u, vb);
+        consume(va, 0);
+        tmem_ld_wait();
+        tmem_ld32(tbase + 64u, va);
+        consume(vb, 32);
+        tmem_ld_wait();
+        tmem_ld32(tbase + 96u, vb);
+        consume(va, 64);
+        tmem_ld_wait();
+        consume(vb, 96);
         bound = fminf(bound, m3);
         const int jbase = p * 256 + hsel * 128;
-        if (m1 < worst) worst = tc_topk_insert(sd, sj, m1, jbase + (int)(__float_as_uint(m1) & 0x7Fu));
-        if (m2 < worst) worst = tc_topk_insert(sd, sj, m2, jbase + (int)(__float_as_uint(m2) & 0x7Fu));
+        const int j1 = (int)(__float_as_uint(m1) & 0x7Fu), j2 = (int)(__float_as_uint(m2) & 0x7Fu);
+        if (m1 < worst) worst = tc_topk_insert(sd, sj, m1, jbase + j1);
+        if (m2 < worst) worst = tc_topk_insert(sd, sj, m2, jbase + j2);
       }
       tc_fence_before();
       __syncwarp();
