@@ -117,14 +117,14 @@ template <bool DENSE>
 __global__ void __launch_bounds__(SWPB * 32)
 lrf_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2, double R, float* __restrict__ rf9,
            TieItem* __restrict__ tie_list, int* __restrict__ tie_count, int tie_cap, const int* __restrict__ qmap,
-           const int* __restrict__ qcount) {
+           const int* __restrict__ qcount, int qpw /* queries per warp, 1..32 */) {
   __shared__ unsigned long long skeys[SWPB][WTIE_CAP];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int qbase = (blockIdx.x * SWPB + wid) * 32;
+  const int qbase = (blockIdx.x * SWPB + wid) * qpw;
   const int limit = qmap ? min(*qcount, nq) : nq;  // qmap: work list of query numbers (optional)
   if (qbase >= limit) return;
   const int n_valid = g.gp->n_valid;
-  const int qend = min(32, limit - qbase);
+  const int qend = min(qpw, limit - qbase);
   LrfAcc mine;
 #pragma unroll
   for (int i = 0; i < 6; ++i) mine.m[i] = 0.0;
@@ -332,15 +332,18 @@ static int lrf_run(Ctx* ctx, Grid* g, double radius, float* rf9_dev, const int* 
   TieItem* tl = ctx->tmp1.as<TieItem>();
   int* flags = ctx->small.as<int>() + 32;  // [0] tie count, [1] overflow
   PFX_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int), ctx->stream));
-  const int blocks = div_up(nq, SWPB * 32);
+  // Queries per warp: 32 keeps every lane busy in the eigen solve, but a few thousand keypoint queries with
+  // hundreds of neighbours each need the warps for the neighbourhood scans instead.
+  const int qpw = std::max(1, std::min(32, nq / (ctx->sm_count * 16)));
+  const int blocks = div_up(nq, SWPB * qpw);
   if (dense) {
     PFX_LAUNCH(ctx, lrf_kernel<true>, blocks, SWPB * 32, 0, g->view(), nullptr, nq, r2, radius, rf9_dev, tl, flags,
-               tie_cap, qmap, qcount);
+               tie_cap, qmap, qcount, qpw);
     PFX_LAUNCH(ctx, lrf_tie_kernel<true>, ctx->sm_count, 128, 0, g->view(), nullptr, r2, rf9_dev, tl, flags, tie_cap,
                flags + 1);
   } else {
     PFX_LAUNCH(ctx, lrf_kernel<false>, blocks, SWPB * 32, 0, g->view(), ctx->qry.as<float4>(), nq, r2, radius,
-               rf9_dev, tl, flags, tie_cap, qmap, qcount);
+               rf9_dev, tl, flags, tie_cap, qmap, qcount, qpw);
     PFX_LAUNCH(ctx, lrf_tie_kernel<false>, ctx->sm_count, 128, 0, g->view(), ctx->qry.as<float4>(), r2, rf9_dev, tl,
                flags, tie_cap, flags + 1);
   }

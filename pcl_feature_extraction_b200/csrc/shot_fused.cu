@@ -259,6 +259,13 @@ int shot_fused_compute(Ctx* ctx, Grid* g, double radius, float* out_dev, size_t 
   const float r2 = (float)(radius * radius);
   const float4* nrm = nullptr;
   PFX_TRY(normals_sorted_for_grid(ctx, g, &nrm));
+  if (!ctx->q_is_surface && nq < ctx->sm_count * 512) {
+    // keypoint queries (the reference's use: evaluation.cpp:770-775 at r = 5 cm, hundreds of neighbours each):
+    // too few queries for the lane-per-query kernel; the generic kernels give every query its own warp
+    PFX_CUDA(ctx->tmp2.ensure((size_t)nq * 9 * sizeof(float)));
+    PFX_TRY(shot_lrf_compute(ctx, g, radius, ctx->tmp2.as<float>(), nullptr));
+    return shot_compute(ctx, g, radius, ctx->tmp2.as<float>(), out_dev, stride_floats);
+  }
   PFX_CUDA(ctx->worklist2.ensure(((size_t)nq + 16) * sizeof(int)));
   int* wl_count = ctx->worklist2.as<int>();
   int* wl = wl_count + 16;
