@@ -113,12 +113,28 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
           float d = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
           d2[r] = (c < M) ? d : INF;
         }
-        // ---- bracketing search: find tau with count(d2 <= tau) == k
+        // ---- find tau with count(d2 <= tau) == k.  Interpolation on the bracket while it still holds many
+        // candidates (the count is nearly linear in tau on a surface); once at most 4 candidates remain between
+        // the bracket ends they are EXTRACTED one distance value at a time (tau = smallest d2 above lo), which
+        // ends in <= 4 steps however close the k-th and (k+1)-th distances are.
         float lo = -1.f, hi = INF, tau = tau0;
         int clo = 0, chi = M;
-        bool done = !active, fail = false;
+        bool done = !active, fail = false, extract = false;
         for (int it = 0; it < 40; ++it) {
           if (__all_sync(FULL, done || fail)) break;
+          const bool ex = extract && !(done || fail);
+          if (__any_sync(FULL, ex)) {
+            float vm = INF;
+#pragma unroll
+            for (int r = 0; r < TR; ++r) {
+              if ((r & 3) == 0 && r * 8 >= M) break;
+              vm = (d2[r] > lo) ? fminf(vm, d2[r]) : vm;
+            }
+            vm = fminf(vm, __shfl_xor_sync(FULL, vm, 1));
+            vm = fminf(vm, __shfl_xor_sync(FULL, vm, 2));
+            vm = fminf(vm, __shfl_xor_sync(FULL, vm, 4));
+            if (ex) tau = vm;
+          }
           int c = 0;
 #pragma unroll
           for (int r = 0; r < TR; ++r) {
@@ -129,23 +145,30 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
           if (!(done || fail)) {
             if (c == k) {
               done = true;
+            } else if (extract) {
+              if (c < k) { lo = tau; clo = c; }
+              else fail = true;  // equal distances straddle rank k: the set depends on the index tie-break
             } else {
               if (c < k) { lo = tau; clo = c; } else { hi = tau; chi = c; }
-              float t;
-              if (hi == INF) {
-                t = lo * fmaxf(1.25f, ((float)k + 1.f) / ((float)clo + 0.5f));
-              } else if (lo < 0.f) {
-                t = hi * ((float)k / ((float)chi + 0.5f));
-              } else if (chi - clo > 4 && (it & 3) != 3) {
-                t = lo + (hi - lo) * (((float)(k - clo) + 0.5f) / (float)(chi - clo + 1));
+              if (hi != INF && chi - clo <= 4) {
+                extract = true;
               } else {
-                t = 0.5f * lo + 0.5f * hi;
+                float t;
+                if (hi == INF) {
+                  t = lo * fmaxf(1.25f, ((float)k + 1.f) / ((float)clo + 0.5f));
+                } else if (lo < 0.f) {
+                  t = hi * ((float)k / ((float)chi + 0.5f));
+                } else if ((it & 3) != 3) {
+                  t = lo + (hi - lo) * (((float)(k - clo) + 0.5f) / (float)(chi - clo + 1));
+                } else {
+                  t = 0.5f * lo + 0.5f * hi;
+                }
+                const float lo_next = (lo < 0.f) ? 0.f : __uint_as_float(__float_as_uint(lo) + 1u);
+                if (!(t > lo)) t = lo_next;
+                if (!(t < hi)) t = __uint_as_float(__float_as_uint(hi) - 1u);
+                if (!(t > lo) || !(t < hi)) fail = true;  // adjacent floats around many equal distances
+                tau = t;
               }
-              const float lo_next = (lo < 0.f) ? 0.f : __uint_as_float(__float_as_uint(lo) + 1u);
-              if (!(t > lo)) t = lo_next;
-              if (!(t < hi)) t = __uint_as_float(__float_as_uint(hi) - 1u);
-              if (!(t > lo) || !(t < hi)) fail = true;  // adjacent floats: a distance tie straddles rank k
-              tau = t;
             }
           }
         }
