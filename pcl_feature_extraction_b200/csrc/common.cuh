@@ -95,6 +95,28 @@ __device__ __forceinline__ float dist2_flann(float ax, float ay, float az, float
   return s;
 }
 
+// atan2 for continuous quantities (interpolation weights, histogram coordinates): octant reduction + the 9-term odd minimax polynomial of Abramowitz &
+// Stegun 4.4.49 (|error| <= 2e-8 on [0, 1]); about half the instructions of atan2f
+// (measured max abs error 3e-7).  (0, 0) -> 0.
+__device__ __forceinline__ float fast_atan2f(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float t = (mx > 0.f) ? __fdividef(mn, mx) : 0.f;
+  const float s = t * t;
+  float r = 0.0028662257f;
+  r = fmaf(r, s, -0.0161657367f);
+  r = fmaf(r, s, 0.0429096138f);
+  r = fmaf(r, s, -0.0752896400f);
+  r = fmaf(r, s, 0.1065626393f);
+  r = fmaf(r, s, -0.1420889944f);
+  r = fmaf(r, s, 0.1999355085f);
+  r = fmaf(r, s, -0.3333314528f);
+  r = fmaf(r * s, t, t);
+  if (ay > ax) r = 1.57079632679489661923f - r;
+  if (x < 0.f) r = 3.14159265358979323846f - r;
+  return copysignf(r, y);
+}
+
 __device__ __forceinline__ uint32_t hash_key(uint32_t k) { return k * 0x9E3779B1u; }
 
 __device__ __forceinline__ int hash_lookup(const GridDev& g, uint32_t key) {

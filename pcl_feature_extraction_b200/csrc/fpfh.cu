@@ -53,7 +53,7 @@ __device__ __forceinline__ bool pair_features(float p1x, float p1y, float p1z, f
   f2 = __fadd_rn(__fadd_rn(__fmul_rn(vx, wx_), __fmul_rn(vy, wy_)), __fmul_rn(vz, wz_));
   float sn = __fadd_rn(__fadd_rn(__fmul_rn(wx, wx_), __fmul_rn(wy, wy_)), __fmul_rn(wz, wz_));
   float cs = __fadd_rn(__fadd_rn(__fmul_rn(ux, wx_), __fmul_rn(uy, wy_)), __fmul_rn(uz, wz_));
-  f1 = atan2f(sn, cs);
+  f1 = fast_atan2f(sn, cs);  // 3e-7 from atan2f: a vote moves only if f1 is that close to a bin edge
   return true;
 }
 
@@ -271,19 +271,25 @@ fpfh_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2, con
 // ------------------------------------------------------------------------------ FPFH from kNN rows
 // k-search (rows of k <= 32 neighbours): lane t first turns neighbour t into a weight 1/d2; the gather
 // then takes THREE neighbours per step - 9 lanes per neighbour, each lane one 32-bit word of the
-// 36-byte count row (4 bins) - so a query costs 11 steps instead of 32.
-template <bool DENSE>
+// 36-byte count row (4 bins) - so a query costs 11 steps instead of 32.  The count -> float-sum table
+// T (PCL's sequential hist += incr, the same for every point of a k-search) is computed once on the host,
+// arrives as a kernel parameter and lives in registers: lane c holds T[c] and a lookup is one shuffle
+// (c <= k - 1 <= 31 because a point is never its own pair).
+struct IncrTable {
+  float t[32];
+};
+
+template <bool DENSE, bool K32>
 __global__ void __launch_bounds__(FWPB * 32)
 fpfh_list_kernel(GridDev g, const float4* __restrict__ queries, int nq, const int* __restrict__ lists,
-                 const float* __restrict__ ld2, int k, const unsigned char* __restrict__ rows8,
-                 float* __restrict__ out, size_t stride) {
-  __shared__ float Ttab[FWPB][36];
+                 const float* __restrict__ ld2, int k_rt, const unsigned char* __restrict__ rows8,
+                 float* __restrict__ out, size_t stride, IncrTable tab) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int qi = blockIdx.x * FWPB + wid;
   if (qi >= nq) return;
+  const int k = K32 ? 32 : k_rt;
   const int n_valid = g.gp->n_valid;
-  float* T = Ttab[wid];
-  build_incr_table(T, min(k, n_valid), lane);
+  const float Treg = tab.t[lane];
   float4 q = DENSE ? g.pts[qi] : queries[qi];
   const size_t row = DENSE ? (size_t)__float_as_int(q.w) : (size_t)qi;
   float* o = out + row * stride;
@@ -302,21 +308,28 @@ fpfh_list_kernel(GridDev g, const float4* __restrict__ queries, int nq, const in
     if (lane == 0) o[32] = nanv;
     return;
   }
-  const int grp = lane / 9, c9 = lane - grp * 9;
+  const int grp = min(lane / 9, 2), c9 = lane - (lane / 9) * 9;
   const bool gl = lane < 27;
   const unsigned* rows32 = reinterpret_cast<const unsigned*>(rows8);
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  for (int s = 0; s < k; s += 3) {
+#pragma unroll
+  for (int s = 0; s < (K32 ? 33 : 33); s += 3) {
+    if (!K32 && s >= k) break;
     const int src = min(s + grp, 31);
     const int j = __shfl_sync(FULL, myj, src);
-    const float w = __shfl_sync(FULL, myw, src);
-    if (gl && s + grp < k && w != 0.f) {
-      const unsigned cw = rows32[(size_t)j * 9 + c9];
-      a0 += T[cw & 255u] * w;
-      a1 += T[(cw >> 8) & 255u] * w;
-      a2 += T[(cw >> 16) & 255u] * w;
-      a3 += T[cw >> 24] * w;
-    }
+    float w = __shfl_sync(FULL, myw, src);
+    if (!gl || s + grp >= k) w = 0.f;
+    unsigned cw = 0u;
+    if (w != 0.f) cw = rows32[(size_t)j * 9 + c9];
+    // counts -> PCL's float sums: four register-table lookups (all lanes take part in the shuffles)
+    const float t0 = __shfl_sync(FULL, Treg, (int)(cw & 31u));
+    const float t1 = __shfl_sync(FULL, Treg, (int)((cw >> 8) & 31u));
+    const float t2 = __shfl_sync(FULL, Treg, (int)((cw >> 16) & 31u));
+    const float t3 = __shfl_sync(FULL, Treg, (int)((cw >> 24) & 31u));
+    a0 = fmaf(t0, w, a0);
+    a1 = fmaf(t1, w, a1);
+    a2 = fmaf(t2, w, a2);
+    a3 = fmaf(t3, w, a3);
   }
   // fold the three neighbour groups: lanes 0..8 end up with bins 4c..4c+3
   a0 += __shfl_down_sync(FULL, a0, 9) + __shfl_down_sync(FULL, a0, 18);
@@ -407,12 +420,36 @@ int fpfh_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t
       PFX_LAUNCH(ctx, spfh_export_kernel, div_up((long long)n * 33, 256), 256, 0, g->view(), nullptr,
                  rows8.as<unsigned char>(), n, k, spfh_out_dev);
     if (out_dev && nq > 0) {
-      if (dense)
-        PFX_LAUNCH(ctx, fpfh_list_kernel<true>, div_up(nq, FWPB), FWPB * 32, 0, g->view(), nullptr, nq,
-                   ctx->knn_idx.as<int>(), ctx->knn_d2.as<float>(), k, rows8.as<unsigned char>(), out_dev, stride_floats);
-      else
-        PFX_LAUNCH(ctx, fpfh_list_kernel<false>, div_up(nq, FWPB), FWPB * 32, 0, g->view(), ctx->qry.as<float4>(), nq,
-                   ctx->tmp2.as<int>(), ctx->tmp3.as<float>(), k, rows8.as<unsigned char>(), out_dev, stride_floats);
+      // T[c] = c sequential float additions of incr = 100 / (n - 1) (PCL's hist += hist_incr), IEEE float on the host
+      IncrTable tab;
+      {
+        int n_nb_row = k;  // every point of a k-search has min(k, #finite points) neighbours
+        if (n <= k) {      // tiny cloud: the finite-point count lives on the device
+          GridParams hp;
+          PFX_CUDA(cudaMemcpyAsync(&hp, g->params.p, sizeof(hp), cudaMemcpyDeviceToHost, ctx->stream));
+          PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+          n_nb_row = std::min(k, hp.n_valid);
+        }
+        const float incr = (n_nb_row > 1) ? 100.0f / (float)(n_nb_row - 1) : 0.f;
+        volatile float v = 0.f;
+        tab.t[0] = 0.f;
+        for (int c = 1; c < 32; ++c) {
+          v = v + incr;
+          tab.t[c] = v;
+        }
+      }
+      const int blocks = div_up(nq, FWPB);
+      if (dense) {
+        if (k == 32)
+          PFX_LAUNCH(ctx, (fpfh_list_kernel<true, true>), blocks, FWPB * 32, 0, g->view(), nullptr, nq, ctx->knn_idx.as<int>(),
+                     ctx->knn_d2.as<float>(), k, rows8.as<unsigned char>(), out_dev, stride_floats, tab);
+        else
+          PFX_LAUNCH(ctx, (fpfh_list_kernel<true, false>), blocks, FWPB * 32, 0, g->view(), nullptr, nq, ctx->knn_idx.as<int>(),
+                     ctx->knn_d2.as<float>(), k, rows8.as<unsigned char>(), out_dev, stride_floats, tab);
+      } else {
+        PFX_LAUNCH(ctx, (fpfh_list_kernel<false, false>), blocks, FWPB * 32, 0, g->view(), ctx->qry.as<float4>(), nq,
+                   ctx->tmp2.as<int>(), ctx->tmp3.as<float>(), k, rows8.as<unsigned char>(), out_dev, stride_floats, tab);
+      }
     }
     PFX_CUDA(cudaGetLastError());
     return 0;

@@ -107,28 +107,6 @@ __device__ __forceinline__ void shot_accumulate_neighbor(int* h, float scale, fl
   shot_add(h, vol + step, w, scale);
 }
 
-// atan2 for the interpolation weights: octant reduction + the 9-term odd minimax polynomial of Abramowitz &
-// Stegun 4.4.49 (|error| <= 2e-8 on [0, 1]); about half the instructions of atan2f.  Not used for any
-// discrete decision.  (0, 0) -> 0.
-__device__ __forceinline__ float fast_atan2f(float y, float x) {
-  const float ax = fabsf(x), ay = fabsf(y);
-  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-  const float t = (mx > 0.f) ? __fdividef(mn, mx) : 0.f;
-  const float s = t * t;
-  float r = 0.0028662257f;
-  r = fmaf(r, s, -0.0161657367f);
-  r = fmaf(r, s, 0.0429096138f);
-  r = fmaf(r, s, -0.0752896400f);
-  r = fmaf(r, s, 0.1065626393f);
-  r = fmaf(r, s, -0.1420889944f);
-  r = fmaf(r, s, 0.1999355085f);
-  r = fmaf(r, s, -0.3333314528f);
-  r = fmaf(r * s, t, t);
-  if (ay > ax) r = 1.57079632679489661923f - r;
-  if (x < 0.f) r = 3.14159265358979323846f - r;
-  return copysignf(r, y);
-}
-
 // Float variant of the above for the fused dense kernel.  The three frame projections keep the CPU's
 // float arithmetic (separate multiply / add); everything else is single precision.  SHOT's quadrilinear
 // interpolation is continuous across every discrete boundary (cosine step, radial shell, elevation and
