@@ -16,7 +16,7 @@
 
 namespace pfx {
 
-constexpr int NCAP = 64;
+constexpr int NCAP = 48;
 constexpr int FS_WPB = 4;
 constexpr int NPAD = 33;  // row pitch of the neighbour table: [position][query lane], conflict-free both ways
 
@@ -48,6 +48,9 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
   const float nanv = __int_as_float(0x7fc00000);
   const float Rf = (float)R;
   const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int i = 0; i < 11; ++i) S->hist[lane + 32 * i] = 0;
+  __syncwarp();
   for (int qbase = (blockIdx.x * FS_WPB + wid) * 32; qbase < nq; qbase += gridDim.x * FS_WPB * 32) {
     // ---------------- phase A (lane = query): one pass over the 3x3x3 stencil builds the neighbour list
     // in shared memory and the (R - d)-weighted scatter matrix of getLocalRF in double
@@ -218,10 +221,7 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
         for (int c = lane; c < 352; c += 32) o[c] = nanv;
         continue;
       }
-#pragma unroll
-      for (int i = 0; i < 11; ++i) S->hist[lane + 32 * i] = 0;
-      __syncwarp();
-      const float scale = shot_scale(n_t);
+      const float scale = shot_scale(n_t);  // (the histogram is zero here: cleared below as it is read out)
       for (int c = lane; c < n_t; c += 32) {
         const int j = S->nbr[c][t];
         const float4 p = g.pts[j];
@@ -229,16 +229,16 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
         shot_accumulate_neighbor_f(S->hist, scale, qt, p, d2, nrm[j], rft, Rf);
       }
       __syncwarp();
-      const float inv_scale = 1.0f / scale;
       float acc = 0.f;
       float hv[11];
 #pragma unroll
       for (int i = 0; i < 11; ++i) {
-        hv[i] = (float)S->hist[lane + 32 * i] * inv_scale;
+        hv[i] = (float)S->hist[lane + 32 * i];  // fixed point: the common scale cancels in the normalisation
+        S->hist[lane + 32 * i] = 0;
         acc = fmaf(hv[i], hv[i], acc);
       }
       acc = warp_sum(acc);
-      const float inv_n = 1.0f / sqrtf(acc);
+      const float inv_n = rsqrtf(acc);
 #pragma unroll
       for (int i = 0; i < 11; ++i) o[lane + 32 * i] = hv[i] * inv_n;
       __syncwarp();
