@@ -55,6 +55,15 @@ def workload_name(side):
             f"dense normals k=32 + FPFH33 k=32 + SHOT352 r=12.8 mm")
 
 
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/), or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -77,7 +86,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -294,7 +303,7 @@ def main():
         alg = ALG_BYTES[dom_key](nbar) * n
         achieved = alg / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": dom_key, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "peak_kind": peak_kind + " (burst copy)", "traffic": None,
+                    "frac": achieved / peaks["hbm_gbs"], "peak_kind": peak_kind + " (burst copy)", "traffic": ncu_traffic(dom_key) if n == (1 << 20) else None,
                     "alg_bytes_per_point": ALG_BYTES[dom_key](nbar), "points_per_launch": n, "mean_neighbours": nbar,
                     "launch_ms": per_launch_s * 1e3, "kernel_shares_of_step": shares,
                     "whole_step": {"alg_bytes_per_point": 3638, "achieved_GBps": 3638.0 * n * args.steps / (total_ms * 1e-3) / 1e9,
