@@ -8,7 +8,7 @@ import numpy as np
 import pcl_feature_extraction_b200 as pfx
 from oracle import binding as orc
 
-Z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "clouds.npz"))
+Z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "clouds.npz"))
 ctx = pfx.Context(0)
 ctx.set_viewpoint(0, 0, 0)
 
