@@ -153,7 +153,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "restated-PCL CPU oracle with OpenMP on all host threads; PCL/ROS cannot be built in this image",
-    }))
+    }), flush=True)
 
 
 def main():
@@ -184,6 +184,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own log lines (version banner, NCCL_DEBUG output) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -263,10 +265,11 @@ def main():
     # ---- e2e: the same C-ABI calls with HOST buffers (pinned), H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        # two sets of page-locked result buffers: the rows of step i are still being copied out (PFX_HOST_ASYNC,
-        # the context's copy stream) while step i + 1 uploads its cloud and computes
-        h_fpfh = [torch.empty((n, 33), dtype=torch.float32).pin_memory() for _ in range(2)]
-        h_shot = [torch.empty((n, 361), dtype=torch.float32).pin_memory() for _ in range(2)]
+        # page-locked result buffers: the rows of step i are still being copied out (PFX_HOST_ASYNC, the context's
+        # copy stream) while step i + 1 uploads its cloud and computes.  One set is enough: the copies of
+        # consecutive steps are serialised on the copy stream (a consumer would drain step i before i + 1 lands).
+        h_fpfh = [torch.empty((n, 33), dtype=torch.float32).pin_memory()] * 2
+        h_shot = [torch.empty((n, 361), dtype=torch.float32).pin_memory()] * 2
         HOST, ASYNC = pfx.capi.HOST, pfx.capi.HOST_ASYNC
 
         def step_host(i):
@@ -329,7 +332,7 @@ def main():
             "points_per_s": value / 2.0,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
