@@ -21,6 +21,8 @@
 // Result: indices and distances are bit-identical to the exact path.
 #include <cuda_bf16.h>
 
+#include <cmath>
+
 #include "internal.h"
 
 namespace pfx {
@@ -525,8 +527,22 @@ static int tc_run(Ctx* ctx, int slot_a, const float* a, int na, int lda, const f
   const int n_at = A.npad / TC_TILE, n_bt = B.npad / TC_TILE;
   const int npairs = (n_bt + 1) / 2;
   // Long units: the running top-K settles after a few hundred columns (insertions decay like K / n), so a
-  // unit should own as many columns as possible; B is split only to give idle SMs work (n_at < #SMs).
+  // unit should own as many columns as possible.  B is split (a) to give idle SMs work when there are fewer A
+  // tiles than SMs and (b) into 2-4 parts when that fills the last wave of CTAs better (512 A tiles on 148 SMs:
+  // 3.46 waves as whole units, 6.92 as halves), as long as a unit keeps >= 32 column pairs.
   int nsplit = std::max(1, std::min(npairs, ctx->sm_count / std::max(n_at, 1)));
+  if (n_at >= ctx->sm_count) {
+    double best_eff = 0.0;
+    for (int cand = 1; cand <= 4; ++cand) {
+      if (cand > 1 && npairs / cand < 32) break;
+      const double waves = (double)n_at * cand / ctx->sm_count;
+      const double eff = waves / std::ceil(waves);
+      if (eff > best_eff + 0.02) {
+        best_eff = eff;
+        nsplit = cand;
+      }
+    }
+  }
   int pps = div_up(npairs, nsplit);
   nsplit = div_up(npairs, pps);
   const size_t a_bytes = (size_t)(A.dpad / 8) * TC_SLAB;
