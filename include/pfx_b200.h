@@ -160,6 +160,19 @@ int pfx_set_match_engine(pfx_ctx* ctx, int engine);
  * they processed, out4[2] rows whose exactness certificate failed and were redone by the exact scan */
 int pfx_match_info(pfx_ctx* ctx, double* out4);
 
+/* ------------------------------------------------------------------ RANSAC correspondence rejection (next row)
+ * pfx_ransac_reject <- Features<T>::filterCorrespondences (features.h:282-297):
+ * CorrespondenceRejectorSampleConsensus with setInlierThreshold(0.015), setMaximumIterations(1000).
+ * src / tgt: the keypoint clouds the correspondences index (records with x, y, z first; strides in bytes).
+ * out: the surviving correspondences in input order (cap >= n_corr); transform16: row-major 4x4 of the winning
+ * 3-point hypothesis (getBestTransformation).  n_corr < 3 keeps everything with the identity, like PCL.
+ * Random samples follow the documented SplitMix64 contract with `seed` (PCL's fixed-seed mt19937 shuffle cannot be
+ * pinned); iterations_out / best_hypothesis_out (optional) report what PCL's sequential loop would have run. */
+int pfx_ransac_reject(pfx_ctx* ctx, const void* src, size_t n_src, size_t stride_src, const void* tgt, size_t n_tgt,
+                      size_t stride_tgt, const pfx_correspondence* corr, size_t n_corr, double inlier_threshold,
+                      int max_iterations, uint64_t seed, pfx_correspondence* out, size_t cap, size_t* n_out,
+                      float* transform16, int* iterations_out, int* best_hypothesis_out, int mem);
+
 /* ------------------------------------------------------------------ range image, NARF keypoints, Narf36
  * pfx_range_image_planar <- RangeImagePlanar::createFromPointCloudWithFixedSize (keypoints.h:204-216,
  * tools.h:65-76); pfx_range_image_spherical <- RangeImage::createFromPointCloud (config C3).  Both project

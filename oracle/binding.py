@@ -281,3 +281,18 @@ def narf36(img, desc, kp_px, support_size, rotation_invariant=True):
     _chk(lib().orc_narf36(_opt(img), C.byref(desc), _opt(kp_px), len(kp_px), C.c_float(support_size),
                           int(bool(rotation_invariant)), _opt(out), cap, C.byref(m)), "narf36")
     return out[: m.value].copy()
+
+
+# ------------------------------------------------------------------ RANSAC rejection
+def ransac_reject(src, tgt, corr_q, corr_m, threshold=0.015, max_iterations=1000, seed=12345):
+    """-> (keep flags [n_corr], T [4, 4], iterations, best hypothesis index)"""
+    src, tgt = _f32(src), _f32(tgt)
+    q = np.ascontiguousarray(corr_q, np.int32)
+    m = np.ascontiguousarray(corr_m, np.int32)
+    keep = np.zeros(max(len(q), 1), np.int32)
+    T = np.zeros(16, np.float32)
+    ninl, it, bh = C.c_int(0), C.c_int(0), C.c_int(0)
+    _chk(lib().orc_ransac_reject(_opt(src), len(src), _opt(tgt), len(tgt), _opt(q), _opt(m), len(q), C.c_double(threshold),
+                                 int(max_iterations), C.c_uint64(seed), _opt(keep), _opt(T), C.byref(ninl), C.byref(it),
+                                 C.byref(bh)), "ransac_reject")
+    return keep[: len(q)].astype(bool), T.reshape(4, 4), it.value, bh.value

@@ -124,6 +124,13 @@ int orc_narf36(const float* img, const orc_ri_desc* d, const int* kp_px, int n_k
                float support_size, int rotation_invariant, float* out /* cap x 42 */,
                int cap, int* n_out);
 
+/* ---- RANSAC correspondence rejection + rigid transform (features.h:282-297 ->
+ * CorrespondenceRejectorSampleConsensus, threshold 0.015, 1000 iterations).  keep: n_corr flags; T16: row-major
+ * 4x4 of the winning 3-point hypothesis; the sampling contract is defined in ransac.cpp. */
+int orc_ransac_reject(const float* src, int ns, const float* tgt, int nt, const int* corr_q, const int* corr_m,
+                      int n_corr, double threshold, int max_iterations, uint64_t seed, int* keep, float* T16,
+                      int* n_inliers, int* iterations, int* best_hypothesis);
+
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 

@@ -78,6 +78,8 @@ SIGNATURES = {
     "pfx_narf_borders": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
     "pfx_narf_keypoints": (_i, [_vp, _f, _vp, _vp, _vp, _sz, C.POINTER(_sz), _vp, _i]),
     "pfx_narf36": (_i, [_vp, _vp, _sz, _f, _i, _vp, _sz, _sz, C.POINTER(_sz), _i]),
+    "pfx_ransac_reject": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _vp, _sz, _d, _i, C.c_uint64, _vp, _sz, C.POINTER(_sz),
+                                _vp, _vp, _vp, _i]),
     "pfx_set_match_engine": (_i, [_vp, _i]),
     "pfx_match_info": (_i, [_vp, _vp]),
     "pfx_voxel_grid": (_i, [_vp, _f, _vp, _sz, C.POINTER(_sz), _i]),
@@ -401,6 +403,21 @@ class Context:
         self._chk(self.lib.pfx_match(self.h, _ptr(a), len(a), dim * 4, _ptr(b), len(b), dim * 4, dim, int(reciprocal),
                                      max_dist2, _ptr(out), len(out), C.byref(m), HOST))
         return out[: m.value].copy()
+
+    def ransac_reject(self, src, tgt, corr, threshold=0.015, max_iterations=1000, seed=12345):
+        """-> (surviving correspondences, T [4, 4], iterations, best hypothesis)"""
+        src = np.ascontiguousarray(src, np.float32)
+        tgt = np.ascontiguousarray(tgt, np.float32)
+        corr = np.ascontiguousarray(corr, CORR_DTYPE)
+        out = np.zeros(max(len(corr), 1), CORR_DTYPE)
+        T = np.zeros(16, np.float32)
+        m = C.c_size_t(0)
+        it, bh = C.c_int(0), C.c_int(0)
+        self._chk(self.lib.pfx_ransac_reject(self.h, _ptr(src), len(src), src.strides[0] if len(src) else 12, _ptr(tgt), len(tgt),
+                                             tgt.strides[0] if len(tgt) else 12, _ptr(corr), len(corr), threshold, max_iterations,
+                                             seed, _ptr(out), len(out) if len(corr) else 0, C.byref(m), _ptr(T), C.byref(it),
+                                             C.byref(bh), HOST))
+        return out[: m.value].copy(), T.reshape(4, 4), it.value, bh.value
 
     def set_match_engine(self, engine):
         self._chk(self.lib.pfx_set_match_engine(self.h, engine))

@@ -893,6 +893,51 @@ extern "C" int pfx_match(pfx_ctx* ctx, const float* a, size_t na, size_t stride_
   return 0;
 }
 
+// ================================================================================== RANSAC rejection
+extern "C" int pfx_ransac_reject(pfx_ctx* ctx, const void* src, size_t n_src, size_t stride_src, const void* tgt,
+                                 size_t n_tgt, size_t stride_tgt, const pfx_correspondence* corr, size_t n_corr,
+                                 double inlier_threshold, int max_iterations, uint64_t seed, pfx_correspondence* out,
+                                 size_t cap, size_t* n_out, float* transform16, int* iterations_out,
+                                 int* best_hypothesis_out, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (!n_out || !transform16 || (n_corr && (!corr || !src || !tgt)) || stride_src < 12 || stride_tgt < 12 ||
+      (stride_src & 3) || (stride_tgt & 3) || !(inlier_threshold > 0) || max_iterations < 1 || n_corr > 0x7fffffffull)
+    return ctx->fail(PFX_E_INVALID, "pfx_ransac_reject: bad arguments");
+  if (cap < n_corr || (n_corr && !out)) return ctx->fail(PFX_E_CAPACITY, "pfx_ransac_reject: output capacity must be >= n_corr");
+  *n_out = 0;
+  const float* dsrc = static_cast<const float*>(src);
+  const float* dtgt = static_cast<const float*>(tgt);
+  const pfx_correspondence* dcorr = corr;
+  pfx_correspondence* dout = out;
+  if (mem == PFX_HOST) {
+    // correspondences index the clouds: validate on the host before anything is dereferenced on the device
+    for (size_t i = 0; i < n_corr; ++i)
+      if (corr[i].index_query < 0 || (size_t)corr[i].index_query >= n_src || corr[i].index_match < 0 ||
+          (size_t)corr[i].index_match >= n_tgt)
+        return ctx->fail(PFX_E_INVALID, "pfx_ransac_reject: correspondence index out of range");
+    const size_t bs = n_src * stride_src, bt = n_tgt * stride_tgt, bc = n_corr * sizeof(pfx_correspondence);
+    PFX_CUDA(ctx->stage.ensure(std::max<size_t>(bs, 16)));
+    PFX_CUDA(ctx->stage2.ensure(std::max<size_t>(bt, 16)));
+    PFX_CUDA(ctx->tmp1.ensure(std::max<size_t>(2 * bc, 16)));
+    if (bs) PFX_CUDA(cudaMemcpyAsync(ctx->stage.p, src, bs, cudaMemcpyHostToDevice, ctx->stream));
+    if (bt) PFX_CUDA(cudaMemcpyAsync(ctx->stage2.p, tgt, bt, cudaMemcpyHostToDevice, ctx->stream));
+    if (bc) PFX_CUDA(cudaMemcpyAsync(ctx->tmp1.p, corr, bc, cudaMemcpyHostToDevice, ctx->stream));
+    dsrc = ctx->stage.as<float>();
+    dtgt = ctx->stage2.as<float>();
+    dcorr = ctx->tmp1.as<pfx_correspondence>();
+    dout = ctx->tmp1.as<pfx_correspondence>() + n_corr;
+  }
+  int cnt = 0, iters = 0, bh = -1;
+  PFX_TRY(ransac_reject_run(ctx, dsrc, stride_src, dtgt, stride_tgt, dcorr, (int)n_corr, inlier_threshold, max_iterations,
+                            seed, dout, &cnt, transform16, &iters, &bh));
+  *n_out = (size_t)cnt;
+  if (iterations_out) *iterations_out = iters;
+  if (best_hypothesis_out) *best_hypothesis_out = bh;
+  if (mem == PFX_HOST) return deliver(ctx, out, dout, (size_t)cnt * sizeof(pfx_correspondence), mem);
+  PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 // ================================================================================== range image / NARF
 extern "C" int pfx_range_image_planar(pfx_ctx* ctx, int width, int height, float cx, float cy, float fx, float fy,
                                       float min_range, pfx_range_image_desc* desc_out) {

@@ -622,8 +622,7 @@ int voxel_grid_run(Ctx* ctx, float leaf, float* out_dev, size_t cap, size_t* n_o
   const int n = (int)ctx->n;
   *n_out = 0;
   if (n == 0) return 0;
-  static Grid scratch;  // sort buffers only
-  Grid* g = &scratch;
+  Grid* g = &ctx->vg_scratch;  // sort buffers only
   PFX_CUDA(g->misc.ensure(sizeof(BuildAcc) + 64));
   PFX_CUDA(g->keys.ensure((size_t)n * sizeof(uint32_t)));
   PFX_CUDA(g->keys2.ensure((size_t)n * sizeof(uint32_t)));
@@ -676,6 +675,7 @@ int voxel_grid_run(Ctx* ctx, float leaf, float* out_dev, size_t cap, size_t* n_o
 }
 
 void grid_free_all(Ctx* ctx) {
+  ctx->vg_scratch.release();
   for (Grid* g : ctx->grids) {
     g->release();
     delete g;

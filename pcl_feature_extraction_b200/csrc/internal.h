@@ -125,6 +125,11 @@ struct Ctx {
   bool copy_pending[2] = {false, false};
   DevBuf async_stage[2];
 
+  // kernels that need > 48 KB of dynamic shared memory get the attribute once per context (= per device;
+  // cudaFuncSetAttribute is a per-device setting, and a process may hold contexts on several devices)
+  bool smem_attr_knn_tile = false, smem_attr_shot_fused = false, smem_attr_match_tc = false, smem_attr_narf = false;
+  Grid vg_scratch;  // sort buffers of pfx_voxel_grid
+
   // scratch
   DevBuf stage, stage2, tmp0, tmp1, tmp2, tmp3, tmp4, small, scanbuf, match_flags, match_best, out_stage;
   void* pinned = nullptr;
@@ -246,6 +251,11 @@ int narf_keypoints(Ctx* ctx, float support_size, int** kp_dev, int* n_kp);
 int narf_keypoint_attrs(Ctx* ctx, const int* kp_dev, int n, float* xyz, float* val, int mem);
 int narf36_compute(Ctx* ctx, const int* kp_dev, int n_kp, float support_size, int rotation_invariant,
                    unsigned char* out_dev, size_t stride, int cap, int* n_out);
+
+// ---- ransac.cu
+int ransac_reject_run(Ctx* ctx, const float* src, size_t stride_s, const float* tgt, size_t stride_t,
+                      const pfx_correspondence* corr, int n_corr, double threshold, int max_iterations, uint64_t seed,
+                      pfx_correspondence* out_dev, int* n_out, float* T16_host, int* iterations, int* best_h);
 
 // ---- helpers (capi.cu)
 int normals_sorted_for_grid(Ctx* ctx, Grid* g, const float4** out);

@@ -272,11 +272,10 @@ int knn_tile_lists(Ctx* ctx, Grid* g, int k, bool with_normals) {
   int* wl_count = ctx->worklist.as<int>();
   int* wl = wl_count + 16;
   const size_t smem = sizeof(KnnTileSmem) * TWPB;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->smem_attr_knn_tile) {
     PFX_CUDA(cudaFuncSetAttribute(knn_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PFX_CUDA(cudaFuncSetAttribute(knn_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    ctx->smem_attr_knn_tile = true;
   }
   const int blocks = ctx->sm_count * 3;
   if (with_normals) {

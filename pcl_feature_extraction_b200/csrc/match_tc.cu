@@ -563,10 +563,9 @@ static int tc_run(Ctx* ctx, int slot_a, const float* a, int na, int lda, const f
   int* redo_count = ctx->tc_redo.as<int>();
   int* redo_list = redo_count + 16;
   PFX_CUDA(cudaMemsetAsync(redo_count, 0, 16 * sizeof(int), ctx->stream));
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->smem_attr_match_tc) {
     PFX_CUDA(cudaFuncSetAttribute(tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    ctx->smem_attr_match_tc = true;
   }
   TcArgs P;
   P.At = A.tiles.as<__nv_bfloat16>();

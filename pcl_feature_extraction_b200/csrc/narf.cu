@@ -1300,10 +1300,9 @@ int narf_prepare(Ctx* ctx, int stage, float support_size) {
     int* overflow = ctx->small.as<int>() + 48;
     PFX_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), ctx->stream));
     const size_t smem = sizeof(NkSmem) * NK_WPB;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->smem_attr_narf) {
       PFX_CUDA(cudaFuncSetAttribute(nk_interest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
+      ctx->smem_attr_narf = true;
     }
     PFX_LAUNCH(ctx, nk_interest_kernel, std::min(div_up(np, NK_WPB), ctx->sm_count * 16), NK_WPB * 32, smem, ri,
                ctx->nb_traits.as<int>(), ctx->nb_change.as<float4>(), support_size, 0.25f, 0.2f,

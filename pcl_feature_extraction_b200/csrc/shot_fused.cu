@@ -271,11 +271,10 @@ int shot_fused_compute(Ctx* ctx, Grid* g, double radius, float* out_dev, size_t 
   int* wl = wl_count + 16;
   PFX_CUDA(cudaMemsetAsync(wl_count, 0, 16 * sizeof(int), ctx->stream));
   const size_t smem = sizeof(FusedSmem) * FS_WPB;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->smem_attr_shot_fused) {
     PFX_CUDA(cudaFuncSetAttribute(shot_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PFX_CUDA(cudaFuncSetAttribute(shot_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    ctx->smem_attr_shot_fused = true;
   }
   const int blocks = std::min(div_up(nq, FS_WPB * 32), ctx->sm_count * 16);
   if (ctx->q_is_surface)

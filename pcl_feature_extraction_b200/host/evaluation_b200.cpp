@@ -37,12 +37,16 @@ static void run_descriptor(const std::string& kp_type, const std::string& desc_t
   feat.compute(target, tkp, tf);
   double desc_runtime = now_s() - t0;
   t0 = now_s();
-  pcl::CorrespondencesPtr corr(new pcl::Correspondences);
+  pcl::CorrespondencesPtr corr(new pcl::Correspondences), filtered(new pcl::Correspondences);
   feat.findCorrespondences(sf, tf, corr);
+  float ransac_tf[16];
+  feat.filterCorrespondences(skp, tkp, corr, filtered, ransac_tf);  // evaluation.cpp:610 (the "Ransac rejector" column)
   double corr_runtime = now_s() - t0;
-  std::printf("%s, %s, %zu, %zu, %zu, %zu, %zu, %zu, %zu, %.6f, %.6f, %.6f\n", kp_type.c_str(), desc_type.c_str(),
-              source->size(), target->size(), skp->size(), tkp->size(), sf->size(), tf->size(), corr->size(), kp_runtime,
-              desc_runtime, corr_runtime);
+  std::printf("%s, %s, %zu, %zu, %zu, %zu, %zu, %zu, %zu, %zu, %.6f, %.6f, %.6f\n", kp_type.c_str(), desc_type.c_str(),
+              source->size(), target->size(), skp->size(), tkp->size(), sf->size(), tf->size(), corr->size(),
+              filtered->size(), kp_runtime, desc_runtime, corr_runtime);
+  dump(dump_dir, kp_type + "_" + desc_type + "_filtered.bin", *filtered);
+  dump(dump_dir, kp_type + "_" + desc_type + "_tf.bin", std::vector<float>(ransac_tf, ransac_tf + 16));
   dump(dump_dir, kp_type + "_" + desc_type + "_src.bin", sf->points);
   dump(dump_dir, kp_type + "_" + desc_type + "_tgt.bin", tf->points);
   dump(dump_dir, kp_type + "_" + desc_type + "_corr.bin", *corr);
@@ -64,7 +68,7 @@ int main(int argc, char** argv) {
   if (!pcl::b200::ctx()) return 3;
   std::printf("Keypoint name, Descriptor name, Source cloud size, Target cloud size, Source keypoints size, "
               "Target keypoints size, Source features size, Target features size, Correspondences, "
-              "Keypoints runtime, Features runtime, Correspondences runtime\n");
+              "Filtered correspondences, Keypoints runtime, Features runtime, Correspondences runtime\n");
   const std::string keypoints_list[] = {KP_HARRIS_3D, KP_ISS};
   for (const std::string& kp_type : keypoints_list) {
     PointCloudRGB::Ptr skp(new PointCloudRGB), tkp(new PointCloudRGB);
@@ -120,9 +124,9 @@ int main(int argc, char** argv) {
                                 reinterpret_cast<pfx_correspondence*>(corr.data()), corr.size(), &nc, PFX_HOST), "match");
       corr.resize(nc);
       double corr_runtime = now_s() - t0;
-      std::printf("%s, %s, %zu, %zu, %zu, %zu, %zu, %zu, %zu, %.6f, %.6f, %.6f\n", KP_NARF.c_str(), DESC_NARF.c_str(),
-                  source->size(), target->size(), skp->size(), tkp->size(), sf->size(), tf->size(), corr.size(), kp_runtime,
-                  desc_runtime, corr_runtime);
+      std::printf("%s, %s, %zu, %zu, %zu, %zu, %zu, %zu, %zu, %zu, %.6f, %.6f, %.6f\n", KP_NARF.c_str(), DESC_NARF.c_str(),
+                  source->size(), target->size(), skp->size(), tkp->size(), sf->size(), tf->size(), corr.size(), (size_t)0,
+                  kp_runtime, desc_runtime, corr_runtime);
       dump(dump_dir, "Narf_src_px.bin", skd.getNarfPixelIndices());
       dump(dump_dir, "Narf_NARF_src.bin", sf->points);
       dump(dump_dir, "Narf_NARF_corr.bin", corr);

@@ -182,6 +182,20 @@ class Features {
       if (descriptor_kdtree.nearestKSearch(*source, (int)i, k, k_indices, k_dist) > 0) source2target[i] = k_indices[0];
   }
 
+  // features.h:282-297.  transformation: row-major 4x4 (Eigen::Matrix4f in the reference)
+  void filterCorrespondences(const PointCloudRGB::Ptr source, const PointCloudRGB::Ptr target,
+                             pcl::CorrespondencesPtr correspondences, pcl::CorrespondencesPtr& filtered_correspondences,
+                             float transformation[16]) {
+    pcl::registration::CorrespondenceRejectorSampleConsensus<PointRGB> rejector;
+    rejector.setInputSource(source);
+    rejector.setInputTarget(target);
+    rejector.setInputCorrespondences(correspondences);
+    rejector.setInlierThreshold(0.015);
+    rejector.setMaximumIterations(1000);
+    rejector.getCorrespondences(*filtered_correspondences);
+    std::memcpy(transformation, rejector.getBestTransformation(), 16 * sizeof(float));
+  }
+
   void setFeatureRadiusSearch(double r) { feat_radius_search_ = r; }
   void setNormalRadiusSearch(double r) { normal_radius_search_ = r; }
 

@@ -59,6 +59,7 @@ static_assert(sizeof(Narf36) == 168 && sizeof(PointWithRange) == 32, "PCL layout
 
 typedef std::vector<Correspondence> Correspondences;
 typedef std::shared_ptr<Correspondences> CorrespondencesPtr;
+typedef std::shared_ptr<const Correspondences> CorrespondencesConstPtr;
 struct PointIndices { std::vector<int> indices; };
 typedef std::shared_ptr<PointIndices> PointIndicesPtr;
 typedef std::shared_ptr<const PointIndices> PointIndicesConstPtr;
@@ -711,6 +712,43 @@ class CorrespondenceEstimation {
     out.resize(n);
   }
   typename PointCloud<FeatureT>::ConstPtr source_, target_;
+};
+
+// pcl::registration::CorrespondenceRejectorSampleConsensus as driven at features.h:289-296
+template <typename PointT>
+class CorrespondenceRejectorSampleConsensus {
+ public:
+  void setInputSource(const typename PointCloud<PointT>::ConstPtr& c) { source_ = c; }
+  void setInputTarget(const typename PointCloud<PointT>::ConstPtr& c) { target_ = c; }
+  void setInputCorrespondences(const CorrespondencesConstPtr& c) { input_ = c; }
+  void setInlierThreshold(double t) { inlier_threshold_ = t; }
+  void setMaximumIterations(int n) { max_iterations_ = n; }
+  void setSeed(uint64_t s) { seed_ = s; }  // PCL seeds its mt19937 with a constant; the contract here is explicit
+  void getCorrespondences(Correspondences& out) {
+    out.clear();
+    for (int i = 0; i < 16; ++i) best_transformation_[i] = (i % 5 == 0) ? 1.f : 0.f;
+    pfx_ctx* c = b200::ctx();
+    if (!c || !source_ || !target_ || !input_) return;
+    out.resize(input_->size());
+    size_t n = 0;
+    int rc = pfx_ransac_reject(c, source_->points.data(), source_->size(), sizeof(PointT), target_->points.data(),
+                               target_->size(), sizeof(PointT), reinterpret_cast<const pfx_correspondence*>(input_->data()),
+                               input_->size(), inlier_threshold_, max_iterations_, seed_,
+                               reinterpret_cast<pfx_correspondence*>(out.data()), out.size(), &n, best_transformation_, nullptr,
+                               nullptr, PFX_HOST);
+    if (!b200::ok(rc, "CorrespondenceRejectorSampleConsensus")) n = 0;
+    out.resize(n);
+  }
+  // row-major 4x4 (Eigen::Matrix4f in PCL)
+  const float* getBestTransformation() const { return best_transformation_; }
+
+ private:
+  typename PointCloud<PointT>::ConstPtr source_, target_;
+  CorrespondencesConstPtr input_;
+  double inlier_threshold_ = 0.05;
+  int max_iterations_ = 1000;
+  uint64_t seed_ = 12345u;
+  float best_transformation_[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
 };
 }  // namespace registration
 

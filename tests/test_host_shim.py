@@ -78,3 +78,11 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     assert np.array_equal(corr[:, 0], q) and np.array_equal(corr[:, 1], m)
     assert np.array_equal(corr[:, 2].view(np.float32), d)
     assert int(rows[2][8]) == len(q)
+    # RANSAC rejection through the shim == the C ABI called from Python == the oracle
+    kp_s, kp_t = kp_xyz("Iss_src_kp.bin"), kp_xyz("Iss_tgt_kp.bin")
+    filt = np.fromfile(tmp_path / "Iss_FPFH_filtered.bin", dtype=np.int32).reshape(-1, 3)
+    tf = np.fromfile(tmp_path / "Iss_FPFH_tf.bin", dtype=np.float32).reshape(4, 4)
+    keep, oT, _, _ = orc.ransac_reject(kp_s, kp_t, q, m, 0.015, 1000)
+    assert np.array_equal(filt[:, 0], q[keep]) and np.array_equal(filt[:, 1], m[keep])
+    assert np.abs(tf - oT).max() < 1e-5
+    assert int(rows[2][9]) == int(keep.sum())
