@@ -7,8 +7,8 @@
 // hypothesis: lane 0 draws the three correspondences and fits the rigid transform (Kabsch: eigen decomposition of
 // H^T H in double), the warp counts the inliers |T s_i - t_i|^2 < thr^2 - and the host then replays PCL's
 // sequential rule over the 1001 counts, so the result is the one the sequential loop would have produced.
-// The sampling contract (SplitMix64 per hypothesis, no re-draw of degenerate samples) is the oracle's
-// (oracle/ransac.cpp); upstream's boost::mt19937 index shuffle cannot be pinned.
+// The sampling contract (SplitMix64 per hypothesis, no re-draw of degenerate samples) is stated in DESIGN.md §3;
+// upstream's boost::mt19937 index shuffle cannot be pinned.
 #include <cmath>
 #include <limits>
 
