@@ -74,6 +74,7 @@ struct Grid {
 struct TcOperand {
   DevBuf tiles, norm, err, maxima;
   int n = 0, npad = 0, dpad = 0;
+  bool tf32 = false;  // element type of the tiles: tf32 (4 bytes) or bf16 (2 bytes)
 };
 
 struct Ctx {

@@ -73,6 +73,14 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -105,12 +113,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = 128
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TILE >> 3) << 17) |
                               ((uint32_t)(TC_TILE >> 4) << 24);
+// kind::tf32: A = B = tf32 (format 2), K = 8 per instruction; a 16-byte K chunk then holds 4 elements, so the
+// slab / stage / descriptor geometry in BYTES is the same as for bf16
+constexpr uint32_t TC_IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_TILE >> 3) << 17) |
+                                   ((uint32_t)(TC_TILE >> 4) << 24);
 
 // ------------------------------------------------------------------------------------------ prep
-// one warp per (padded) row: bf16 tile order + |x~|^2 + |x - x~| (+ max of the latter two over the rows)
+// one warp per (padded) row: operand tile order + |x~|^2 + |x - x~| (+ max of the latter two over the rows).
+// TF32 = false: bf16 elements (8 per 16-byte chunk); true: tf32 = fp32 with a 10-bit mantissa (4 per chunk).
+template <bool TF32>
 __global__ void tc_prep_kernel(const float* __restrict__ X, int n, int ld, int dim, int dpad, int npad,
-                               __nv_bfloat16* __restrict__ Xt, float* __restrict__ norm, float* __restrict__ err,
+                               unsigned char* __restrict__ Xt, float* __restrict__ norm, float* __restrict__ err,
                                unsigned* __restrict__ maxima /* [0] max err bits, [1] max finite norm bits */) {
+  constexpr int EPC = TF32 ? 4 : 8;  // elements per 16-byte K chunk
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= npad) return;
@@ -120,18 +135,27 @@ __global__ void tc_prep_kernel(const float* __restrict__ X, int n, int ld, int d
     for (int k = lane; k < dim; k += 32) good = good && isfinite(X[(size_t)r * ld + k]);
     fin = __all_sync(FULL, good);
   }
-  const size_t tile_base = (size_t)(r >> 7) * (size_t)(dpad >> 3) * (TC_SLAB / 2);
+  const size_t tile_base = (size_t)(r >> 7) * (size_t)(dpad / EPC) * TC_SLAB;  // bytes
   const int rr = r & 127;
-  const size_t row_off = (size_t)(rr >> 3) * 64 + (size_t)(rr & 7) * 8;
+  const size_t row_off = (size_t)(rr >> 3) * 128 + (size_t)(rr & 7) * 16;
   float s2 = 0.f, e2 = 0.f;
   for (int k = lane; k < dpad; k += 32) {
     float v = (fin && k < dim) ? X[(size_t)r * ld + k] : 0.f;
-    __nv_bfloat16 h = __float2bfloat16_rn(v);
-    float vr = __bfloat162float(h);
+    float vr;
+    unsigned char* dst = Xt + tile_base + (size_t)(k / EPC) * TC_SLAB + row_off;
+    if (TF32) {
+      uint32_t bits;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bits) : "f"(v));
+      vr = __uint_as_float(bits);
+      reinterpret_cast<float*>(dst)[k % EPC] = vr;
+    } else {
+      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      vr = __bfloat162float(h);
+      reinterpret_cast<__nv_bfloat16*>(dst)[k % EPC] = h;
+    }
     s2 = fmaf(vr, vr, s2);
     float dv = v - vr;
     e2 = fmaf(dv, dv, e2);
-    Xt[tile_base + (size_t)(k >> 3) * (TC_SLAB / 2) + row_off + (k & 7)] = h;
   }
   s2 = warp_sum(s2);
   e2 = warp_sum(e2);
@@ -165,12 +189,12 @@ __device__ __noinline__ float tc_topk_insert(float* sd, int* sj, float d, int j)
 }
 
 struct TcArgs {
-  const __nv_bfloat16* At;
-  const __nv_bfloat16* Bt;
+  const unsigned char* At;  // operand tiles (bf16 or tf32, see tc_prep_kernel)
+  const unsigned char* Bt;
   const float* na;
   const float* nb;
   int n_btiles;         // 128-row tiles of B
-  int dpad;
+  int nslab;            // 16-byte K chunks per row (dpad / 8 for bf16, dpad / 4 for tf32)
   int nsplit;           // column splits (units per A tile)
   int pairs_per_split;  // 256-column tile pairs per unit
   int nstage;
@@ -178,11 +202,12 @@ struct TcArgs {
   int* cand_j;
 };
 
+template <bool TF32>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int a_tile = blockIdx.x / P.nsplit, split = blockIdx.x % P.nsplit;
-  const int nslab = P.dpad >> 3;
+  const int nslab = P.nslab;
   const int nchunk = (nslab + 3) >> 2;
   const int npairs_all = (P.n_btiles + 1) >> 1;
   const int p0 = split * P.pairs_per_split, p1 = min(npairs_all, p0 + P.pairs_per_split);
@@ -224,14 +249,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
   if (warp == 0) {
     // ===================== producer: A once, then the B slabs of every tile pair through the ring
     if (lane == 0) {
-      const unsigned char* srcA = reinterpret_cast<const unsigned char*>(P.At) + (size_t)a_tile * nslab * TC_SLAB;
+      const unsigned char* srcA = P.At + (size_t)a_tile * nslab * TC_SLAB;
       const uint32_t a_bytes = (uint32_t)nslab * TC_SLAB;
       mbar_expect_tx(bar_afull, a_bytes);
       for (uint32_t off = 0; off < a_bytes; off += 16384u)
         bulk_g2s(smem_u32(sA + off), srcA + off, min(16384u, a_bytes - off), bar_afull);
       int s = 0;
       uint32_t ph = 0;
-      const unsigned char* srcB = reinterpret_cast<const unsigned char*>(P.Bt);
+      const unsigned char* srcB = P.Bt;
       for (int p = p0; p < p1; ++p) {
         const int nh = min(2, P.n_btiles - 2 * p);
         for (int c = 0; c < nchunk; ++c) {
@@ -261,7 +286,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
       const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFFu) | lbo;
       const uint32_t b_lo0 = ((smem_u32(sB) >> 4) & 0x3FFFu) | lbo;
       constexpr uint32_t SLAB16 = TC_SLAB >> 4, STAGE16 = TC_STAGE >> 4;
-      const int last_nm = (nslab - 4 * (nchunk - 1)) >> 1;  // K = 16 steps of the last chunk (1 or 2)
+      const int last_nm = (nslab - 4 * (nchunk - 1)) >> 1;  // MMA steps (two K chunks each) of the last chunk: 1 or 2
+      auto mma = [](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
+        if (TF32) umma_tf32(d, ad, bd, TC_IDESC_TF32, acc);
+        else umma_bf16(d, ad, bd, TC_IDESC, acc);
+      };
       int s = 0;
       uint32_t ph = 0;
       for (int p = p0; p < p1; ++p) {
@@ -276,11 +305,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
           const uint32_t a_lo = a_lo0 + (uint32_t)c * (4 * SLAB16);
           const uint32_t b_lo = b_lo0 + (uint32_t)s * STAGE16;
           const uint32_t acc0 = c ? 1u : 0u;
-          umma_bf16(d0, desc_hi | a_lo, desc_hi | b_lo, TC_IDESC, acc0);
-          if (two) umma_bf16(d1, desc_hi | a_lo, desc_hi | (b_lo + 4 * SLAB16), TC_IDESC, acc0);
+          mma(d0, desc_hi | a_lo, desc_hi | b_lo, acc0);
+          if (two) mma(d1, desc_hi | a_lo, desc_hi | (b_lo + 4 * SLAB16), acc0);
           if (c + 1 < nchunk || last_nm == 2) {
-            umma_bf16(d0, desc_hi | (a_lo + 2 * SLAB16), desc_hi | (b_lo + 2 * SLAB16), TC_IDESC, 1u);
-            if (two) umma_bf16(d1, desc_hi | (a_lo + 2 * SLAB16), desc_hi | (b_lo + 6 * SLAB16), TC_IDESC, 1u);
+            mma(d0, desc_hi | (a_lo + 2 * SLAB16), desc_hi | (b_lo + 2 * SLAB16), 1u);
+            if (two) mma(d1, desc_hi | (a_lo + 2 * SLAB16), desc_hi | (b_lo + 6 * SLAB16), 1u);
           }
           umma_commit(bar_empty + 8 * s);  // frees the stage when these MMAs have read it
           if (++s == P.nstage) {
@@ -508,17 +537,28 @@ __global__ void tc_scatter_kernel(const int* __restrict__ rows, int nrows, const
 }
 
 // ------------------------------------------------------------------------------------------ host
+// tf32 operands (10-bit mantissa: 8x tighter candidate distances than bf16, so fewer rows need the exact redo)
+// whenever the resident A tile still leaves room for the B ring; bf16 for long descriptors (SHOT352).  The epilogue
+// paces the kernel for short descriptors, so the tf32 MMAs (half the bf16 rate) cost nothing there.
+static bool tc_use_tf32(int dim) { return ((dim + 7) & ~7) * 4 * TC_TILE <= 96 * 1024; }
+
 static int tc_prepare(Ctx* ctx, TcOperand& op, const float* x, int n, int ld, int dim) {
+  const bool tf32 = tc_use_tf32(dim);
   op.n = n;
-  op.dpad = (dim + 15) & ~15;
+  op.tf32 = tf32;
+  op.dpad = tf32 ? ((dim + 7) & ~7) : ((dim + 15) & ~15);
   op.npad = std::max(1, div_up(n, TC_TILE)) * TC_TILE;
-  PFX_CUDA(op.tiles.ensure((size_t)op.npad * op.dpad * sizeof(__nv_bfloat16)));
+  PFX_CUDA(op.tiles.ensure((size_t)op.npad * op.dpad * (tf32 ? 4 : 2)));
   PFX_CUDA(op.norm.ensure((size_t)(op.npad + 256) * sizeof(float)));
   PFX_CUDA(op.err.ensure((size_t)op.npad * sizeof(float)));
   PFX_CUDA(op.maxima.ensure(16));
   PFX_CUDA(cudaMemsetAsync(op.maxima.p, 0, 16, ctx->stream));
-  PFX_LAUNCH(ctx, tc_prep_kernel, div_up(op.npad, 8), 256, 0, x, n, ld, dim, op.dpad, op.npad,
-             op.tiles.as<__nv_bfloat16>(), op.norm.as<float>(), op.err.as<float>(), op.maxima.as<unsigned>());
+  if (tf32)
+    PFX_LAUNCH(ctx, tc_prep_kernel<true>, div_up(op.npad, 8), 256, 0, x, n, ld, dim, op.dpad, op.npad,
+               op.tiles.as<unsigned char>(), op.norm.as<float>(), op.err.as<float>(), op.maxima.as<unsigned>());
+  else
+    PFX_LAUNCH(ctx, tc_prep_kernel<false>, div_up(op.npad, 8), 256, 0, x, n, ld, dim, op.dpad, op.npad,
+               op.tiles.as<unsigned char>(), op.norm.as<float>(), op.err.as<float>(), op.maxima.as<unsigned>());
   PFX_CUDA(cudaGetLastError());
   return 0;
 }
@@ -550,7 +590,8 @@ static int tc_run(Ctx* ctx, int slot_a, const float* a, int na, int lda, const f
   }
   int pps = div_up(npairs, nsplit);
   nsplit = div_up(npairs, pps);
-  const size_t a_bytes = (size_t)(A.dpad / 8) * TC_SLAB;
+  const int nslab = A.tf32 ? A.dpad / 4 : A.dpad / 8;
+  const size_t a_bytes = (size_t)nslab * TC_SLAB;
   const size_t fixed = a_bytes + 512 * sizeof(float) + 2 * TC_K * TC_EPI_THREADS * 4 + 32 * 8 + 64;
   int nstage = (int)std::min<size_t>(8, (225 * 1024 - fixed) / TC_STAGE);
   if (nstage < 2) return ctx->fail(PFX_E_INVALID, "tensor-core matching: descriptor dimension too large for one A tile");
@@ -564,22 +605,26 @@ static int tc_run(Ctx* ctx, int slot_a, const float* a, int na, int lda, const f
   int* redo_list = redo_count + 16;
   PFX_CUDA(cudaMemsetAsync(redo_count, 0, 16 * sizeof(int), ctx->stream));
   if (!ctx->smem_attr_match_tc) {
-    PFX_CUDA(cudaFuncSetAttribute(tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PFX_CUDA(cudaFuncSetAttribute(tc_candidates_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PFX_CUDA(cudaFuncSetAttribute(tc_candidates_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     ctx->smem_attr_match_tc = true;
   }
   TcArgs P;
-  P.At = A.tiles.as<__nv_bfloat16>();
-  P.Bt = B.tiles.as<__nv_bfloat16>();
+  P.At = A.tiles.as<unsigned char>();
+  P.Bt = B.tiles.as<unsigned char>();
   P.na = A.norm.as<float>();
   P.nb = B.norm.as<float>();
   P.n_btiles = n_bt;
-  P.dpad = A.dpad;
+  P.nslab = nslab;
   P.nsplit = nsplit;
   P.pairs_per_split = pps;
   P.nstage = nstage;
   P.cand_d = ctx->tc_cand_d.as<float>();
   P.cand_j = ctx->tc_cand_j.as<int>();
-  PFX_LAUNCH(ctx, tc_candidates_kernel, n_at * nsplit, TC_THREADS, smem, P);
+  if (A.tf32)
+    PFX_LAUNCH(ctx, tc_candidates_kernel<true>, n_at * nsplit, TC_THREADS, smem, P);
+  else
+    PFX_LAUNCH(ctx, tc_candidates_kernel<false>, n_at * nsplit, TC_THREADS, smem, P);
   PFX_LAUNCH(ctx, tc_rescore_kernel, div_up(na, 8), 256, 0, a, na, lda, b, nb, ldb, dim, P.cand_d, P.cand_j, nlists,
              A.norm.as<float>(), A.err.as<float>(), B.maxima.as<unsigned>(), nn_idx, nn_d2, redo_list, redo_count);
   PFX_CUDA(cudaGetLastError());
