@@ -173,6 +173,29 @@ int pfx_ransac_reject(pfx_ctx* ctx, const void* src, size_t n_src, size_t stride
                       int max_iterations, uint64_t seed, pfx_correspondence* out, size_t cap, size_t* n_out,
                       float* transform16, int* iterations_out, int* best_hypothesis_out, int mem);
 
+/* ------------------------------------------------------------------ ICP (next row)
+ * pfx_icp_align <- Evaluation::icpAlign (evaluation.cpp:863-885): pcl::IterativeClosestPoint<PointXYZRGB,
+ * PointXYZRGB> with setMaxCorrespondenceDistance(0.07), setTransformationEpsilon(1e-6),
+ * setEuclideanFitnessEpsilon(1e-4), setMaximumIterations(100); setInputTarget = the context's cloud
+ * (pfx_set_cloud), setInputSource = src (records with x, y, z first; stride in bytes).
+ * guess16 (optional): row-major 4x4 initial transform (align(output, guess)).  result: getFinalTransformation
+ * (row-major), getFitnessScore(), hasConverged(), the iteration count and the convergence state
+ * (1 ITERATIONS, 2 TRANSFORM, 3 ABS_MSE, 4 REL_MSE, 5 NO_CORRESPONDENCES; 0 = not converged).
+ * aligned (optional): the source cloud moved by the final transform, n_src rows of x, y, z at stride_aligned. */
+typedef struct {
+  double max_correspondence_distance;
+  int max_iterations;
+  double transformation_epsilon;
+  double euclidean_fitness_epsilon;
+} pfx_icp_params;
+typedef struct {
+  float transform[16];
+  double fitness;
+  int converged, iterations, state, correspondences;
+} pfx_icp_result;
+int pfx_icp_align(pfx_ctx* ctx, const void* src, size_t n_src, size_t stride_src, const pfx_icp_params* params,
+                  const float* guess16, pfx_icp_result* result, void* aligned, size_t stride_aligned, int mem);
+
 /* ------------------------------------------------------------------ range image, NARF keypoints, Narf36
  * pfx_range_image_planar <- RangeImagePlanar::createFromPointCloudWithFixedSize (keypoints.h:204-216,
  * tools.h:65-76); pfx_range_image_spherical <- RangeImage::createFromPointCloud (config C3).  Both project

@@ -296,3 +296,19 @@ def ransac_reject(src, tgt, corr_q, corr_m, threshold=0.015, max_iterations=1000
                                  int(max_iterations), C.c_uint64(seed), _opt(keep), _opt(T), C.byref(ninl), C.byref(it),
                                  C.byref(bh)), "ransac_reject")
     return keep[: len(q)].astype(bool), T.reshape(4, 4), it.value, bh.value
+
+
+# ------------------------------------------------------------------ ICP
+def icp(src, tgt, max_corr_dist=0.07, max_iterations=100, transformation_epsilon=1e-6,
+        euclidean_fitness_epsilon=1e-4, guess=None):
+    """-> dict(T [4, 4] float32, fitness, converged, iterations, state)"""
+    src, tgt = _f32(src), _f32(tgt)
+    T = np.zeros(16, np.float32)
+    g = None if guess is None else np.ascontiguousarray(guess, np.float32).reshape(16)
+    fit = C.c_double(0)
+    conv, it, st = C.c_int(0), C.c_int(0), C.c_int(0)
+    _chk(lib().orc_icp(_opt(src), len(src), _opt(tgt), len(tgt), C.c_double(max_corr_dist), int(max_iterations),
+                       C.c_double(transformation_epsilon), C.c_double(euclidean_fitness_epsilon),
+                       None if g is None else g.ctypes.data_as(C.c_void_p), _opt(T), C.byref(fit), C.byref(conv),
+                       C.byref(it), C.byref(st)), "icp")
+    return dict(T=T.reshape(4, 4), fitness=fit.value, converged=bool(conv.value), iterations=it.value, state=st.value)

@@ -131,6 +131,13 @@ int orc_ransac_reject(const float* src, int ns, const float* tgt, int nt, const 
                       int n_corr, double threshold, int max_iterations, uint64_t seed, int* keep, float* T16,
                       int* n_inliers, int* iterations, int* best_hypothesis);
 
+/* ---- ICP (evaluation.cpp:863-885 -> IterativeClosestPoint, max correspondence distance 0.07, epsilons 1e-6 /
+ * 1e-4, 100 iterations).  guess16 optional (row-major 4x4).  state: 1 ITERATIONS, 2 TRANSFORM, 3 ABS_MSE,
+ * 4 REL_MSE, 5 NO_CORRESPONDENCES.  fitness = getFitnessScore() (mean squared NN distance of all source points). */
+int orc_icp(const float* src, int ns, const float* tgt, int nt, double max_corr_dist, int max_iterations,
+            double transformation_epsilon, double euclidean_fitness_epsilon, const float* guess16,
+            float* T16, double* fitness, int* converged, int* iterations, int* state);
+
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 

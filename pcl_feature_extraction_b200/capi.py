@@ -34,6 +34,17 @@ class RangeImageDesc(C.Structure):
                 ("fx", C.c_float), ("fy", C.c_float), ("ang_res", C.c_float), ("off_x", C.c_int32), ("off_y", C.c_int32)]
 
 
+class IcpParams(C.Structure):
+    """pfx_icp_params; defaults = the reference's settings (evaluation.cpp:863-885)"""
+    _fields_ = [("max_correspondence_distance", C.c_double), ("max_iterations", C.c_int),
+                ("transformation_epsilon", C.c_double), ("euclidean_fitness_epsilon", C.c_double)]
+
+
+class IcpResult(C.Structure):
+    _fields_ = [("transform", C.c_float * 16), ("fitness", C.c_double), ("converged", C.c_int), ("iterations", C.c_int),
+                ("state", C.c_int), ("correspondences", C.c_int)]
+
+
 CORR_DTYPE = np.dtype([("index_query", "<i4"), ("index_match", "<i4"), ("distance", "<f4")])
 
 # name -> (restype, argtypes); mirrors include/pfx_b200.h one to one
@@ -80,6 +91,7 @@ SIGNATURES = {
     "pfx_narf36": (_i, [_vp, _vp, _sz, _f, _i, _vp, _sz, _sz, C.POINTER(_sz), _i]),
     "pfx_ransac_reject": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _vp, _sz, _d, _i, C.c_uint64, _vp, _sz, C.POINTER(_sz),
                                 _vp, _vp, _vp, _i]),
+    "pfx_icp_align": (_i, [_vp, _vp, _sz, _sz, _vp, _vp, _vp, _vp, _sz, _i]),
     "pfx_set_match_engine": (_i, [_vp, _i]),
     "pfx_match_info": (_i, [_vp, _vp]),
     "pfx_voxel_grid": (_i, [_vp, _f, _vp, _sz, C.POINTER(_sz), _i]),
@@ -418,6 +430,24 @@ class Context:
                                              seed, _ptr(out), len(out) if len(corr) else 0, C.byref(m), _ptr(T), C.byref(it),
                                              C.byref(bh), HOST))
         return out[: m.value].copy(), T.reshape(4, 4), it.value, bh.value
+
+    def icp_align(self, src, max_corr_dist=0.07, max_iterations=100, transformation_epsilon=1e-6,
+                  euclidean_fitness_epsilon=1e-4, guess=None, want_aligned=False):
+        """ICP of `src` onto the current surface -> dict(T [4, 4], fitness, converged, iterations, state,
+        correspondences[, aligned])"""
+        src = np.ascontiguousarray(src, np.float32)
+        prm = IcpParams(max_corr_dist, max_iterations, transformation_epsilon, euclidean_fitness_epsilon)
+        res = IcpResult()
+        g = None if guess is None else np.ascontiguousarray(guess, np.float32).reshape(16)
+        al = np.zeros((len(src), 3), np.float32) if want_aligned else None
+        self._chk(self.lib.pfx_icp_align(self.h, _ptr(src), len(src), src.strides[0] if len(src) else 12, C.byref(prm),
+                                         None if g is None else _ptr(g), C.byref(res),
+                                         None if al is None else _ptr(al), 12, HOST))
+        out = dict(T=np.array(res.transform, np.float32).reshape(4, 4), fitness=res.fitness, converged=bool(res.converged),
+                   iterations=res.iterations, state=res.state, correspondences=res.correspondences)
+        if want_aligned:
+            out["aligned"] = al
+        return out
 
     def set_match_engine(self, engine):
         self._chk(self.lib.pfx_set_match_engine(self.h, engine))

@@ -938,6 +938,34 @@ extern "C" int pfx_ransac_reject(pfx_ctx* ctx, const void* src, size_t n_src, si
   return 0;
 }
 
+// ================================================================================== ICP
+extern "C" int pfx_icp_align(pfx_ctx* ctx, const void* src, size_t n_src, size_t stride_src, const pfx_icp_params* params,
+                             const float* guess16, pfx_icp_result* result, void* aligned, size_t stride_aligned, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (!params || !result || (n_src && !src) || stride_src < 12 || (stride_src & 3) || n_src > 0x7fffffffull ||
+      (aligned && (stride_aligned < 12 || (stride_aligned & 3))) || (mem != PFX_HOST && mem != PFX_DEVICE))
+    return ctx->fail(PFX_E_INVALID, "pfx_icp_align: bad arguments");
+  const float* dsrc = static_cast<const float*>(src);
+  float* dal = static_cast<float*>(aligned);
+  if (mem == PFX_HOST) {
+    const size_t bs = n_src * stride_src;
+    PFX_CUDA(ctx->stage.ensure(std::max<size_t>(bs, 16)));
+    if (bs) PFX_CUDA(cudaMemcpyAsync(ctx->stage.p, src, bs, cudaMemcpyHostToDevice, ctx->stream));
+    dsrc = ctx->stage.as<float>();
+    if (aligned) {
+      PFX_CUDA(ctx->out_stage.ensure(std::max<size_t>(n_src * 12, 16)));
+      dal = ctx->out_stage.as<float>();
+    }
+  }
+  PFX_TRY(icp_align_run(ctx, dsrc, (int)n_src, stride_src / 4, params, guess16, result, dal,
+                        mem == PFX_HOST ? 3 : stride_aligned / 4));
+  if (mem == PFX_HOST && aligned && n_src) {
+    PFX_CUDA(cudaMemcpy2DAsync(aligned, stride_aligned, dal, 12, 12, n_src, cudaMemcpyDeviceToHost, ctx->stream));
+    PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
 // ================================================================================== range image / NARF
 extern "C" int pfx_range_image_planar(pfx_ctx* ctx, int width, int height, float cx, float cy, float fx, float fy,
                                       float min_range, pfx_range_image_desc* desc_out) {

@@ -143,6 +143,8 @@ struct Ctx {
   int ri_stage = 0;  // 0 image only, 1 borders extracted, 2 interest image for ri_support
   float ri_support = 0.f;
 
+  DevBuf icp_state, icp_cur, icp_nn, icp_partials;  // icp.cu
+
   int match_engine = -1;  // -1 auto, 0 exact fp32 scan, 1 tcgen05 candidates + fp32 rescore
   TcOperand tc_ops[2];
   DevBuf tc_cand_d, tc_cand_j, tc_redo, tc_rows, tc_res;
@@ -259,6 +261,8 @@ int ransac_reject_run(Ctx* ctx, const float* src, size_t stride_s, const float* 
                       pfx_correspondence* out_dev, int* n_out, float* T16_host, int* iterations, int* best_h);
 
 // ---- helpers (capi.cu)
+int icp_align_run(Ctx* ctx, const float* src_dev, int n, size_t stride_floats, const pfx_icp_params* prm,
+                  const float* guess16, pfx_icp_result* res, float* aligned_dev, size_t aligned_stride_floats);
 int normals_sorted_for_grid(Ctx* ctx, Grid* g, const float4** out);
 int ensure_pinned(Ctx* ctx, size_t bytes);
 

@@ -1,7 +1,8 @@
 // evaluation_b200.cpp — ROS-free driver with the sequencing of the reference's evaluate() loop
 // (src/evaluation.cpp:272-852): for every keypoint detector x descriptor of the B200 path, detect
 // keypoints on source and target, describe them, match reciprocally, and print one CSV row with the
-// reference's column meaning (evaluation.cpp:190-206; ICP / RANSAC columns are outside the path).
+// reference's column meaning (evaluation.cpp:190-206), preceded by the direct ICP of the two clouds
+// (evaluation.cpp:246-266) and, per detector, the ICP of the keypoint clouds (evaluation.cpp:289-293).
 //
 //   evaluation_b200 <source.pcd> <target.pcd> [feat_radius=0.08] [normal_radius=0.05] [dump_dir]
 //
@@ -23,6 +24,34 @@ static void dump(const std::string& dir, const std::string& name, const std::vec
   if (dir.empty()) return;
   std::ofstream f(dir + "/" + name, std::ios::binary);
   f.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)(v.size() * sizeof(T)));
+}
+
+// Evaluation::icpAlign (evaluation.cpp:863-885), same settings
+static void icpAlign(const PointCloudRGB::Ptr& src, const PointCloudRGB::Ptr& tgt, pcl::Matrix4f& output, double& score,
+                     bool& convergence) {
+  PointCloudRGB::Ptr aligned(new PointCloudRGB);
+  pcl::IterativeClosestPoint<PointRGB, PointRGB> icp;
+  icp.setMaxCorrespondenceDistance(0.07);
+  icp.setRANSACOutlierRejectionThreshold(0.005);
+  icp.setTransformationEpsilon(0.000001);
+  icp.setEuclideanFitnessEpsilon(0.0001);
+  icp.setMaximumIterations(100);
+  icp.setInputSource(src);
+  icp.setInputTarget(tgt);
+  icp.align(*aligned);
+  output = icp.getFinalTransformation();
+  score = icp.getFitnessScore();
+  convergence = icp.hasConverged();
+}
+
+static void print_icp(const char* what, const pcl::Matrix4f& tf, double runtime, double score, bool convergence,
+                      const std::string& dump_dir, const std::string& dump_name) {
+  std::printf("# %s: (%g | %g | %g), runtime %.6f, score %.9g, convergence %d\n", what, tf(0, 3), tf(1, 3), tf(2, 3), runtime,
+              score, convergence ? 1 : 0);
+  std::vector<float> v(tf.m, tf.m + 16);
+  v.push_back((float)score);
+  v.push_back(convergence ? 1.f : 0.f);
+  dump(dump_dir, dump_name, v);
 }
 
 template <typename FeatureT>
@@ -69,6 +98,14 @@ int main(int argc, char** argv) {
   std::printf("Keypoint name, Descriptor name, Source cloud size, Target cloud size, Source keypoints size, "
               "Target keypoints size, Source features size, Target features size, Correspondences, "
               "Filtered correspondences, Keypoints runtime, Features runtime, Correspondences runtime\n");
+  {  // Step 1: direct ICP (evaluation.cpp:246-266)
+    pcl::Matrix4f icp_tf;
+    double score = 0;
+    bool convergence = false;
+    double t0 = now_s();
+    icpAlign(source, target, icp_tf, score, convergence);
+    print_icp("direct ICP", icp_tf, now_s() - t0, score, convergence, dump_dir, "direct_icp.bin");
+  }
   const std::string keypoints_list[] = {KP_HARRIS_3D, KP_ISS};
   for (const std::string& kp_type : keypoints_list) {
     PointCloudRGB::Ptr skp(new PointCloudRGB), tkp(new PointCloudRGB);
@@ -78,6 +115,15 @@ int main(int argc, char** argv) {
     kp.compute(target, tkp);
     double kp_runtime = now_s() - t0;
     if (skp->points.empty() || tkp->points.empty()) continue;  // evaluation.cpp:286-287
+    {  // ICP of the keypoint clouds (evaluation.cpp:289-293)
+      pcl::Matrix4f icp_kp_tf;
+      double score = 0;
+      bool convergence = false;
+      double t1 = now_s();
+      icpAlign(skp, tkp, icp_kp_tf, score, convergence);
+      print_icp((kp_type + " keypoints ICP").c_str(), icp_kp_tf, now_s() - t1, score, convergence, dump_dir,
+                kp_type + "_icp_kp.bin");
+    }
     dump(dump_dir, kp_type + "_src_kp.bin", skp->points);
     dump(dump_dir, kp_type + "_tgt_kp.bin", tkp->points);
     {

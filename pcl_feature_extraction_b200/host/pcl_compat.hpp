@@ -752,4 +752,68 @@ class CorrespondenceRejectorSampleConsensus {
 };
 }  // namespace registration
 
+// Eigen::Matrix4f stand-in for the transforms the registration classes hand back: m(row, col), row-major storage
+struct Matrix4f {
+  float m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  float operator()(int r, int c) const { return m[4 * r + c]; }
+  float& operator()(int r, int c) { return m[4 * r + c]; }
+  static Matrix4f Identity() { return Matrix4f(); }
+};
+
+// pcl::transformPointCloud(in, out, Matrix4f) as used at evaluation.cpp:257 (xyz moved, the other fields copied)
+template <typename PointT>
+inline void transformPointCloud(const PointCloud<PointT>& in, PointCloud<PointT>& out, const Matrix4f& t) {
+  if (&in != &out) out = in;
+  for (auto& p : out.points) {
+    if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
+    const float x = p.x, y = p.y, z = p.z;
+    p.x = ((t(0, 0) * x + t(0, 1) * y) + t(0, 2) * z) + t(0, 3);
+    p.y = ((t(1, 0) * x + t(1, 1) * y) + t(1, 2) * z) + t(1, 3);
+    p.z = ((t(2, 0) * x + t(2, 1) * y) + t(2, 2) * z) + t(2, 3);
+  }
+}
+
+// pcl::IterativeClosestPoint as driven by Evaluation::icpAlign (evaluation.cpp:863-885): the whole loop runs on
+// the device (pfx_icp_align); align() fills the moved source cloud.
+template <typename PointSource, typename PointTarget>
+class IterativeClosestPoint {
+ public:
+  void setMaxCorrespondenceDistance(double d) { prm_.max_correspondence_distance = d; }
+  void setRANSACOutlierRejectionThreshold(double t) { ransac_threshold_ = t; }  // stored; PCL 1.7's ICP never reads it
+  void setTransformationEpsilon(double e) { prm_.transformation_epsilon = e; }
+  void setEuclideanFitnessEpsilon(double e) { prm_.euclidean_fitness_epsilon = e; }
+  void setMaximumIterations(int n) { prm_.max_iterations = n; }
+  void setInputSource(const typename PointCloud<PointSource>::ConstPtr& c) { source_ = c; }
+  void setInputTarget(const typename PointCloud<PointTarget>::ConstPtr& c) { target_ = c; }
+  void align(PointCloud<PointSource>& output) { align(output, Matrix4f::Identity()); }
+  void align(PointCloud<PointSource>& output, const Matrix4f& guess) {
+    res_ = pfx_icp_result();
+    final_ = guess;
+    res_.fitness = std::numeric_limits<double>::max();
+    pfx_ctx* c = b200::ctx();
+    if (!c || !source_ || !target_) return;
+    output = *source_;
+    if (!b200::ok(pfx_set_surface(c, target_->points.data(), target_->size(), sizeof(PointTarget), PFX_HOST),
+                  "IterativeClosestPoint"))
+      return;
+    int rc = pfx_icp_align(c, source_->points.data(), source_->size(), sizeof(PointSource), &prm_, guess.m, &res_,
+                           output.points.data(), sizeof(PointSource), PFX_HOST);
+    if (!b200::ok(rc, "IterativeClosestPoint")) return;
+    std::memcpy(final_.m, res_.transform, sizeof(final_.m));
+  }
+  Matrix4f getFinalTransformation() const { return final_; }
+  double getFitnessScore() const { return res_.fitness; }
+  bool hasConverged() const { return res_.converged != 0; }
+  int getNumberOfIterations() const { return res_.iterations; }
+
+ private:
+  typename PointCloud<PointSource>::ConstPtr source_;
+  typename PointCloud<PointTarget>::ConstPtr target_;
+  // PCL's defaults: corr distance sqrt(DBL_MAX), 10 iterations, epsilons 0 / -DBL_MAX
+  pfx_icp_params prm_ = {1.3407807929942596e154, 10, 0.0, -std::numeric_limits<double>::max()};
+  double ransac_threshold_ = 0.05;
+  pfx_icp_result res_ = pfx_icp_result();
+  Matrix4f final_;
+};
+
 }  // namespace pcl

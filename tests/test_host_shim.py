@@ -28,7 +28,9 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     r = subprocess.run([BIN, str(tmp_path / "s.pcd"), str(tmp_path / "t.pcd"), "0.05", "0.03", str(tmp_path)],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
-    rows = [l.split(", ") for l in r.stdout.strip().splitlines()[1:]]
+    lines = r.stdout.strip().splitlines()
+    rows = [l.split(", ") for l in lines[1:] if not l.startswith("#")]
+    assert sum(l.startswith("# direct ICP") for l in lines) == 1
     assert [(x[0], x[1]) for x in rows][:4] == [("Harris3D", "FPFH"), ("Harris3D", "SHOT"), ("Iss", "FPFH"), ("Iss", "SHOT")]
     # NARF row (present when both clouds yield keypoints): the shim's RangeImagePlanar / NarfKeypoint /
     # NarfDescriptor objects against the C ABI called from Python on the same cloud
@@ -86,3 +88,15 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     assert np.array_equal(filt[:, 0], q[keep]) and np.array_equal(filt[:, 1], m[keep])
     assert np.abs(tf - oT).max() < 1e-5
     assert int(rows[2][9]) == int(keep.sum())
+    # ICP through the shim's IterativeClosestPoint == the C ABI called from Python (bit for bit); the keypoint
+    # clouds' ICP also against the oracle
+    icp = np.fromfile(tmp_path / "direct_icp.bin", dtype=np.float32)
+    ctx.set_surface(tgt)
+    g = ctx.icp_align(src)
+    assert np.array_equal(icp[:16].reshape(4, 4), g["T"]) and icp[16] == np.float32(g["fitness"]) and bool(icp[17]) == g["converged"]
+    icp_kp = np.fromfile(tmp_path / "Iss_icp_kp.bin", dtype=np.float32)
+    o = orc.icp(kp_s, kp_t)
+    assert bool(icp_kp[17]) == o["converged"]
+    assert np.abs(icp_kp[:16].reshape(4, 4) - o["T"]).max() < 1e-5
+    if o["fitness"] < 1e300:
+        assert abs(icp_kp[16] - o["fitness"]) <= 1e-4 * o["fitness"] + 1e-12
