@@ -25,9 +25,12 @@ constexpr int TCAP = 256;
 constexpr int TR = TCAP / 8;
 constexpr int TWPB = 8;
 
+constexpr int XCAP = 16;  // bracket candidates ranked directly
+
 struct KnnTileSmem {
   float4 pts[TCAP];
   int gidx[TCAP];
+  float xs[4][XCAP];
   TileTab tab;
 };
 
@@ -113,27 +116,94 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
           float d = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
           d2[r] = (c < M) ? d : INF;
         }
-        // ---- find tau with count(d2 <= tau) == k.  Interpolation on the bracket while it still holds many
-        // candidates (the count is nearly linear in tau on a surface); once at most 4 candidates remain between
-        // the bracket ends they are EXTRACTED one distance value at a time (tau = smallest d2 above lo), which
-        // ends in <= 4 steps however close the k-th and (k+1)-th distances are.
+        // ---- find tau with count(d2 <= tau) == k.  The first sweep counts at two thresholds around the density
+        // estimate (0.8 / 1.25 tau0), which usually brackets rank k at once; interpolation narrows a wide bracket
+        // (the count is nearly linear in tau on a surface); as soon as at most XCAP candidates lie between the
+        // bracket ends they are written to shared memory and the (k - clo)-th smallest of them is picked by rank
+        // counting - one step, however close the k-th and (k+1)-th distances are.
         float lo = -1.f, hi = INF, tau = tau0;
         int clo = 0, chi = M;
-        bool done = !active, fail = false, extract = false;
+        bool done = !active, fail = false;
+        {
+          const float ta = 0.8f * tau0, tb = 1.25f * tau0;
+          int ca = 0, cb = 0;
+#pragma unroll
+          for (int r = 0; r < TR; ++r) {
+            if ((r & 3) == 0 && r * 8 >= M) break;
+            ca += (d2[r] <= ta) ? 1 : 0;
+            cb += (d2[r] <= tb) ? 1 : 0;
+          }
+          ca = group_sum8(ca);
+          cb = group_sum8(cb);
+          if (cb < k) { lo = tb; clo = cb; }
+          else if (ca >= k) { hi = ta; chi = ca; }
+          else { lo = ta; clo = ca; hi = tb; chi = cb; }
+          if (!done && ca == k) { tau = ta; done = true; }
+          if (!done && cb == k) { tau = tb; done = true; }
+        }
         for (int it = 0; it < 40; ++it) {
           if (__all_sync(FULL, done || fail)) break;
-          const bool ex = extract && !(done || fail);
-          if (__any_sync(FULL, ex)) {
-            float vm = INF;
+          const bool want_x = !(done || fail) && hi != INF && (chi - clo) <= XCAP;
+          if (__any_sync(FULL, want_x)) {
+            unsigned mask = 0;
 #pragma unroll
             for (int r = 0; r < TR; ++r) {
               if ((r & 3) == 0 && r * 8 >= M) break;
-              vm = (d2[r] > lo) ? fminf(vm, d2[r]) : vm;
+              if (d2[r] > lo && d2[r] <= hi) mask |= 1u << r;
             }
-            vm = fminf(vm, __shfl_xor_sync(FULL, vm, 1));
-            vm = fminf(vm, __shfl_xor_sync(FULL, vm, 2));
-            vm = fminf(vm, __shfl_xor_sync(FULL, vm, 4));
-            if (ex) tau = vm;
+            if (!want_x) mask = 0;
+            int pos = group_excl_scan8(__popc(mask), sl);
+            float* xs = S->xs[sub];
+            while (mask) {
+              const int c = (__ffs(mask) - 1) * 8 + sl;
+              mask &= mask - 1;
+              const float4 p = S->pts[c];
+              xs[pos++] = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);  // the same value as the d2 register
+            }
+            __syncwarp();
+            const int nb = want_x ? chi - clo : 0, need = k - clo;
+            const float v0 = (sl < nb) ? xs[sl] : INF, v1 = (sl + 8 < nb) ? xs[sl + 8] : INF;
+            int r0 = 0, e0 = 0, r1 = 0, e1 = 0;
+            const int nbmax = __reduce_max_sync(FULL, nb);
+            for (int j = 0; j < nbmax; ++j) {
+              const float x = (j < nb) ? xs[j] : INF;
+              r0 += (x < v0) ? 1 : 0; e0 += (x == v0) ? 1 : 0;
+              r1 += (x < v1) ? 1 : 0; e1 += (x == v1) ? 1 : 0;
+            }
+            // the value of rank need-1 (0-based); a run of equal values across rank k leaves the set to the index
+            // tie-break, which only the generic kernel implements
+            float cand = INF;
+            int bad = 0;
+            if (v0 != INF && r0 < need && need <= r0 + e0) { cand = v0; bad = (r0 + e0 != need); }
+            if (v1 != INF && r1 < need && need <= r1 + e1) { cand = v1; bad = (r1 + e1 != need); }
+            cand = fminf(cand, __shfl_xor_sync(FULL, cand, 1));
+            cand = fminf(cand, __shfl_xor_sync(FULL, cand, 2));
+            cand = fminf(cand, __shfl_xor_sync(FULL, cand, 4));
+            bad = group_sum8(bad);
+            if (want_x) {
+              if (cand == INF || bad) fail = true;
+              else { tau = cand; done = true; }
+            }
+            __syncwarp();
+          }
+          const bool want_c = !(done || fail);
+          if (!__any_sync(FULL, want_c)) continue;
+          if (want_c) {
+            float t;
+            if (hi == INF) {
+              t = lo * fmaxf(1.25f, ((float)k + 1.f) / ((float)clo + 0.5f));
+            } else if (lo < 0.f) {
+              t = hi * ((float)k / ((float)chi + 0.5f));
+            } else if ((it & 3) != 3) {
+              t = lo + (hi - lo) * (((float)(k - clo) + 0.5f) / (float)(chi - clo + 1));
+            } else {
+              t = 0.5f * lo + 0.5f * hi;
+            }
+            const float lo_next = (lo < 0.f) ? 0.f : __uint_as_float(__float_as_uint(lo) + 1u);
+            if (!(t > lo)) t = lo_next;
+            if (!(t < hi)) t = __uint_as_float(__float_as_uint(hi) - 1u);
+            if (!(t > lo) || !(t < hi)) fail = true;  // adjacent floats around many equal distances
+            tau = t;
           }
           int c = 0;
 #pragma unroll
@@ -142,34 +212,10 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
             c += (d2[r] <= tau) ? 1 : 0;
           }
           c = group_sum8(c);
-          if (!(done || fail)) {
-            if (c == k) {
-              done = true;
-            } else if (extract) {
-              if (c < k) { lo = tau; clo = c; }
-              else fail = true;  // equal distances straddle rank k: the set depends on the index tie-break
-            } else {
-              if (c < k) { lo = tau; clo = c; } else { hi = tau; chi = c; }
-              if (hi != INF && chi - clo <= 4) {
-                extract = true;
-              } else {
-                float t;
-                if (hi == INF) {
-                  t = lo * fmaxf(1.25f, ((float)k + 1.f) / ((float)clo + 0.5f));
-                } else if (lo < 0.f) {
-                  t = hi * ((float)k / ((float)chi + 0.5f));
-                } else if ((it & 3) != 3) {
-                  t = lo + (hi - lo) * (((float)(k - clo) + 0.5f) / (float)(chi - clo + 1));
-                } else {
-                  t = 0.5f * lo + 0.5f * hi;
-                }
-                const float lo_next = (lo < 0.f) ? 0.f : __uint_as_float(__float_as_uint(lo) + 1u);
-                if (!(t > lo)) t = lo_next;
-                if (!(t < hi)) t = __uint_as_float(__float_as_uint(hi) - 1u);
-                if (!(t > lo) || !(t < hi)) fail = true;  // adjacent floats around many equal distances
-                tau = t;
-              }
-            }
+          if (want_c && !fail) {
+            if (c == k) done = true;
+            else if (c < k) { lo = tau; clo = c; }
+            else { hi = tau; chi = c; }
           }
         }
         if (!done) fail = true;
