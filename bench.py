@@ -156,6 +156,27 @@ def run_reference(args, rank, world):
     }), flush=True)
 
 
+def bind_to_gpu_numa(local):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, so that the page-locked
+    staging buffers (first touch) and the copy threads sit on the GPU's NUMA node.  Returns the previous CPU set
+    (restored for the CPU baseline leg), or None when nothing was changed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1}
+        before = os.sched_getaffinity(0)
+        cpus &= before
+        if cpus and cpus != before:
+            os.sched_setaffinity(0, cpus)
+            return before
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -183,6 +204,7 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpus_before = bind_to_gpu_numa(local)
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's own log lines (version banner, NCCL_DEBUG output) go to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -313,6 +335,8 @@ def main():
                                    "frac": 3638.0 * n * args.steps / (total_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
         cpu = None
         if world == 1 and not args.no_cpu:
+            if cpus_before:
+                os.sched_setaffinity(0, cpus_before)  # the CPU baseline gets every host core
             from oracle import binding as orc
             cs = args.cpu_side
             cp = sheet_cloud(side=cs, pitch=PITCH, seed=20240601)
@@ -331,6 +355,7 @@ def main():
                        "l2": "working set per step ~1.9 GB (1.5 GB SHOT output) >> 126 MB L2; input alternates between 2 clouds"},
             "points_per_s": value / 2.0,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,
+            "host_binding": "GPU-local CPUs (NVML affinity)" if cpus_before else "none",
         }
         print(json.dumps(out), flush=True)
     ctx.close()

@@ -160,6 +160,20 @@ int pfx_set_match_engine(pfx_ctx* ctx, int engine);
  * they processed, out4[2] rows whose exactness certificate failed and were redone by the exact scan */
 int pfx_match_info(pfx_ctx* ctx, double* out4);
 
+/* ------------------------------------------------------------------ PFH125, PrincipalCurvatures (next rows)
+ * pfx_pfh125 <- PFHEstimation<PointXYZRGB, Normal, PFHSignature125>::compute (evaluation.cpp:676-695 through
+ * features.h:181-195): rows of 125 floats (pcl::PFHSignature125, 500 B) for the current queries; same
+ * preconditions and search parameters as pfx_fpfh.  A row is NaN when the query has no neighbours.
+ * pfx_principal_curvatures <- PrincipalCurvaturesEstimation<PointXYZRGB, Normal, PrincipalCurvatures>::compute
+ * (evaluation.cpp:696-715): rows of 5 floats (pcl::PrincipalCurvatures: principal_curvature_x/y/z, pc1, pc2).
+ * The tangent plane of query i is that of surface normal i - upstream indexes the normals with the query's
+ * ordinal - which is the query's own normal when the queries are the surface. */
+int pfx_pfh125(pfx_ctx* ctx, double radius, int k, float* out, size_t stride, int mem);
+int pfx_principal_curvatures(pfx_ctx* ctx, double radius, int k, float* out, size_t stride, int mem);
+/* the float PCL's `hist[bin] += incr` holds after `count` additions (IEEE binary32, sequential): turns integer vote
+ * counts (pfx_spfh count rows, PFH votes) into PCL's histogram values bit for bit.  Pure host function. */
+float pfx_seq_float_sum(float incr, long long count);
+
 /* ------------------------------------------------------------------ RANSAC correspondence rejection (next row)
  * pfx_ransac_reject <- Features<T>::filterCorrespondences (features.h:282-297):
  * CorrespondenceRejectorSampleConsensus with setInlierThreshold(0.015), setMaximumIterations(1000).

@@ -71,6 +71,13 @@ def radius_search(surf, q, radius, brute=False):
     return offsets, idx, d2
 
 
+def radius_count(surf, q, radius):
+    surf, q = _f32(surf), _f32(q)
+    counts = np.zeros(len(q), np.int32)
+    _chk(lib().orc_radius_count(_opt(surf), len(surf), _opt(q), len(q), C.c_double(radius), _opt(counts)), "radius_count")
+    return counts.astype(np.int64)
+
+
 def knn(surf, q, k, brute=False):
     surf, q = _f32(surf), _f32(q)
     idx = np.zeros((len(q), k), np.int32)
@@ -312,3 +319,25 @@ def icp(src, tgt, max_corr_dist=0.07, max_iterations=100, transformation_epsilon
                        None if g is None else g.ctypes.data_as(C.c_void_p), _opt(T), C.byref(fit), C.byref(conv),
                        C.byref(it), C.byref(st)), "icp")
     return dict(T=T.reshape(4, 4), fitness=fit.value, converged=bool(conv.value), iterations=it.value, state=st.value)
+
+
+# ------------------------------------------------------------------ PFH125 / PrincipalCurvatures
+def pfh125(surf, normals4, q, radius=0.0, k=0, want_counts=False):
+    surf, q = _f32(surf), _f32(q)
+    nr = np.ascontiguousarray(normals4, np.float32)
+    out = np.zeros((len(q), 125), np.float32)
+    cnt = np.zeros((len(q), 125), np.int32) if want_counts else None
+    _chk(lib().orc_pfh125(_opt(surf), _opt(nr), len(surf), _opt(q), len(q), C.c_double(radius), int(k), _opt(out),
+                          None if cnt is None else _opt(cnt)), "pfh125")
+    return (out, cnt) if want_counts else out
+
+
+def principal_curvatures(surf, normals4, q, radius=0.0, k=0):
+    """-> (rows [nq, 5], relative eigen gap [nq])"""
+    surf, q = _f32(surf), _f32(q)
+    nr = np.ascontiguousarray(normals4, np.float32)
+    out = np.zeros((len(q), 5), np.float32)
+    gap = np.zeros(len(q), np.float32)
+    _chk(lib().orc_principal_curvatures(_opt(surf), _opt(nr), len(surf), _opt(q), len(q), C.c_double(radius), int(k),
+                                        _opt(out), _opt(gap)), "principal_curvatures")
+    return out, gap

@@ -79,6 +79,15 @@ int orc_fpfh(const float* surf, const float* normals4, int n, const float* q, in
 int orc_spfh(const float* surf, const float* normals4, int n, const int* pidx, int np,
              double radius, int k, float* out33);
 
+/* ---- PFH125 (evaluation.cpp:676-695 -> PFHEstimation) and PrincipalCurvatures (evaluation.cpp:696-715).
+ * out125: nq x 125 (NaN rows for queries without neighbours); counts125 (optional): the integer votes.
+ * out5: nq x 5 (principal direction, pc1, pc2); the tangent plane of query i is that of normals4[i] (upstream's
+ * indexing); gap (optional): (l2 - l1) / l2, -1 for NaN rows. */
+int orc_pfh125(const float* surf, const float* normals4, int n, const float* q, int nq, double radius, int k,
+               float* out125, int* counts125);
+int orc_principal_curvatures(const float* surf, const float* normals4, int n, const float* q, int nq,
+                             double radius, int k, float* out5, float* gap);
+
 /* ---- SHOT (evaluation.cpp:770-775 -> SHOTEstimationOMP + SHOTLocalReferenceFrameEstimation).
  * rf: nq x 9 (x_axis, y_axis, z_axis). lrf_in (optional): use these frames instead.
  * lrf_gap (optional, nq x 2): relative eigen gaps (l2-l1)/l2 and (l1-l0)/l2 of the LRF matrix. */

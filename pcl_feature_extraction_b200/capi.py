@@ -78,6 +78,9 @@ SIGNATURES = {
     "pfx_harris_nms": (_i, [_vp, _vp, _d, _f, _vp, _sz, C.POINTER(_sz), _i]),
     "pfx_fpfh": (_i, [_vp, _d, _i, _vp, _sz, _i]),
     "pfx_spfh": (_i, [_vp, _d, _i, _vp, _i]),
+    "pfx_pfh125": (_i, [_vp, _d, _i, _vp, _sz, _i]),
+    "pfx_principal_curvatures": (_i, [_vp, _d, _i, _vp, _sz, _i]),
+    "pfx_seq_float_sum": (_f, [_f, C.c_longlong]),
     "pfx_shot352": (_i, [_vp, _d, _vp, _vp, _sz, _i]),
     "pfx_shot_lrf": (_i, [_vp, _d, _vp, _i]),
     "pfx_match": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _f, _vp, _sz, C.POINTER(_sz), _i]),
@@ -305,6 +308,17 @@ class Context:
 
     def fpfh_dev(self, radius, k, out_ptr, stride=132):
         self._chk(self.lib.pfx_fpfh(self.h, radius, k, _ptr(out_ptr), stride, DEVICE))
+
+    def pfh125(self, radius=0.0, k=0):
+        out = np.zeros((self.num_queries, 125), np.float32)
+        self._chk(self.lib.pfx_pfh125(self.h, radius, k, _ptr(out), 500, HOST))
+        return out
+
+    def principal_curvatures(self, radius=0.0, k=0):
+        """rows of (principal direction x, y, z, pc1, pc2)"""
+        out = np.zeros((self.num_queries, 5), np.float32)
+        self._chk(self.lib.pfx_principal_curvatures(self.h, radius, k, _ptr(out), 20, HOST))
+        return out
 
     def spfh(self, radius=0.0, k=0):
         out = np.zeros((self.num_surface, 33), np.float32)

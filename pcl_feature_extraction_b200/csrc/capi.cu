@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include "internal.h"
+#include "seqsum.h"
 
 using namespace pfx;
 
@@ -667,6 +668,42 @@ extern "C" int pfx_fpfh(pfx_ctx* ctx, double radius, int k, float* out, size_t s
   if (mem == PFX_HOST) return deliver(ctx, out, dout, nq * stride, mem);
   return 0;
 }
+
+// shared body of the per-query descriptor calls that write fixed-size float rows
+template <typename F>
+static int rows_call(pfx_ctx* ctx, double radius, int k, float* out, size_t stride, int mem, size_t row_bytes,
+                     const char* what, F&& compute) {
+  PFX_TRY(check_ctx(ctx));
+  PFX_TRY(check_search_params(ctx, radius, k, what));
+  if (k > 32) return ctx->fail(PFX_E_INVALID, std::string(what) + ": k must be <= 32");
+  if (!ctx->have_normals) return ctx->fail(PFX_E_STATE, std::string(what) + ": no input normals (setInputNormals)");
+  if (!out || stride < row_bytes || (stride & 3) || (mem != PFX_HOST && mem != PFX_DEVICE))
+    return ctx->fail(PFX_E_INVALID, std::string(what) + ": bad output / stride / mem");
+  const size_t nq = ctx->num_queries();
+  Grid* g = nullptr;
+  PFX_TRY(grid_get(ctx, radius > 0 ? radius : 0.0, k, &g));
+  float* dout = out;
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->out_stage.ensure(std::max<size_t>(nq * stride, 16)));
+    dout = ctx->out_stage.as<float>();
+    if (stride != row_bytes) PFX_CUDA(cudaMemsetAsync(dout, 0, nq * stride, ctx->stream));
+  }
+  PFX_TRY(compute(g, dout));
+  if (mem == PFX_HOST) return deliver(ctx, out, dout, nq * stride, mem);
+  return 0;
+}
+
+extern "C" int pfx_pfh125(pfx_ctx* ctx, double radius, int k, float* out, size_t stride, int mem) {
+  return rows_call(ctx, radius, k, out, stride, mem, 500, "pfx_pfh125",
+                   [&](Grid* g, float* dout) { return pfh_compute(ctx, g, radius, k, dout, stride / 4); });
+}
+
+extern "C" int pfx_principal_curvatures(pfx_ctx* ctx, double radius, int k, float* out, size_t stride, int mem) {
+  return rows_call(ctx, radius, k, out, stride, mem, 20, "pfx_principal_curvatures",
+                   [&](Grid* g, float* dout) { return curvature_compute(ctx, g, radius, k, dout, stride / 4); });
+}
+
+extern "C" float pfx_seq_float_sum(float incr, long long count) { return seq_float_sum(incr, count < 0 ? 0 : count); }
 
 extern "C" int pfx_spfh(pfx_ctx* ctx, double radius, int k, float* out, int mem) {
   PFX_TRY(check_ctx(ctx));

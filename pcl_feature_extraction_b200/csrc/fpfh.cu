@@ -14,53 +14,12 @@
 //                    gathered per step (9 lanes x 4 bins of a count row each).
 //  fpfh_kernel       radius search: lanes are bins, 33-float rows gathered during the stencil scan.
 #include "internal.h"
+#include "pair_features.cuh"
 
 namespace pfx {
 
 constexpr int FWPB = 8;
 constexpr int SROW = 36;  // bytes per count row
-
-__device__ __forceinline__ bool pair_features(float p1x, float p1y, float p1z, float4 n1, float p2x, float p2y,
-                                              float p2z, float4 n2, float& f1, float& f2, float& f3) {
-  float dx = p2x - p1x, dy = p2y - p1y, dz = p2z - p1z;
-  float f4 = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-  if (f4 == 0.0f) return false;
-  float a1 = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(n1.x, dx), __fmul_rn(n1.y, dy)), __fmul_rn(n1.z, dz)), f4);
-  float a2 = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(n2.x, dx), __fmul_rn(n2.y, dy)), __fmul_rn(n2.z, dz)), f4);
-  // upstream: acos(|a1|) > acos(|a2|)  (false when either is NaN, i.e. |a| > 1)
-  float b1 = fabsf(a1), b2 = fabsf(a2);
-  bool swap = (b1 < b2) && (b2 <= 1.0f);
-  float ux, uy, uz, wx_, wy_, wz_;
-  if (swap) {
-    ux = n2.x; uy = n2.y; uz = n2.z;
-    wx_ = n1.x; wy_ = n1.y; wz_ = n1.z;
-    dx = -dx; dy = -dy; dz = -dz;
-    f3 = -a2;
-  } else {
-    ux = n1.x; uy = n1.y; uz = n1.z;
-    wx_ = n2.x; wy_ = n2.y; wz_ = n2.z;
-    f3 = a1;
-  }
-  float vx = __fsub_rn(__fmul_rn(dy, uz), __fmul_rn(dz, uy));
-  float vy = __fsub_rn(__fmul_rn(dz, ux), __fmul_rn(dx, uz));
-  float vz = __fsub_rn(__fmul_rn(dx, uy), __fmul_rn(dy, ux));
-  float vn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz)));
-  if (vn == 0.0f) return false;
-  vx = __fdiv_rn(vx, vn); vy = __fdiv_rn(vy, vn); vz = __fdiv_rn(vz, vn);
-  float wx = __fsub_rn(__fmul_rn(uy, vz), __fmul_rn(uz, vy));
-  float wy = __fsub_rn(__fmul_rn(uz, vx), __fmul_rn(ux, vz));
-  float wz = __fsub_rn(__fmul_rn(ux, vy), __fmul_rn(uy, vx));
-  f2 = __fadd_rn(__fadd_rn(__fmul_rn(vx, wx_), __fmul_rn(vy, wy_)), __fmul_rn(vz, wz_));
-  float sn = __fadd_rn(__fadd_rn(__fmul_rn(wx, wx_), __fmul_rn(wy, wy_)), __fmul_rn(wz, wz_));
-  float cs = __fadd_rn(__fadd_rn(__fmul_rn(ux, wx_), __fmul_rn(uy, wy_)), __fmul_rn(uz, wz_));
-  f1 = fast_atan2f(sn, cs);  // 3e-7 from atan2f: a vote moves only if f1 is that close to a bin edge
-  return true;
-}
-
-__device__ __forceinline__ int clamp_bin(double v) {
-  int b = (int)floor(v);
-  return min(max(b, 0), 10);
-}
 
 // the three bins of one pair (b1 in 0..10, b2 in 11..21, b3 in 22..32), or false when the pair fails
 __device__ __forceinline__ bool pair_bins(float4 q, float4 nq, float4 p, float4 nj, int& b1, int& b2, int& b3) {

@@ -261,6 +261,8 @@ int ransac_reject_run(Ctx* ctx, const float* src, size_t stride_s, const float* 
                       pfx_correspondence* out_dev, int* n_out, float* T16_host, int* iterations, int* best_h);
 
 // ---- helpers (capi.cu)
+int pfh_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t stride_floats);
+int curvature_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t stride_floats);
 int icp_align_run(Ctx* ctx, const float* src_dev, int n, size_t stride_floats, const pfx_icp_params* prm,
                   const float* guess16, pfx_icp_result* res, float* aligned_dev, size_t aligned_stride_floats);
 int normals_sorted_for_grid(Ctx* ctx, Grid* g, const float4** out);

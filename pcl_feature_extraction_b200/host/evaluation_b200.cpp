@@ -134,6 +134,16 @@ int main(int argc, char** argv) {
       pcl::Feature<PointRGB, pcl::SHOT352>::Ptr ex(new pcl::SHOTEstimationOMP<PointRGB, pcl::Normal, pcl::SHOT352>);
       run_descriptor<pcl::SHOT352>(kp_type, DESC_SHOT, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime, dump_dir);
     }
+    {  // evaluation.cpp:676-695
+      pcl::Feature<PointRGB, pcl::PFHSignature125>::Ptr ex(new pcl::PFHEstimation<PointRGB, pcl::Normal, pcl::PFHSignature125>);
+      run_descriptor<pcl::PFHSignature125>(kp_type, DESC_PFH, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime, dump_dir);
+    }
+    {  // evaluation.cpp:696-715
+      pcl::Feature<PointRGB, pcl::PrincipalCurvatures>::Ptr ex(
+          new pcl::PrincipalCurvaturesEstimation<PointRGB, pcl::Normal, pcl::PrincipalCurvatures>);
+      run_descriptor<pcl::PrincipalCurvatures>(kp_type, DESC_PPAL_CURV, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime,
+                                               dump_dir);
+    }
   }
   {
     // NARF keypoints + Narf36 (keypoints.h:199-231, evaluation.cpp:613-648).  Each cloud is described on ITS

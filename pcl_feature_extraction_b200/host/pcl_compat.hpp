@@ -42,6 +42,12 @@ struct alignas(16) Normal {
   float pad2_[3] = {0, 0, 0};
 };
 struct FPFHSignature33 { float histogram[33]; static int descriptorSize() { return 33; } };
+struct PFHSignature125 { float histogram[125]; static int descriptorSize() { return 125; } };
+struct PrincipalCurvatures {
+  float principal_curvature[3];  // principal_curvature_x / _y / _z
+  float pc1, pc2;
+  static int descriptorSize() { return 5; }
+};
 struct SHOT352 { float descriptor[352]; float rf[9]; static int descriptorSize() { return 352; } };
 struct ReferenceFrame { float x_axis[3], y_axis[3], z_axis[3]; };
 // pcl::Narf36: 168 bytes; the representation used for matching is the 36 descriptor floats only
@@ -56,6 +62,7 @@ static_assert(sizeof(Normal) == 32 && sizeof(FPFHSignature33) == 132 && sizeof(S
 static_assert(sizeof(ReferenceFrame) == 36 && sizeof(Correspondence) == 12, "PCL layout");
 static_assert(sizeof(Correspondence) == sizeof(pfx_correspondence), "ABI layout");
 static_assert(sizeof(Narf36) == 168 && sizeof(PointWithRange) == 32, "PCL layout");
+static_assert(sizeof(PFHSignature125) == 500 && sizeof(PrincipalCurvatures) == 20, "PCL layout");
 
 typedef std::vector<Correspondence> Correspondences;
 typedef std::shared_ptr<Correspondences> CorrespondencesPtr;
@@ -313,6 +320,36 @@ class FPFHEstimation : public FeatureFromNormals<PointInT, PointNT, PointOutT> {
 };
 template <typename PointInT, typename PointNT, typename PointOutT = FPFHSignature33>
 class FPFHEstimationOMP : public FPFHEstimation<PointInT, PointNT, PointOutT> {};
+
+// ------------------------------------------------------------------------------- PFH, PrincipalCurvatures
+template <typename PointInT, typename PointNT, typename PointOutT = PFHSignature125>
+class PFHEstimation : public FeatureFromNormals<PointInT, PointNT, PointOutT> {
+ protected:
+  const char* name() const override { return "PFHEstimation"; }
+  bool computeFeature(PointCloud<PointOutT>& output) override {
+    if (!this->uploadWithNormals()) return false;
+    int rc = pfx_pfh125(b200::ctx(), this->search_radius_, this->k_, reinterpret_cast<float*>(output.points.data()),
+                        sizeof(PointOutT), PFX_HOST);
+    if (!b200::ok(rc, name())) return false;
+    for (const auto& p : output.points)
+      if (!std::isfinite(p.histogram[0])) { output.is_dense = false; break; }
+    return true;
+  }
+};
+template <typename PointInT, typename PointNT, typename PointOutT = PrincipalCurvatures>
+class PrincipalCurvaturesEstimation : public FeatureFromNormals<PointInT, PointNT, PointOutT> {
+ protected:
+  const char* name() const override { return "PrincipalCurvaturesEstimation"; }
+  bool computeFeature(PointCloud<PointOutT>& output) override {
+    if (!this->uploadWithNormals()) return false;
+    int rc = pfx_principal_curvatures(b200::ctx(), this->search_radius_, this->k_,
+                                      reinterpret_cast<float*>(output.points.data()), sizeof(PointOutT), PFX_HOST);
+    if (!b200::ok(rc, name())) return false;
+    for (const auto& p : output.points)
+      if (!std::isfinite(p.pc1)) { output.is_dense = false; break; }
+    return true;
+  }
+};
 
 // ------------------------------------------------------------------------------- SHOT
 template <typename PointInT, typename PointNT, typename PointOutT = SHOT352, typename PointRFT = ReferenceFrame>

@@ -31,19 +31,21 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     lines = r.stdout.strip().splitlines()
     rows = [l.split(", ") for l in lines[1:] if not l.startswith("#")]
     assert sum(l.startswith("# direct ICP") for l in lines) == 1
-    assert [(x[0], x[1]) for x in rows][:4] == [("Harris3D", "FPFH"), ("Harris3D", "SHOT"), ("Iss", "FPFH"), ("Iss", "SHOT")]
+    byname = {(x[0], x[1]): x for x in rows}
+    for kp_name in ("Harris3D", "Iss"):
+        for d_name in ("FPFH", "SHOT", "PFH", "PrincipalCurvatures"):
+            assert (kp_name, d_name) in byname
     # NARF row (present when both clouds yield keypoints): the shim's RangeImagePlanar / NarfKeypoint /
     # NarfDescriptor objects against the C ABI called from Python on the same cloud
     ctx.set_surface(src)
     ctx.range_image_planar(640, 480, 320.0, 240.0, 525.0, 525.0)
     kp_px, kp_xyz_abi, _, _ = ctx.narf_keypoints(0.2)
-    if len(rows) > 4:
-        assert (rows[4][0], rows[4][1]) == ("Narf", "NARF")
+    if ("Narf", "NARF") in byname:
         px = np.fromfile(tmp_path / "Narf_src_px.bin", dtype=np.int32)
         assert np.array_equal(px, kp_px)
         f36 = np.fromfile(tmp_path / "Narf_NARF_src.bin", dtype=np.float32).reshape(-1, 42)
         assert np.array_equal(f36, ctx.narf36(kp_px, 0.2, True))
-        assert int(rows[4][6]) == len(f36)
+        assert int(byname[("Narf", "NARF")][6]) == len(f36)
 
     def kp_xyz(name):
         a = np.fromfile(tmp_path / name, dtype=np.float32).reshape(-1, 8)
@@ -79,7 +81,7 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     q, m, d = orc.match_reciprocal(f_shim, f_tgt)
     assert np.array_equal(corr[:, 0], q) and np.array_equal(corr[:, 1], m)
     assert np.array_equal(corr[:, 2].view(np.float32), d)
-    assert int(rows[2][8]) == len(q)
+    assert int(byname[("Iss", "FPFH")][8]) == len(q)
     # RANSAC rejection through the shim == the C ABI called from Python == the oracle
     kp_s, kp_t = kp_xyz("Iss_src_kp.bin"), kp_xyz("Iss_tgt_kp.bin")
     filt = np.fromfile(tmp_path / "Iss_FPFH_filtered.bin", dtype=np.int32).reshape(-1, 3)
@@ -87,7 +89,7 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     keep, oT, _, _ = orc.ransac_reject(kp_s, kp_t, q, m, 0.015, 1000)
     assert np.array_equal(filt[:, 0], q[keep]) and np.array_equal(filt[:, 1], m[keep])
     assert np.abs(tf - oT).max() < 1e-5
-    assert int(rows[2][9]) == int(keep.sum())
+    assert int(byname[("Iss", "FPFH")][9]) == int(keep.sum())
     # ICP through the shim's IterativeClosestPoint == the C ABI called from Python (bit for bit); the keypoint
     # clouds' ICP also against the oracle
     icp = np.fromfile(tmp_path / "direct_icp.bin", dtype=np.float32)
@@ -100,3 +102,13 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     assert np.abs(icp_kp[:16].reshape(4, 4) - o["T"]).max() < 1e-5
     if o["fitness"] < 1e300:
         assert abs(icp_kp[16] - o["fitness"]) <= 1e-4 * o["fitness"] + 1e-12
+    # PFH125 / PrincipalCurvatures rows through the shim == the C ABI called from Python (bit for bit)
+    ctx.set_surface(src)
+    ctx.set_queries(None)
+    ctx.normals(radius=0.03, want_output=False)
+    ctx.set_queries(src[kp])
+    p_shim = np.fromfile(tmp_path / "Iss_PFH_src.bin", dtype=np.float32).reshape(-1, 125)
+    assert np.array_equal(p_shim, ctx.pfh125(radius=0.05), equal_nan=True)
+    c_shim = np.fromfile(tmp_path / "Iss_PrincipalCurvatures_src.bin", dtype=np.float32).reshape(-1, 5)
+    assert np.array_equal(c_shim, ctx.principal_curvatures(radius=0.05), equal_nan=True)
+    ctx.set_queries(None)
