@@ -174,6 +174,17 @@ int pfx_principal_curvatures(pfx_ctx* ctx, double radius, int k, float* out, siz
  * counts (pfx_spfh count rows, PFH votes) into PCL's histogram values bit for bit.  Pure host function. */
 float pfx_seq_float_sum(float incr, long long count);
 
+/* ------------------------------------------------------------------ SHOT1344: shape + colour (next row)
+ * pfx_shot1344 <- SHOTColorEstimation<PointXYZRGB, Normal, SHOT1344>::compute (evaluation.cpp:786-805 through
+ * features.h:181-195).  Colours are the packed 0x00RRGGBB words of pcl::PointXYZRGB (pass &points[0].rgba with
+ * stride sizeof(PointXYZRGB)); pfx_set_surface_colors after pfx_set_surface (one per surface point),
+ * pfx_set_query_colors after pfx_set_queries (the reference colour of a descriptor is its query point's).
+ * Rows = pcl::SHOT1344: descriptor[1344] (352 shape slots, then 32 x 31 colour slots) + rf[9], 5412 B.
+ * lrf_in as for pfx_shot352. */
+int pfx_set_surface_colors(pfx_ctx* ctx, const void* rgb, size_t n, size_t stride, int mem);
+int pfx_set_query_colors(pfx_ctx* ctx, const void* rgb, size_t n, size_t stride, int mem);
+int pfx_shot1344(pfx_ctx* ctx, double radius, const float* lrf_in, float* out, size_t stride, int mem);
+
 /* ------------------------------------------------------------------ RANSAC correspondence rejection (next row)
  * pfx_ransac_reject <- Features<T>::filterCorrespondences (features.h:282-297):
  * CorrespondenceRejectorSampleConsensus with setInlierThreshold(0.015), setMaximumIterations(1000).

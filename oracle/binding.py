@@ -341,3 +341,20 @@ def principal_curvatures(surf, normals4, q, radius=0.0, k=0):
     _chk(lib().orc_principal_curvatures(_opt(surf), _opt(nr), len(surf), _opt(q), len(q), C.c_double(radius), int(k),
                                         _opt(out), _opt(gap)), "principal_curvatures")
     return out, gap
+
+
+# ------------------------------------------------------------------ SHOT1344 (shape + colour)
+def shot1344(surf, rgb, normals4, q, qrgb, radius, lrf_in=None, want_lab=False):
+    """-> (rows [nq, 1344], frames [nq, 9][, lab [n, 3]]); rgb / qrgb: packed 0x00RRGGBB uint32"""
+    surf, q = _f32(surf), _f32(q)
+    nr = np.ascontiguousarray(normals4, np.float32)
+    rgb = np.ascontiguousarray(rgb, np.uint32)
+    qrgb = np.ascontiguousarray(qrgb, np.uint32)
+    out = np.zeros((len(q), 1344), np.float32)
+    rf = np.zeros((len(q), 9), np.float32)
+    lab = np.zeros((len(surf), 3), np.float32) if want_lab else None
+    lrf = None if lrf_in is None else np.ascontiguousarray(lrf_in, np.float32)
+    _chk(lib().orc_shot1344(_opt(surf), _opt(rgb), _opt(nr), len(surf), _opt(q), _opt(qrgb), len(q), C.c_double(radius),
+                            None if lrf is None else _opt(lrf), _opt(out), _opt(rf), None if lab is None else _opt(lab)),
+         "shot1344")
+    return (out, rf, lab) if want_lab else (out, rf)

@@ -96,6 +96,12 @@ int orc_shot_lrf(const float* surf, int n, const float* q, int nq, double radius
 int orc_shot352(const float* surf, const float* normals4, int n, const float* q, int nq,
                 double radius, const float* lrf_in, float* out352, float* rf9);
 
+/* ---- SHOT1344 = shape + colour (evaluation.cpp:786-805 -> SHOTColorEstimation).  rgb / qrgb: packed 0x00RRGGBB
+ * of the surface points / queries; out: nq x 1344; lab_out (optional): n x 3 (L/100, a/120, b/120). */
+int orc_shot1344(const float* surf, const uint32_t* rgb, const float* normals4, int n, const float* q,
+                 const uint32_t* qrgb, int nq, double radius, const float* lrf_in, float* out1344, float* rf9,
+                 float* lab_out);
+
 /* ---- matching (features.h:224-273): exact L2 1-NN with sequential float sum.
  * nn_idx: na (argmin over b; -1 for NaN query rows / empty b), nn_d2: na */
 int orc_match_nn(const float* a, int na, const float* b, int nb, int dim, int* nn_idx, float* nn_d2);

@@ -83,6 +83,9 @@ SIGNATURES = {
     "pfx_seq_float_sum": (_f, [_f, C.c_longlong]),
     "pfx_shot352": (_i, [_vp, _d, _vp, _vp, _sz, _i]),
     "pfx_shot_lrf": (_i, [_vp, _d, _vp, _i]),
+    "pfx_set_surface_colors": (_i, [_vp, _vp, _sz, _sz, _i]),
+    "pfx_set_query_colors": (_i, [_vp, _vp, _sz, _sz, _i]),
+    "pfx_shot1344": (_i, [_vp, _d, _vp, _vp, _sz, _i]),
     "pfx_match": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _f, _vp, _sz, C.POINTER(_sz), _i]),
     "pfx_match_nn": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _vp, _vp, _i]),
     "pfx_range_image_planar": (_i, [_vp, _i, _i, _f, _f, _f, _f, _f, _vp]),
@@ -335,6 +338,21 @@ class Context:
         lrf = np.ascontiguousarray(lrf_in, np.float32) if lrf_in is not None else None
         self._chk(self.lib.pfx_shot352(self.h, radius, _ptr(lrf), _ptr(out), 1444, HOST))
         return out[:, :352].copy(), out[:, 352:].copy()
+
+    def set_surface_colors(self, rgb):
+        """packed 0x00RRGGBB uint32 per surface point"""
+        rgb = np.ascontiguousarray(rgb, np.uint32)
+        self._chk(self.lib.pfx_set_surface_colors(self.h, _ptr(rgb), len(rgb), 4, HOST))
+
+    def set_query_colors(self, rgb):
+        rgb = np.ascontiguousarray(rgb, np.uint32)
+        self._chk(self.lib.pfx_set_query_colors(self.h, _ptr(rgb), len(rgb), 4, HOST))
+
+    def shot1344(self, radius, lrf_in=None):
+        out = np.zeros((self.num_queries, 1353), np.float32)
+        lrf = np.ascontiguousarray(lrf_in, np.float32) if lrf_in is not None else None
+        self._chk(self.lib.pfx_shot1344(self.h, radius, _ptr(lrf), _ptr(out), 5412, HOST))
+        return out[:, :1344].copy(), out[:, 1344:].copy()
 
     def shot352_dev(self, radius, out_ptr, stride=1444):
         self._chk(self.lib.pfx_shot352(self.h, radius, None, _ptr(out_ptr), stride, DEVICE))

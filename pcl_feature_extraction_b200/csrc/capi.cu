@@ -785,6 +785,65 @@ extern "C" int pfx_shot352(pfx_ctx* ctx, double radius, const float* lrf_in, flo
   return 0;
 }
 
+// SHOT1344: colours of the surface / the queries, then the descriptor
+extern "C" int pfx_set_surface_colors(pfx_ctx* ctx, const void* rgb, size_t n, size_t stride, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_set_surface_colors: no surface set");
+  if (n != ctx->n) return ctx->fail(PFX_E_PRECOND, "pfx_set_surface_colors: the number of colours differs from the surface size");
+  if ((n && !rgb) || stride < 4 || (stride & 3) || (mem != PFX_HOST && mem != PFX_DEVICE))
+    return ctx->fail(PFX_E_INVALID, "pfx_set_surface_colors: bad pointer / stride / mem");
+  const unsigned char* src = nullptr;
+  PFX_TRY(upload_records(ctx, rgb, n, stride, mem, ctx->stage, &src));
+  PFX_TRY(colors_to_lab(ctx, src, stride, (int)n, ctx->surf_lab));
+  ctx->surf_lab_version = ctx->surf_version;
+  return 0;
+}
+
+extern "C" int pfx_set_query_colors(pfx_ctx* ctx, const void* rgb, size_t n, size_t stride, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->q_is_surface) return ctx->fail(PFX_E_PRECOND, "pfx_set_query_colors: the queries are the surface (pfx_set_surface_colors)");
+  if (n != ctx->nq) return ctx->fail(PFX_E_PRECOND, "pfx_set_query_colors: the number of colours differs from the number of queries");
+  if ((n && !rgb) || stride < 4 || (stride & 3) || (mem != PFX_HOST && mem != PFX_DEVICE))
+    return ctx->fail(PFX_E_INVALID, "pfx_set_query_colors: bad pointer / stride / mem");
+  const unsigned char* src = nullptr;
+  PFX_TRY(upload_records(ctx, rgb, n, stride, mem, ctx->stage, &src));
+  PFX_TRY(colors_to_lab(ctx, src, stride, (int)n, ctx->qry_lab));
+  ctx->qry_lab_version = ctx->qry_version;
+  return 0;
+}
+
+extern "C" int pfx_shot1344(pfx_ctx* ctx, double radius, const float* lrf_in, float* out, size_t stride, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_shot1344: no surface set");
+  if (!(radius > 0)) return ctx->fail(PFX_E_PRECOND, "pfx_shot1344: SHOT needs a radius search (setRadiusSearch)");
+  if (!ctx->have_normals) return ctx->fail(PFX_E_STATE, "pfx_shot1344: no input normals (setInputNormals)");
+  if (ctx->surf_lab_version != ctx->surf_version) return ctx->fail(PFX_E_STATE, "pfx_shot1344: no surface colours (pfx_set_surface_colors)");
+  if (!ctx->q_is_surface && ctx->qry_lab_version != ctx->qry_version)
+    return ctx->fail(PFX_E_STATE, "pfx_shot1344: no query colours (pfx_set_query_colors)");
+  if (!out || stride < 5412 || (stride & 3) || (mem != PFX_HOST && mem != PFX_DEVICE))
+    return ctx->fail(PFX_E_INVALID, "pfx_shot1344: bad output / stride / mem");
+  const size_t nq = ctx->num_queries();
+  if (nq == 0) return 0;
+  Grid* g = nullptr;
+  PFX_TRY(grid_get(ctx, radius, 0, &g));
+  float* dout = out;
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->out_stage.ensure(nq * stride));
+    dout = ctx->out_stage.as<float>();
+    if (stride != 5412) PFX_CUDA(cudaMemsetAsync(dout, 0, nq * stride, ctx->stream));
+  }
+  PFX_CUDA(ctx->tmp2.ensure(nq * 9 * sizeof(float)));
+  float* drf = ctx->tmp2.as<float>();
+  if (lrf_in)
+    PFX_CUDA(cudaMemcpyAsync(drf, lrf_in, nq * 9 * sizeof(float),
+                             mem == PFX_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+  else
+    PFX_TRY(shot_lrf_compute(ctx, g, radius, drf, nullptr));
+  PFX_TRY(shot_color_compute(ctx, g, radius, drf, dout, stride / 4));
+  if (mem == PFX_HOST) return deliver(ctx, out, dout, nq * stride, mem);
+  return 0;
+}
+
 // ================================================================================== matching
 namespace pfx {
 __global__ void reciprocal_kernel(const int* __restrict__ s2t, const float* __restrict__ sd2,

@@ -144,6 +144,9 @@ struct Ctx {
   float ri_support = 0.f;
 
   DevBuf icp_state, icp_cur, icp_nn, icp_partials;  // icp.cu
+  // colours (shot_color.cu): normalised CIELab of the surface points / queries, valid for these versions
+  DevBuf lab_tab, surf_lab, qry_lab;
+  uint64_t surf_lab_version = 0, qry_lab_version = 0;
 
   int match_engine = -1;  // -1 auto, 0 exact fp32 scan, 1 tcgen05 candidates + fp32 rescore
   TcOperand tc_ops[2];
@@ -263,6 +266,8 @@ int ransac_reject_run(Ctx* ctx, const float* src, size_t stride_s, const float* 
 // ---- helpers (capi.cu)
 int pfh_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t stride_floats);
 int curvature_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t stride_floats);
+int colors_to_lab(Ctx* ctx, const unsigned char* rgb_dev, size_t stride_bytes, int n, DevBuf& lab);
+int shot_color_compute(Ctx* ctx, Grid* g, double radius, const float* rf9_dev, float* out_dev, size_t stride_floats);
 int icp_align_run(Ctx* ctx, const float* src_dev, int n, size_t stride_floats, const pfx_icp_params* prm,
                   const float* guess16, pfx_icp_result* res, float* aligned_dev, size_t aligned_stride_floats);
 int normals_sorted_for_grid(Ctx* ctx, Grid* g, const float4** out);

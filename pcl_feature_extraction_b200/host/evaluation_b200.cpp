@@ -134,6 +134,10 @@ int main(int argc, char** argv) {
       pcl::Feature<PointRGB, pcl::SHOT352>::Ptr ex(new pcl::SHOTEstimationOMP<PointRGB, pcl::Normal, pcl::SHOT352>);
       run_descriptor<pcl::SHOT352>(kp_type, DESC_SHOT, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime, dump_dir);
     }
+    {  // evaluation.cpp:786-805
+      pcl::Feature<PointRGB, pcl::SHOT1344>::Ptr ex(new pcl::SHOTColorEstimationOMP<PointRGB, pcl::Normal, pcl::SHOT1344>);
+      run_descriptor<pcl::SHOT1344>(kp_type, DESC_SHOT_COLOR, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime, dump_dir);
+    }
     {  // evaluation.cpp:676-695
       pcl::Feature<PointRGB, pcl::PFHSignature125>::Ptr ex(new pcl::PFHEstimation<PointRGB, pcl::Normal, pcl::PFHSignature125>);
       run_descriptor<pcl::PFHSignature125>(kp_type, DESC_PFH, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime, dump_dir);

@@ -11,6 +11,7 @@
 #pragma once
 #include <array>
 #include <cmath>
+#include <cstddef>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -49,6 +50,7 @@ struct PrincipalCurvatures {
   static int descriptorSize() { return 5; }
 };
 struct SHOT352 { float descriptor[352]; float rf[9]; static int descriptorSize() { return 352; } };
+struct SHOT1344 { float descriptor[1344]; float rf[9]; static int descriptorSize() { return 1344; } };
 struct ReferenceFrame { float x_axis[3], y_axis[3], z_axis[3]; };
 // pcl::Narf36: 168 bytes; the representation used for matching is the 36 descriptor floats only
 struct Narf36 { float x, y, z, roll, pitch, yaw; float descriptor[36]; static int descriptorSize() { return 36; } };
@@ -63,6 +65,7 @@ static_assert(sizeof(ReferenceFrame) == 36 && sizeof(Correspondence) == 12, "PCL
 static_assert(sizeof(Correspondence) == sizeof(pfx_correspondence), "ABI layout");
 static_assert(sizeof(Narf36) == 168 && sizeof(PointWithRange) == 32, "PCL layout");
 static_assert(sizeof(PFHSignature125) == 500 && sizeof(PrincipalCurvatures) == 20, "PCL layout");
+static_assert(sizeof(SHOT1344) == 5412 && offsetof(PointXYZRGB, rgba) == 16, "PCL layout");
 
 typedef std::vector<Correspondence> Correspondences;
 typedef std::shared_ptr<Correspondences> CorrespondencesPtr;
@@ -396,6 +399,46 @@ class SHOTEstimation : public FeatureFromNormals<PointInT, PointNT, PointOutT> {
 };
 template <typename PointInT, typename PointNT, typename PointOutT = SHOT352, typename PointRFT = ReferenceFrame>
 class SHOTEstimationOMP : public SHOTEstimation<PointInT, PointNT, PointOutT, PointRFT> {};
+
+// SHOT1344: shape + colour; PointInT carries PCL's packed rgba word (PointXYZRGB)
+template <typename PointInT, typename PointNT, typename PointOutT = SHOT1344, typename PointRFT = ReferenceFrame>
+class SHOTColorEstimation : public FeatureFromNormals<PointInT, PointNT, PointOutT> {
+ public:
+  void setInputReferenceFrames(const typename PointCloud<PointRFT>::ConstPtr& f) { frames_ = f; }
+
+ protected:
+  const char* name() const override { return "SHOTColorEstimation"; }
+  bool initCompute() override {
+    if (!FeatureFromNormals<PointInT, PointNT, PointOutT>::initCompute()) return false;
+    if (this->k_ != 0) {
+      std::fprintf(stderr, "[pcl::%s::initCompute] Error! Search method set to k-neighborhood. Call setKSearch(0) and setRadiusSearch( radius ) to use this class.\n", name());
+      return false;
+    }
+    if (frames_ && frames_->size() != this->input_->size()) {
+      std::fprintf(stderr, "[pcl::%s::initCompute] The number of reference frames differs from the number of input points!\n", name());
+      return false;
+    }
+    return true;
+  }
+  bool computeFeature(PointCloud<PointOutT>& output) override {
+    if (!this->uploadWithNormals()) return false;
+    pfx_ctx* c = b200::ctx();
+    const bool dense = this->input_.get() == this->surface_.get();
+    if (!b200::ok(pfx_set_surface_colors(c, &this->surface_->points.data()->rgba, this->surface_->size(), sizeof(PointInT), PFX_HOST), name()))
+      return false;
+    if (!dense && !b200::ok(pfx_set_query_colors(c, &this->input_->points.data()->rgba, this->input_->size(), sizeof(PointInT), PFX_HOST), name()))
+      return false;
+    const float* lrf_in = frames_ ? reinterpret_cast<const float*>(frames_->points.data()) : nullptr;
+    int rc = pfx_shot1344(c, this->search_radius_, lrf_in, reinterpret_cast<float*>(output.points.data()), sizeof(PointOutT), PFX_HOST);
+    if (!b200::ok(rc, name())) return false;
+    for (const auto& p : output.points)
+      if (!std::isfinite(p.descriptor[0])) { output.is_dense = false; break; }
+    return true;
+  }
+  typename PointCloud<PointRFT>::ConstPtr frames_;
+};
+template <typename PointInT, typename PointNT, typename PointOutT = SHOT1344, typename PointRFT = ReferenceFrame>
+class SHOTColorEstimationOMP : public SHOTColorEstimation<PointInT, PointNT, PointOutT, PointRFT> {};
 
 // ------------------------------------------------------------------------------- keypoints
 template <typename PointInT, typename PointOutT>

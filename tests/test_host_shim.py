@@ -23,8 +23,11 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     from pcl_feature_extraction_b200.pcd import write_pcd
     src = np.ascontiguousarray(clouds["underwater_source"][:30000])
     tgt = np.ascontiguousarray(clouds["underwater_target"][:30000])
-    write_pcd(tmp_path / "s.pcd", src)
-    write_pcd(tmp_path / "t.pcd", tgt)
+    rng = np.random.default_rng(11)
+    src_rgb = rng.integers(0, 1 << 24, len(src)).astype(np.uint32)
+    tgt_rgb = rng.integers(0, 1 << 24, len(tgt)).astype(np.uint32)
+    write_pcd(tmp_path / "s.pcd", src, src_rgb)
+    write_pcd(tmp_path / "t.pcd", tgt, tgt_rgb)
     r = subprocess.run([BIN, str(tmp_path / "s.pcd"), str(tmp_path / "t.pcd"), "0.05", "0.03", str(tmp_path)],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
@@ -33,7 +36,7 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     assert sum(l.startswith("# direct ICP") for l in lines) == 1
     byname = {(x[0], x[1]): x for x in rows}
     for kp_name in ("Harris3D", "Iss"):
-        for d_name in ("FPFH", "SHOT", "PFH", "PrincipalCurvatures"):
+        for d_name in ("FPFH", "SHOT", "SHOTColor", "PFH", "PrincipalCurvatures"):
             assert (kp_name, d_name) in byname
     # NARF row (present when both clouds yield keypoints): the shim's RangeImagePlanar / NarfKeypoint /
     # NarfDescriptor objects against the C ABI called from Python on the same cloud
@@ -111,4 +114,24 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     assert np.array_equal(p_shim, ctx.pfh125(radius=0.05), equal_nan=True)
     c_shim = np.fromfile(tmp_path / "Iss_PrincipalCurvatures_src.bin", dtype=np.float32).reshape(-1, 5)
     assert np.array_equal(c_shim, ctx.principal_curvatures(radius=0.05), equal_nan=True)
+    ctx.set_queries(None)
+    # SHOT1344 through the shim (colours from the PointXYZRGB records) == the C ABI called from Python
+    ctx.set_surface(src)
+    ctx.set_queries(None)
+    ctx.normals(radius=0.03, want_output=False)
+    ctx.set_surface_colors(src_rgb)
+    for kp_name in ("Iss", "Harris3D"):
+        rec = np.fromfile(tmp_path / (kp_name + "_src_kp.bin"), dtype=np.float32).reshape(-1, 8)
+        q_rgb = np.ascontiguousarray(rec[:, 4]).view(np.uint32) & 0xffffff
+        # ISSKeypoint3D copies only x, y, z into its output points (colour stays PointXYZRGB's default black), the
+        # Harris keypoints are cloud points found by the 1 cm snap and keep their colour
+        if kp_name == "Iss":
+            assert np.all(q_rgb == 0)
+        else:
+            assert np.array_equal(q_rgb, src_rgb[snapped])
+        ctx.set_queries(np.ascontiguousarray(rec[:, :3]))
+        ctx.set_query_colors(q_rgb)
+        sc_shim = np.fromfile(tmp_path / (kp_name + "_SHOTColor_src.bin"), dtype=np.float32).reshape(-1, 1353)
+        sc_abi, sc_rf = ctx.shot1344(0.05)
+        assert np.array_equal(sc_shim[:, :1344], sc_abi, equal_nan=True) and np.array_equal(sc_shim[:, 1344:], sc_rf, equal_nan=True)
     ctx.set_queries(None)
