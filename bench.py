@@ -233,6 +233,7 @@ def main():
 
     def step_device(i):
         ctx.set_surface_dev(devs[i & 1].data_ptr(), n, 16)
+        ctx.prepare_radius(SHOT_RADIUS)  # the SHOT index is built on the auxiliary stream, under the kNN / FPFH stages
         ctx.normals_dev(0.0, K_NN, None)
         ctx.fpfh_dev(0.0, K_NN, d_fpfh.data_ptr())
         ctx.shot352_dev(SHOT_RADIUS, d_shot.data_ptr())
@@ -297,6 +298,7 @@ def main():
         def step_host(i):
             h = hosts[i & 1]
             ctx._chk(ctx.lib.pfx_set_surface(ctx.h, pfx.capi._ptr(h), n, 16, HOST))
+            ctx.prepare_radius(SHOT_RADIUS)
             ctx._chk(ctx.lib.pfx_normals(ctx.h, 0.0, K_NN, None, 16, 3, HOST))
             ctx._chk(ctx.lib.pfx_fpfh(ctx.h, 0.0, K_NN, pfx.capi._ptr(h_fpfh[i & 1]), 132, ASYNC))
             ctx._chk(ctx.lib.pfx_shot352(ctx.h, SHOT_RADIUS, None, pfx.capi._ptr(h_shot[i & 1]), 1444, ASYNC))

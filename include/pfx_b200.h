@@ -80,6 +80,10 @@ int pfx_profile_end(pfx_ctx* ctx, char* buf, size_t buflen);
  * pfx_set_viewpoint <- cloud.sensor_origin_ used by flipNormalTowardsViewpoint (default 0,0,0) */
 int pfx_set_surface(pfx_ctx* ctx, const void* pts, size_t n, size_t stride, int mem);
 int pfx_set_queries(pfx_ctx* ctx, const void* pts, size_t n, size_t stride, int mem);
+/* Optional hint: build the search index of `radius` now, on an auxiliary stream, behind the surface upload.  A
+ * later radius stage with the same radius (pfx_shot352, pfx_fpfh, pfx_radius_*, ...) finds it ready instead of
+ * building it in line; everything enqueued in between overlaps the build.  Results are unaffected. */
+int pfx_prepare_radius(pfx_ctx* ctx, double radius);
 int pfx_set_surface_normals(pfx_ctx* ctx, const void* normals, size_t n, size_t stride,
                             int curv_off, int mem);
 int pfx_set_viewpoint(pfx_ctx* ctx, float vx, float vy, float vz);

@@ -63,6 +63,7 @@ SIGNATURES = {
     "pfx_profile_end": (_i, [_vp, C.c_char_p, _sz]),
     "pfx_set_surface": (_i, [_vp, _vp, _sz, _sz, _i]),
     "pfx_set_queries": (_i, [_vp, _vp, _sz, _sz, _i]),
+    "pfx_prepare_radius": (_i, [_vp, _d]),
     "pfx_set_surface_normals": (_i, [_vp, _vp, _sz, _sz, _i, _i]),
     "pfx_set_viewpoint": (_i, [_vp, _f, _f, _f]),
     "pfx_num_surface": (_sz, [_vp]),
@@ -212,6 +213,10 @@ class Context:
     def set_queries_dev(self, ptr, n, stride):
         self._chk(self.lib.pfx_set_queries(self.h, _ptr(ptr), n, stride, DEVICE))
 
+    def prepare_radius(self, radius):
+        """hint: build the radius index now on the auxiliary stream (overlaps the calls that follow)"""
+        self._chk(self.lib.pfx_prepare_radius(self.h, radius))
+
     def set_surface_normals(self, normals4):
         nr = np.ascontiguousarray(normals4, np.float32)
         assert nr.ndim == 2 and nr.shape[1] in (4, 8)
@@ -236,6 +241,12 @@ class Context:
         d2 = np.zeros((nq, k), np.float32)
         self._chk(self.lib.pfx_knn(self.h, k, _ptr(idx), _ptr(d2), HOST))
         return idx, d2
+
+    def radius_count(self, radius):
+        counts = np.zeros(self.num_queries, np.int32)
+        total = C.c_int64(0)
+        self._chk(self.lib.pfx_radius_count(self.h, radius, _ptr(counts), C.byref(total), HOST))
+        return counts
 
     def radius_search(self, radius, sorted=True):
         nq = self.num_queries

@@ -175,6 +175,11 @@ extern "C" int pfx_destroy(pfx_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->aux_stream) {
+    cudaStreamSynchronize(ctx->aux_stream);
+    cudaStreamDestroy(ctx->aux_stream);
+    cudaEventDestroy(ctx->ev_surface);
+  }
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
@@ -205,8 +210,16 @@ extern "C" int pfx_set_stream(pfx_ctx* ctx, void* s) {
   return 0;
 }
 
+extern "C" int pfx_prepare_radius(pfx_ctx* ctx, double radius) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_prepare_radius: no surface set");
+  if (!(radius > 0)) return ctx->fail(PFX_E_INVALID, "pfx_prepare_radius: radius must be positive");
+  return grid_prepare_async(ctx, radius);
+}
+
 extern "C" int pfx_sync(pfx_ctx* ctx) {
   PFX_TRY(check_ctx(ctx));
+  if (ctx->aux_stream) PFX_CUDA(cudaStreamSynchronize(ctx->aux_stream));
   PFX_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ctx->copy_stream) {
     PFX_CUDA(cudaStreamSynchronize(ctx->copy_stream));
@@ -260,6 +273,7 @@ extern "C" int pfx_profile_begin(pfx_ctx* ctx, const char* filter) {
 extern "C" int pfx_profile_end(pfx_ctx* ctx, char* buf, size_t buflen) {
   PFX_TRY(check_ctx(ctx));
   ctx->prof_on = false;
+  if (ctx->aux_stream) PFX_CUDA(cudaStreamSynchronize(ctx->aux_stream));
   PFX_CUDA(cudaStreamSynchronize(ctx->stream));
   std::vector<std::pair<std::string, std::pair<int, double>>> agg;
   for (size_t i = 0; i < ctx->prof_used; ++i) {
@@ -299,6 +313,7 @@ extern "C" int pfx_set_surface(pfx_ctx* ctx, const void* pts, size_t n, size_t s
   if ((n && !pts) || stride < 12 || (stride & 3) || n > 0x7fffffffull)
     return ctx->fail(PFX_E_INVALID, "pfx_set_surface: bad pointer / stride / size");
   const unsigned char* src = nullptr;
+  PFX_TRY(grid_wait_pending(ctx));  // a build in flight on the auxiliary stream still reads the old surface
   PFX_TRY(upload_records(ctx, pts, n, stride, mem, ctx->stage, &src));
   PFX_CUDA(ctx->surf.ensure(std::max<size_t>(n, 1) * sizeof(float4)));
   if (n) PFX_LAUNCH(ctx, aos_to_float4_kernel, div_up((long long)n, 256), 256, 0, src, stride, (int)n, ctx->surf.as<float4>());

@@ -531,12 +531,52 @@ static int grid_build(Ctx* ctx, Grid* g, double radius, int knn_k) {
 
 // Grids are cached per (surface version, radius | k): repeated compute() calls on the same cloud do
 // not rebuild the index (the reference rebuilds a kd-tree per Feature object, features.h:192-193).
+static int grid_consume_pending(Ctx* ctx, Grid* g) {
+  if (g->pending) {
+    PFX_CUDA(cudaStreamWaitEvent(ctx->stream, g->ready, 0));
+    g->pending = false;
+  }
+  return 0;
+}
+
+int grid_wait_pending(Ctx* ctx) {
+  for (Grid* g : ctx->grids) PFX_TRY(grid_consume_pending(ctx, g));
+  return 0;
+}
+
+// Builds the grid of `radius` on the auxiliary stream, behind everything the main stream has enqueued so far
+// (the surface upload), so that the build overlaps whatever the main stream does next.  The Grid's buffers are its
+// own and the surface is only read, so the two streams share nothing else.
+int grid_prepare_async(Ctx* ctx, double radius) {
+  for (Grid* g : ctx->grids)
+    if (g->surf_version == ctx->surf_version && g->radius == radius) return 0;  // cached or already in flight
+  if (!ctx->aux_stream) {
+    PFX_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    PFX_CUDA(cudaEventCreateWithFlags(&ctx->ev_surface, cudaEventDisableTiming));
+  }
+  PFX_CUDA(cudaEventRecord(ctx->ev_surface, ctx->stream));
+  PFX_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_surface, 0));
+  cudaStream_t main_stream = ctx->stream;
+  ctx->stream = ctx->aux_stream;
+  Grid* g = nullptr;
+  int rc = grid_get(ctx, radius, 0, &g);
+  if (rc == 0) {
+    if (!g->ready && cudaEventCreateWithFlags(&g->ready, cudaEventDisableTiming) != cudaSuccess) rc = PFX_E_STATE;
+    if (rc == 0 && cudaEventRecord(g->ready, ctx->aux_stream) != cudaSuccess) rc = PFX_E_STATE;
+    if (rc == 0) g->pending = true;
+  }
+  ctx->stream = main_stream;
+  if (rc != 0 && ctx->err.empty()) ctx->err = "pfx_prepare_radius: could not enqueue the build";
+  return rc;
+}
+
 int grid_get(Ctx* ctx, double radius, int knn_k, Grid** out) {
   ctx->tick++;
   Grid* victim = nullptr;
   for (Grid* g : ctx->grids) {
     if (g->surf_version == ctx->surf_version &&
         ((radius > 0 && g->radius == radius) || (!(radius > 0) && g->knn_k == knn_k && !(g->radius > 0)))) {
+      PFX_TRY(grid_consume_pending(ctx, g));
       g->last_use = ctx->tick;
       *out = g;
       ctx->last_grid = g;
@@ -555,6 +595,7 @@ int grid_get(Ctx* ctx, double radius, int knn_k, Grid** out) {
   }
   if (ctx->normals_sorted_for == victim) ctx->normals_sorted_for = nullptr;
   if (ctx->knn_grid == victim) ctx->knn_grid = nullptr;
+  PFX_TRY(grid_consume_pending(ctx, victim));  // a build still in flight on the other stream owns these buffers
   victim->last_use = ctx->tick;
   int rc = grid_build(ctx, victim, radius, knn_k);
   if (rc != 0) {
@@ -677,6 +718,7 @@ int voxel_grid_run(Ctx* ctx, float leaf, float* out_dev, size_t cap, size_t* n_o
 void grid_free_all(Ctx* ctx) {
   ctx->vg_scratch.release();
   for (Grid* g : ctx->grids) {
+    if (g->ready) cudaEventDestroy(g->ready);
     g->release();
     delete g;
   }

@@ -44,6 +44,10 @@ struct Grid {
   double radius = -1;  // radius grids: cell edge = radius * (1 + 1e-3)
   int knn_k = 0;       // kNN grids: cell edge estimated on the device from the point density
   uint64_t last_use = 0;
+  // built ahead of use on the context's auxiliary stream (pfx_prepare_radius): `ready` is recorded behind the
+  // build; the first consumer makes the main stream wait for it
+  cudaEvent_t ready = nullptr;
+  bool pending = false;
   int n = 0;
   uint32_t hmask = 0;
   DevBuf params, pts, inv_perm, keys, vals, keys2, vals2, ghist, cell_start, cell_key, hkeys, hvals,
@@ -143,6 +147,8 @@ struct Ctx {
   int ri_stage = 0;  // 0 image only, 1 borders extracted, 2 interest image for ri_support
   float ri_support = 0.f;
 
+  cudaStream_t aux_stream = nullptr;  // index builds ahead of use (pfx_prepare_radius)
+  cudaEvent_t ev_surface = nullptr;
   DevBuf icp_state, icp_cur, icp_nn, icp_partials;  // icp.cu
   // colours (shot_color.cu): normalised CIELab of the surface points / queries, valid for these versions
   DevBuf lab_tab, surf_lab, qry_lab;
@@ -197,6 +203,8 @@ struct Ctx {
 
 // ---- grid.cu
 int grid_get(Ctx* ctx, double radius, int knn_k, Grid** out);
+int grid_prepare_async(Ctx* ctx, double radius);  // build the radius grid on the auxiliary stream
+int grid_wait_pending(Ctx* ctx);                  // main stream waits for every build in flight
 void grid_free_all(Ctx* ctx);
 int voxel_grid_run(Ctx* ctx, float leaf, float* out_dev, size_t cap, size_t* n_out);
 // device-wide exclusive scan of int32 -> int32 / int64 (total written to *total_dev when non-null)

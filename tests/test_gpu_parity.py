@@ -654,3 +654,38 @@ def test_async_host_delivery_equals_synchronous(ctx, sheet):
     for rep in range(2):
         assert np.array_equal(fa[rep], f_sync, equal_nan=True)
         assert np.array_equal(sa[rep][:, :352], s_sync, equal_nan=True) and np.array_equal(sa[rep][:, 352:], rf_sync, equal_nan=True)
+
+
+def test_prepare_radius_hint_changes_nothing_but_the_schedule(ctx, orc):
+    """pfx_prepare_radius builds the radius index on the auxiliary stream while the main stream runs the k-search
+    stages: same bits with and without the hint, also when surfaces change under a build in flight"""
+    rng = np.random.default_rng(3)
+    clouds_ = []
+    for s in range(3):
+        u = rng.uniform(0, 1, (40000, 2))
+        clouds_.append(np.c_[u, 0.05 * np.sin(9 * u[:, 0] + s)].astype(np.float32))
+    outs = {}
+    for hint in (False, True, True):
+        for ci, pts in enumerate(clouds_):
+            ctx.set_surface(pts)
+            if hint:
+                ctx.prepare_radius(0.03)
+                ctx.prepare_radius(0.03)   # a second hint for the same radius is a no-op
+            ctx.set_viewpoint(0, 0, 5)
+            ctx.normals(k=16, want_output=False)
+            f = ctx.fpfh(k=16)
+            s352, rf = ctx.shot352(0.03)
+            cnt = ctx.radius_count(0.03)
+            key = ci
+            if key in outs:
+                for a, b in zip(outs[key], (f, s352, rf, cnt)):
+                    assert np.array_equal(a, b, equal_nan=True)
+            else:
+                outs[key] = (f, s352, rf, cnt)
+    # a hint followed at once by a new surface: the build in flight is waited for, not corrupted
+    ctx.set_surface(clouds_[0])
+    ctx.prepare_radius(0.03)
+    ctx.set_surface(clouds_[1])
+    assert np.array_equal(ctx.radius_count(0.03), outs[1][3])
+    with pytest.raises(RuntimeError):
+        ctx.prepare_radius(0.0)

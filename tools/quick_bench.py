@@ -24,7 +24,10 @@ def ev():
 
 for it in range(3):
     t = [ev()]
-    ctx.set_surface_dev(d_pts.data_ptr(), n, 16); t.append(ev())
+    ctx.set_surface_dev(d_pts.data_ptr(), n, 16)
+    if not os.environ.get("PFX_NO_HINT"):
+        ctx.prepare_radius(0.0128)
+    t.append(ev())
     ctx.normals_dev(0.0, 32, None); t.append(ev())
     ctx.fpfh_dev(0.0, 32, d_f.data_ptr()); t.append(ev())
     ctx.shot352_dev(0.0128, d_s.data_ptr()); t.append(ev())
@@ -34,6 +37,8 @@ for it in range(3):
     print(it, " ".join(f"{nm}={m:.3f}ms" for nm, m in zip(names, ms)), f"total={sum(ms):.3f}ms launches={ctx.launches}")
 ctx.profile_begin(None)
 ctx.set_surface_dev(d_pts.data_ptr(), n, 16)
+if not os.environ.get("PFX_NO_HINT"):
+    ctx.prepare_radius(0.0128)
 ctx.normals_dev(0.0, 32, None)
 ctx.fpfh_dev(0.0, 32, d_f.data_ptr())
 ctx.shot352_dev(0.0128, d_s.data_ptr())
