@@ -202,3 +202,63 @@ def sharded_match_nn(match_fn, a, b_local, b_offset, device=None, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
     return unpack_nn(t.cpu().numpy())
+
+
+def ring_match_nn(match_fn, a_local, b_local, b_offset, b_total, rank, world, device=None, group=None):
+    """Exact 1-NN when BOTH descriptor sets are sharded (ring rotation of target blocks).
+
+    Rank r holds its queries `a_local` and the target block `b_local` (global index of its first row: b_offset;
+    b_total rows over all ranks).  In step s it matches its queries against the block that started on rank
+    (r + s) % world while that block is already on its way to rank r - 1 (isend / irecv posted BEFORE the match,
+    so the transfer - NCCL P2P over NVLink on GPUs - overlaps the GEMM of the current block), and keeps the
+    smaller packed (d2, global index) key.  No all-reduce: a rank ends with the final answer for its own queries.
+
+    a_local / b_local: numpy arrays (CPU ranks, gloo) or torch tensors that already live on `device` (GPU ranks:
+    blocks then travel device to device and are handed to match_fn as tensors).  match_fn(a, b) -> (idx int32
+    [-1 = none], d2 float32) as numpy arrays is the single-GPU matcher.  Returns (idx, d2) of a_local."""
+    as_tensor = torch is not None and isinstance(b_local, torch.Tensor)
+    n_a = len(a_local)
+    dim = a_local.shape[1]
+    best = np.full(n_a, np.iinfo(np.int64).max, np.int64)
+    dev = device or (b_local.device if as_tensor else torch.device("cpu"))
+    if as_tensor:
+        cur = b_local.reshape(-1, dim).contiguous()
+    else:
+        a_local = np.ascontiguousarray(a_local, np.float32)
+        cur = torch.from_numpy(np.ascontiguousarray(b_local, np.float32).reshape(-1, dim)).to(dev)
+    cur_off = int(b_offset)
+
+    def match(block, off):
+        if len(block) == 0 or n_a == 0:
+            return
+        idx, d2 = match_fn(a_local, block if as_tensor else block.cpu().numpy())
+        np.minimum(best, pack_nn(d2, idx, off), out=best)
+
+    if world == 1:
+        match(cur, cur_off)
+        return unpack_nn(best)
+    left, right = (rank - 1) % world, (rank + 1) % world
+    for step in range(world):
+        nxt, hdr_in, works = None, None, []
+        if step < world - 1:
+            # header (rows, offset) and payload of the block travel to the left neighbour; ours arrives from the right
+            hdr_out = torch.tensor([len(cur), cur_off], dtype=torch.int64, device=dev)
+            hdr_in = torch.zeros(2, dtype=torch.int64, device=dev)
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, hdr_out, left, group),
+                                             dist.P2POp(dist.irecv, hdr_in, right, group)]):
+                w.wait()
+            nxt = torch.empty((int(hdr_in[0].item()), dim), dtype=torch.float32, device=dev)
+            ops = []
+            if cur.numel():
+                ops.append(dist.P2POp(dist.isend, cur, left, group))
+            if nxt.numel():
+                ops.append(dist.P2POp(dist.irecv, nxt, right, group))
+            works = dist.batch_isend_irecv(ops) if ops else []
+        match(cur, cur_off)
+        for w in works:
+            w.wait()
+        if nxt is not None:
+            cur, cur_off = nxt, int(hdr_in[1].item())
+    idx, d2 = unpack_nn(best)
+    assert idx.max(initial=-1) < b_total
+    return idx, d2

@@ -105,6 +105,25 @@ def _match_worker(rank, world, port, path, out_path):
         dist.destroy_process_group()
 
 
+def _ring_worker(rank, world, port, path, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import binding as orc
+        orc.set_num_threads(2)
+        z = np.load(path)
+        a, b = z["a"], z["b"]
+        ab = np.linspace(0, len(a), world + 1).astype(int)
+        bb = np.array(z["b_bounds"])
+        idx, d2 = sharding.ring_match_nn(orc.match_nn, a[ab[rank]:ab[rank + 1]], np.ascontiguousarray(b[bb[rank]:bb[rank + 1]]),
+                                         bb[rank], len(b), rank, world)
+        np.savez(os.path.join(out_dir, f"ring_{rank}.npz"), idx=idx, d2=d2, lo=ab[rank])
+    finally:
+        dist.destroy_process_group()
+
+
 def test_pack_nn_orders_like_distance_then_index():
     d2 = np.array([0.5, 0.5, 0.25, 3.0, 0.0], np.float32)
     idx = np.array([7, 3, 9, -1, 2], np.int32)
@@ -129,6 +148,28 @@ def test_target_sharded_matching_equals_single_process(tmp_path, orc):
     idx, d2 = orc.match_nn(a, b)
     assert np.array_equal(got["idx"], idx) and got["idx"][3] == -1
     assert np.array_equal(got["d2"][idx >= 0], d2[idx >= 0])
+
+
+def test_ring_matching_with_both_sides_sharded_equals_single_process(tmp_path, orc):
+    """queries AND targets sharded over 3 ranks; target blocks rotate around the ring (one of them empty)"""
+    import torch.multiprocessing as mp
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, 4, (500, 36)).astype(np.float32)
+    b = rng.integers(0, 4, (777, 36)).astype(np.float32)
+    a[11, 5] = np.nan
+    world = 3
+    path = str(tmp_path / "ab.npz")
+    np.savez(path, a=a, b=b, b_bounds=np.array([0, 400, 400, 777]))   # rank 1 holds no targets
+    mp.spawn(_ring_worker, args=(world, _free_port(), path, str(tmp_path)), nprocs=world, join=True)
+    idx, d2 = orc.match_nn(a, b)
+    for r in range(world):
+        got = np.load(tmp_path / f"ring_{r}.npz")
+        lo = int(got["lo"])
+        sl = slice(lo, lo + len(got["idx"]))
+        assert np.array_equal(got["idx"], idx[sl])
+        ok = idx[sl] >= 0
+        assert np.array_equal(got["d2"][ok], d2[sl][ok])
+    assert idx[11] == -1
 
 
 def test_slab_sharded_equals_single_process(tmp_path, orc, clouds):
