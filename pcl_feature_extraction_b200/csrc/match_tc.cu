@@ -171,6 +171,13 @@ __global__ void tc_prep_kernel(const float* __restrict__ X, int n, int ld, int d
 }
 
 // ------------------------------------------------------------------------------------------ GEMM + top-K
+// (bits(v) & ~127) | col in one LOP3 (truth table 0xEA = (a & b) | c)
+__device__ __forceinline__ float tc_embed(float v, int col) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(__float_as_uint(v)), "r"(0xFFFFFF80u), "r"((uint32_t)col));
+  return __uint_as_float(r);
+}
+
 // Cold path of the epilogue: insert (d, j) into the calling thread's ascending top-K list, which lives in
 // shared memory ([slot][thread], conflict-free) so that the hot loop carries only the K-th value in a
 // register and stays small enough for the instruction cache.  Returns the new K-th value.
@@ -369,10 +376,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
             for (int u = 0; u < 4; u += 2) {
               // two columns per step: with their min / max in hand the sorted insertion of both into
               // (m1 <= m2 <= m3) takes 8 min/max instructions (two of them 3-input) instead of 10
-              const float dx = fmaf(-2.f, __uint_as_float(v[c + u]), na + nn[u]);
-              const float dy = fmaf(-2.f, __uint_as_float(v[c + u + 1]), na + nn[u + 1]);
-              const float x = __uint_as_float((__float_as_uint(dx) & 0xFFFFFF80u) | (uint32_t)(c0 + c + u));
-              const float y = __uint_as_float((__float_as_uint(dy) & 0xFFFFFF80u) | (uint32_t)(c0 + c + u + 1));
+              // keys are |b~|^2 - 2 a~.b~: the row constant |a~|^2 does not change their order and is added to the
+              // three survivors only.  (bits & ~127) | column as ONE three-input logic instruction.
+              const float dx = fmaf(-2.f, __uint_as_float(v[c + u]), nn[u]);
+              const float dy = fmaf(-2.f, __uint_as_float(v[c + u + 1]), nn[u + 1]);
+              const float x = tc_embed(dx, c0 + c + u);
+              const float y = tc_embed(dy, c0 + c + u + 1);
               const float lo = fminf(x, y), hi = fmaxf(x, y);
               const float n3 = fminf(m3, fminf(fmaxf(m2, lo), fmaxf(m1, hi)));
               const float n2 = fminf(fmaxf(m1, lo), fminf(m2, hi));
@@ -396,9 +405,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
         consume(va, 64);
         tmem_ld_wait();
         consume(vb, 96);
-        bound = fminf(bound, m3);
         const int jbase = p * 256 + hsel * 128;
         const int j1 = (int)(__float_as_uint(m1) & 0x7Fu), j2 = (int)(__float_as_uint(m2) & 0x7Fu);
+        m1 += na;
+        m2 += na;
+        m3 += na;
+        bound = fminf(bound, m3);
         if (m1 < worst) worst = tc_topk_insert(sd, sj, m1, jbase + j1);
         if (m2 < worst) worst = tc_topk_insert(sd, sj, m2, jbase + j2);
       }
