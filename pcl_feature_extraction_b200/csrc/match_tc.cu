@@ -368,6 +368,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
         float m1 = 3e38f, m2 = 3e38f, m3 = 3e38f;
         // sorted insertion of the 32 keys of one accumulator slab into (m1 <= m2 <= m3)
         auto consume = [&](const uint32_t (&v)[32], int c0) {
+#ifdef TC_SKIP_NETWORK  // experiment: pace of the MMA / TMA side alone
+          uint32_t acc = 0;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) acc ^= v[c];
+          if (acc == 0x12345678u) m1 = 0.f;
+          return;
+#endif
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
             const float4 n4 = *reinterpret_cast<const float4*>(nh_buf + c0 + c);

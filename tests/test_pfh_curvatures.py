@@ -167,3 +167,51 @@ def test_gpu_curvatures_on_a_cylinder(ctx):
     g = ctx.principal_curvatures(radius=0.05)
     assert np.all(np.abs(g[:, 4]) < 1e-7) and np.all(g[:, 3] > 1e-4)
     assert np.all(np.abs(g[:, 2]) < 1e-5)
+
+
+@pytest.mark.gpu
+def test_device_resident_buffers_give_the_same_rows(ctx):
+    """PFX_DEVICE outputs (and a padded record stride) == PFX_HOST outputs for the widened descriptors and ICP"""
+    import torch
+    import ctypes as C
+    import pcl_feature_extraction_b200 as pfx
+    from pcl_feature_extraction_b200.capi import _ptr, DEVICE, IcpParams, IcpResult
+    pts = bumpy(12000, 9)
+    rng = np.random.default_rng(2)
+    rgb = rng.integers(0, 1 << 24, len(pts)).astype(np.uint32)
+    ctx.set_surface(pts)
+    ctx.set_viewpoint(0, 0, 10)
+    ctx.normals(radius=0.03, want_output=False)
+    ctx.set_surface_colors(rgb)
+    q = pts[:257]
+    ctx.set_queries(q)
+    ctx.set_query_colors(rgb[:257])
+    dev = torch.device("cuda:0")
+    h_pfh, h_pc = ctx.pfh125(radius=0.04), ctx.principal_curvatures(radius=0.04)
+    h_sc, h_rf = ctx.shot1344(0.04)
+    d_pfh = torch.full((257, 128), -7.0, dtype=torch.float32, device=dev)      # stride 512 B > 500 B
+    d_pc = torch.full((257, 8), -7.0, dtype=torch.float32, device=dev)         # stride 32 B > 20 B
+    d_sc = torch.full((257, 1353), -7.0, dtype=torch.float32, device=dev)
+    ctx._chk(ctx.lib.pfx_pfh125(ctx.h, 0.04, 0, _ptr(d_pfh), 512, DEVICE))
+    ctx._chk(ctx.lib.pfx_principal_curvatures(ctx.h, 0.04, 0, _ptr(d_pc), 32, DEVICE))
+    ctx._chk(ctx.lib.pfx_shot1344(ctx.h, 0.04, None, _ptr(d_sc), 5412, DEVICE))
+    ctx.sync()
+    torch.cuda.synchronize()
+    assert np.array_equal(d_pfh.cpu().numpy()[:, :125], h_pfh, equal_nan=True) and np.all(d_pfh.cpu().numpy()[:, 125:] == -7.0)
+    assert np.array_equal(d_pc.cpu().numpy()[:, :5], h_pc, equal_nan=True) and np.all(d_pc.cpu().numpy()[:, 5:] == -7.0)
+    assert np.array_equal(d_sc.cpu().numpy()[:, :1344], h_sc, equal_nan=True)
+    assert np.array_equal(d_sc.cpu().numpy()[:, 1344:], h_rf, equal_nan=True)
+    ctx.set_queries(None)
+    # ICP with the source and the aligned cloud on the device (PointXYZRGB-like 32-byte records)
+    src = (pts[::3] + np.float32([0.004, -0.003, 0.002])).astype(np.float32)
+    h = ctx.icp_align(src, want_aligned=True)
+    rec = np.zeros((len(src), 8), np.float32)
+    rec[:, :3] = src
+    d_src = torch.from_numpy(rec).to(dev)
+    d_al = torch.zeros((len(src), 8), dtype=torch.float32, device=dev)
+    prm, res = IcpParams(0.07, 100, 1e-6, 1e-4), IcpResult()
+    ctx._chk(ctx.lib.pfx_icp_align(ctx.h, _ptr(d_src), len(src), 32, C.byref(prm), None, C.byref(res), _ptr(d_al), 32, DEVICE))
+    torch.cuda.synchronize()
+    assert np.array_equal(np.array(res.transform, np.float32).reshape(4, 4), h["T"]) and res.iterations == h["iterations"]
+    assert res.fitness == h["fitness"]
+    assert np.array_equal(d_al.cpu().numpy()[:, :3], h["aligned"]) and np.all(d_al.cpu().numpy()[:, 3:] == 0)
