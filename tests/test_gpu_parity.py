@@ -689,3 +689,4 @@ def test_prepare_radius_hint_changes_nothing_but_the_schedule(ctx, orc):
     assert np.array_equal(ctx.radius_count(0.03), outs[1][3])
     with pytest.raises(RuntimeError):
         ctx.prepare_radius(0.0)
+    ctx.set_viewpoint(0, 0, 0)   # the context is shared by the session: leave the default viewpoint behind

@@ -55,6 +55,7 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
         return np.ascontiguousarray(a[:, :3])
 
     # ISS keypoints: same as the C ABI called from Python, and as the oracle NMS on the GPU saliency
+    ctx.set_viewpoint(0, 0, 0)   # the clouds' sensor origin (VIEWPOINT 0 0 0 ...), what the shim passes
     ctx.set_surface(src)
     res = ctx.cloud_resolution()
     kp, sal = ctx.iss(6 * res, 4 * res)

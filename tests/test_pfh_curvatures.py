@@ -77,7 +77,9 @@ def gpu_normals(ctx, pts, radius=None, k=0):
     ctx.set_surface(pts)
     ctx.set_queries(None)
     ctx.set_viewpoint(0, 0, 10)
-    return ctx.normals(radius=radius or 0.0, k=k)
+    nr = ctx.normals(radius=radius or 0.0, k=k)
+    ctx.set_viewpoint(0, 0, 0)   # shared session context: restore the default
+    return nr
 
 
 @pytest.mark.gpu
@@ -182,6 +184,7 @@ def test_device_resident_buffers_give_the_same_rows(ctx):
     ctx.set_surface(pts)
     ctx.set_viewpoint(0, 0, 10)
     ctx.normals(radius=0.03, want_output=False)
+    ctx.set_viewpoint(0, 0, 0)
     ctx.set_surface_colors(rgb)
     q = pts[:257]
     ctx.set_queries(q)
