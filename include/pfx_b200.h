@@ -174,6 +174,10 @@ int pfx_match_info(pfx_ctx* ctx, double* out4);
  * ordinal - which is the query's own normal when the queries are the surface. */
 int pfx_pfh125(pfx_ctx* ctx, double radius, int k, float* out, size_t stride, int mem);
 int pfx_principal_curvatures(pfx_ctx* ctx, double radius, int k, float* out, size_t stride, int mem);
+/* pfx_moment_invariants <- MomentInvariantsEstimation<PointXYZRGB, MomentInvariants>::compute (evaluation.cpp:555-574):
+ * rows of 3 floats (pcl::MomentInvariants: j1, j2, j3) from the central second moments of each neighbourhood;
+ * needs no normals. */
+int pfx_moment_invariants(pfx_ctx* ctx, double radius, int k, float* out, size_t stride, int mem);
 /* the float PCL's `hist[bin] += incr` holds after `count` additions (IEEE binary32, sequential): turns integer vote
  * counts (pfx_spfh count rows, PFH votes) into PCL's histogram values bit for bit.  Pure host function. */
 float pfx_seq_float_sum(float incr, long long count);

@@ -358,3 +358,11 @@ def shot1344(surf, rgb, normals4, q, qrgb, radius, lrf_in=None, want_lab=False):
                             None if lrf is None else _opt(lrf), _opt(out), _opt(rf), None if lab is None else _opt(lab)),
          "shot1344")
     return (out, rf, lab) if want_lab else (out, rf)
+
+
+def moment_invariants(surf, q, radius=0.0, k=0):
+    surf, q = _f32(surf), _f32(q)
+    out = np.zeros((len(q), 3), np.float32)
+    _chk(lib().orc_moment_invariants(_opt(surf), len(surf), _opt(q), len(q), C.c_double(radius), int(k), _opt(out)),
+         "moment_invariants")
+    return out

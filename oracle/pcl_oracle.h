@@ -88,6 +88,9 @@ int orc_pfh125(const float* surf, const float* normals4, int n, const float* q, 
 int orc_principal_curvatures(const float* surf, const float* normals4, int n, const float* q, int nq,
                              double radius, int k, float* out5, float* gap);
 
+/* ---- MomentInvariants (evaluation.cpp:555-574): out nq x 3 (j1, j2, j3) */
+int orc_moment_invariants(const float* surf, int n, const float* q, int nq, double radius, int k, float* out3);
+
 /* ---- SHOT (evaluation.cpp:770-775 -> SHOTEstimationOMP + SHOTLocalReferenceFrameEstimation).
  * rf: nq x 9 (x_axis, y_axis, z_axis). lrf_in (optional): use these frames instead.
  * lrf_gap (optional, nq x 2): relative eigen gaps (l2-l1)/l2 and (l1-l0)/l2 of the LRF matrix. */

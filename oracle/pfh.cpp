@@ -185,3 +185,41 @@ extern "C" int orc_principal_curvatures(const float* surf, const float* normals4
   }
   return 0;
 }
+
+// MomentInvariants (reference evaluation.cpp:555-574 -> MomentInvariantsEstimation::computePointMomentInvariants):
+// central second moments of the neighbourhood about its centroid, j1 = trace, j2 = sum of principal 2x2 minors,
+// j3 = determinant.  Sums in double (upstream: float, sequential); no normals involved.  out: nq x 3.
+extern "C" int orc_moment_invariants(const float* surf, int n, const float* q, int nq, double radius, int k, float* out3) {
+  if ((radius > 0) == (k > 0)) return -1;
+  Searcher s;
+  s.init(surf, n, radius, k);
+  const float nanv = std::numeric_limits<float>::quiet_NaN();
+#pragma omp parallel
+  {
+    std::vector<Nbr> nb;
+#pragma omp for schedule(dynamic, 64)
+    for (int i = 0; i < nq; ++i) {
+      float* O = out3 + 3 * (size_t)i;
+      nb.clear();
+      if (finite3(q + 3 * (size_t)i)) s.query(q + 3 * (size_t)i, nb);
+      if (nb.empty()) {
+        O[0] = O[1] = O[2] = nanv;
+        continue;
+      }
+      double c[3] = {0, 0, 0};
+      for (const Nbr& b : nb)
+        for (int a = 0; a < 3; ++a) c[a] += surf[3 * (size_t)b.idx + a];
+      for (int a = 0; a < 3; ++a) c[a] /= (double)nb.size();
+      double m200 = 0, m020 = 0, m002 = 0, m110 = 0, m101 = 0, m011 = 0;
+      for (const Nbr& b : nb) {
+        const double x = surf[3 * (size_t)b.idx] - c[0], y = surf[3 * (size_t)b.idx + 1] - c[1], z = surf[3 * (size_t)b.idx + 2] - c[2];
+        m200 += x * x; m020 += y * y; m002 += z * z;
+        m110 += x * y; m101 += x * z; m011 += y * z;
+      }
+      O[0] = (float)(m200 + m020 + m002);
+      O[1] = (float)(m200 * m020 + m200 * m002 + m020 * m002 - m110 * m110 - m101 * m101 - m011 * m011);
+      O[2] = (float)(m200 * m020 * m002 + 2 * m110 * m101 * m011 - m002 * m110 * m110 - m020 * m101 * m101 - m200 * m011 * m011);
+    }
+  }
+  return 0;
+}

@@ -81,6 +81,7 @@ SIGNATURES = {
     "pfx_spfh": (_i, [_vp, _d, _i, _vp, _i]),
     "pfx_pfh125": (_i, [_vp, _d, _i, _vp, _sz, _i]),
     "pfx_principal_curvatures": (_i, [_vp, _d, _i, _vp, _sz, _i]),
+    "pfx_moment_invariants": (_i, [_vp, _d, _i, _vp, _sz, _i]),
     "pfx_seq_float_sum": (_f, [_f, C.c_longlong]),
     "pfx_shot352": (_i, [_vp, _d, _vp, _vp, _sz, _i]),
     "pfx_shot_lrf": (_i, [_vp, _d, _vp, _i]),
@@ -332,6 +333,11 @@ class Context:
         """rows of (principal direction x, y, z, pc1, pc2)"""
         out = np.zeros((self.num_queries, 5), np.float32)
         self._chk(self.lib.pfx_principal_curvatures(self.h, radius, k, _ptr(out), 20, HOST))
+        return out
+
+    def moment_invariants(self, radius=0.0, k=0):
+        out = np.zeros((self.num_queries, 3), np.float32)
+        self._chk(self.lib.pfx_moment_invariants(self.h, radius, k, _ptr(out), 12, HOST))
         return out
 
     def spfh(self, radius=0.0, k=0):

@@ -687,11 +687,11 @@ extern "C" int pfx_fpfh(pfx_ctx* ctx, double radius, int k, float* out, size_t s
 // shared body of the per-query descriptor calls that write fixed-size float rows
 template <typename F>
 static int rows_call(pfx_ctx* ctx, double radius, int k, float* out, size_t stride, int mem, size_t row_bytes,
-                     const char* what, F&& compute) {
+                     const char* what, bool needs_normals, F&& compute) {
   PFX_TRY(check_ctx(ctx));
   PFX_TRY(check_search_params(ctx, radius, k, what));
   if (k > 32) return ctx->fail(PFX_E_INVALID, std::string(what) + ": k must be <= 32");
-  if (!ctx->have_normals) return ctx->fail(PFX_E_STATE, std::string(what) + ": no input normals (setInputNormals)");
+  if (needs_normals && !ctx->have_normals) return ctx->fail(PFX_E_STATE, std::string(what) + ": no input normals (setInputNormals)");
   if (!out || stride < row_bytes || (stride & 3) || (mem != PFX_HOST && mem != PFX_DEVICE))
     return ctx->fail(PFX_E_INVALID, std::string(what) + ": bad output / stride / mem");
   const size_t nq = ctx->num_queries();
@@ -709,13 +709,18 @@ static int rows_call(pfx_ctx* ctx, double radius, int k, float* out, size_t stri
 }
 
 extern "C" int pfx_pfh125(pfx_ctx* ctx, double radius, int k, float* out, size_t stride, int mem) {
-  return rows_call(ctx, radius, k, out, stride, mem, 500, "pfx_pfh125",
+  return rows_call(ctx, radius, k, out, stride, mem, 500, "pfx_pfh125", true,
                    [&](Grid* g, float* dout) { return pfh_compute(ctx, g, radius, k, dout, stride / 4); });
 }
 
 extern "C" int pfx_principal_curvatures(pfx_ctx* ctx, double radius, int k, float* out, size_t stride, int mem) {
-  return rows_call(ctx, radius, k, out, stride, mem, 20, "pfx_principal_curvatures",
+  return rows_call(ctx, radius, k, out, stride, mem, 20, "pfx_principal_curvatures", true,
                    [&](Grid* g, float* dout) { return curvature_compute(ctx, g, radius, k, dout, stride / 4); });
+}
+
+extern "C" int pfx_moment_invariants(pfx_ctx* ctx, double radius, int k, float* out, size_t stride, int mem) {
+  return rows_call(ctx, radius, k, out, stride, mem, 12, "pfx_moment_invariants", false,
+                   [&](Grid* g, float* dout) { return moments_compute(ctx, g, radius, k, dout, stride / 4); });
 }
 
 extern "C" float pfx_seq_float_sum(float incr, long long count) { return seq_float_sum(incr, count < 0 ? 0 : count); }

@@ -273,6 +273,7 @@ int ransac_reject_run(Ctx* ctx, const float* src, size_t stride_s, const float* 
 
 // ---- helpers (capi.cu)
 int pfh_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t stride_floats);
+int moments_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t stride_floats);
 int curvature_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t stride_floats);
 int colors_to_lab(Ctx* ctx, const unsigned char* rgb_dev, size_t stride_bytes, int n, DevBuf& lab);
 int shot_color_compute(Ctx* ctx, Grid* g, double radius, const float* rf9_dev, float* out_dev, size_t stride_floats);

@@ -313,4 +313,90 @@ int curvature_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, s
   return 0;
 }
 
+// ------------------------------------------------------------------------------------ MomentInvariants
+// pcl::MomentInvariantsEstimation (reference evaluation.cpp:555-574): central second moments of the neighbourhood
+// about its centroid -> j1 (trace), j2 (sum of the principal 2x2 minors), j3 (determinant).  One warp per query,
+// moments about the query point in double, shifted to the centroid in closed form.
+template <bool DENSE, bool USE_LIST>
+__global__ void __launch_bounds__(PC_WPB * 32)
+moments_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2, const int* __restrict__ lists, int k,
+               float* __restrict__ out, size_t stride) {
+  const int lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * PC_WPB + (threadIdx.x >> 5);
+  if (qi >= nq) return;
+  const GridParams P = *g.gp;
+  const float4 q = DENSE ? g.pts[qi] : queries[qi];
+  const int row = DENSE ? __float_as_int(q.w) : qi;
+  float* o = out + (size_t)row * stride;
+  const bool ok = finite3(q.x, q.y, q.z) && (!DENSE || qi < P.n_valid);
+  double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int cnt = 0;
+  auto add = [&](const float4& p) {
+    const double x = (double)p.x - (double)q.x, y = (double)p.y - (double)q.y, z = (double)p.z - (double)q.z;
+    s[0] += x; s[1] += y; s[2] += z;
+    s[3] += x * x; s[4] += y * y; s[5] += z * z;
+    s[6] += x * y; s[7] += x * z; s[8] += y * z;
+    ++cnt;
+  };
+  if (ok) {
+    if (USE_LIST) {
+      for (int t = lane; t < k; t += 32) {
+        const int j = lists[(size_t)qi * k + t];
+        if (j >= 0) add(g.pts[j]);
+      }
+    } else {
+      const CellBlock blk = DENSE ? stencil_of_point(g, qi, lane) : stencil_of_pos(g, q.x, q.y, q.z, lane);
+      for (int base = 0; base < blk.total; base += 32) {
+        const int t = base + lane;
+        const bool valid = t < blk.total;
+        const int j = block_candidate(blk, valid ? t : 0);
+        if (valid) {
+          const float4 p = g.pts[j];
+          if (dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z) < r2) add(p);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) s[i] = warp_sum(s[i]);
+  cnt = warp_sum(cnt);
+  if (lane != 0) return;
+  if (!ok || cnt == 0) {
+    o[0] = o[1] = o[2] = __int_as_float(0x7fc00000);
+    return;
+  }
+  const double m = (double)cnt, cx = s[0] / m, cy = s[1] / m, cz = s[2] / m;
+  const double m200 = s[3] - m * cx * cx, m020 = s[4] - m * cy * cy, m002 = s[5] - m * cz * cz;
+  const double m110 = s[6] - m * cx * cy, m101 = s[7] - m * cx * cz, m011 = s[8] - m * cy * cz;
+  o[0] = (float)(m200 + m020 + m002);
+  o[1] = (float)(m200 * m020 + m200 * m002 + m020 * m002 - m110 * m110 - m101 * m101 - m011 * m011);
+  o[2] = (float)(m200 * m020 * m002 + 2 * m110 * m101 * m011 - m002 * m110 * m110 - m020 * m101 * m101 - m200 * m011 * m011);
+}
+
+// out_dev: rows of 3 floats (j1, j2, j3) at stride_floats, caller query order
+int moments_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t stride_floats) {
+  const int nq = (int)ctx->num_queries();
+  if (nq == 0 || ctx->n == 0) return 0;
+  const float r2 = (float)(radius * radius);
+  const int blocks = div_up(nq, PC_WPB);
+  if (k > 0) {
+    PFX_TRY(knn_lists(ctx, g, k, false));
+    if (ctx->q_is_surface)
+      PFX_LAUNCH(ctx, (moments_kernel<true, true>), blocks, PC_WPB * 32, 0, g->view(), nullptr, nq, r2, ctx->knn_idx.as<int>(), k,
+                 out_dev, stride_floats);
+    else
+      PFX_LAUNCH(ctx, (moments_kernel<false, true>), blocks, PC_WPB * 32, 0, g->view(), ctx->qry.as<float4>(), nq, r2,
+                 ctx->knn_idx.as<int>(), k, out_dev, stride_floats);
+  } else {
+    if (ctx->q_is_surface)
+      PFX_LAUNCH(ctx, (moments_kernel<true, false>), blocks, PC_WPB * 32, 0, g->view(), nullptr, nq, r2, nullptr, 0, out_dev,
+                 stride_floats);
+    else
+      PFX_LAUNCH(ctx, (moments_kernel<false, false>), blocks, PC_WPB * 32, 0, g->view(), ctx->qry.as<float4>(), nq, r2, nullptr, 0,
+                 out_dev, stride_floats);
+  }
+  PFX_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace pfx

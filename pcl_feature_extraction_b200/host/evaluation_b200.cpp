@@ -138,6 +138,11 @@ int main(int argc, char** argv) {
       pcl::Feature<PointRGB, pcl::SHOT1344>::Ptr ex(new pcl::SHOTColorEstimationOMP<PointRGB, pcl::Normal, pcl::SHOT1344>);
       run_descriptor<pcl::SHOT1344>(kp_type, DESC_SHOT_COLOR, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime, dump_dir);
     }
+    {  // evaluation.cpp:555-574
+      pcl::Feature<PointRGB, pcl::MomentInvariants>::Ptr ex(new pcl::MomentInvariantsEstimation<PointRGB, pcl::MomentInvariants>);
+      run_descriptor<pcl::MomentInvariants>(kp_type, DESC_MOMENT_INV, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime,
+                                            dump_dir);
+    }
     {  // evaluation.cpp:676-695
       pcl::Feature<PointRGB, pcl::PFHSignature125>::Ptr ex(new pcl::PFHEstimation<PointRGB, pcl::Normal, pcl::PFHSignature125>);
       run_descriptor<pcl::PFHSignature125>(kp_type, DESC_PFH, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime, dump_dir);

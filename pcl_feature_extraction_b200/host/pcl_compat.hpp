@@ -50,6 +50,7 @@ struct PrincipalCurvatures {
   static int descriptorSize() { return 5; }
 };
 struct SHOT352 { float descriptor[352]; float rf[9]; static int descriptorSize() { return 352; } };
+struct MomentInvariants { float j1, j2, j3; static int descriptorSize() { return 3; } };
 struct SHOT1344 { float descriptor[1344]; float rf[9]; static int descriptorSize() { return 1344; } };
 struct ReferenceFrame { float x_axis[3], y_axis[3], z_axis[3]; };
 // pcl::Narf36: 168 bytes; the representation used for matching is the 36 descriptor floats only
@@ -323,6 +324,22 @@ class FPFHEstimation : public FeatureFromNormals<PointInT, PointNT, PointOutT> {
 };
 template <typename PointInT, typename PointNT, typename PointOutT = FPFHSignature33>
 class FPFHEstimationOMP : public FPFHEstimation<PointInT, PointNT, PointOutT> {};
+
+// ------------------------------------------------------------------------------- MomentInvariants (no normals)
+template <typename PointInT, typename PointOutT = MomentInvariants>
+class MomentInvariantsEstimation : public Feature<PointInT, PointOutT> {
+ protected:
+  const char* name() const override { return "MomentInvariantsEstimation"; }
+  bool computeFeature(PointCloud<PointOutT>& output) override {
+    if (!this->upload()) return false;
+    int rc = pfx_moment_invariants(b200::ctx(), this->search_radius_, this->k_, reinterpret_cast<float*>(output.points.data()),
+                                   sizeof(PointOutT), PFX_HOST);
+    if (!b200::ok(rc, name())) return false;
+    for (const auto& p : output.points)
+      if (!std::isfinite(p.j1)) { output.is_dense = false; break; }
+    return true;
+  }
+};
 
 // ------------------------------------------------------------------------------- PFH, PrincipalCurvatures
 template <typename PointInT, typename PointNT, typename PointOutT = PFHSignature125>

@@ -36,7 +36,7 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     assert sum(l.startswith("# direct ICP") for l in lines) == 1
     byname = {(x[0], x[1]): x for x in rows}
     for kp_name in ("Harris3D", "Iss"):
-        for d_name in ("FPFH", "SHOT", "SHOTColor", "PFH", "PrincipalCurvatures"):
+        for d_name in ("FPFH", "SHOT", "SHOTColor", "MomentInvariants", "PFH", "PrincipalCurvatures"):
             assert (kp_name, d_name) in byname
     # NARF row (present when both clouds yield keypoints): the shim's RangeImagePlanar / NarfKeypoint /
     # NarfDescriptor objects against the C ABI called from Python on the same cloud

@@ -218,3 +218,43 @@ def test_device_resident_buffers_give_the_same_rows(ctx):
     assert np.array_equal(np.array(res.transform, np.float32).reshape(4, 4), h["T"]) and res.iterations == h["iterations"]
     assert res.fitness == h["fitness"]
     assert np.array_equal(d_al.cpu().numpy()[:, :3], h["aligned"]) and np.all(d_al.cpu().numpy()[:, 3:] == 0)
+
+
+def test_oracle_moment_invariants_known_answer(orc):
+    # a flat disc of radius r sampled densely: second moments about the centroid are n r^2 / 4 on the two in-plane
+    # axes and 0 across -> j1 = n r^2 / 2, j2 = (n r^2 / 4)^2, j3 = 0
+    rng = np.random.default_rng(1)
+    n = 200000
+    u = rng.uniform(-1, 1, (n, 2))
+    pts = np.c_[u, np.zeros(n)].astype(np.float32)
+    r = 0.2
+    out = orc.moment_invariants(pts, np.zeros((1, 3), np.float32), radius=r)[0]
+    m = orc.radius_count(pts, np.zeros((1, 3), np.float32), r)[0]
+    assert abs(out[0] / (m * r * r / 2) - 1) < 0.02
+    assert abs(out[1] / (m * r * r / 4) ** 2 - 1) < 0.04
+    assert abs(out[2]) < 1e-6 * out[0] ** 3
+    assert np.isnan(orc.moment_invariants(pts, np.array([[9, 9, 9]], np.float32), radius=r)).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("radius,k,dense", [(0.03, 0, True), (0.0, 24, True), (0.05, 0, False), (0.0, 16, False)])
+def test_gpu_moment_invariants_equal_oracle(ctx, orc, radius, k, dense):
+    """tolerance: both sides sum in double (about the query on the GPU, about the centroid on the CPU):
+    1e-5 of the natural scale j1^p of each invariant"""
+    pts = bumpy(20000, 12)
+    q = pts if dense else (pts[:400] + np.float32(0.001))
+    ctx.set_surface(pts)
+    ctx.set_queries(None if dense else q)
+    g = ctx.moment_invariants(radius=radius, k=k)
+    ctx.set_queries(None)
+    o = orc.moment_invariants(pts, q, radius=radius, k=k)
+    assert np.array_equal(np.isnan(g), np.isnan(o)) and not np.isnan(o).all()
+    ok = ~np.isnan(o[:, 0])
+    j1 = np.abs(o[ok, 0]).astype(np.float64) + 1e-30
+    assert np.all(np.abs(g[ok, 0] - o[ok, 0]) <= 1e-5 * j1)
+    assert np.all(np.abs(g[ok, 1] - o[ok, 1]) <= 1e-5 * j1 ** 2)
+    assert np.all(np.abs(g[ok, 2] - o[ok, 2]) <= 1e-5 * j1 ** 3)
+    # far / non-finite queries -> NaN rows
+    ctx.set_queries(np.array([[9, 9, 9], [np.nan, 0, 0]], np.float32))
+    assert np.isnan(ctx.moment_invariants(radius=0.05)).all()
+    ctx.set_queries(None)
