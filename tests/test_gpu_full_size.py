@@ -1,0 +1,125 @@
+"""BASELINE.json's full size (config C4 / C5: the 2^20-point synthetic sheet, dense normals k = 32 + FPFH33 k = 32 +
+SHOT352 r = 12.8 mm) through the C ABI.  The oracle cannot describe a million points in test time, so the full
+cloud is checked through size-independent properties, and a random sample of its rows against the oracle run on the
+FULL surface:
+ * kNN: 32 distinct in-range neighbours per row, ascending (d2, index), the point itself first; sampled rows
+   bit-exact against the oracle's search;
+ * normals: unit length, oriented to the viewpoint, curvature in [0, 1/3];
+ * FPFH: every 11-bin block sums to 100; SHOT: unit L2 rows, orthonormal right-handed frames;
+ * idempotence: a second pass gives the same bits; equivariance: a permuted copy of the cloud gives the permuted rows
+   - bit for bit for normals and SHOT (order-independent sums; the few rows that differ have an exact distance tie at
+   rank k, where the index tie-break decides), to float round-off for FPFH (its weighted sum runs in list order);
+ * sampled FPFH / SHOT rows within the tolerances of tests/test_gpu_parity.py against the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+SIDE, K, R_SHOT = 1024, 32, 0.0128
+
+
+@pytest.fixture(scope="module")
+def full(ctx):
+    from pcl_feature_extraction_b200.synth import sheet_cloud
+    pts = sheet_cloud(side=SIDE, pitch=0.004, seed=20240601)
+    ctx.set_viewpoint(0, 0, 0)
+    ctx.set_surface(pts)
+    ctx.set_queries(None)
+    nr = ctx.normals(k=K)
+    f = ctx.fpfh(k=K)
+    s, rf = ctx.shot352(R_SHOT)
+    idx, d2 = ctx.knn(K)
+    return dict(pts=pts, nr=nr, f=f, s=s, rf=rf, idx=idx, d2=d2)
+
+
+def test_full_size_knn_properties(ctx, orc, full):
+    pts, idx, d2 = full["pts"], full["idx"], full["d2"]
+    n = len(pts)
+    assert idx.shape == (n, K) and idx.min() >= 0 and idx.max() < n
+    assert np.array_equal(idx[:, 0], np.arange(n)) and np.all(d2[:, 0] == 0)
+    assert np.all(np.diff(d2, axis=1) >= 0)
+    tie = np.diff(d2, axis=1) == 0
+    assert np.all(np.diff(idx, axis=1)[tie] > 0)                      # ties ascend by index
+    srt = np.sort(idx, axis=1)
+    assert np.all(np.diff(srt, axis=1) > 0)                           # 32 distinct neighbours
+    # the stored d2 is FLANN's float expression of the two points
+    rows = np.random.default_rng(0).choice(n, 4096, replace=False)
+    a, b = pts[rows][:, None, :], pts[idx[rows]]
+    dd = a - b
+    e = dd[..., 0] * dd[..., 0]
+    e = e + dd[..., 1] * dd[..., 1]
+    e = e + dd[..., 2] * dd[..., 2]
+    assert np.array_equal(e.astype(np.float32), d2[rows])
+    # sampled rows against the oracle's search on the full surface: bit-exact
+    oi, od = orc.knn(pts, pts[rows], K)
+    assert np.array_equal(oi, idx[rows]) and np.array_equal(od, d2[rows])
+
+
+def test_full_size_descriptor_properties(ctx, full):
+    pts, nr, f, s, rf = full["pts"], full["nr"], full["f"], full["s"], full["rf"]
+    assert not np.isnan(nr).any() and not np.isnan(f).any()
+    assert np.abs(np.linalg.norm(nr[:, :3], axis=1) - 1).max() < 1e-5
+    assert np.all(np.sum(nr[:, :3] * (0 - pts), axis=1) >= 0)         # flipped towards the viewpoint (0, 0, 0)
+    assert nr[:, 3].min() >= 0 and nr[:, 3].max() <= 1.0 / 3 + 1e-6
+    assert np.abs(f.reshape(-1, 3, 11).sum(2) - 100).max() < 1e-2 and f.min() >= 0
+    ok = ~np.isnan(s[:, 0])
+    assert ok.mean() > 0.999
+    assert np.abs(np.linalg.norm(s[ok], axis=1) - 1).max() < 1e-5 and s[ok].min() >= 0
+    F = rf[ok].reshape(-1, 3, 3).astype(np.float64)
+    assert np.abs(F @ F.transpose(0, 2, 1) - np.eye(3)).max() < 1e-5
+    assert np.abs(np.linalg.det(F) - 1).max() < 1e-5
+
+
+def test_full_size_idempotent_and_permutation_equivariant(ctx, full):
+    pts = full["pts"]
+    n = len(pts)
+    ctx.set_viewpoint(0, 0, 0)
+    ctx.set_surface(pts)
+    ctx.set_queries(None)
+    nr = ctx.normals(k=K)
+    f = ctx.fpfh(k=K)
+    s, rf = ctx.shot352(R_SHOT)
+    assert np.array_equal(nr, full["nr"]) and np.array_equal(f, full["f"])
+    assert np.array_equal(s, full["s"], equal_nan=True) and np.array_equal(rf, full["rf"], equal_nan=True)
+    perm = np.random.default_rng(7).permutation(n)
+    ctx.set_surface(np.ascontiguousarray(pts[perm]))
+    nr_p = ctx.normals(k=K)
+    f_p = ctx.fpfh(k=K)
+    s_p, rf_p = ctx.shot352(R_SHOT)
+    same_n = np.all(nr_p == full["nr"][perm], axis=1)
+    same_f = np.all(f_p == full["f"][perm], axis=1)
+    same_s = np.all((s_p == full["s"][perm]) | np.isnan(s_p), axis=1)
+    assert same_n.mean() > 0.9999 and same_s.mean() > 0.9999, (same_n.mean(), same_s.mean())
+    # FPFH adds its 32 weighted neighbour rows in float in the order of the (unsorted) neighbour set, which follows
+    # the input order: rows agree to float round-off of a 100-scale histogram, not to the bit
+    df = np.abs(f_p - full["f"][perm]).max(1)
+    assert (df <= 1e-3).mean() > 0.9999 and df.max() < 12.0, ((df <= 1e-3).mean(), df.max(), same_f.mean())
+
+
+def test_full_size_sampled_rows_against_the_oracle(ctx, orc, full):
+    pts, nr = full["pts"], full["nr"]
+    rows = np.random.default_rng(3).choice(len(pts), 600, replace=False)
+    q = np.ascontiguousarray(pts[rows])
+    # normals: k-search on the full surface, double-centred oracle (tolerance of test_normals_knn_sheet)
+    onr, _, gap = orc.normals(pts, q, k=K, vp=(0, 0, 0))
+    good = gap > 1e-3
+    ang = np.abs(np.sum(onr[good, :3] * nr[rows][good, :3], axis=1))
+    assert good.mean() > 0.95 and (1 - ang).max() < 1e-6
+    # FPFH with the GPU's own normals as input normals on both sides
+    of = orc.fpfh(pts, nr, q, k=K)
+    d = np.abs(of - full["f"][rows]).max(1)
+    assert (d <= 1e-2).mean() >= 0.97 and np.median(d) < 1e-4 and d.max() < 12.0
+    # SHOT with the oracle's frames given to both sides: the descriptor stage alone
+    os_, orf = orc.shot352(pts, nr, q, R_SHOT)
+    ctx.set_surface(pts)
+    ctx.set_surface_normals(nr)
+    ctx.set_queries(q)
+    s, rf = ctx.shot352(R_SHOT, lrf_in=orf)
+    ctx.set_queries(None)
+    ok = ~np.isnan(os_[:, 0])
+    assert np.array_equal(np.isnan(s[:, 0]), ~ok)
+    assert np.abs(s[ok] - os_[ok]).max() <= 1e-4
+    # and end to end (frames from the dense fused kernel) where the frame is well defined
+    _, gap2 = orc.shot_lrf(pts, q, R_SHOT)
+    clear = ok & (gap2.min(1) > 1e-2)
+    assert clear.mean() > 0.5
+    assert (np.abs(full["s"][rows][clear] - os_[clear]).max(1) <= 1e-4).mean() > 0.99
