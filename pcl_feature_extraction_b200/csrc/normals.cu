@@ -91,7 +91,13 @@ int normals_compute(Ctx* ctx, Grid* g, double radius, int k, float4* out_query_o
     PFX_CUDA(ctx->normals.ensure(std::max<size_t>(ctx->n, 1) * sizeof(float4)));
     PFX_CUDA(ctx->normals_sorted.ensure(std::max<size_t>(ctx->n, 1) * sizeof(float4)));
   }
-  if (nq == 0) return 0;
+  if (nq == 0) {
+    if (dense) {  // an empty surface has (zero) normals: later stages see their precondition met
+      ctx->have_normals = true;
+      ctx->normals_version++;
+    }
+    return 0;
+  }
   const int blocks = div_up(nq, NWPB * 32);
   if (dense) {
     float4* sorted = ctx->normals_sorted.as<float4>();

@@ -1,0 +1,91 @@
+"""Degenerate clouds through the whole dense path (set_surface -> normals -> FPFH -> SHOT -> matching): no crash, no
+hang, PCL's NaN conventions, and agreement with the oracle where the answer is well defined."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def run_dense(ctx, pts, k=8, r=0.05):
+    ctx.set_viewpoint(0, 0, 0)
+    ctx.set_surface(pts)
+    ctx.set_queries(None)
+    nr = ctx.normals(k=k)
+    f = ctx.fpfh(k=k)
+    s, rf = ctx.shot352(r)
+    return nr, f, s, rf
+
+
+def test_tiny_clouds(ctx, orc):
+    for n in (0, 1, 2, 3, 7):
+        pts = np.random.default_rng(n).uniform(0, 0.05, (n, 3)).astype(np.float32)
+        nr, f, s, rf = run_dense(ctx, pts)
+        assert nr.shape == (n, 4) and f.shape == (n, 33) and s.shape == (n, 352)
+        if n:
+            onr, _, _ = orc.normals(pts, k=8)
+            assert np.array_equal(np.isnan(nr[:, 0]), np.isnan(onr[:, 0]))
+            of = orc.fpfh(pts, nr, k=8)
+            assert np.array_equal(np.isnan(f), np.isnan(of))
+            os_, orf = orc.shot352(pts, nr, None, 0.05)
+            assert np.array_equal(np.isnan(s[:, 0]), np.isnan(os_[:, 0]))
+            idx, d2 = ctx.knn(8)
+            oi, od = orc.knn(pts, pts, 8)
+            assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+
+
+def test_all_points_identical(ctx, orc):
+    pts = np.full((3000, 3), 0.25, np.float32)
+    nr, f, s, rf = run_dense(ctx, pts, k=8, r=0.01)
+    idx, d2 = ctx.knn(8)
+    oi, od = orc.knn(pts, pts, 8)
+    assert np.array_equal(idx, oi) and np.all(d2 == 0)          # all ties: ascending index decides
+    assert np.isnan(s).all()                                    # SHOT: no neighbour differs from the query -> NaN frame
+    onr, _, _ = orc.normals(pts, k=8)
+    assert np.array_equal(np.isnan(nr[:, 0]), np.isnan(onr[:, 0]))
+
+
+def test_collinear_and_exact_grid(ctx, orc):
+    line = np.c_[np.arange(2000) * 0.001, np.zeros(2000), np.zeros(2000)].astype(np.float32)
+    nr, f, s, rf = run_dense(ctx, line, k=8, r=0.01)
+    idx, d2 = ctx.knn(8)
+    oi, od = orc.knn(line, line, 8)
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od)   # symmetric ties on a line
+    assert not np.isnan(f).any() or np.isnan(nr[:, 0]).any()
+    # an exact lattice: every k-th distance is tied many times over
+    g = np.stack(np.meshgrid(np.arange(40), np.arange(40), np.arange(3)), -1).reshape(-1, 3).astype(np.float32) * 0.01
+    ctx.set_surface(g)
+    ctx.set_queries(None)
+    for k in (1, 7, 27, 32):
+        idx, d2 = ctx.knn(k)
+        oi, od = orc.knn(g, g, k)
+        assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+    off, ridx, rd2 = ctx.radius_search(0.0101)
+    ooff, oidx, od2 = orc.radius_search(g, g, 0.0101)
+    assert np.array_equal(off, ooff) and np.array_equal(ridx, oidx) and np.array_equal(rd2, od2)
+    nr, f, s, rf = run_dense(ctx, g, k=16, r=0.025)
+    onr, _, gap = orc.normals(g, k=16)
+    assert np.array_equal(np.isnan(nr[:, 0]), np.isnan(onr[:, 0]))
+    ok = gap > 1e-3
+    assert np.abs(np.abs(np.sum(nr[ok, :3] * onr[ok, :3], 1)) - 1).max() < 1e-5
+
+
+def test_nan_and_far_outliers(ctx, orc):
+    rng = np.random.default_rng(4)
+    pts = rng.uniform(0, 0.3, (6000, 3)).astype(np.float32)
+    pts[::17] = np.nan
+    pts[5] = [1e6, -1e6, 1e6]          # outliers stretch the bounding box by seven orders of magnitude
+    pts[6] = [-1e6, 1e6, -1e6]
+    nr, f, s, rf = run_dense(ctx, pts, k=12, r=0.04)
+    bad = np.isnan(pts[:, 0])
+    assert np.isnan(nr[bad]).all() and np.isnan(f[bad]).all() and np.isnan(s[bad]).all()
+    idx, d2 = ctx.knn(12)
+    oi, od = orc.knn(pts, pts, 12)
+    assert np.array_equal(idx, oi) and np.array_equal(d2[~bad], od[~bad])
+    # matching with NaN rows and duplicates on both sides
+    a = f[:500].copy()
+    b = f[500:1500].copy()
+    b[10] = a[20]
+    corr = ctx.match(a, b, reciprocal=False)
+    oi2, od2 = orc.match_nn(a, b)
+    keep = oi2 >= 0
+    assert np.array_equal(corr["index_match"], oi2[keep]) and np.array_equal(corr["distance"], od2[keep])
