@@ -193,6 +193,14 @@ int pfx_set_surface_colors(pfx_ctx* ctx, const void* rgb, size_t n, size_t strid
 int pfx_set_query_colors(pfx_ctx* ctx, const void* rgb, size_t n, size_t stride, int mem);
 int pfx_shot1344(pfx_ctx* ctx, double radius, const float* lrf_in, float* out, size_t stride, int mem);
 
+/* ------------------------------------------------------------------ Unique Shape Context (next row)
+ * pfx_usc1980 <- UniqueShapeContext<PointXYZRGB, ShapeContext1980>::compute (evaluation.cpp:344-371, which sets
+ * setMinimalRadius(r / 10), setPointDensityRadius(r / 5) and leaves PCL's local radius 2.5 for the frames).
+ * Rows = pcl::ShapeContext1980: descriptor[1980] (12 azimuth x 11 elevation x 15 log-spaced radius bins) + rf[9],
+ * 7956 B.  lrf_in (optional): frames of the queries; otherwise SHOT frames at local_radius.  Needs no normals. */
+int pfx_usc1980(pfx_ctx* ctx, double search_radius, double min_radius, double density_radius, double local_radius,
+                const float* lrf_in, float* out, size_t stride, int mem);
+
 /* ------------------------------------------------------------------ RANSAC correspondence rejection (next row)
  * pfx_ransac_reject <- Features<T>::filterCorrespondences (features.h:282-297):
  * CorrespondenceRejectorSampleConsensus with setInlierThreshold(0.015), setMaximumIterations(1000).

@@ -366,3 +366,19 @@ def moment_invariants(surf, q, radius=0.0, k=0):
     _chk(lib().orc_moment_invariants(_opt(surf), len(surf), _opt(q), len(q), C.c_double(radius), int(k), _opt(out)),
          "moment_invariants")
     return out
+
+
+# ------------------------------------------------------------------ Unique Shape Context
+def usc1980(surf, q, search_radius, min_radius=None, density_radius=None, local_radius=2.5, lrf_in=None):
+    """-> (rows [nq, 1980], frames [nq, 9], density [n]); defaults = the reference's settings (r / 10, r / 5, 2.5)"""
+    surf, q = _f32(surf), _f32(q)
+    out = np.zeros((len(q), 1980), np.float32)
+    rf = np.zeros((len(q), 9), np.float32)
+    dens = np.zeros(max(len(surf), 1), np.int32)
+    lrf = None if lrf_in is None else np.ascontiguousarray(lrf_in, np.float32)
+    _chk(lib().orc_usc1980(_opt(surf), len(surf), _opt(q), len(q), C.c_double(search_radius),
+                           C.c_double(min_radius if min_radius is not None else search_radius / 10.0),
+                           C.c_double(density_radius if density_radius is not None else search_radius / 5.0),
+                           C.c_double(local_radius), None if lrf is None else _opt(lrf), _opt(out), _opt(rf), _opt(dens)),
+         "usc1980")
+    return out, rf, dens[: len(surf)]

@@ -105,6 +105,12 @@ int orc_shot1344(const float* surf, const uint32_t* rgb, const float* normals4, 
                  const uint32_t* qrgb, int nq, double radius, const float* lrf_in, float* out1344, float* rf9,
                  float* lab_out);
 
+/* ---- Unique Shape Context (evaluation.cpp:344-371 -> UniqueShapeContext<PointXYZRGB, ShapeContext1980>):
+ * out nq x 1980, rf9 nq x 9 (SHOT frames at local_radius unless lrf_in is given); density_out (optional, n). */
+int orc_usc1980(const float* surf, int n, const float* q, int nq, double search_radius, double min_radius,
+                double density_radius, double local_radius, const float* lrf_in, float* out1980, float* rf9,
+                int* density_out);
+
 /* ---- matching (features.h:224-273): exact L2 1-NN with sequential float sum.
  * nn_idx: na (argmin over b; -1 for NaN query rows / empty b), nn_d2: na */
 int orc_match_nn(const float* a, int na, const float* b, int nb, int dim, int* nn_idx, float* nn_d2);

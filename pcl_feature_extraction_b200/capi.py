@@ -88,6 +88,7 @@ SIGNATURES = {
     "pfx_set_surface_colors": (_i, [_vp, _vp, _sz, _sz, _i]),
     "pfx_set_query_colors": (_i, [_vp, _vp, _sz, _sz, _i]),
     "pfx_shot1344": (_i, [_vp, _d, _vp, _vp, _sz, _i]),
+    "pfx_usc1980": (_i, [_vp, _d, _d, _d, _d, _vp, _vp, _sz, _i]),
     "pfx_match": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _f, _vp, _sz, C.POINTER(_sz), _i]),
     "pfx_match_nn": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _vp, _vp, _i]),
     "pfx_range_image_planar": (_i, [_vp, _i, _i, _f, _f, _f, _f, _f, _vp]),
@@ -370,6 +371,15 @@ class Context:
         lrf = np.ascontiguousarray(lrf_in, np.float32) if lrf_in is not None else None
         self._chk(self.lib.pfx_shot1344(self.h, radius, _ptr(lrf), _ptr(out), 5412, HOST))
         return out[:, :1344].copy(), out[:, 1344:].copy()
+
+    def usc1980(self, search_radius, min_radius=None, density_radius=None, local_radius=2.5, lrf_in=None):
+        """-> (rows [nq, 1980], frames [nq, 9]); defaults = the reference's settings (r / 10, r / 5, 2.5)"""
+        out = np.zeros((self.num_queries, 1989), np.float32)
+        lrf = np.ascontiguousarray(lrf_in, np.float32) if lrf_in is not None else None
+        self._chk(self.lib.pfx_usc1980(self.h, search_radius, min_radius if min_radius is not None else search_radius / 10.0,
+                                       density_radius if density_radius is not None else search_radius / 5.0, local_radius,
+                                       _ptr(lrf), _ptr(out), 7956, HOST))
+        return out[:, :1980].copy(), out[:, 1980:].copy()
 
     def shot352_dev(self, radius, out_ptr, stride=1444):
         self._chk(self.lib.pfx_shot352(self.h, radius, None, _ptr(out_ptr), stride, DEVICE))

@@ -864,6 +864,35 @@ extern "C" int pfx_shot1344(pfx_ctx* ctx, double radius, const float* lrf_in, fl
   return 0;
 }
 
+extern "C" int pfx_usc1980(pfx_ctx* ctx, double search_radius, double min_radius, double density_radius, double local_radius,
+                           const float* lrf_in, float* out, size_t stride, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_usc1980: no surface set");
+  if (!(search_radius > 0)) return ctx->fail(PFX_E_PRECOND, "pfx_usc1980: needs a radius search (setRadiusSearch)");
+  // UniqueShapeContext::initCompute: "search_radius_ must be GREATER than min_radius_"
+  if (!(min_radius > 0) || !(density_radius > 0) || !(local_radius > 0) || search_radius < min_radius)
+    return ctx->fail(PFX_E_PRECOND, "pfx_usc1980: radii must be positive and search_radius >= min_radius");
+  if (!out || stride < 7956 || (stride & 3) || (mem != PFX_HOST && mem != PFX_DEVICE))
+    return ctx->fail(PFX_E_INVALID, "pfx_usc1980: bad output / stride / mem");
+  const size_t nq = ctx->num_queries();
+  if (nq == 0) return 0;
+  float* dout = out;
+  const float* dlrf = lrf_in;
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->out_stage.ensure(nq * stride));
+    dout = ctx->out_stage.as<float>();
+    if (stride != 7956) PFX_CUDA(cudaMemsetAsync(dout, 0, nq * stride, ctx->stream));
+    if (lrf_in) {
+      PFX_CUDA(ctx->tmp4.ensure(nq * 9 * sizeof(float)));
+      PFX_CUDA(cudaMemcpyAsync(ctx->tmp4.p, lrf_in, nq * 9 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+      dlrf = ctx->tmp4.as<float>();
+    }
+  }
+  PFX_TRY(usc_compute(ctx, search_radius, min_radius, density_radius, local_radius, dlrf, dout, stride / 4));
+  if (mem == PFX_HOST) return deliver(ctx, out, dout, nq * stride, mem);
+  return 0;
+}
+
 // ================================================================================== matching
 namespace pfx {
 __global__ void reciprocal_kernel(const int* __restrict__ s2t, const float* __restrict__ sd2,

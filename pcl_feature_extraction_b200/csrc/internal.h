@@ -151,6 +151,7 @@ struct Ctx {
   cudaEvent_t ev_surface = nullptr;
   DevBuf icp_state, icp_cur, icp_nn, icp_partials;  // icp.cu
   // colours (shot_color.cu): normalised CIELab of the surface points / queries, valid for these versions
+  DevBuf usc_tab;  // usc.cu
   DevBuf lab_tab, surf_lab, qry_lab;
   uint64_t surf_lab_version = 0, qry_lab_version = 0;
 
@@ -277,6 +278,8 @@ int moments_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, siz
 int curvature_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t stride_floats);
 int colors_to_lab(Ctx* ctx, const unsigned char* rgb_dev, size_t stride_bytes, int n, DevBuf& lab);
 int shot_color_compute(Ctx* ctx, Grid* g, double radius, const float* rf9_dev, float* out_dev, size_t stride_floats);
+int usc_compute(Ctx* ctx, double search_radius, double min_radius, double density_radius, double local_radius,
+                const float* lrf_dev, float* out_dev, size_t stride_floats);
 int icp_align_run(Ctx* ctx, const float* src_dev, int n, size_t stride_floats, const pfx_icp_params* prm,
                   const float* guess16, pfx_icp_result* res, float* aligned_dev, size_t aligned_stride_floats);
 int normals_sorted_for_grid(Ctx* ctx, Grid* g, const float4** out);

@@ -138,6 +138,13 @@ int main(int argc, char** argv) {
       pcl::Feature<PointRGB, pcl::SHOT1344>::Ptr ex(new pcl::SHOTColorEstimationOMP<PointRGB, pcl::Normal, pcl::SHOT1344>);
       run_descriptor<pcl::SHOT1344>(kp_type, DESC_SHOT_COLOR, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime, dump_dir);
     }
+    {  // evaluation.cpp:344-371
+      pcl::UniqueShapeContext<PointRGB, pcl::ShapeContext1980>::Ptr usc(new pcl::UniqueShapeContext<PointRGB, pcl::ShapeContext1980>);
+      usc->setMinimalRadius(feat_r / 10.0);
+      usc->setPointDensityRadius(feat_r / 5.0);
+      pcl::Feature<PointRGB, pcl::ShapeContext1980>::Ptr ex(usc);
+      run_descriptor<pcl::ShapeContext1980>(kp_type, DESC_USC, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime, dump_dir);
+    }
     {  // evaluation.cpp:555-574
       pcl::Feature<PointRGB, pcl::MomentInvariants>::Ptr ex(new pcl::MomentInvariantsEstimation<PointRGB, pcl::MomentInvariants>);
       run_descriptor<pcl::MomentInvariants>(kp_type, DESC_MOMENT_INV, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime,

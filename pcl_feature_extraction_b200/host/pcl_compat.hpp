@@ -50,6 +50,7 @@ struct PrincipalCurvatures {
   static int descriptorSize() { return 5; }
 };
 struct SHOT352 { float descriptor[352]; float rf[9]; static int descriptorSize() { return 352; } };
+struct ShapeContext1980 { float descriptor[1980]; float rf[9]; static int descriptorSize() { return 1980; } };
 struct MomentInvariants { float j1, j2, j3; static int descriptorSize() { return 3; } };
 struct SHOT1344 { float descriptor[1344]; float rf[9]; static int descriptorSize() { return 1344; } };
 struct ReferenceFrame { float x_axis[3], y_axis[3], z_axis[3]; };
@@ -67,6 +68,7 @@ static_assert(sizeof(Correspondence) == sizeof(pfx_correspondence), "ABI layout"
 static_assert(sizeof(Narf36) == 168 && sizeof(PointWithRange) == 32, "PCL layout");
 static_assert(sizeof(PFHSignature125) == 500 && sizeof(PrincipalCurvatures) == 20, "PCL layout");
 static_assert(sizeof(SHOT1344) == 5412 && offsetof(PointXYZRGB, rgba) == 16, "PCL layout");
+static_assert(sizeof(ShapeContext1980) == 7956, "PCL layout");
 
 typedef std::vector<Correspondence> Correspondences;
 typedef std::shared_ptr<Correspondences> CorrespondencesPtr;
@@ -324,6 +326,44 @@ class FPFHEstimation : public FeatureFromNormals<PointInT, PointNT, PointOutT> {
 };
 template <typename PointInT, typename PointNT, typename PointOutT = FPFHSignature33>
 class FPFHEstimationOMP : public FPFHEstimation<PointInT, PointNT, PointOutT> {};
+
+// ------------------------------------------------------------------------------- Unique Shape Context (no normals)
+template <typename PointInT, typename PointOutT = ShapeContext1980, typename PointRFT = ReferenceFrame>
+class UniqueShapeContext : public Feature<PointInT, PointOutT> {
+ public:
+  typedef std::shared_ptr<UniqueShapeContext<PointInT, PointOutT, PointRFT>> Ptr;
+  void setMinimalRadius(double r) { min_radius_ = r; }
+  void setPointDensityRadius(double r) { point_density_radius_ = r; }
+  void setLocalRadius(double r) { local_radius_ = r; }
+  void setInputReferenceFrames(const typename PointCloud<PointRFT>::ConstPtr& f) { frames_ = f; }
+
+ protected:
+  const char* name() const override { return "UniqueShapeContext"; }
+  bool initCompute() override {
+    if (!Feature<PointInT, PointOutT>::initCompute()) return false;
+    if (this->search_radius_ < min_radius_) {
+      std::fprintf(stderr, "[pcl::%s::initCompute] search_radius_ must be GREATER than min_radius_.\n", name());
+      return false;
+    }
+    if (frames_ && frames_->size() != this->input_->size()) {
+      std::fprintf(stderr, "[pcl::%s::initCompute] The number of reference frames differs from the number of input points!\n", name());
+      return false;
+    }
+    return true;
+  }
+  bool computeFeature(PointCloud<PointOutT>& output) override {
+    if (!this->upload()) return false;
+    const float* lrf_in = frames_ ? reinterpret_cast<const float*>(frames_->points.data()) : nullptr;
+    int rc = pfx_usc1980(b200::ctx(), this->search_radius_, min_radius_, point_density_radius_, local_radius_, lrf_in,
+                         reinterpret_cast<float*>(output.points.data()), sizeof(PointOutT), PFX_HOST);
+    if (!b200::ok(rc, name())) return false;
+    for (const auto& p : output.points)
+      if (!std::isfinite(p.descriptor[0])) { output.is_dense = false; break; }
+    return true;
+  }
+  typename PointCloud<PointRFT>::ConstPtr frames_;
+  double min_radius_ = 0.1, point_density_radius_ = 0.2, local_radius_ = 2.5;  // PCL's defaults
+};
 
 // ------------------------------------------------------------------------------- MomentInvariants (no normals)
 template <typename PointInT, typename PointOutT = MomentInvariants>

@@ -36,7 +36,7 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     assert sum(l.startswith("# direct ICP") for l in lines) == 1
     byname = {(x[0], x[1]): x for x in rows}
     for kp_name in ("Harris3D", "Iss"):
-        for d_name in ("FPFH", "SHOT", "SHOTColor", "MomentInvariants", "PFH", "PrincipalCurvatures"):
+        for d_name in ("FPFH", "SHOT", "SHOTColor", "USC", "MomentInvariants", "PFH", "PrincipalCurvatures"):
             assert (kp_name, d_name) in byname
     # NARF row (present when both clouds yield keypoints): the shim's RangeImagePlanar / NarfKeypoint /
     # NarfDescriptor objects against the C ABI called from Python on the same cloud
@@ -135,4 +135,12 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
         sc_shim = np.fromfile(tmp_path / (kp_name + "_SHOTColor_src.bin"), dtype=np.float32).reshape(-1, 1353)
         sc_abi, sc_rf = ctx.shot1344(0.05)
         assert np.array_equal(sc_shim[:, :1344], sc_abi, equal_nan=True) and np.array_equal(sc_shim[:, 1344:], sc_rf, equal_nan=True)
+    ctx.set_queries(None)
+    # USC through the shim (r / 10, r / 5, PCL's local radius 2.5) == the C ABI called from Python
+    rec = np.fromfile(tmp_path / "Iss_src_kp.bin", dtype=np.float32).reshape(-1, 8)
+    ctx.set_surface(src)
+    ctx.set_queries(np.ascontiguousarray(rec[:, :3]))
+    u_shim = np.fromfile(tmp_path / "Iss_USC_src.bin", dtype=np.float32).reshape(-1, 1989)
+    u_abi, u_rf = ctx.usc1980(0.05)
+    assert np.array_equal(u_shim[:, :1980], u_abi, equal_nan=True) and np.array_equal(u_shim[:, 1980:], u_rf, equal_nan=True)
     ctx.set_queries(None)

@@ -112,3 +112,31 @@ def test_gpu_shot1344_preconditions(ctx):
     s, rf = ctx.shot1344(0.05)
     assert np.isnan(s).all() and np.isnan(rf).all()
     ctx.set_queries(None)
+
+
+@pytest.mark.gpu
+def test_gpu_binary_pcd_payload_is_the_record_layout(ctx, tmp_path):
+    """a binary PCD payload (x, y, z, rgb records of 16 bytes) goes to pfx_set_surface / pfx_set_surface_colors as it is"""
+    import ctypes as C
+    from pcl_feature_extraction_b200.pcd import write_pcd, read_pcd
+    from pcl_feature_extraction_b200.capi import HOST
+    pts, rgb = textured_sheet(8000, 8)
+    write_pcd(tmp_path / "c.pcd", pts, rgb)
+    xyz2, rgb2, hdr = read_pcd(tmp_path / "c.pcd")
+    assert np.array_equal(xyz2, pts) and np.array_equal(rgb2, rgb)
+    raw = open(tmp_path / "c.pcd", "rb").read()
+    payload = np.frombuffer(raw[raw.index(b"DATA binary\n") + len(b"DATA binary\n"):], dtype=np.uint8).copy()
+    assert len(payload) == 16 * len(pts)
+    # reference result from separate arrays
+    ctx.set_surface(pts)
+    ctx.set_viewpoint(0, 0, 0)
+    ctx.normals(radius=0.04, want_output=False)
+    ctx.set_surface_colors(rgb)
+    s_ref, rf_ref = ctx.shot1344(0.05)
+    # the same from the file payload, stride 16
+    base = payload.ctypes.data
+    ctx._chk(ctx.lib.pfx_set_surface(ctx.h, C.c_void_p(base), len(pts), 16, HOST))
+    ctx.normals(radius=0.04, want_output=False)
+    ctx._chk(ctx.lib.pfx_set_surface_colors(ctx.h, C.c_void_p(base + 12), len(pts), 16, HOST))
+    s, rf = ctx.shot1344(0.05)
+    assert np.array_equal(s, s_ref, equal_nan=True) and np.array_equal(rf, rf_ref, equal_nan=True)
