@@ -201,6 +201,14 @@ int pfx_shot1344(pfx_ctx* ctx, double radius, const float* lrf_in, float* out, s
 int pfx_usc1980(pfx_ctx* ctx, double search_radius, double min_radius, double density_radius, double local_radius,
                 const float* lrf_in, float* out, size_t stride, int mem);
 
+/* ------------------------------------------------------------------ spin images (next row)
+ * pfx_spin_image153 <- SpinImageEstimation<PointXYZRGB, Normal, Histogram<153>>::compute with its defaults
+ * (evaluation.cpp:515-554): rows of 153 floats (9 alpha rows x 17 beta columns, pcl::Histogram<153>, 612 B).
+ * query_normals: one normal per QUERY (setInputNormals of the input cloud; records with nx, ny, nz first) - the
+ * rotation axis of its spin image; the surface needs no normals. */
+int pfx_spin_image153(pfx_ctx* ctx, double radius, const void* query_normals, size_t n_normals, size_t stride_normals,
+                      float* out, size_t stride, int mem);
+
 /* ------------------------------------------------------------------ RANSAC correspondence rejection (next row)
  * pfx_ransac_reject <- Features<T>::filterCorrespondences (features.h:282-297):
  * CorrespondenceRejectorSampleConsensus with setInlierThreshold(0.015), setMaximumIterations(1000).

@@ -382,3 +382,12 @@ def usc1980(surf, q, search_radius, min_radius=None, density_radius=None, local_
                            C.c_double(local_radius), None if lrf is None else _opt(lrf), _opt(out), _opt(rf), _opt(dens)),
          "usc1980")
     return out, rf, dens[: len(surf)]
+
+
+def spin_image153(surf, q, qnormals4, radius):
+    surf, q = _f32(surf), _f32(q)
+    nr = np.ascontiguousarray(qnormals4, np.float32)
+    assert nr.shape == (len(q), 4)
+    out = np.zeros((len(q), 153), np.float32)
+    _chk(lib().orc_spin_image153(_opt(surf), len(surf), _opt(q), _opt(nr), len(q), C.c_double(radius), _opt(out)), "spin_image153")
+    return out

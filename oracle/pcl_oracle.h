@@ -111,6 +111,11 @@ int orc_usc1980(const float* surf, int n, const float* q, int nq, double search_
                 double density_radius, double local_radius, const float* lrf_in, float* out1980, float* rf9,
                 int* density_out);
 
+/* ---- spin images (evaluation.cpp:515-554 -> SpinImageEstimation<PointXYZRGB, Normal, Histogram<153>>, defaults):
+ * qnormals4: the normals of the QUERIES (nq x 4); out nq x 153 (9 alpha rows x 17 beta columns). */
+int orc_spin_image153(const float* surf, int n, const float* q, const float* qnormals4, int nq, double radius,
+                      float* out153);
+
 /* ---- matching (features.h:224-273): exact L2 1-NN with sequential float sum.
  * nn_idx: na (argmin over b; -1 for NaN query rows / empty b), nn_d2: na */
 int orc_match_nn(const float* a, int na, const float* b, int nb, int dim, int* nn_idx, float* nn_d2);

@@ -88,6 +88,7 @@ SIGNATURES = {
     "pfx_set_surface_colors": (_i, [_vp, _vp, _sz, _sz, _i]),
     "pfx_set_query_colors": (_i, [_vp, _vp, _sz, _sz, _i]),
     "pfx_shot1344": (_i, [_vp, _d, _vp, _vp, _sz, _i]),
+    "pfx_spin_image153": (_i, [_vp, _d, _vp, _sz, _sz, _vp, _sz, _i]),
     "pfx_usc1980": (_i, [_vp, _d, _d, _d, _d, _vp, _vp, _sz, _i]),
     "pfx_match": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _f, _vp, _sz, C.POINTER(_sz), _i]),
     "pfx_match_nn": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _vp, _vp, _i]),
@@ -371,6 +372,13 @@ class Context:
         lrf = np.ascontiguousarray(lrf_in, np.float32) if lrf_in is not None else None
         self._chk(self.lib.pfx_shot1344(self.h, radius, _ptr(lrf), _ptr(out), 5412, HOST))
         return out[:, :1344].copy(), out[:, 1344:].copy()
+
+    def spin_image153(self, radius, query_normals):
+        """query_normals: [nq, 3 or 4] normals of the QUERIES (the surface itself when no queries are set)"""
+        nr = np.ascontiguousarray(query_normals, np.float32)
+        out = np.zeros((self.num_queries, 153), np.float32)
+        self._chk(self.lib.pfx_spin_image153(self.h, radius, _ptr(nr), len(nr), nr.strides[0] if len(nr) else 12, _ptr(out), 612, HOST))
+        return out
 
     def usc1980(self, search_radius, min_radius=None, density_radius=None, local_radius=2.5, lrf_in=None):
         """-> (rows [nq, 1980], frames [nq, 9]); defaults = the reference's settings (r / 10, r / 5, 2.5)"""

@@ -864,6 +864,34 @@ extern "C" int pfx_shot1344(pfx_ctx* ctx, double radius, const float* lrf_in, fl
   return 0;
 }
 
+extern "C" int pfx_spin_image153(pfx_ctx* ctx, double radius, const void* query_normals, size_t n_normals,
+                                 size_t stride_normals, float* out, size_t stride, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_spin_image153: no surface set");
+  // SpinImageEstimation::initCompute: radius search only, normals of the input cloud required
+  if (!(radius > 0)) return ctx->fail(PFX_E_PRECOND, "pfx_spin_image153: needs a radius search (setRadiusSearch)");
+  const size_t nq = ctx->num_queries();
+  if (!query_normals) return ctx->fail(PFX_E_PRECOND, "pfx_spin_image153: no input normals (setInputNormals)");
+  if (n_normals != nq)
+    return ctx->fail(PFX_E_PRECOND, "pfx_spin_image153: the number of normals differs from the number of input points");
+  if (!out || stride < 612 || (stride & 3) || stride_normals < 12 || (stride_normals & 3) || (mem != PFX_HOST && mem != PFX_DEVICE))
+    return ctx->fail(PFX_E_INVALID, "pfx_spin_image153: bad output / stride / mem");
+  if (nq == 0) return 0;
+  Grid* g = nullptr;
+  PFX_TRY(grid_get(ctx, radius, 0, &g));
+  const unsigned char* dn = nullptr;
+  PFX_TRY(upload_records(ctx, query_normals, nq, stride_normals, mem, ctx->stage2, &dn));
+  float* dout = out;
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->out_stage.ensure(nq * stride));
+    dout = ctx->out_stage.as<float>();
+    if (stride != 612) PFX_CUDA(cudaMemsetAsync(dout, 0, nq * stride, ctx->stream));
+  }
+  PFX_TRY(spin_compute(ctx, g, radius, reinterpret_cast<const float*>(dn), stride_normals / 4, dout, stride / 4));
+  if (mem == PFX_HOST) return deliver(ctx, out, dout, nq * stride, mem);
+  return 0;
+}
+
 extern "C" int pfx_usc1980(pfx_ctx* ctx, double search_radius, double min_radius, double density_radius, double local_radius,
                            const float* lrf_in, float* out, size_t stride, int mem) {
   PFX_TRY(check_ctx(ctx));

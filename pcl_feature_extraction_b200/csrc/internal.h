@@ -280,6 +280,8 @@ int colors_to_lab(Ctx* ctx, const unsigned char* rgb_dev, size_t stride_bytes, i
 int shot_color_compute(Ctx* ctx, Grid* g, double radius, const float* rf9_dev, float* out_dev, size_t stride_floats);
 int usc_compute(Ctx* ctx, double search_radius, double min_radius, double density_radius, double local_radius,
                 const float* lrf_dev, float* out_dev, size_t stride_floats);
+int spin_compute(Ctx* ctx, Grid* g, double radius, const float* qnormals_dev, size_t nstride_floats, float* out_dev,
+                 size_t stride_floats);
 int icp_align_run(Ctx* ctx, const float* src_dev, int n, size_t stride_floats, const pfx_icp_params* prm,
                   const float* guess16, pfx_icp_result* res, float* aligned_dev, size_t aligned_stride_floats);
 int normals_sorted_for_grid(Ctx* ctx, Grid* g, const float4** out);

@@ -138,6 +138,40 @@ int main(int argc, char** argv) {
       pcl::Feature<PointRGB, pcl::SHOT1344>::Ptr ex(new pcl::SHOTColorEstimationOMP<PointRGB, pcl::Normal, pcl::SHOT1344>);
       run_descriptor<pcl::SHOT1344>(kp_type, DESC_SHOT_COLOR, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime, dump_dir);
     }
+    {  // evaluation.cpp:515-554: the normals are estimated on the keypoint clouds, the surface is the full cloud
+      typedef pcl::Histogram<153> Spin;
+      double t1 = now_s();
+      pcl::PointCloud<Spin>::Ptr sf(new pcl::PointCloud<Spin>), tf(new pcl::PointCloud<Spin>);
+      pcl::PointCloud<pcl::Normal>::Ptr sn(new pcl::PointCloud<pcl::Normal>), tn(new pcl::PointCloud<pcl::Normal>);
+      Tools::estimateNormals(skp, sn, normal_r);
+      Tools::estimateNormals(tkp, tn, normal_r);
+      pcl::SpinImageEstimation<PointRGB, pcl::Normal, Spin> ex;
+      pcl::search::KdTree<PointRGB>::Ptr kdtree(new pcl::search::KdTree<PointRGB>);
+      ex.setInputNormals(sn);
+      ex.setSearchSurface(source);
+      ex.setInputCloud(skp);
+      ex.setSearchMethod(kdtree);
+      ex.setRadiusSearch(feat_r);
+      ex.compute(*sf);
+      ex.setInputNormals(tn);
+      ex.setSearchSurface(target);
+      ex.setInputCloud(tkp);
+      ex.setSearchMethod(kdtree);
+      ex.setRadiusSearch(feat_r);
+      ex.compute(*tf);
+      double desc_runtime = now_s() - t1;
+      t1 = now_s();
+      Features<Spin> feat;
+      pcl::CorrespondencesPtr corr(new pcl::Correspondences), filtered(new pcl::Correspondences);
+      feat.findCorrespondences(sf, tf, corr);
+      float ransac_tf[16];
+      feat.filterCorrespondences(skp, tkp, corr, filtered, ransac_tf);
+      std::printf("%s, %s, %zu, %zu, %zu, %zu, %zu, %zu, %zu, %zu, %.6f, %.6f, %.6f\n", kp_type.c_str(), DESC_SPIN_IMAGE.c_str(),
+                  source->size(), target->size(), skp->size(), tkp->size(), sf->size(), tf->size(), corr->size(),
+                  filtered->size(), kp_runtime, desc_runtime, now_s() - t1);
+      dump(dump_dir, kp_type + "_SpinImage_src.bin", sf->points);
+      dump(dump_dir, kp_type + "_SpinImage_src_normals.bin", sn->points);
+    }
     {  // evaluation.cpp:344-371
       pcl::UniqueShapeContext<PointRGB, pcl::ShapeContext1980>::Ptr usc(new pcl::UniqueShapeContext<PointRGB, pcl::ShapeContext1980>);
       usc->setMinimalRadius(feat_r / 10.0);

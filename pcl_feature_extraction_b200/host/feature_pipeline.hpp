@@ -24,6 +24,7 @@ static const std::string DESC_NARF = "NARF";
 static const std::string DESC_FPFH = "FPFH";
 static const std::string DESC_SHOT = "SHOT";
 static const std::string DESC_SHOT_COLOR = "SHOTColor";
+static const std::string DESC_SPIN_IMAGE = "SpinImage";
 static const std::string DESC_USC = "USC";
 static const std::string DESC_MOMENT_INV = "MomentInvariants";
 static const std::string DESC_PFH = "PFH";

@@ -50,6 +50,7 @@ struct PrincipalCurvatures {
   static int descriptorSize() { return 5; }
 };
 struct SHOT352 { float descriptor[352]; float rf[9]; static int descriptorSize() { return 352; } };
+template <int N> struct Histogram { float histogram[N]; static int descriptorSize() { return N; } };
 struct ShapeContext1980 { float descriptor[1980]; float rf[9]; static int descriptorSize() { return 1980; } };
 struct MomentInvariants { float j1, j2, j3; static int descriptorSize() { return 3; } };
 struct SHOT1344 { float descriptor[1344]; float rf[9]; static int descriptorSize() { return 1344; } };
@@ -326,6 +327,53 @@ class FPFHEstimation : public FeatureFromNormals<PointInT, PointNT, PointOutT> {
 };
 template <typename PointInT, typename PointNT, typename PointOutT = FPFHSignature33>
 class FPFHEstimationOMP : public FPFHEstimation<PointInT, PointNT, PointOutT> {};
+
+// ------------------------------------------------------------------------------- spin images
+// pcl::SpinImageEstimation with its defaults (image width 8 -> Histogram<153>); the normals are those of the INPUT
+// cloud (one per query), as the reference sets them at evaluation.cpp:521-529
+template <typename PointInT, typename PointNT, typename PointOutT = Histogram<153>>
+class SpinImageEstimation : public Feature<PointInT, PointOutT> {
+ public:
+  explicit SpinImageEstimation(unsigned int image_width = 8, double support_angle_cos = 0.0, unsigned int min_pts_neighb = 0)
+      : image_width_(image_width), support_angle_cos_(support_angle_cos), min_pts_neighb_(min_pts_neighb) {}
+  void setInputNormals(const typename PointCloud<PointNT>::ConstPtr& n) { input_normals_ = n; }
+
+ protected:
+  const char* name() const override { return "SpinImageEstimation"; }
+  bool initCompute() override {
+    if (!Feature<PointInT, PointOutT>::initCompute()) return false;
+    if (!input_normals_) {
+      std::fprintf(stderr, "[pcl::%s::initCompute] No input dataset containing normals was given!\n", name());
+      return false;
+    }
+    if (input_normals_->size() != this->input_->size()) {
+      std::fprintf(stderr, "[pcl::%s::initCompute] The number of points in the input dataset differs from the number of points in the dataset containing the normals!\n", name());
+      return false;
+    }
+    if (this->k_ != 0) {
+      std::fprintf(stderr, "[pcl::%s::initCompute] K-nearest neighbor search for spin images not implemented. Used a neighborhood radius search instead\n", name());
+      return false;
+    }
+    if (image_width_ != 8 || support_angle_cos_ != 0.0 || PointOutT::descriptorSize() != 153) {
+      std::fprintf(stderr, "[pcl::%s::initCompute] only the default 8-bin, full-support spin image (Histogram<153>) is on the B200 path\n", name());
+      return false;
+    }
+    return true;
+  }
+  bool computeFeature(PointCloud<PointOutT>& output) override {
+    if (!this->upload()) return false;
+    int rc = pfx_spin_image153(b200::ctx(), this->search_radius_, input_normals_->points.data(), input_normals_->size(),
+                               sizeof(PointNT), reinterpret_cast<float*>(output.points.data()), sizeof(PointOutT), PFX_HOST);
+    if (!b200::ok(rc, name())) return false;
+    for (const auto& p : output.points)
+      if (!std::isfinite(p.histogram[0])) { output.is_dense = false; break; }
+    return true;
+  }
+  typename PointCloud<PointNT>::ConstPtr input_normals_;
+  unsigned int image_width_;
+  double support_angle_cos_;
+  unsigned int min_pts_neighb_;
+};
 
 // ------------------------------------------------------------------------------- Unique Shape Context (no normals)
 template <typename PointInT, typename PointOutT = ShapeContext1980, typename PointRFT = ReferenceFrame>

@@ -36,7 +36,7 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     assert sum(l.startswith("# direct ICP") for l in lines) == 1
     byname = {(x[0], x[1]): x for x in rows}
     for kp_name in ("Harris3D", "Iss"):
-        for d_name in ("FPFH", "SHOT", "SHOTColor", "USC", "MomentInvariants", "PFH", "PrincipalCurvatures"):
+        for d_name in ("FPFH", "SHOT", "SHOTColor", "SpinImage", "USC", "MomentInvariants", "PFH", "PrincipalCurvatures"):
             assert (kp_name, d_name) in byname
     # NARF row (present when both clouds yield keypoints): the shim's RangeImagePlanar / NarfKeypoint /
     # NarfDescriptor objects against the C ABI called from Python on the same cloud
@@ -143,4 +143,15 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     u_shim = np.fromfile(tmp_path / "Iss_USC_src.bin", dtype=np.float32).reshape(-1, 1989)
     u_abi, u_rf = ctx.usc1980(0.05)
     assert np.array_equal(u_shim[:, :1980], u_abi, equal_nan=True) and np.array_equal(u_shim[:, 1980:], u_rf, equal_nan=True)
+    ctx.set_queries(None)
+    # spin images through the shim (normals estimated on the keypoint cloud, as the reference does) == C ABI from Python
+    sp_shim = np.fromfile(tmp_path / "Iss_SpinImage_src.bin", dtype=np.float32).reshape(-1, 153)
+    sp_nrm = np.fromfile(tmp_path / "Iss_SpinImage_src_normals.bin", dtype=np.float32).reshape(-1, 8)
+    kq = np.ascontiguousarray(rec[:, :3])
+    ctx.set_surface(kq)                      # Tools::estimateNormals(keypoints): the keypoint cloud is its own surface
+    ctx.set_queries(None)
+    assert np.array_equal(ctx.normals(radius=0.03)[:, :3], sp_nrm[:, :3], equal_nan=True)
+    ctx.set_surface(src)
+    ctx.set_queries(kq)
+    assert np.array_equal(sp_shim, ctx.spin_image153(0.05, np.ascontiguousarray(sp_nrm[:, :4])), equal_nan=True)
     ctx.set_queries(None)
