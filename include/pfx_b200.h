@@ -227,7 +227,7 @@ int pfx_ransac_reject(pfx_ctx* ctx, const void* src, size_t n_src, size_t stride
  * PointXYZRGB> with setMaxCorrespondenceDistance(0.07), setTransformationEpsilon(1e-6),
  * setEuclideanFitnessEpsilon(1e-4), setMaximumIterations(100); setInputTarget = the context's cloud
  * (pfx_set_cloud), setInputSource = src (records with x, y, z first; stride in bytes).
- * guess16 (optional): row-major 4x4 initial transform (align(output, guess)).  result: getFinalTransformation
+ * guess16 (optional, always HOST memory): row-major 4x4 initial transform (align(output, guess)).  result: getFinalTransformation
  * (row-major), getFitnessScore(), hasConverged(), the iteration count and the convergence state
  * (1 ITERATIONS, 2 TRANSFORM, 3 ABS_MSE, 4 REL_MSE, 5 NO_CORRESPONDENCES; 0 = not converged).
  * aligned (optional): the source cloud moved by the final transform, n_src rows of x, y, z at stride_aligned. */

@@ -226,7 +226,7 @@ shot_color_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
 
 static int lab_tables(Ctx* ctx) {
   if (ctx->lab_tab.p) return 0;
-  static LabTab host;  // PCL's two lookup tables, same libm calls (features/impl/shot.hpp, RGB2CIELAB)
+  LabTab host;  // PCL's two lookup tables, same libm calls (features/impl/shot.hpp, RGB2CIELAB)
   for (int i = 0; i < 256; ++i) {
     float f = static_cast<float>(i) / 255.0f;
     host.srgb[i] = (f > 0.04045) ? powf((f + 0.055f) / 1.055f, 2.4f) : f / 12.92f;
