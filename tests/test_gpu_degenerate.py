@@ -89,3 +89,32 @@ def test_nan_and_far_outliers(ctx, orc):
     oi2, od2 = orc.match_nn(a, b)
     keep = oi2 >= 0
     assert np.array_equal(corr["index_match"], oi2[keep]) and np.array_equal(corr["distance"], od2[keep])
+
+
+def test_two_contexts_side_by_side(ctx):
+    """contexts own all of their state (grids, caches, shared-memory attributes, streams): interleaved use of two
+    contexts on one device gives the results of using either alone"""
+    import pcl_feature_extraction_b200 as pfx
+    rng = np.random.default_rng(8)
+    a = rng.uniform(0, 0.4, (9000, 3)).astype(np.float32)
+    b = rng.uniform(0, 0.3, (7000, 3)).astype(np.float32)
+    ref_a = run_dense(ctx, a, k=10, r=0.03)
+    ref_b = run_dense(ctx, b, k=10, r=0.03)
+    other = pfx.Context(0)
+    try:
+        other.set_viewpoint(0, 0, 0)
+        ctx.set_surface(a)
+        other.set_surface(b)
+        ctx.prepare_radius(0.03)
+        other.prepare_radius(0.03)
+        na, nb_ = ctx.normals(k=10), other.normals(k=10)
+        fa, fb = ctx.fpfh(k=10), other.fpfh(k=10)
+        sa, sb = ctx.shot352(0.03), other.shot352(0.03)
+        for got, ref in ((na, ref_a[0]), (fa, ref_a[1]), (sa[0], ref_a[2]), (sa[1], ref_a[3]),
+                         (nb_, ref_b[0]), (fb, ref_b[1]), (sb[0], ref_b[2]), (sb[1], ref_b[3])):
+            assert np.array_equal(got, ref, equal_nan=True)
+        m1 = ctx.match(fa[:300], fa[300:900])
+        m2 = other.match(fa[:300], fa[300:900])
+        assert np.array_equal(m1, m2)
+    finally:
+        other.close()
