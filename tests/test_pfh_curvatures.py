@@ -84,7 +84,7 @@ def gpu_normals(ctx, pts, radius=None, k=0):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,radius,k,dense", [(20000, 0.03, 0, False), (20000, 0.0, 24, False), (3000, 0.06, 0, True),
-                                               (60000, 0.05, 0, False)])
+                                               (60000, 0.05, 0, False), (4000, 0.0, 16, True)])
 def test_gpu_pfh125_equals_oracle(ctx, orc, n, radius, k, dense):
     pts = bumpy(n, 3)
     nr = gpu_normals(ctx, pts, radius=0.03)
@@ -138,7 +138,8 @@ def test_gpu_pfh125_edge_cases(ctx, orc):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,radius,k,dense", [(20000, 0.03, 0, True), (20000, 0.0, 20, True), (20000, 0.04, 0, False)])
+@pytest.mark.parametrize("n,radius,k,dense", [(20000, 0.03, 0, True), (20000, 0.0, 20, True), (20000, 0.04, 0, False),
+                                               (20000, 0.0, 12, False)])
 def test_gpu_principal_curvatures_equal_oracle(ctx, orc, n, radius, k, dense):
     pts = bumpy(n, 7)
     nr = gpu_normals(ctx, pts, radius=0.03)
