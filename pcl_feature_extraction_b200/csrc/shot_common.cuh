@@ -122,7 +122,9 @@ __device__ __forceinline__ void shot_accumulate_neighbor_f(int* h, float scale, 
   cosd = fminf(1.0f, fmaxf(-1.0f, cosd));
   float bd = (1.0f + cosd) * 5.0f;
   const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
-  const float dist = sqrtf(d2);
+  // sqrt through the reciprocal-square-root unit (2 ulp): distances only enter continuous weights and shell tests
+  // that the interpolation makes continuous
+  const float dist = (d2 > 0.f) ? d2 * rsqrtf(d2) : 0.f;
   if (dist < 1e-15f) return;
   float x = __fadd_rn(__fadd_rn(__fmul_rn(dx, rf[0]), __fmul_rn(dy, rf[1])), __fmul_rn(dz, rf[2]));
   float y = __fadd_rn(__fadd_rn(__fmul_rn(dx, rf[3]), __fmul_rn(dy, rf[4])), __fmul_rn(dz, rf[5]));
@@ -165,7 +167,8 @@ __device__ __forceinline__ void shot_accumulate_neighbor_f(int* h, float scale, 
       atomicAdd(&h[(di + 2) * 11 + step], __float2int_rn(rd * scale));
     }
   }
-  const float rho = sqrtf(fmaf(x, x, y * y));  // inc = acos(z / dist) = atan2(|(x, y)|, z), in [0, pi]
+  const float rho2 = fmaf(x, x, y * y);
+  const float rho = (rho2 > 0.f) ? rho2 * rsqrtf(rho2) : 0.f;  // inc = acos(z / dist) = atan2(|(x, y)|, z), in [0, pi]
   const float inc = fast_atan2f(rho, z);
   if (z <= 0.f) {
     const float e = (inc - RAD135) * INV_RAD90;
