@@ -230,25 +230,21 @@ fpfh_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2, con
 // ------------------------------------------------------------------------------ FPFH from kNN rows
 // k-search (rows of k <= 32 neighbours): lane t first turns neighbour t into a weight 1/d2; the gather
 // then takes THREE neighbours per step - 9 lanes per neighbour, each lane one 32-bit word of the
-// 36-byte count row (4 bins) - so a query costs 11 steps instead of 32.  The count -> float-sum table
-// T (PCL's sequential hist += incr, the same for every point of a k-search) is computed once on the host,
-// arrives as a kernel parameter and lives in registers: lane c holds T[c] and a lookup is one shuffle
-// (c <= k - 1 <= 31 because a point is never its own pair).
-struct IncrTable {
-  float t[32];
-};
-
+// 36-byte count row (4 bins) - so a query costs 11 steps instead of 32.  The counts are weighted as they are:
+// PCL's SPFH value of a count c is the float sum of c increments 100 / (k - 1), the same increment for every
+// point of a k-search, and FPFH's rescaling of each 11-bin block to 100 divides it out (the sum differs from
+// c * incr by < 2e-6 relative).  Bytes become floats on the ALU / FMA pipes (PRMT under the exponent of 2^23,
+// minus 2^23): the shuffle unit, which a register-table lookup per bin kept 80 % busy, only broadcasts (j, w).
 template <bool DENSE, bool K32>
 __global__ void __launch_bounds__(FWPB * 32)
 fpfh_list_kernel(GridDev g, const float4* __restrict__ queries, int nq, const int* __restrict__ lists,
                  const float* __restrict__ ld2, int k_rt, const unsigned char* __restrict__ rows8,
-                 float* __restrict__ out, size_t stride, IncrTable tab) {
+                 float* __restrict__ out, size_t stride) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int qi = blockIdx.x * FWPB + wid;
   if (qi >= nq) return;
   const int k = K32 ? 32 : k_rt;
   const int n_valid = g.gp->n_valid;
-  const float Treg = tab.t[lane];
   float4 q = DENSE ? g.pts[qi] : queries[qi];
   const size_t row = DENSE ? (size_t)__float_as_int(q.w) : (size_t)qi;
   float* o = out + row * stride;
@@ -280,11 +276,14 @@ fpfh_list_kernel(GridDev g, const float4* __restrict__ queries, int nq, const in
     if (!gl || s + grp >= k) w = 0.f;
     unsigned cw = 0u;
     if (w != 0.f) cw = rows32[(size_t)j * 9 + c9];
-    // counts -> PCL's float sums: four register-table lookups (all lanes take part in the shuffles)
-    const float t0 = __shfl_sync(FULL, Treg, (int)(cw & 31u));
-    const float t1 = __shfl_sync(FULL, Treg, (int)((cw >> 8) & 31u));
-    const float t2 = __shfl_sync(FULL, Treg, (int)((cw >> 16) & 31u));
-    const float t3 = __shfl_sync(FULL, Treg, (int)((cw >> 24) & 31u));
+    // counts as floats.  PCL's SPFH value of a count c is the float sum T[c] of c increments of 100 / (k - 1); every
+    // point of a k-search has the same increment, and the final per-block rescaling to 100 divides it out, so the
+    // counts themselves are weighted (T[c] = c * incr up to 2e-6 relative: far inside the 1e-4 tolerance).
+    // byte -> float without the conversion unit: the byte under the exponent of 2^23, minus 2^23
+    const float t0 = __uint_as_float(__byte_perm(cw, 0x4B000000u, 0x7540)) - 8388608.0f;
+    const float t1 = __uint_as_float(__byte_perm(cw, 0x4B000000u, 0x7541)) - 8388608.0f;
+    const float t2 = __uint_as_float(__byte_perm(cw, 0x4B000000u, 0x7542)) - 8388608.0f;
+    const float t3 = __uint_as_float(__byte_perm(cw, 0x4B000000u, 0x7543)) - 8388608.0f;
     a0 = fmaf(t0, w, a0);
     a1 = fmaf(t1, w, a1);
     a2 = fmaf(t2, w, a2);
@@ -379,35 +378,17 @@ int fpfh_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t
       PFX_LAUNCH(ctx, spfh_export_kernel, div_up((long long)n * 33, 256), 256, 0, g->view(), nullptr,
                  rows8.as<unsigned char>(), n, k, spfh_out_dev);
     if (out_dev && nq > 0) {
-      // T[c] = c sequential float additions of incr = 100 / (n - 1) (PCL's hist += hist_incr), IEEE float on the host
-      IncrTable tab;
-      {
-        int n_nb_row = k;  // every point of a k-search has min(k, #finite points) neighbours
-        if (n <= k) {      // tiny cloud: the finite-point count lives on the device
-          GridParams hp;
-          PFX_CUDA(cudaMemcpyAsync(&hp, g->params.p, sizeof(hp), cudaMemcpyDeviceToHost, ctx->stream));
-          PFX_CUDA(cudaStreamSynchronize(ctx->stream));
-          n_nb_row = std::min(k, hp.n_valid);
-        }
-        const float incr = (n_nb_row > 1) ? 100.0f / (float)(n_nb_row - 1) : 0.f;
-        volatile float v = 0.f;
-        tab.t[0] = 0.f;
-        for (int c = 1; c < 32; ++c) {
-          v = v + incr;
-          tab.t[c] = v;
-        }
-      }
       const int blocks = div_up(nq, FWPB);
       if (dense) {
         if (k == 32)
           PFX_LAUNCH(ctx, (fpfh_list_kernel<true, true>), blocks, FWPB * 32, 0, g->view(), nullptr, nq, ctx->knn_idx.as<int>(),
-                     ctx->knn_d2.as<float>(), k, rows8.as<unsigned char>(), out_dev, stride_floats, tab);
+                     ctx->knn_d2.as<float>(), k, rows8.as<unsigned char>(), out_dev, stride_floats);
         else
           PFX_LAUNCH(ctx, (fpfh_list_kernel<true, false>), blocks, FWPB * 32, 0, g->view(), nullptr, nq, ctx->knn_idx.as<int>(),
-                     ctx->knn_d2.as<float>(), k, rows8.as<unsigned char>(), out_dev, stride_floats, tab);
+                     ctx->knn_d2.as<float>(), k, rows8.as<unsigned char>(), out_dev, stride_floats);
       } else {
         PFX_LAUNCH(ctx, (fpfh_list_kernel<false, false>), blocks, FWPB * 32, 0, g->view(), ctx->qry.as<float4>(), nq,
-                   ctx->tmp2.as<int>(), ctx->tmp3.as<float>(), k, rows8.as<unsigned char>(), out_dev, stride_floats, tab);
+                   ctx->tmp2.as<int>(), ctx->tmp3.as<float>(), k, rows8.as<unsigned char>(), out_dev, stride_floats);
       }
     }
     PFX_CUDA(cudaGetLastError());

@@ -108,14 +108,24 @@ __device__ __forceinline__ void shot_accumulate_neighbor(int* h, float scale, fl
 }
 
 // Float variant of the above for the fused dense kernel.  The three frame projections keep the CPU's
-// float arithmetic (separate multiply / add); everything else is single precision.  SHOT's quadrilinear
-// interpolation is continuous across every discrete boundary (cosine step, radial shell, elevation and
-// azimuth sector: the weight that leaves one bin enters its neighbour), so a decision that flips within
-// float round-off of a boundary moves O(1e-7) of weight, far inside the 1e-4 tolerance.
+// float arithmetic (separate multiply / add), so every sign / sector decision is the CPU's.  PCL adds the four
+// interpolation weights of a neighbour into ITS bin (a sum, not a product): where the bin itself changes - the
+// cosine step and the radial shell at R / 2 - the descriptor is discontinuous, and those two decisions are taken
+// exactly like the CPU (the step in double, the shell from d2 against shot_d2_threshold).  The remaining branch
+// points (R / 4, 3 R / 4, 45 / 135 degrees, the azimuth sector centre) are bin CENTRES, where the weight that
+// leaves one bin enters its neighbour continuously: single precision and a 2-ulp square root are enough there.
+// largest float f with sqrt((double)f) <= r: "sqrt((double)d2) > r" (the CPU's shell test) is then exactly "d2 > f"
+__device__ __forceinline__ float shot_d2_threshold(double r) {
+  float t = (float)(r * r);
+  while (sqrt((double)t) > r) t = nextafterf(t, 0.f);
+  while (sqrt((double)nextafterf(t, CUDART_INF_F)) <= r) t = nextafterf(t, CUDART_INF_F);
+  return t;
+}
+
 __device__ __forceinline__ void shot_accumulate_neighbor_f(int* h, float scale, float4 q, float4 p, float d2, float4 nj,
-                                                           const float* rf, float R) {
+                                                           const float* rf, float R, float t12) {
   if (!finite3(nj.x, nj.y, nj.z)) return;
-  const float r12 = 0.5f * R, r14 = 0.25f * R, r34 = 0.75f * R, inv_r12 = 2.0f / R;
+  const float r14 = 0.25f * R, r34 = 0.75f * R, inv_r12 = 2.0f / R;
   const float RAD45 = 0.78539816339744830962f, RAD135 = 2.35619449019234492885f, RAD_PI_7_8 = 2.7488935718910690836f,
               INV_RAD90 = 0.63661977236758134308f, INV_RAD45 = 1.27323954473516268615f;
   float cosd = __fadd_rn(__fadd_rn(__fmul_rn(nj.x, rf[6]), __fmul_rn(nj.y, rf[7])), __fmul_rn(nj.z, rf[8]));
@@ -141,8 +151,11 @@ __device__ __forceinline__ void shot_accumulate_neighbor_f(int* h, float scale, 
   else
     di += (fabsf(x) > fabsf(y)) ? 4 : 0;
   di += z > 0.f ? 1 : 0;
-  di += (dist > r12) ? 2 : 0;
-  const int step = __float2int_rd(bd + 0.5f);
+  // the two decisions at which PCL's additive interpolation is NOT continuous (the neighbour's whole weight changes
+  // bin) replicate the CPU exactly: the radial shell from d2 itself, the cosine step in double
+  const bool outer = d2 > t12;
+  di += outer ? 2 : 0;
+  const int step = (int)floor(((1.0 + (double)cosd) * 10) / 2 + 0.5);
   const int vol = di * 11;
   bd -= (float)step;
   float w = 1.0f - fabsf(bd);
@@ -150,7 +163,7 @@ __device__ __forceinline__ void shot_accumulate_neighbor_f(int* h, float scale, 
     const int nb_step = (bd > 0.f) ? ((step + 1) % 10) : ((step + 9) % 10);
     atomicAdd(&h[vol + nb_step], __float2int_rn(fabsf(bd) * scale));
   }
-  if (dist > r12) {
+  if (outer) {
     const float rd = (dist - r34) * inv_r12;
     if (dist > r34)
       w += 1.0f - rd;

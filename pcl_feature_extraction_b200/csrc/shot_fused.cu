@@ -47,6 +47,7 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
   const int n_valid = P.n_valid;
   const float nanv = __int_as_float(0x7fc00000);
   const float Rf = (float)R;
+  const float t12 = shot_d2_threshold(R / 2);  // d2 > t12  <=>  sqrt((double)d2) > R / 2
   const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
   for (int i = 0; i < 11; ++i) S->hist[lane + 32 * i] = 0;
@@ -226,7 +227,7 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
         const int j = S->nbr[c][t];
         const float4 p = g.pts[j];
         const float d2 = dist2_flann(qt.x, qt.y, qt.z, p.x, p.y, p.z);
-        shot_accumulate_neighbor_f(S->hist, scale, qt, p, d2, nrm[j], rft, Rf);
+        shot_accumulate_neighbor_f(S->hist, scale, qt, p, d2, nrm[j], rft, Rf, t12);
       }
       __syncwarp();
       float acc = 0.f;

@@ -358,6 +358,24 @@ def test_shot_end_to_end_dense(ctx, orc, clouds):
     assert (d <= 1e-4).mean() > 0.99, (d <= 1e-4).mean()
 
 
+def test_shot_dense_whole_cloud_has_no_outlier_rows(ctx, orc):
+    """PCL's interpolation is discontinuous where a neighbour changes its cosine step or its radial shell: the dense
+    float kernel must take those decisions exactly like the CPU.  The 96 x 96 sheet holds a pair of points exactly
+    R / 2 apart; every row of two whole clouds is compared (same frames on both sides)."""
+    from pcl_feature_extraction_b200.synth import sheet_cloud
+    for side in (96, 160):
+        pts = sheet_cloud(side=side, pitch=0.004)
+        ctx.set_viewpoint(0, 0, 0)
+        ctx.set_surface(pts)
+        ctx.set_queries(None)
+        nr = ctx.normals(k=32)
+        s, rf = ctx.shot352(0.0128)
+        ref, _ = orc.shot352(pts, nr, None, 0.0128, lrf_in=rf)
+        ok = ~np.isnan(ref[:, 0])
+        assert np.array_equal(np.isnan(s[:, 0]), ~ok)
+        assert np.abs(s[ok] - ref[ok]).max() <= 1e-6
+
+
 def test_shot_rejects_k_search_and_few_neighbours(ctx, orc):
     import pcl_feature_extraction_b200 as pfx
     rng = np.random.default_rng(5)
