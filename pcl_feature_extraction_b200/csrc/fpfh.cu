@@ -254,7 +254,7 @@ fpfh_list_kernel(GridDev g, const float4* __restrict__ queries, int nq, const in
   if (ok && lane < k) {
     myj = lists[(size_t)qi * k + lane];
     float d2 = ld2[(size_t)qi * k + lane];
-    if (myj >= 0 && d2 != 0.f) myw = __fdiv_rn(1.0f, d2);  // "minus the query point itself": dists == 0 skipped
+    if (myj >= 0 && d2 != 0.f) myw = __frcp_rn(d2);  // "minus the query point itself": dists == 0 skipped
   }
   const int n_nb = __popc(__ballot_sync(FULL, myj >= 0));
   if (!ok || n_nb == 0) {  // PCL: NaN row, is_dense = false
@@ -313,8 +313,9 @@ fpfh_list_kernel(GridDev g, const float4* __restrict__ queries, int nq, const in
     s2 += __shfl_xor_sync(FULL, s2, of);
   }
   if (lane < 9) {
-    const float k0 = (s0 != 0.f) ? 100.0f / s0 : 0.f, k1 = (s1 != 0.f) ? 100.0f / s1 : 0.f,
-                k2 = (s2 != 0.f) ? 100.0f / s2 : 0.f;
+    // (2-ulp division: the scale factor of a block, far inside the tolerance)
+    const float k0 = (s0 != 0.f) ? __fdividef(100.0f, s0) : 0.f, k1 = (s1 != 0.f) ? __fdividef(100.0f, s1) : 0.f,
+                k2 = (s2 != 0.f) ? __fdividef(100.0f, s2) : 0.f;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       int bin = lane * 4 + b;
