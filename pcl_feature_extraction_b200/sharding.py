@@ -127,6 +127,18 @@ def knn_support_radius(kth_dist_local_max, chain_len, device=None, group=None):
     return chain_len * float(t.item())
 
 
+def cloud_resolution_over_ranks(nn_dist_owned, device=None, group=None):
+    """computeCloudResolution (keypoints.h:401-428) of a slab-sharded cloud: every rank passes the distances of its
+    OWNED points to their nearest other point (searched among owned + halo points); one all-reduce of (sum, count).
+    Non-finite distances (points without a neighbour) are left out, as in the reference."""
+    d = np.asarray(nn_dist_owned, np.float64)
+    d = d[np.isfinite(d)]
+    t = torch.tensor([float(d.sum()), float(len(d))], dtype=torch.float64, device=device or torch.device("cpu"))
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return float(t[0].item() / t[1].item()) if t[1].item() > 0 else 0.0
+
+
 def max_over_ranks(seconds, device=None, group=None):
     """the time every multi-GPU number is quoted with: MAX over ranks of a device-measured duration"""
     t = torch.tensor([float(seconds)], dtype=torch.float64, device=device or torch.device("cpu"))

@@ -79,6 +79,10 @@ def _worker(rank, world, port, cloud_path, out_path):
         full = sharding.gather_rows(rows, n, mine, rank, world)
         t = sharding.max_over_ranks(1.0 + rank)
         assert t == 2.0
+        # cloud resolution of the whole cloud from the owned points of every rank (2-NN among owned + halo points)
+        _, d2nn = orc.knn(xyz, xyz[:n_owned], 2)
+        res = sharding.cloud_resolution_over_ranks(np.sqrt(d2nn[:, 1].astype(np.float64)))
+        assert abs(res - orc.cloud_resolution(pts)) < 1e-9
         assert sharding.knn_support_radius(0.01 * (rank + 1), 3) == pytest.approx(0.06)
         if rank == 0:
             np.save(out_path, full)
