@@ -55,6 +55,20 @@ def workload_name(side):
             f"dense normals k=32 + FPFH33 k=32 + SHOT352 r=12.8 mm")
 
 
+def make_config(side):
+    """the workload both arms (--impl ours / reference) run, word for word the same"""
+    return {"workload": workload_name(side), "points_per_cloud": side * side, "clouds_per_step_per_gpu": 1,
+            "descriptors_per_point": 2,
+            "l2": "working set per step ~1.9 GB (1.5 GB SHOT output) >> 126 MB L2; input alternates between 2 clouds"}
+
+
+def whole_step_bytes(nbar):
+    """hash build 38 + k-search list (16 + 8k) + normals (32 + 4k) + SPFH (164 + 4k) + FPFH
+    (264 + 8k) at k = 32, + radius list (24 + 8n) + SHOT frame (52 + 8n) + SHOT352 (1512 + 8n) at the MEASURED mean
+    neighbour count n of the radius stages (3 638 B/pt at n = 32)"""
+    return 1282.0 + 1588.0 + 24.0 * nbar
+
+
 def ncu_traffic(kernel_key):
     """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/), or None"""
     try:
@@ -128,31 +142,43 @@ def cpu_pipeline(orc, pts):
     return f, s
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the CPU path (oracle port of PCL) on all host threads, bounded sample per step."""
+    """--impl reference: the CPU path (oracle port of PCL) on ALL host threads, the full cloud per step.
+    torchrun exports OMP_NUM_THREADS=1 to its workers: the thread count is set explicitly."""
     if rank != 0:
         return
     from oracle import binding as orc
     from pcl_feature_extraction_b200.synth import sheet_cloud
-    side = args.ref_side
+    cores = host_threads()
+    orc.set_num_threads(cores)
+    side = args.ref_side or args.side
     pts = sheet_cloud(side=side, pitch=PITCH, seed=20240601)
-    cores = orc.num_threads()
-    for _ in range(min(args.warmup, 1)):
-        cpu_pipeline(orc, pts)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    cpu_pipeline(orc, pts)  # warm-up (one pass is enough for a CPU code; it also sizes the timed leg)
+    t1 = time.perf_counter() - t0
+    steps = max(1, min(args.steps, int(150.0 / max(t1, 1e-3))))  # the run ends within a few minutes on any box
+    t0 = time.perf_counter()
+    for _ in range(steps):
         cpu_pipeline(orc, pts)
     dt = time.perf_counter() - t0
-    val = 2.0 * len(pts) * args.steps / dt
-    sample = f"{side}x{side}-point sheet per step ({len(pts)} points), same stages and parameters"
+    val = 2.0 * len(pts) * steps / dt
+    sample = (f"the full {side}x{side}-point cloud per step ({len(pts)} points), {steps} timed steps after one warm-up pass"
+              if side == args.side else f"{side}x{side}-point sheet per step ({len(pts)} points), same stages and parameters")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.side), "sample": sample},
+        "warmup": args.warmup, "steps_timed": steps, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": make_config(args.side),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "restated-PCL CPU oracle with OpenMP on all host threads; PCL/ROS cannot be built in this image",
+        "note": f"restated-PCL CPU oracle with OpenMP on {cores} host threads (set explicitly); PCL/ROS cannot be built in this "
+                "image; under torchrun rank 0 alone runs the CPU arm",
     }), flush=True)
 
 
@@ -184,7 +210,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--side", type=int, default=1024, help="sheet is side x side points (1024 -> 2^20)")
-    ap.add_argument("--ref-side", type=int, default=320)
+    ap.add_argument("--ref-side", type=int, default=0, help="reference arm: sheet side (0 = the full --side cloud)")
     ap.add_argument("--cpu-side", type=int, default=448)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -254,12 +280,12 @@ def main():
     shares = {nm: round(ms / step_ms_prof, 4) for nm, (_, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
 
     # mean neighbour count of the radius stages (for their algorithmic bytes), outside the timed region
-    nbar = float(K_NN)
-    if dom_key in ("lrf_kernel", "shot_kernel", "shot_fused_kernel"):
-        cnt = torch.empty(n, dtype=torch.int32, device=dev)
-        ctx._chk(ctx.lib.pfx_radius_count(ctx.h, SHOT_RADIUS, pfx.capi._ptr(cnt), None, pfx.capi.DEVICE))
-        torch.cuda.synchronize()
-        nbar = float(cnt.float().mean().item())
+    cnt = torch.empty(n, dtype=torch.int32, device=dev)
+    ctx._chk(ctx.lib.pfx_radius_count(ctx.h, SHOT_RADIUS, pfx.capi._ptr(cnt), None, pfx.capi.DEVICE))
+    torch.cuda.synchronize()
+    nbar_radius = float(cnt.float().mean().item())
+    del cnt
+    nbar = nbar_radius if dom_key in ("lrf_kernel", "shot_kernel", "shot_fused_kernel") else float(K_NN)
 
     # ---- second context on its own stream: two clouds in flight per GPU.  The index builds and the tails of one
     # cloud's kernels run in the gaps of the other's (contexts own all of their state; results are bit-identical
@@ -377,37 +403,65 @@ def main():
         ms_dom = sum(m for nm, (_, m) in dom_prof.items())
         per_launch_s = (ms_dom / max(cnt_dom, 1)) * 1e-3
         alg = ALG_BYTES[dom_key](nbar) * n
+        wsb = whole_step_bytes(nbar_radius)
         achieved = alg / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": dom_key, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm_gbs"], "peak_kind": peak_kind + " (burst copy)", "traffic": ncu_traffic(dom_key) if n == (1 << 20) else None,
                     "alg_bytes_per_point": ALG_BYTES[dom_key](nbar), "points_per_launch": n, "mean_neighbours": nbar,
                     "launch_ms": per_launch_s * 1e3, "timed": "CUDA events on the launching stream over the single-cloud timed region (kernel alone on the GPU)",
                     "kernel_shares_of_step": shares,
-                    "whole_step": {"alg_bytes_per_point": 3638, "achieved_GBps": 3638.0 * n * args.steps / (total_ms * 1e-3) / 1e9,
-                                   "frac": 3638.0 * n * args.steps / (total_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+                    "whole_step": {"alg_bytes_per_point": wsb, "mean_neighbours_radius_stages": nbar_radius,
+                                   "achieved_GBps": wsb * n * args.steps / (total_ms * 1e-3) / 1e9,
+                                   "frac": wsb * n * args.steps / (total_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                   "timed": f"the reported region ({IN_FLIGHT} clouds in flight)",
+                                   "single_cloud": {"ms_per_step": latency_ms, "achieved_GBps": wsb * n / (latency_ms * 1e-3) / 1e9,
+                                                    "frac": wsb * n / (latency_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}}}
         cpu = None
         if world == 1 and not args.no_cpu:
             if cpus_before:
                 os.sched_setaffinity(0, cpus_before)  # the CPU baseline gets every host core
             from oracle import binding as orc
+            cores = host_threads()
+            orc.set_num_threads(cores)
             cs = args.cpu_side
             cp = sheet_cloud(side=cs, pitch=PITCH, seed=20240601)
             t0 = time.perf_counter()
             cpu_pipeline(orc, cp)
             dtc = time.perf_counter() - t0
-            cpu = {"value": 2.0 * len(cp) / dtc, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+            # the reference's own thread settings: NormalEstimationOMP and SHOTEstimationOMP on
+            # all cores (tools.h:26, evaluation.cpp:770), FPFHEstimation single-threaded (evaluation.cpp:597)
+            fs = min(cs, 224)
+            fp = sheet_cloud(side=fs, pitch=PITCH, seed=20240601)
+            t0 = time.perf_counter()
+            nr_f, _, _ = orc.normals(fp, k=K_NN)
+            t_n = time.perf_counter() - t0
+            orc.set_num_threads(1)
+            t0 = time.perf_counter()
+            orc.fpfh(fp, nr_f, k=K_NN)
+            t_f = time.perf_counter() - t0
+            orc.set_num_threads(cores)
+            t0 = time.perf_counter()
+            orc.shot352(fp, nr_f, None, SHOT_RADIUS)
+            t_s = time.perf_counter() - t0
+            cpu = {"value": 2.0 * len(cp) / dtc, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{cs}x{cs}-point sheet ({len(cp)} points), same stages and parameters, one pass, "
-                             f"{dtc:.1f} s; restated-PCL oracle with OpenMP (PCL itself cannot be built here)"}
+                             f"{dtc:.1f} s; restated-PCL oracle with OpenMP on all host threads (PCL itself cannot be built here)",
+                   "reference_faithful": {
+                       "value": 2.0 * len(fp) / (t_n + t_f + t_s), "unit": UNIT, "cores": cores,
+                       "threads": {"normals": cores, "fpfh": 1, "shot": cores},
+                       "stage_s": {"normals": round(t_n, 3), "fpfh": round(t_f, 3), "shot": round(t_s, 3)},
+                       "sample": f"{fs}x{fs}-point sheet ({len(fp)} points); thread settings of the reference: NormalEstimationOMP / "
+                                 "SHOTEstimationOMP all cores, FPFHEstimation 1 thread (evaluation.cpp:597)"}}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.side), "points_per_cloud": n, "clouds_per_step_per_gpu": 1,
-                       "descriptors_per_point": 2, "clouds_in_flight_per_gpu": IN_FLIGHT,
-                       "parallelism": f"cloud-sharded x{world}, no data-path collective; {IN_FLIGHT} clouds in flight per GPU "
-                                      "(one context and stream each)",
-                       "l2": "working set per step ~1.9 GB (1.5 GB SHOT output) >> 126 MB L2; input alternates between 2 clouds"},
-            "points_per_s": value / 2.0, "single_cloud_latency_ms": latency_ms,
+            "config": make_config(args.side),
+            "run": {"clouds_in_flight_per_gpu": IN_FLIGHT,
+                    "parallelism": f"cloud-sharded x{world}, no data-path collective; {IN_FLIGHT} clouds in flight per GPU "
+                                   "(one context and stream each)"},
+            "points_per_s": value / 2.0, "single_cloud_latency_ms": latency_ms, "ms_per_step_single_cloud": latency_ms,
+            "matching": matching, "bundled": bundled, "slab": slab,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,
             "host_binding": "GPU-local CPUs (NVML affinity)" if cpus_before else "none",
         }

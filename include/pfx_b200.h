@@ -164,6 +164,18 @@ int pfx_set_match_engine(pfx_ctx* ctx, int engine);
  * they processed, out4[2] rows whose exactness certificate failed and were redone by the exact scan */
 int pfx_match_info(pfx_ctx* ctx, double* out4);
 
+/* ------------------------------------------------------------------ parity mode
+ * PFX_PARITY_FAST (default): the throughput kernels; floats within the tolerances of DESIGN.md section 4.
+ * PFX_PARITY_STRICT: the stages whose floats feed INDEX outputs of the reference pipeline run in reference-order
+ * arithmetic (strict.cu) - neighbours in ascending (d2, index) order, sequential sums, the CPU restatement's
+ * eigen solver, no FMA contraction - so that NormalEstimation (tools.h:26-31), HarrisKeypoint3D response /
+ * refinement / snap (keypoints.h:154-162, :360-395) and radius-search FPFH at keypoints (evaluation.cpp:597-602)
+ * are bit-identical to the CPU path and the keypoint / correspondence indices of Features::findCorrespondences
+ * (features.h:240-250) agree end to end, degenerate neighbourhoods included.  Meant for the reference's own
+ * keypoint pipelines (1e4 .. 1e5 points); k-search FPFH, SHOT and the dense 1M-point path keep the fast kernels. */
+enum { PFX_PARITY_FAST = 0, PFX_PARITY_STRICT = 1 };
+int pfx_set_parity_mode(pfx_ctx* ctx, int mode);
+
 /* ------------------------------------------------------------------ PFH125, PrincipalCurvatures (next rows)
  * pfx_pfh125 <- PFHEstimation<PointXYZRGB, Normal, PFHSignature125>::compute (evaluation.cpp:676-695 through
  * features.h:181-195): rows of 125 floats (pcl::PFHSignature125, 500 B) for the current queries; same

@@ -55,6 +55,7 @@ SIGNATURES = {
     "pfx_destroy": (_i, [_vp]),
     "pfx_last_error": (C.c_char_p, [_vp]),
     "pfx_set_stream": (_i, [_vp, _vp]),
+    "pfx_set_parity_mode": (_i, [_vp, _i]),
     "pfx_sync": (_i, [_vp]),
     "pfx_launch_count": (C.c_uint64, [_vp]),
     "pfx_grid_info": (_i, [_vp, C.POINTER(_d)]),
@@ -515,6 +516,11 @@ class Context:
         if want_aligned:
             out["aligned"] = al
         return out
+
+    def set_parity_mode(self, strict):
+        """True: reference-order arithmetic for normals / Harris3D / radius-search FPFH (bit-identical to the CPU
+        path, include/pfx_b200.h); False: the throughput kernels (default)"""
+        self._chk(self.lib.pfx_set_parity_mode(self.h, 1 if strict else 0))
 
     def set_match_engine(self, engine):
         self._chk(self.lib.pfx_set_match_engine(self.h, engine))

@@ -195,8 +195,14 @@ extern "C" int pfx_destroy(pfx_ctx* ctx) {
                     &ctx->stage, &ctx->stage2, &ctx->tmp0, &ctx->tmp1, &ctx->tmp2, &ctx->tmp3, &ctx->tmp4,
                     &ctx->small, &ctx->scanbuf, &ctx->match_flags, &ctx->match_best, &ctx->out_stage, &ctx->qflag,
                     &ctx->worklist, &ctx->worklist2, &ctx->ri_img, &ctx->nb_surf, &ctx->nb_scores, &ctx->nb_shadow,
-                    &ctx->nb_traits, &ctx->nb_dir, &ctx->nb_change, &ctx->nk_interest})
+                    &ctx->nb_traits, &ctx->nb_dir, &ctx->nb_change, &ctx->nk_interest, &ctx->icp_state, &ctx->icp_cur,
+                    &ctx->icp_nn, &ctx->icp_partials, &ctx->usc_tab, &ctx->lab_tab, &ctx->surf_lab, &ctx->qry_lab})
     b->release();
+  ctx->vg_scratch.release();
+  for (Ctx::ProfRec& r : ctx->prof_recs) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   delete ctx;
   return 0;
@@ -473,7 +479,8 @@ extern "C" int pfx_normals(pfx_ctx* ctx, double radius, int k, void* out, size_t
     rows = ctx->tmp0.as<float4>();
   }
   if (!out && !ctx->q_is_surface) return 0;
-  PFX_TRY(normals_compute(ctx, g, radius, k, rows));
+  if (ctx->parity_mode == PFX_PARITY_STRICT) PFX_TRY(strict_normals(ctx, g, radius, k, rows));
+  else PFX_TRY(normals_compute(ctx, g, radius, k, rows));
   if (!out || nq == 0) return 0;
   if (mem == PFX_DEVICE) {
     if (stride == 16 && curv_off == 3) return deliver(ctx, out, rows, nq * sizeof(float4), mem);
@@ -599,13 +606,15 @@ static int harris3d_impl(pfx_ctx* ctx, double radius, float threshold, int nonma
   if (!ctx->have_normals) {
     bool saved = ctx->q_is_surface;
     ctx->q_is_surface = true;
-    int rc = normals_compute(ctx, g, radius, 0, nullptr);
+    int rc = ctx->parity_mode == PFX_PARITY_STRICT ? strict_normals(ctx, g, radius, 0, nullptr)
+                                                   : normals_compute(ctx, g, radius, 0, nullptr);
     ctx->q_is_surface = saved;
     if (rc) return rc;
   }
   PFX_CUDA(ctx->tmp1.ensure(n * sizeof(float)));
   float* dresp = ctx->tmp1.as<float>();
-  PFX_TRY(harris_response(ctx, g, radius, dresp));
+  if (ctx->parity_mode == PFX_PARITY_STRICT) PFX_TRY(harris_response_strict(ctx, g, radius, dresp));
+  else PFX_TRY(harris_response(ctx, g, radius, dresp));
   if (response) {
     if (mem == PFX_DEVICE) PFX_TRY(deliver(ctx, response, dresp, n * sizeof(float), mem));
     else PFX_CUDA(cudaMemcpyAsync(response, dresp, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -629,7 +638,10 @@ static int harris3d_impl(pfx_ctx* ctx, double radius, float threshold, int nonma
   float* dxyz = ctx->stage2.as<float>();
   int* dsnap = reinterpret_cast<int*>(dxyz + cnt * 3);
   PFX_LAUNCH(ctx, gather_xyz_kernel, div_up((long long)cnt, 256), 256, 0, ctx->surf.as<float4>(), didx, (int)cnt, dxyz);
-  if (refine) PFX_TRY(harris_refine(ctx, g, radius, dxyz, (int)cnt));
+  if (refine) {
+    if (ctx->parity_mode == PFX_PARITY_STRICT) PFX_TRY(harris_refine_strict(ctx, g, radius, dxyz, (int)cnt));
+    else PFX_TRY(harris_refine(ctx, g, radius, dxyz, (int)cnt));
+  }
   if (kp_xyz) {
     if (mem == PFX_DEVICE) PFX_TRY(deliver(ctx, kp_xyz, dxyz, cnt * 3 * sizeof(float), mem));
     else PFX_CUDA(cudaMemcpyAsync(kp_xyz, dxyz, cnt * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -964,7 +976,9 @@ static int match_upload(Ctx* ctx, const float* m, size_t rows, size_t stride, in
 // engine: 1 = tcgen05 candidate GEMM + exact fp32 rescore (match_tc.cu), 0 = exact fp32 all-pairs scan.
 // Both return bit-identical results; auto picks the tensor cores once the all-pairs work is large.
 static bool match_use_tc(const Ctx* ctx, size_t na, size_t nb, int dim) {
-  if (nb == 0 || dim > 2048) return false;
+  // a descriptor whose A tile does not fit in shared memory (SHOT1344, USC1980) goes to the exact scan whatever
+  // engine was asked for: both engines return the same bits
+  if (nb == 0 || !match_tc_fits(dim)) return false;
   if (ctx->match_engine >= 0) return ctx->match_engine == 1;
   return (double)na * (double)nb * (double)dim >= 1.5e9;
 }
@@ -983,6 +997,14 @@ extern "C" int pfx_match_info(pfx_ctx* ctx, double* out4) {
   out4[1] = (double)ctx->match_rows;
   out4[2] = (double)ctx->match_redo;
   out4[3] = 0;
+  return 0;
+}
+
+extern "C" int pfx_set_parity_mode(pfx_ctx* ctx, int mode) {
+  if (!ctx || (mode != PFX_PARITY_FAST && mode != PFX_PARITY_STRICT)) return PFX_E_INVALID;
+  if (ctx->parity_mode != mode) {  // normals of the other mode are not reused
+    ctx->parity_mode = mode;
+  }
   return 0;
 }
 
@@ -1067,6 +1089,15 @@ extern "C" int pfx_match(pfx_ctx* ctx, const float* a, size_t na, size_t stride_
 }
 
 // ================================================================================== RANSAC rejection
+// device-resident correspondences (e.g. the output of pfx_match with PFX_DEVICE): count the out-of-range indices
+__global__ void corr_validate_kernel(const pfx_correspondence* __restrict__ corr, int n, int n_src, int n_tgt,
+                                     int* __restrict__ bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const pfx_correspondence c = corr[i];
+  if (c.index_query < 0 || c.index_query >= n_src || c.index_match < 0 || c.index_match >= n_tgt) atomicAdd(bad, 1);
+}
+
 extern "C" int pfx_ransac_reject(pfx_ctx* ctx, const void* src, size_t n_src, size_t stride_src, const void* tgt,
                                  size_t n_tgt, size_t stride_tgt, const pfx_correspondence* corr, size_t n_corr,
                                  double inlier_threshold, int max_iterations, uint64_t seed, pfx_correspondence* out,
@@ -1099,6 +1130,17 @@ extern "C" int pfx_ransac_reject(pfx_ctx* ctx, const void* src, size_t n_src, si
     dtgt = ctx->stage2.as<float>();
     dcorr = ctx->tmp1.as<pfx_correspondence>();
     dout = ctx->tmp1.as<pfx_correspondence>() + n_corr;
+  } else if (n_corr) {
+    // same validation for device buffers, before the hypothesis kernels dereference the indices
+    PFX_CUDA(ctx->small.ensure(256));
+    int* bad = ctx->small.as<int>() + 32;
+    PFX_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+    PFX_LAUNCH(ctx, corr_validate_kernel, div_up((long long)n_corr, 256), 256, 0, dcorr, (int)n_corr,
+               (int)std::min<size_t>(n_src, 0x7fffffff), (int)std::min<size_t>(n_tgt, 0x7fffffff), bad);
+    int nbad = 0;
+    PFX_CUDA(cudaMemcpyAsync(&nbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (nbad) return ctx->fail(PFX_E_INVALID, "pfx_ransac_reject: correspondence index out of range");
   }
   int cnt = 0, iters = 0, bh = -1;
   PFX_TRY(ransac_reject_run(ctx, dsrc, stride_src, dtgt, stride_tgt, dcorr, (int)n_corr, inlier_threshold, max_iterations,

@@ -10,8 +10,8 @@
 // Kernels (one warp per point / query)
 //  spfh_kernel       Darboux pair features of the neighbours, one per lane; the 3 x 11 histogram is
 //                    counted with __match_any_sync (integer hit counts in shared memory, no atomics).
-//  fpfh_list_kernel  k-search: lane t turns neighbour t into a weight 1/d2, then three neighbours are
-//                    gathered per step (9 lanes x 4 bins of a count row each).
+//  fpfh_list_kernel  k-search: three queries per warp, nine lanes per query (lane c = word c of the 36-byte
+//                    count rows); the 1/d2-weighted sum is taken in fixed point, independent of list order.
 //  fpfh_kernel       radius search: lanes are bins, 33-float rows gathered during the stencil scan.
 #include "internal.h"
 #include "pair_features.cuh"
@@ -25,7 +25,7 @@ constexpr int SROW = 36;  // bytes per count row
 __device__ __forceinline__ bool pair_bins(float4 q, float4 nq, float4 p, float4 nj, int& b1, int& b2, int& b3) {
   const double d_pi = (double)(1.0f / (2.0f * 3.14159265358979323846f));
   float f1, f2, f3;
-  if (!finite3(nj.x, nj.y, nj.z) || !pair_features(q.x, q.y, q.z, nq, p.x, p.y, p.z, nj, f1, f2, f3)) return false;
+  if (!finite3(nj.x, nj.y, nj.z) || !pair_features<11>(q.x, q.y, q.z, nq, p.x, p.y, p.z, nj, f1, f2, f3)) return false;
   b1 = clamp_bin(11 * (((double)f1 + 3.14159265358979323846) * d_pi));
   b2 = 11 + clamp_bin(11 * (((double)f2 + 1.0) * 0.5));
   b3 = 22 + clamp_bin(11 * (((double)f3 + 1.0) * 0.5));
@@ -228,99 +228,159 @@ fpfh_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2, con
 }
 
 // ------------------------------------------------------------------------------ FPFH from kNN rows
-// k-search (rows of k <= 32 neighbours): lane t first turns neighbour t into a weight 1/d2; the gather
-// then takes THREE neighbours per step - 9 lanes per neighbour, each lane one 32-bit word of the
-// 36-byte count row (4 bins) - so a query costs 11 steps instead of 32.  The counts are weighted as they are:
-// PCL's SPFH value of a count c is the float sum of c increments 100 / (k - 1), the same increment for every
-// point of a k-search, and FPFH's rescaling of each 11-bin block to 100 divides it out (the sum differs from
-// c * incr by < 2e-6 relative).  Bytes become floats on the ALU / FMA pipes (PRMT under the exponent of 2^23,
-// minus 2^23): the shuffle unit, which a register-table lookup per bin kept 80 % busy, only broadcasts (j, w).
+// k-search.  A warp describes THREE queries at a time: nine lanes per query, lane c of a group owning 32-bit word c
+// of the 36-byte count rows (bins 4c .. 4c+3) for ALL neighbours of its query, so nothing is folded across lanes
+// until the three block sums.  The weighted sum is taken in FIXED POINT and is therefore independent of the order
+// of the neighbour list (the cell-tile k-search emits unsorted sets whose order depends on the voxel grid: a cloud
+// described whole and the same cloud described slab by slab on several GPUs must give the same bits):
+//   w_s = 1 / d2_s (PCL's weight), q_s = rint(w_s / max_s w_s * 2^24), W = sum q_s (exact integers),
+//   i_s = q_s >> sh (rounded) with sh chosen from W so that sum i_s ~ 2^wbits, acc[bin] = sum_s count_s[bin] * i_s.
+// A bin receives at most k - 1 votes per neighbour row, so acc < (k - 1) * 2^wbits < 2^32 with
+// wbits = 31 - bits(k - 1).  The counts are weighted as they are: PCL's SPFH value of a count c is the float sum of
+// c increments 100 / (k - 1), the same increment for every point of a k-search, and FPFH's rescaling of each 11-bin
+// block to 100 divides it out.  Quantisation: 2^-26 of the block's weight per neighbour (k = 32): < 3e-5 in PCL's
+// percent units, typically 2e-6 - closer to the exact sum than PCL's own float accumulation.
+// reductions over the nine lanes of a group (lane c9 of group grp = lane grp * 9 + c9), every lane of the warp
+// taking part in the shuffles; the result lands in all nine lanes
+__device__ __forceinline__ unsigned group9_sum(unsigned v, int c9, int grp) {
+#pragma unroll
+  for (int d = 1; d < 16; d <<= 1) {
+    const unsigned t = __shfl_down_sync(FULL, v, d);
+    if (c9 + d < 9) v += t;
+  }
+  return __shfl_sync(FULL, v, grp * 9);
+}
+__device__ __forceinline__ float group9_max(float v, int c9, int grp) {
+#pragma unroll
+  for (int d = 1; d < 16; d <<= 1) {
+    const float t = __shfl_down_sync(FULL, v, d);
+    if (c9 + d < 9) v = fmaxf(v, t);
+  }
+  return __shfl_sync(FULL, v, grp * 9);
+}
+
 template <bool DENSE, bool K32>
 __global__ void __launch_bounds__(FWPB * 32)
 fpfh_list_kernel(GridDev g, const float4* __restrict__ queries, int nq, const int* __restrict__ lists,
-                 const float* __restrict__ ld2, int k_rt, const unsigned char* __restrict__ rows8,
+                 const float* __restrict__ ld2, int k_rt, int wbits, const unsigned char* __restrict__ rows8,
                  float* __restrict__ out, size_t stride) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int qi = blockIdx.x * FWPB + wid;
-  if (qi >= nq) return;
+  const int grp = lane / 9, c9 = lane - grp * 9;
+  const int qi = (blockIdx.x * FWPB + wid) * 3 + grp;
   const int k = K32 ? 32 : k_rt;
+  // every shuffle below names all 32 lanes (a compile-time full mask: no collective-sync sequences); lanes 27..31
+  // and the groups past the last query idle through them
+  const bool member = grp < 3 && qi < nq;
+  if (__all_sync(FULL, !member)) return;
   const int n_valid = g.gp->n_valid;
-  float4 q = DENSE ? g.pts[qi] : queries[qi];
-  const size_t row = DENSE ? (size_t)__float_as_int(q.w) : (size_t)qi;
+  const int qs = member ? qi : 0;
+  const float4 q = DENSE ? g.pts[qs] : queries[qs];
+  const size_t row = DENSE ? (size_t)__float_as_int(q.w) : (size_t)qs;
   float* o = out + row * stride;
-  const bool ok = finite3(q.x, q.y, q.z) && (!DENSE || qi < n_valid);
-  int myj = -1;
-  float myw = 0.f;
-  if (ok && lane < k) {
-    myj = lists[(size_t)qi * k + lane];
-    float d2 = ld2[(size_t)qi * k + lane];
-    if (myj >= 0 && d2 != 0.f) myw = __frcp_rn(d2);  // "minus the query point itself": dists == 0 skipped
-  }
-  const int n_nb = __popc(__ballot_sync(FULL, myj >= 0));
-  if (!ok || n_nb == 0) {  // PCL: NaN row, is_dense = false
-    const float nanv = __int_as_float(0x7fc00000);
-    o[lane] = nanv;
-    if (lane == 0) o[32] = nanv;
-    return;
-  }
-  const int grp = min(lane / 9, 2), c9 = lane - (lane / 9) * 9;
-  const bool gl = lane < 27;
+  const bool ok = member && finite3(q.x, q.y, q.z) && (!DENSE || qi < n_valid);
+  const int* lj = lists + (size_t)qs * k;
+  const float* ldd = ld2 + (size_t)qs * k;
   const unsigned* rows32 = reinterpret_cast<const unsigned*>(rows8);
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  int n_nb = 0;
+
+  if (K32) {
+    // lane c holds neighbours c, c + 9, c + 18, c + 27 of its query
+    int myj[4];
+    float myw[4];
 #pragma unroll
-  for (int s = 0; s < (K32 ? 33 : 33); s += 3) {
-    if (!K32 && s >= k) break;
-    const int src = min(s + grp, 31);
-    const int j = __shfl_sync(FULL, myj, src);
-    float w = __shfl_sync(FULL, myw, src);
-    if (!gl || s + grp >= k) w = 0.f;
-    unsigned cw = 0u;
-    if (w != 0.f) cw = rows32[(size_t)j * 9 + c9];
-    // counts as floats.  PCL's SPFH value of a count c is the float sum T[c] of c increments of 100 / (k - 1); every
-    // point of a k-search has the same increment, and the final per-block rescaling to 100 divides it out, so the
-    // counts themselves are weighted (T[c] = c * incr up to 2e-6 relative: far inside the 1e-4 tolerance).
-    // byte -> float without the conversion unit: the byte under the exponent of 2^23, minus 2^23
-    const float t0 = __uint_as_float(__byte_perm(cw, 0x4B000000u, 0x7540)) - 8388608.0f;
-    const float t1 = __uint_as_float(__byte_perm(cw, 0x4B000000u, 0x7541)) - 8388608.0f;
-    const float t2 = __uint_as_float(__byte_perm(cw, 0x4B000000u, 0x7542)) - 8388608.0f;
-    const float t3 = __uint_as_float(__byte_perm(cw, 0x4B000000u, 0x7543)) - 8388608.0f;
-    a0 = fmaf(t0, w, a0);
-    a1 = fmaf(t1, w, a1);
-    a2 = fmaf(t2, w, a2);
-    a3 = fmaf(t3, w, a3);
-  }
-  // fold the three neighbour groups: lanes 0..8 end up with bins 4c..4c+3
-  a0 += __shfl_down_sync(FULL, a0, 9) + __shfl_down_sync(FULL, a0, 18);
-  a1 += __shfl_down_sync(FULL, a1, 9) + __shfl_down_sync(FULL, a1, 18);
-  a2 += __shfl_down_sync(FULL, a2, 9) + __shfl_down_sync(FULL, a2, 18);
-  a3 += __shfl_down_sync(FULL, a3, 9) + __shfl_down_sync(FULL, a3, 18);
-  // per-block sums (bins 0..10 | 11..21 | 22..32)
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-  const float v[4] = {a0, a1, a2, a3};
-  if (lane < 9) {
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      int bin = lane * 4 + b;
-      if (bin < 11) s0 += v[b];
-      else if (bin < 22) s1 += v[b];
-      else if (bin < 33) s2 += v[b];
+    for (int t = 0; t < 4; ++t) {
+      const int sidx = c9 + 9 * t;
+      myj[t] = -1;
+      myw[t] = 0.f;
+      if (ok && sidx < 32) {
+        myj[t] = lj[sidx];
+        const float d2 = ldd[sidx];
+        if (myj[t] >= 0 && d2 != 0.f) myw[t] = __frcp_rn(d2);  // "minus the query point itself": dists == 0 skipped
+      }
+      n_nb += (myj[t] >= 0) ? 1 : 0;
     }
-  }
+    n_nb = (int)group9_sum((unsigned)n_nb, c9, grp);
+    const float wl = fmaxf(fmaxf(myw[0], myw[1]), fmaxf(myw[2], myw[3]));
+    const float wmax = group9_max(wl, c9, grp);
+    const float inv = (wmax > 0.f) ? __frcp_rn(wmax) * 16777216.0f : 0.f;
+    unsigned qv[4], wsum = 0;
 #pragma unroll
-  for (int of = 8; of > 0; of >>= 1) {
-    s0 += __shfl_xor_sync(FULL, s0, of);
-    s1 += __shfl_xor_sync(FULL, s1, of);
-    s2 += __shfl_xor_sync(FULL, s2, of);
-  }
-  if (lane < 9) {
-    // (2-ulp division: the scale factor of a block, far inside the tolerance)
-    const float k0 = (s0 != 0.f) ? __fdividef(100.0f, s0) : 0.f, k1 = (s1 != 0.f) ? __fdividef(100.0f, s1) : 0.f,
-                k2 = (s2 != 0.f) ? __fdividef(100.0f, s2) : 0.f;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      int bin = lane * 4 + b;
-      if (bin < 33) o[bin] = v[b] * (bin < 11 ? k0 : (bin < 22 ? k1 : k2));
+    for (int t = 0; t < 4; ++t) {
+      qv[t] = (unsigned)__float2int_rn(myw[t] * inv);
+      wsum += qv[t];
     }
+    wsum = group9_sum(wsum, c9, grp);
+    const int sh = max(0, (32 - __clz((int)wsum)) - wbits);
+    const unsigned half = (1u << sh) >> 1;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) qv[t] = (qv[t] + half) >> sh;
+#pragma unroll
+    for (int sidx = 0; sidx < 32; ++sidx) {
+      const int src = grp * 9 + (sidx % 9), t = sidx / 9;
+      const int j = __shfl_sync(FULL, myj[t], src);
+      const unsigned wi = __shfl_sync(FULL, qv[t], src);
+      const unsigned cw = (wi != 0u && member) ? rows32[(size_t)j * 9 + c9] : 0u;
+      a0 += __byte_perm(cw, 0u, 0x4440) * wi;  // one PRMT per zero-extended byte
+      a1 += __byte_perm(cw, 0u, 0x4441) * wi;
+      a2 += __byte_perm(cw, 0u, 0x4442) * wi;
+      a3 += __byte_perm(cw, 0u, 0x4443) * wi;
+    }
+  } else {
+    // any k: every lane of the group walks the whole list (broadcast loads), three passes
+    float wmax = 0.f;
+    if (ok)
+      for (int sidx = 0; sidx < k; ++sidx) {
+        const int j = lj[sidx];
+        const float d2 = ldd[sidx];
+        n_nb += (j >= 0) ? 1 : 0;
+        if (j >= 0 && d2 != 0.f) wmax = fmaxf(wmax, __frcp_rn(d2));
+      }
+    const float inv = (wmax > 0.f) ? __frcp_rn(wmax) * 16777216.0f : 0.f;
+    unsigned long long wsum64 = 0;
+    if (ok)
+      for (int sidx = 0; sidx < k; ++sidx) {
+        const int j = lj[sidx];
+        const float d2 = ldd[sidx];
+        if (j >= 0 && d2 != 0.f) wsum64 += (unsigned)__float2int_rn(__frcp_rn(d2) * inv);
+      }
+    const int sh = max(0, (64 - __clzll((long long)wsum64)) - wbits);
+    const unsigned half = (1u << sh) >> 1;
+    if (ok)
+      for (int sidx = 0; sidx < k; ++sidx) {
+        const int j = lj[sidx];
+        const float d2 = ldd[sidx];
+        if (j < 0 || d2 == 0.f) continue;
+        const unsigned wi = ((unsigned)__float2int_rn(__frcp_rn(d2) * inv) + half) >> sh;
+        const unsigned cw = rows32[(size_t)j * 9 + c9];
+        a0 += __byte_perm(cw, 0u, 0x4440) * wi;  // one PRMT per zero-extended byte
+        a1 += __byte_perm(cw, 0u, 0x4441) * wi;
+        a2 += __byte_perm(cw, 0u, 0x4442) * wi;
+        a3 += __byte_perm(cw, 0u, 0x4443) * wi;
+      }
+  }
+  const bool nan_row = !ok || n_nb == 0;  // PCL: NaN row, is_dense = false
+  // per-block sums (bins 0..10 | 11..21 | 22..32); lane c owns bins 4c .. 4c+3
+  const unsigned v[4] = {a0, a1, a2, a3};
+  unsigned s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int bin = c9 * 4 + b;
+    if (bin < 11) s0 += v[b];
+    else if (bin < 22) s1 += v[b];
+    else if (bin < 33) s2 += v[b];
+  }
+  s0 = group9_sum(s0, c9, grp);
+  s1 = group9_sum(s1, c9, grp);
+  s2 = group9_sum(s2, c9, grp);
+  const float k0 = s0 ? __fdiv_rn(100.0f, (float)s0) : 0.f, k1 = s1 ? __fdiv_rn(100.0f, (float)s1) : 0.f,
+              k2 = s2 ? __fdiv_rn(100.0f, (float)s2) : 0.f;
+  if (!member) return;
+  const float nanv = __int_as_float(0x7fc00000);
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int bin = c9 * 4 + b;
+    if (bin < 33) o[bin] = nan_row ? nanv : __fmul_rn((float)v[b], bin < 11 ? k0 : (bin < 22 ? k1 : k2));
   }
 }
 
@@ -379,17 +439,20 @@ int fpfh_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t
       PFX_LAUNCH(ctx, spfh_export_kernel, div_up((long long)n * 33, 256), 256, 0, g->view(), nullptr,
                  rows8.as<unsigned char>(), n, k, spfh_out_dev);
     if (out_dev && nq > 0) {
-      const int blocks = div_up(nq, FWPB);
+      const int blocks = div_up(nq, FWPB * 3);  // three queries per warp
+      int kb = 0;  // bits of k - 1: a bin holds at most k - 1 votes of a neighbour row
+      while ((1 << kb) <= std::max(k - 1, 1)) ++kb;
+      const int wbits = 31 - kb;
       if (dense) {
         if (k == 32)
           PFX_LAUNCH(ctx, (fpfh_list_kernel<true, true>), blocks, FWPB * 32, 0, g->view(), nullptr, nq, ctx->knn_idx.as<int>(),
-                     ctx->knn_d2.as<float>(), k, rows8.as<unsigned char>(), out_dev, stride_floats);
+                     ctx->knn_d2.as<float>(), k, wbits, rows8.as<unsigned char>(), out_dev, stride_floats);
         else
           PFX_LAUNCH(ctx, (fpfh_list_kernel<true, false>), blocks, FWPB * 32, 0, g->view(), nullptr, nq, ctx->knn_idx.as<int>(),
-                     ctx->knn_d2.as<float>(), k, rows8.as<unsigned char>(), out_dev, stride_floats);
+                     ctx->knn_d2.as<float>(), k, wbits, rows8.as<unsigned char>(), out_dev, stride_floats);
       } else {
         PFX_LAUNCH(ctx, (fpfh_list_kernel<false, false>), blocks, FWPB * 32, 0, g->view(), ctx->qry.as<float4>(), nq,
-                   ctx->tmp2.as<int>(), ctx->tmp3.as<float>(), k, rows8.as<unsigned char>(), out_dev, stride_floats);
+                   ctx->tmp2.as<int>(), ctx->tmp3.as<float>(), k, wbits, rows8.as<unsigned char>(), out_dev, stride_floats);
       }
     }
     PFX_CUDA(cudaGetLastError());
@@ -412,7 +475,11 @@ int fpfh_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t
   if (spfh_out_dev)
     PFX_LAUNCH(ctx, spfh_export_kernel, div_up((long long)n * 33, 256), 256, 0, g->view(), spfh.as<float>(), nullptr, n,
                0, spfh_out_dev);
-  if (out_dev && nq > 0) {
+  if (out_dev && nq > 0 && ctx->parity_mode == PFX_PARITY_STRICT) {
+    // reference-order weighting (strict.cu): rows come out in caller order, which is the surface's original order
+    // for dense queries
+    PFX_TRY(fpfh_sorted(ctx, g, radius, spfh.as<float>(), out_dev, stride_floats));
+  } else if (out_dev && nq > 0) {
     const int blocks = div_up(nq, FWPB);
     if (dense)
       PFX_LAUNCH(ctx, fpfh_kernel<true>, blocks, FWPB * 32, 0, g->view(), nullptr, nq, r2, spfh.as<float>(), out_dev,

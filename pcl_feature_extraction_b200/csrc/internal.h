@@ -155,6 +155,13 @@ struct Ctx {
   DevBuf lab_tab, surf_lab, qry_lab;
   uint64_t surf_lab_version = 0, qry_lab_version = 0;
 
+  // parity mode (pfx_set_parity_mode): 0 fast kernels (tolerance contract), 1 strict = reference-order arithmetic
+  // for the stages whose floats feed index outputs (strict.cu)
+  int parity_mode = 0;
+  DevBuf st_cnt, st_off, st_idx, st_d2;  // sorted neighbour lists of strict.cu
+  int st_k = 0;
+  long long st_total = 0;
+
   int match_engine = -1;  // -1 auto, 0 exact fp32 scan, 1 tcgen05 candidates + fp32 rescore
   TcOperand tc_ops[2];
   DevBuf tc_cand_d, tc_cand_j, tc_redo, tc_rows, tc_res;
@@ -257,6 +264,7 @@ int match_nn_tc(Ctx* ctx, const float* a, int na, int lda, const float* b, int n
 int match_pair_tc(Ctx* ctx, const float* a, int na, int lda, const float* b, int nb, int ldb, int dim, int* s2t,
                   float* sd2, int* t2s, float* td2);
 void match_tc_release(Ctx* ctx);
+bool match_tc_fits(int dim);  // the resident A tile + two ring stages fit in shared memory
 
 // ---- narf.cu
 int range_image_build(Ctx* ctx, const pfx_range_image_desc* want, float max_angle_w, float max_angle_h, float min_range,
@@ -271,6 +279,13 @@ int narf36_compute(Ctx* ctx, const int* kp_dev, int n_kp, float support_size, in
 int ransac_reject_run(Ctx* ctx, const float* src, size_t stride_s, const float* tgt, size_t stride_t,
                       const pfx_correspondence* corr, int n_corr, double threshold, int max_iterations, uint64_t seed,
                       pfx_correspondence* out_dev, int* n_out, float* T16_host, int* iterations, int* best_h);
+
+// ---- strict.cu (reference-order arithmetic, pfx_set_parity_mode)
+int strict_lists_build(Ctx* ctx, Grid* g, double radius, int k);
+int strict_normals(Ctx* ctx, Grid* g, double radius, int k, float4* out_query_order);
+int harris_response_strict(Ctx* ctx, Grid* g, double radius, float* resp_dev_orig);
+int harris_refine_strict(Ctx* ctx, Grid* g, double radius, float* corners_dev, int nc);
+int fpfh_sorted(Ctx* ctx, Grid* g, double radius, const float* spfh_sorted_rows, float* out_dev, size_t stride_floats);
 
 // ---- helpers (capi.cu)
 int pfh_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t stride_floats);

@@ -561,6 +561,18 @@ __global__ void tc_scatter_kernel(const int* __restrict__ rows, int nrows, const
 // paces the kernel for short descriptors, so the tf32 MMAs (half the bf16 rate) cost nothing there.
 static bool tc_use_tf32(int dim) { return ((dim + 7) & ~7) * 4 * TC_TILE <= 96 * 1024; }
 
+constexpr size_t TC_FIXED_SMEM = 512 * sizeof(float) + 2 * TC_K * TC_EPI_THREADS * 4 + 32 * 8 + 64;
+constexpr size_t TC_SMEM_BUDGET = 225 * 1024;
+
+// does the resident A tile of a dim-wide descriptor leave room for at least two ring stages?  (bf16 rows up to
+// 696 elements; SHOT1344 and USC1980 do not fit and are matched by the exact fp32 scan, which gives the same bits)
+bool match_tc_fits(int dim) {
+  const bool tf32 = tc_use_tf32(dim);
+  const int dpad = tf32 ? ((dim + 7) & ~7) : ((dim + 15) & ~15);
+  const size_t nslab = tf32 ? dpad / 4 : dpad / 8;
+  return nslab * TC_SLAB + TC_FIXED_SMEM + 2 * (size_t)TC_STAGE <= TC_SMEM_BUDGET;
+}
+
 static int tc_prepare(Ctx* ctx, TcOperand& op, const float* x, int n, int ld, int dim) {
   const bool tf32 = tc_use_tf32(dim);
   op.n = n;
@@ -611,8 +623,10 @@ static int tc_run(Ctx* ctx, int slot_a, const float* a, int na, int lda, const f
   nsplit = div_up(npairs, pps);
   const int nslab = A.tf32 ? A.dpad / 4 : A.dpad / 8;
   const size_t a_bytes = (size_t)nslab * TC_SLAB;
-  const size_t fixed = a_bytes + 512 * sizeof(float) + 2 * TC_K * TC_EPI_THREADS * 4 + 32 * 8 + 64;
-  int nstage = (int)std::min<size_t>(8, (225 * 1024 - fixed) / TC_STAGE);
+  const size_t fixed = a_bytes + TC_FIXED_SMEM;
+  // signed arithmetic: a resident A tile beyond the budget must give nstage < 2, not a wrapped size_t
+  const long long room = (long long)TC_SMEM_BUDGET - (long long)fixed;
+  const int nstage = room < 0 ? 0 : (int)std::min<long long>(8, room / (long long)TC_STAGE);
   if (nstage < 2) return ctx->fail(PFX_E_INVALID, "tensor-core matching: descriptor dimension too large for one A tile");
   const size_t smem = std::max<size_t>(fixed + (size_t)nstage * TC_STAGE, 120 * 1024);
   const int nlists = nsplit * TC_LISTS;

@@ -5,6 +5,8 @@
 
 namespace pfx {
 
+// F1_BINS: number of bins the caller cuts f1's range [-pi, pi] into (11 for FPFH, 5 for PFH)
+template <int F1_BINS>
 __device__ __forceinline__ bool pair_features(float p1x, float p1y, float p1z, float4 n1, float p2x, float p2y,
                                               float p2z, float4 n2, float& f1, float& f2, float& f3) {
   float dx = p2x - p1x, dy = p2y - p1y, dz = p2z - p1z;
@@ -38,7 +40,15 @@ __device__ __forceinline__ bool pair_features(float p1x, float p1y, float p1z, f
   f2 = __fadd_rn(__fadd_rn(__fmul_rn(vx, wx_), __fmul_rn(vy, wy_)), __fmul_rn(vz, wz_));
   float sn = __fadd_rn(__fadd_rn(__fmul_rn(wx, wx_), __fmul_rn(wy, wy_)), __fmul_rn(wz, wz_));
   float cs = __fadd_rn(__fadd_rn(__fmul_rn(ux, wx_), __fmul_rn(uy, wy_)), __fmul_rn(uz, wz_));
-  f1 = fast_atan2f(sn, cs);  // 3e-7 from atan2f: a vote moves only if f1 is that close to a bin edge
+  // f1 only selects one of F1_BINS bins (floor(F1_BINS (f1 + pi) / 2 pi)): the 9-term polynomial (3e-7 from atan2f) decides
+  // it unless f1 lies within 2e-5 bins of an edge; those pairs (about 4 in 1e5) take the correctly rounded value -
+  // atan2 in double, rounded to float - so the bin is the CPU's (computePairFeatures calls atan2f)
+  f1 = fast_atan2f(sn, cs);
+  {
+    const float u = (f1 + 3.14159274f) * ((float)F1_BINS * 0.159154943f);  // F1_BINS / (2 pi)
+    const float fr = u - floorf(u);
+    if (fr < 2e-5f || fr > 1.0f - 2e-5f) f1 = (float)atan2((double)sn, (double)cs);
+  }
   return true;
 }
 

@@ -121,7 +121,7 @@ pfh_kernel(GridDev g, const float4* __restrict__ nrm, const float4* __restrict__
       }
       float f1, f2, f3;
       if (finite3(na.x, na.y, na.z) && finite3(nb.x, nb.y, nb.z) &&
-          pair_features(pa.x, pa.y, pa.z, na, pb.x, pb.y, pb.z, nb, f1, f2, f3)) {
+          pair_features<5>(pa.x, pa.y, pa.z, na, pb.x, pb.y, pb.z, nb, f1, f2, f3)) {
         const int b1 = clamp_bin_n(5 * (((double)f1 + 3.14159265358979323846) * d_pi), 5);
         const int b2 = clamp_bin_n(5 * (((double)f2 + 1.0) * 0.5), 5);
         const int b3 = clamp_bin_n(5 * (((double)f3 + 1.0) * 0.5), 5);

@@ -79,42 +79,57 @@ def halo_masks(coord, cuts, rank, halo):
     return to_left, to_right
 
 
+def halo_mask_for(coord, cuts, peer, halo):
+    """which of the given (owned) points rank `peer` needs: those within `halo` of its slab
+    [cuts[peer-1], cuts[peer]).  For peer = rank +- 1 this is `halo_masks`; a farther peer only gets points when
+    the slabs between are narrower than the halo (equal-count cuts through a dense region)."""
+    world = len(cuts) + 1
+    m = np.isfinite(coord)
+    if peer > 0:
+        m &= coord >= cuts[peer - 1] - halo
+    if peer < world - 1:
+        m &= coord < cuts[peer] + halo
+    return m
+
+
 def exchange_halo(owned, axis, cuts, rank, world, halo, device=None, group=None):
-    """One-off halo exchange with the two neighbouring slabs.
+    """One-off halo exchange with every slab that lies within `halo` of this one.
 
     owned: [n, C] float32 rows of this rank (xyz first).  Returns (local, n_owned): local = owned rows followed
-    by the halo rows received from the left and right neighbours.  Works on any backend: sizes travel first,
-    then the payload, as pairwise isend / irecv (NCCL P2P over NVLink when the tensors are on GPUs)."""
+    by the halo rows received from the other ranks in ascending rank order.  Usually only the two neighbours
+    trade points; equal-count cuts through a dense region can make a slab narrower than the halo, and then an
+    owned point needs neighbours from rank r +- 2 and beyond, so every pair of ranks whose slabs come within
+    `halo` of each other trades.  Works on any backend: the count matrix travels first (all-gather), then the
+    payload as pairwise isend / irecv (NCCL P2P over NVLink when the tensors are on GPUs)."""
     owned = np.ascontiguousarray(owned, np.float32)
     if world == 1:
         return owned, len(owned)
-    to_left, to_right = halo_masks(owned[:, axis].astype(np.float64), cuts, rank, halo)
+    coord = owned[:, axis].astype(np.float64)
     dev = device if device is not None else torch.device("cpu")
-    send = {rank - 1: owned[to_left], rank + 1: owned[to_right]}
-    peers = [p for p in (rank - 1, rank + 1) if 0 <= p < world]
+    peers = [p for p in range(world) if p != rank]
+    send = {p: owned[halo_mask_for(coord, cuts, p, halo)] for p in peers}
     width = owned.shape[1]
-    # sizes
-    size_out = {p: torch.tensor([len(send[p])], dtype=torch.int64, device=dev) for p in peers}
-    size_in = {p: torch.zeros(1, dtype=torch.int64, device=dev) for p in peers}
-    ops = []
+    # counts: row r of the matrix = what rank r sends to each rank
+    mine = torch.zeros(world, dtype=torch.int64, device=dev)
     for p in peers:
-        ops.append(dist.P2POp(dist.isend, size_out[p], p, group))
-        ops.append(dist.P2POp(dist.irecv, size_in[p], p, group))
-    for r in dist.batch_isend_irecv(ops):
-        r.wait()
+        mine[p] = len(send[p])
+    rows = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(rows, mine, group=group)
+    counts = torch.stack(rows).cpu().numpy()
     # payload
-    bufs_out = {p: torch.from_numpy(np.ascontiguousarray(send[p])).to(dev) for p in peers}
-    bufs_in = {p: torch.empty((int(size_in[p].item()), width), dtype=torch.float32, device=dev) for p in peers}
+    bufs_out = {p: torch.from_numpy(np.ascontiguousarray(send[p])).to(dev) for p in peers if len(send[p])}
+    bufs_in = {p: torch.empty((int(counts[p, rank]), width), dtype=torch.float32, device=dev) for p in peers
+               if counts[p, rank] > 0}
     ops = []
     for p in peers:
-        if bufs_out[p].numel():
+        if p in bufs_out:
             ops.append(dist.P2POp(dist.isend, bufs_out[p], p, group))
-        if bufs_in[p].numel():
+        if p in bufs_in:
             ops.append(dist.P2POp(dist.irecv, bufs_in[p], p, group))
     if ops:
         for r in dist.batch_isend_irecv(ops):
             r.wait()
-    parts = [owned] + [bufs_in[p].cpu().numpy() for p in peers]
+    parts = [owned] + [bufs_in[p].cpu().numpy() for p in peers if p in bufs_in]
     return np.concatenate(parts, 0), len(owned)
 
 
@@ -186,8 +201,12 @@ def pack_nn(d2, idx, offset=0):
     d2 >= 0, so the float's bit pattern orders like its value; a missing match (-1) packs to the largest key."""
     d2 = np.ascontiguousarray(d2, np.float32)
     idx = np.ascontiguousarray(idx, np.int64)
+    # sanitise what a user-supplied match_fn may return: -0.0 has its sign bit set (a negative key that would win
+    # every MIN), a NaN distance is not a match
+    none = (idx < 0) | np.isnan(d2)
+    d2 = np.abs(np.where(none, np.float32(0), d2)).astype(np.float32)
     key = (d2.view(np.uint32).astype(np.int64) << 32) | (idx + offset)
-    key[idx < 0] = np.iinfo(np.int64).max
+    key[none] = np.iinfo(np.int64).max
     return key
 
 

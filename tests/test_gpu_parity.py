@@ -524,6 +524,32 @@ def test_match_tensor_core_bit_exact(ctx, orc, dim, na, nb):
     assert redone <= 0.05 * (after["rows"] - before["rows"]) + 2, (redone, after["rows"] - before["rows"])
 
 
+@pytest.mark.parametrize("dim,engine,tc_expected", [(688, 1, True), (704, 1, False), (1344, 1, False), (1344, -1, False),
+                                                    (1980, 1, False), (1980, -1, False)])
+def test_match_wide_descriptors(ctx, orc, dim, engine, tc_expected):
+    """SHOT1344 / USC1980 rows: the resident A tile of the tensor-core engine holds bf16 rows up to 696 elements;
+    wider descriptors must be matched by the exact scan (same bits) whatever engine was asked for, not fail."""
+    rng = np.random.default_rng(dim)
+    na, nb = 1050, 1100  # na * nb * dim >= 1.5e9 for 1344 and 1980: auto would pick the tensor cores
+    a = rng.uniform(0, 1, (na, dim)).astype(np.float32)
+    b = rng.uniform(0, 1, (nb, dim)).astype(np.float32)
+    b[:400] = a[:400] + rng.normal(0, 0.01, (400, dim)).astype(np.float32)
+    ctx.set_match_engine(engine)
+    try:
+        before = ctx.match_info()
+        idx, d2 = ctx.match_nn(a, b)
+        c = ctx.match(a, b, reciprocal=True)
+        after = ctx.match_info()
+    finally:
+        ctx.set_match_engine(-1)
+    assert (after["tc_passes"] > before["tc_passes"]) == tc_expected
+    oidx, od2 = orc.match_nn(a, b)
+    assert np.array_equal(idx, oidx)
+    assert np.array_equal(d2.view(np.uint32), od2.view(np.uint32))
+    q, mm, dist = orc.match_reciprocal(a, b)
+    assert np.array_equal(c["index_query"], q) and np.array_equal(c["index_match"], mm)
+
+
 def test_match_tensor_core_ties_nan_and_near_duplicates(ctx, orc):
     rng = np.random.default_rng(12)
     a = rng.integers(0, 3, (300, 33)).astype(np.float32)  # many exact ties -> certificate fails -> exact redo

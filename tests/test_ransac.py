@@ -93,6 +93,43 @@ def test_gpu_ransac_edge_cases(ctx, orc):
 
 
 @pytest.mark.gpu
+def test_gpu_ransac_device_buffers_validate_indices(ctx, orc):
+    """PFX_DEVICE correspondences (e.g. straight from pfx_match) with a -1 / out-of-range index: a clean error,
+    not an out-of-bounds read; valid device buffers give the host-buffer result."""
+    import ctypes as C
+    import torch
+    import pcl_feature_extraction_b200 as pfx
+    src, tgt, q, m, inl, R, t = planted(200)
+    corr = np.zeros(len(q), pfx.capi.CORR_DTYPE)
+    corr["index_query"], corr["index_match"] = q, m
+    ref, Tref, it_ref, bh_ref = ctx.ransac_reject(src, tgt, corr)
+
+    def run(c):
+        d_src = torch.from_numpy(np.ascontiguousarray(src, np.float32)).cuda()
+        d_tgt = torch.from_numpy(np.ascontiguousarray(tgt, np.float32)).cuda()
+        d_c = torch.from_numpy(c.view(np.int32).reshape(-1, 3).copy()).cuda()
+        d_out = torch.zeros_like(d_c)
+        T = np.zeros(16, np.float32)
+        n_out = C.c_size_t(0)
+        it, bh = C.c_int(0), C.c_int(0)
+        torch.cuda.synchronize()
+        ctx._chk(ctx.lib.pfx_ransac_reject(ctx.h, d_src.data_ptr(), len(src), 12, d_tgt.data_ptr(), len(tgt), 12,
+                                           d_c.data_ptr(), len(c), 0.015, 1000, 12345, d_out.data_ptr(), len(c),
+                                           C.byref(n_out), pfx.capi._ptr(T), C.byref(it), C.byref(bh), pfx.capi.DEVICE))
+        return d_out[: n_out.value].cpu().numpy(), T.reshape(4, 4), it.value, bh.value
+
+    out, T, it, bh = run(corr)
+    assert (it, bh) == (it_ref, bh_ref) and np.array_equal(out[:, 0], ref["index_query"]) and np.array_equal(T, Tref)
+    for col, val in (("index_match", -1), ("index_query", len(src)), ("index_match", 1 << 30)):
+        bad = corr.copy()
+        bad[col][7] = val
+        with pytest.raises(RuntimeError):
+            run(bad)
+    out, T, it, bh = run(corr)  # the context is still usable
+    assert np.array_equal(out[:, 0], ref["index_query"])
+
+
+@pytest.mark.gpu
 def test_gpu_ransac_on_config_c1_correspondences(ctx, orc, clouds):
     """the reference's use: filterCorrespondences on the ISS keypoints + FPFH matches of the indoor pair"""
     kps, feats = [], []

@@ -66,8 +66,10 @@ def _worker(rank, world, port, cloud_path, out_path):
         local, n_owned = sharding.exchange_halo(owned, axis, cuts, rank, world, halo)
         xyz = np.ascontiguousarray(local[:, :3])
         # every point within `halo` of an owned point must be present locally
-        d_cut = np.minimum(np.abs(pts[:, axis] - cuts[0]), np.inf)
-        need = (slab == rank) | (d_cut <= halo * 0.999)
+        x = pts[:, axis].astype(np.float64)
+        lo_r = cuts[rank - 1] if rank > 0 else -np.inf
+        hi_r = cuts[rank] if rank < world - 1 else np.inf
+        need = (slab == rank) | ((x >= lo_r - halo * 0.999) & (x < hi_r + halo * 0.999))
         have = np.zeros(n, bool)
         have[local[:, 3].astype(np.int64)] = True
         assert have[need].all()
@@ -78,12 +80,12 @@ def _worker(rank, world, port, cloud_path, out_path):
         rows = np.concatenate([nr[:n_owned], f, s, rf], 1).astype(np.float32)
         full = sharding.gather_rows(rows, n, mine, rank, world)
         t = sharding.max_over_ranks(1.0 + rank)
-        assert t == 2.0
+        assert t == float(world)
         # cloud resolution of the whole cloud from the owned points of every rank (2-NN among owned + halo points)
         _, d2nn = orc.knn(xyz, xyz[:n_owned], 2)
         res = sharding.cloud_resolution_over_ranks(np.sqrt(d2nn[:, 1].astype(np.float64)))
         assert abs(res - orc.cloud_resolution(pts)) < 1e-9
-        assert sharding.knn_support_radius(0.01 * (rank + 1), 3) == pytest.approx(0.06)
+        assert sharding.knn_support_radius(0.01 * (rank + 1), 3) == pytest.approx(0.03 * world)
         if rank == 0:
             np.save(out_path, full)
     finally:
@@ -176,12 +178,27 @@ def test_ring_matching_with_both_sides_sharded_equals_single_process(tmp_path, o
     assert idx[11] == -1
 
 
-def test_slab_sharded_equals_single_process(tmp_path, orc, clouds):
+@pytest.mark.parametrize("case", ["wide_slabs", "clustered"])
+def test_slab_sharded_equals_single_process(tmp_path, orc, clouds, case):
     import torch.multiprocessing as mp
-    pts = np.ascontiguousarray(clouds["underwater_source"][:6000])
+    if case == "wide_slabs":
+        pts = np.ascontiguousarray(clouds["underwater_source"][:6000])
+        world = 2
+    else:
+        # equal-count cuts through a dense cluster: the two middle slabs of four are far narrower than the halo
+        # (0.13 m), so owned points need neighbours from ranks r +- 2 and r +- 3 (sharding.py:82)
+        rng = np.random.default_rng(5)
+        base = clouds["underwater_source"]
+        ax = int(np.argmax(base.max(0) - base.min(0)))
+        mid = np.median(base[:, ax])
+        dense = base[np.abs(base[:, ax] - mid) < 0.03][:4000]
+        sparse = base[rng.choice(len(base), 2000, replace=False)]
+        pts = np.unique(np.concatenate([dense, sparse]), axis=0).astype(np.float32)
+        world = 4
+        cuts = sharding.slab_cuts(pts[:, ax], world)
+        assert np.diff(cuts).min() < 0.13
     cloud_path, out_path = str(tmp_path / "cloud.npy"), str(tmp_path / "out.npy")
     np.save(cloud_path, pts)
-    world = 2
     mp.spawn(_worker, args=(world, _free_port(), cloud_path, out_path), nprocs=world, join=True)
     got = np.load(out_path)
     r_n, r_f = 0.03, 0.05
