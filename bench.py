@@ -182,6 +182,117 @@ def run_reference(args, rank, world):
     }), flush=True)
 
 
+def matching_record(pfx, ctx, torch, dev, peaks, rows=65536, dim=352, reps=5):
+    """descriptor matching, the one dense contraction (features.h:224-273): rows x rows x dim exact 1-NN through the
+    tcgen05 engine (candidate GEMM + fp32 rescore + exact redo), device-resident; TFLOP/s = 2 * na * nb * dim / time"""
+    g = torch.Generator(device=dev).manual_seed(rows + dim)
+    a = torch.rand((rows, dim), device=dev, generator=g)
+    b = torch.rand((rows, dim), device=dev, generator=g)
+    m = rows // 2
+    b[:m] = a[:m] + 0.01 * torch.randn((m, dim), device=dev, generator=g)
+    idx = torch.empty(rows, dtype=torch.int32, device=dev)
+    d2 = torch.empty(rows, dtype=torch.float32, device=dev)
+    ctx.set_match_engine(1)
+    try:
+        for _ in range(2):
+            ctx.match_nn_dev(a.data_ptr(), rows, b.data_ptr(), rows, dim, idx.data_ptr(), d2.data_ptr())
+        torch.cuda.synchronize()
+        i0 = ctx.match_info()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            ctx.match_nn_dev(a.data_ptr(), rows, b.data_ptr(), rows, dim, idx.data_ptr(), d2.data_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        i1 = ctx.match_info()
+        ms = e0.elapsed_time(e1) / reps
+        ctx.profile_begin("tc_candidates_kernel")
+        ctx.match_nn_dev(a.data_ptr(), rows, b.data_ptr(), rows, dim, idx.data_ptr(), d2.data_ptr())
+        prof = ctx.profile_end()
+        cand_ms = sum(t for _, t in prof.values())
+    finally:
+        ctx.set_match_engine(-1)
+    tf = 2.0 * rows * rows * dim / (ms * 1e-3) / 1e12
+    planted_found = float((idx[:m].long() == torch.arange(m, device=dev)).float().mean().item())
+    return {"workload": f"{rows} x {rows} x {dim} exact 1-NN (random rows, half of the targets planted near a query)",
+            "ms": ms, "tflops": tf, "frac_of_bf16_burst": tf / peaks["bf16_tflops"], "bf16_tflops_peak": peaks["bf16_tflops"],
+            "candidates_kernel_ms": cand_ms, "candidates_kernel_tflops": 2.0 * rows * rows * dim / (cand_ms * 1e-3) / 1e12 if cand_ms else None,
+            "redo_rate": (i1["redone_exact"] - i0["redone_exact"]) / max(1, i1["rows"] - i0["rows"]),
+            "planted_matches_found": planted_found, "bound": "tensor"}
+
+
+def bundled_record(pfx, ctx):
+    """configs C1, C2, C3 of BASELINE.json on the bundled clouds (the copies under tests/golden/, taken from the
+    reference's data/ directory), GPU only, host buffers in and out (what a user of the reference gets), wall clock
+    of the second pass.  C1 and C2 run in PFX_PARITY_STRICT (index-for-index equal to the CPU path:
+    tests/test_gpu_end_to_end.py) and, for comparison, with the fast kernels."""
+    path = os.path.join(ROOT, "tests", "golden", "clouds.npz")
+    if not os.path.exists(path):
+        return None
+    Z = np.load(path)
+
+    def c1():
+        feats, n_in, n_kp = [], 0, []
+        for name in ("indoor_source", "indoor_target"):
+            pts = Z[name]
+            n_in += len(pts)
+            ctx.set_surface(pts)
+            xyz = ctx.voxel_grid(0.01)
+            ctx.set_surface(xyz)
+            ctx.normals(radius=0.03, want_output=False)
+            res = ctx.cloud_resolution()
+            kp, _ = ctx.iss(6 * res, 4 * res)
+            ctx.set_queries(xyz[kp])
+            feats.append(ctx.fpfh(radius=0.05))
+            ctx.set_queries(None)
+            n_kp.append(int(len(kp)))
+        c = ctx.match(feats[0], feats[1], reciprocal=True)
+        return n_in, {"keypoints": n_kp, "correspondences": int(len(c))}
+
+    def c2():
+        feats, n_in, n_kp = [], 0, []
+        for name in ("underwater_source", "underwater_target"):
+            pts = Z[name]
+            n_in += len(pts)
+            ctx.set_surface(pts)
+            h = ctx.harris3d(0.01, 1e-6)
+            snapped = h["snapped_idx"][h["snapped_idx"] >= 0]
+            ctx.normals(radius=0.03, want_output=False)
+            ctx.set_queries(pts[snapped])
+            sdesc, _ = ctx.shot352(0.05)
+            ctx.set_queries(None)
+            feats.append(np.ascontiguousarray(sdesc[~np.isnan(sdesc[:, 0])]))
+            n_kp.append(int(len(snapped)))
+        c = ctx.match(feats[0], feats[1], reciprocal=True)
+        return n_in, {"keypoints": n_kp, "correspondences": int(len(c))}
+
+    def c3():
+        pts = Z["indoor_source"]
+        ctx.set_surface(pts)
+        ctx.range_image_spherical(float(np.deg2rad(0.5)))
+        kp, _, _, _ = ctx.narf_keypoints(0.2)
+        f = ctx.narf36(kp, 0.2, True)
+        return len(pts), {"keypoints": int(len(kp)), "descriptors": int(len(f))}
+
+    out = {}
+    for name, fn, modes in (("c1_indoor_iss_fpfh_match", c1, (True, False)), ("c2_underwater_harris_shot_match", c2, (True, False)),
+                            ("c3_indoor_narf_narf36", c3, (False,))):
+        rec = {}
+        for strict in modes:
+            ctx.set_parity_mode(strict)
+            try:
+                fn()  # warm-up: allocations, first-use costs
+                t0 = time.perf_counter()
+                n_in, info = fn()
+                dt = time.perf_counter() - t0
+            finally:
+                ctx.set_parity_mode(False)
+            key = "strict" if strict else "fast"
+            rec[key] = {"ms": 1e3 * dt, "points_per_s": n_in / dt, **info}
+        out[name] = rec
+    return out
+
+
 def bind_to_gpu_numa(local):
     """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, so that the page-locked
     staging buffers (first touch) and the copy threads sit on the GPU's NUMA node.  Returns the previous CPU set
@@ -214,6 +325,7 @@ def main():
     ap.add_argument("--cpu-side", type=int, default=448)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the matching / bundled-cloud / slab sub-records")
     ap.add_argument("--in-flight", type=int, default=2, help="clouds in flight per GPU (contexts on separate streams)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -359,6 +471,38 @@ def main():
         c2.close()
     del outs[1:]
     torch.cuda.empty_cache()
+
+    # ---- sub-records of the one JSON line: matching GEMM and the bundled clouds (rank 0), outside the timed regions
+    matching = bundled = slab = None
+    if rank == 0 and not args.no_extras:
+        peaks_x, _ = measured_peaks()
+        try:
+            matching = matching_record(pfx, ctx, torch, dev, peaks_x)
+        except Exception as e:  # a sub-record must never take the headline down
+            matching = {"error": str(e)}
+        try:
+            bundled = bundled_record(pfx, ctx)
+        except Exception as e:
+            bundled = {"error": str(e)}
+        ctx.set_queries(None)
+        torch.cuda.empty_cache()
+    barrier()
+    if world > 1 and not args.no_extras:
+        # ---- one cloud slab-sharded over the ranks and both-sides-sharded matching, through the C ABI's group API
+        # (NCCL inside the library; torch.distributed only carries the 128-byte group id).  Collective: every rank.
+        try:
+            from tools.slab_bench import join_group, slab_record
+            from tools.ring_match_bench import ring_record
+            join_group(ctx, dist, rank, world)
+            slab = slab_record(pfx, ctx, torch, dist, dev, rank, world, side=args.side, steps=3, warmup=1, verify=True)
+            slab["ring_matching"] = ring_record(pfx, ctx, torch, dist, dev, rank, world, rows=32768, dim=352, reps=2,
+                                                check_rows=32768 * 8)
+            ctx.group_leave()
+        except Exception as e:
+            slab = {"error": str(e)}
+        ctx.set_queries(None)
+        torch.cuda.empty_cache()
+        barrier()
 
     # ---- e2e: the same C-ABI calls with HOST buffers (pinned), H2D + D2H inside the timed region
     e2e = None

@@ -164,6 +164,42 @@ int pfx_set_match_engine(pfx_ctx* ctx, int engine);
  * they processed, out4[2] rows whose exactness certificate failed and were redone by the exact scan */
 int pfx_match_info(pfx_ctx* ctx, double* out4);
 
+/* ------------------------------------------------------------------ multi-GPU: groups, slabs, sharded matching
+ * The reference is a single CPU process; its per-point stages (features.h:181-195) shard over
+ * GPUs either cloud by cloud (no communication) or, for ONE large cloud, as spatial slabs with a halo.  A context
+ * joins a GROUP = one NCCL communicator with one rank per GPU; ranks may be processes (one per GPU, the id
+ * broadcast by the launcher) or threads of one process (one context per device, pfx_group_join from each thread).
+ * Collective calls (pfx_slab_distribute, pfx_match_ring, pfx_group_allreduce) must be made by every rank.
+ *
+ * pfx_group_unique_id   fills 128 bytes (ncclUniqueId) on one rank; hand them to all ranks
+ * pfx_group_join        ncclCommInitRank for this context's device
+ * pfx_slab_distribute   the ranks hold arbitrary disjoint parts of one cloud (records of `stride` bytes, xyz first;
+ *                       global_ids optional int32 per point, default = position in the concatenation of the parts
+ *                       in rank order).  The cloud is cut into `world` slabs along its longest axis at equal-count
+ *                       cuts; on return the surface of this context = the points of its slab (rows 0 .. n_owned-1)
+ *                       followed by every point within `halo` of the slab (n_local rows in all), moved device to
+ *                       device by grouped ncclSend / ncclRecv.  With halo >= the support of the stage chain
+ *                       (normals r_n; FPFH 2 r_f + r_n; SHOT r_s + r_n; k-searches: multiples of the largest k-th
+ *                       neighbour distance) the dense stages give every owned point the rows it gets on one GPU.
+ * pfx_slab_global_ids   int32 [n_local]: the global id of every local surface point
+ * pfx_match_ring        exact 1-NN with both descriptor sets sharded: every rank passes its query rows `a` and its
+ *                       target block `b` (first global row b_offset); target blocks rotate around the ring under the
+ *                       match; nn_idx = GLOBAL target row (-1 none), ties -> lowest global row, as pfx_match_nn.
+ * pfx_group_allreduce   n host doubles reduced in place over the ranks: op 0 sum, 1 max, 2 min */
+#define PFX_GROUP_ID_BYTES 128
+int pfx_group_unique_id(void* id128);
+int pfx_group_join(pfx_ctx* ctx, int rank, int world, const void* id128);
+int pfx_group_leave(pfx_ctx* ctx);
+int pfx_group_info(const pfx_ctx* ctx, int* rank, int* world);
+int pfx_group_allreduce(pfx_ctx* ctx, double* vals, int n, int op);
+int pfx_slab_distribute(pfx_ctx* ctx, const void* part, size_t n_part, size_t stride, const int32_t* global_ids, int mem,
+                        double halo, size_t* n_owned, size_t* n_local);
+int pfx_slab_global_ids(pfx_ctx* ctx, int32_t* out, int mem);
+/* info6: [0] axis, [1] n_owned, [2] n_local, [3] points over all ranks, [4] / [5] lower / upper bound of the slab */
+int pfx_slab_info(const pfx_ctx* ctx, double* info6);
+int pfx_match_ring(pfx_ctx* ctx, const float* a, size_t na, size_t stride_a, const float* b, size_t nb, size_t stride_b,
+                   int dim, int b_offset, int32_t* nn_idx, float* nn_d2, int mem);
+
 /* ------------------------------------------------------------------ parity mode
  * PFX_PARITY_FAST (default): the throughput kernels; floats within the tolerances of DESIGN.md section 4.
  * PFX_PARITY_STRICT: the stages whose floats feed INDEX outputs of the reference pipeline run in reference-order

@@ -56,6 +56,15 @@ SIGNATURES = {
     "pfx_last_error": (C.c_char_p, [_vp]),
     "pfx_set_stream": (_i, [_vp, _vp]),
     "pfx_set_parity_mode": (_i, [_vp, _i]),
+    "pfx_group_unique_id": (_i, [_vp]),
+    "pfx_group_join": (_i, [_vp, _i, _i, _vp]),
+    "pfx_group_leave": (_i, [_vp]),
+    "pfx_group_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "pfx_group_allreduce": (_i, [_vp, C.POINTER(_d), _i, _i]),
+    "pfx_slab_distribute": (_i, [_vp, _vp, _sz, _sz, _vp, _i, _d, C.POINTER(_sz), C.POINTER(_sz)]),
+    "pfx_slab_global_ids": (_i, [_vp, _vp, _i]),
+    "pfx_slab_info": (_i, [_vp, C.POINTER(_d)]),
+    "pfx_match_ring": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _vp, _i]),
     "pfx_sync": (_i, [_vp]),
     "pfx_launch_count": (C.c_uint64, [_vp]),
     "pfx_grid_info": (_i, [_vp, C.POINTER(_d)]),
@@ -516,6 +525,60 @@ class Context:
         if want_aligned:
             out["aligned"] = al
         return out
+
+    # -- multi-GPU (group.cu): one rank per GPU, NCCL inside the library
+    @staticmethod
+    def group_unique_id():
+        """128 bytes (ncclUniqueId) made on one rank; every rank passes them to group_join"""
+        buf = (C.c_ubyte * 128)()
+        rc = load().pfx_group_unique_id(buf)
+        if rc != 0:
+            raise PfxError(rc, "pfx_group_unique_id failed (NCCL not available)")
+        return bytes(buf)
+
+    def group_join(self, rank, world, unique_id):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        self._chk(self.lib.pfx_group_join(self.h, rank, world, buf))
+
+    def group_leave(self):
+        self._chk(self.lib.pfx_group_leave(self.h))
+
+    def group_allreduce(self, vals, op="sum"):
+        a = (C.c_double * len(vals))(*[float(v) for v in vals])
+        self._chk(self.lib.pfx_group_allreduce(self.h, a, len(vals), {"sum": 0, "max": 1, "min": 2}[op]))
+        return [float(v) for v in a]
+
+    def slab_distribute(self, part, halo, global_ids=None, mem=HOST, stride=None):
+        """part: [n, >=3] float32 rows (numpy for HOST; a device pointer + explicit n via (ptr, n) for DEVICE).
+        -> (n_owned, n_local); the context's surface becomes owned + halo points"""
+        if mem == HOST:
+            part = np.ascontiguousarray(part, np.float32)
+            n, st = len(part), part.strides[0] if len(part) else 12
+            ptr = _ptr(part)
+            gid = None if global_ids is None else _ptr(np.ascontiguousarray(global_ids, np.int32))
+        else:
+            ptr_i, n = part
+            ptr, st = _ptr(ptr_i), stride or 16
+            gid = None if global_ids is None else _ptr(global_ids)
+        no, nl = C.c_size_t(0), C.c_size_t(0)
+        self._chk(self.lib.pfx_slab_distribute(self.h, ptr, n, st, gid, mem, float(halo), C.byref(no), C.byref(nl)))
+        return no.value, nl.value
+
+    def slab_global_ids(self):
+        info = self.slab_info()
+        out = np.zeros(info["n_local"], np.int32)
+        self._chk(self.lib.pfx_slab_global_ids(self.h, _ptr(out), HOST))
+        return out
+
+    def slab_info(self):
+        a = (C.c_double * 6)()
+        self._chk(self.lib.pfx_slab_info(self.h, a))
+        return dict(axis=int(a[0]), n_owned=int(a[1]), n_local=int(a[2]), n_total=int(a[3]), lo=a[4], hi=a[5])
+
+    def match_ring_dev(self, a_ptr, na, b_ptr, nb, dim, b_offset, idx_ptr, d2_ptr, stride_a=None, stride_b=None):
+        """both sides sharded over the group's ranks, device buffers; idx = GLOBAL target rows"""
+        self._chk(self.lib.pfx_match_ring(self.h, _ptr(a_ptr), na, stride_a or dim * 4, _ptr(b_ptr), nb, stride_b or dim * 4,
+                                          dim, int(b_offset), _ptr(idx_ptr), _ptr(d2_ptr), DEVICE))
 
     def set_parity_mode(self, strict):
         """True: reference-order arithmetic for normals / Harris3D / radius-search FPFH (bit-identical to the CPU

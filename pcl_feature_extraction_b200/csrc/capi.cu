@@ -189,6 +189,7 @@ extern "C" int pfx_destroy(pfx_ctx* ctx) {
       ctx->async_stage[s].release();
     }
   }
+  group_release(ctx);
   grid_free_all(ctx);
   match_tc_release(ctx);
   for (DevBuf* b : {&ctx->surf, &ctx->normals, &ctx->normals_sorted, &ctx->qry, &ctx->knn_idx, &ctx->knn_d2,
@@ -196,7 +197,9 @@ extern "C" int pfx_destroy(pfx_ctx* ctx) {
                     &ctx->small, &ctx->scanbuf, &ctx->match_flags, &ctx->match_best, &ctx->out_stage, &ctx->qflag,
                     &ctx->worklist, &ctx->worklist2, &ctx->ri_img, &ctx->nb_surf, &ctx->nb_scores, &ctx->nb_shadow,
                     &ctx->nb_traits, &ctx->nb_dir, &ctx->nb_change, &ctx->nk_interest, &ctx->icp_state, &ctx->icp_cur,
-                    &ctx->icp_nn, &ctx->icp_partials, &ctx->usc_tab, &ctx->lab_tab, &ctx->surf_lab, &ctx->qry_lab})
+                    &ctx->icp_nn, &ctx->icp_partials, &ctx->usc_tab, &ctx->lab_tab, &ctx->surf_lab, &ctx->qry_lab,
+                    &ctx->st_cnt, &ctx->st_off, &ctx->st_idx, &ctx->st_d2, &ctx->grp_tmp, &ctx->slab_rows, &ctx->slab_pack,
+                    &ctx->slab_recv, &ctx->slab_gid, &ctx->ring_buf[0], &ctx->ring_buf[1], &ctx->ring_best, &ctx->ring_res})
     b->release();
   ctx->vg_scratch.release();
   for (Ctx::ProfRec& r : ctx->prof_recs) {
@@ -331,6 +334,7 @@ extern "C" int pfx_set_surface(pfx_ctx* ctx, const void* pts, size_t n, size_t s
   ctx->knn_grid = nullptr;
   ctx->q_is_surface = true;
   ctx->nq = 0;
+  ctx->slab_active = false;
   return 0;
 }
 
@@ -790,7 +794,7 @@ extern "C" int pfx_shot352(pfx_ctx* ctx, double radius, const float* lrf_in, flo
   const size_t nq = ctx->num_queries();
   if (nq == 0) return 0;
   Grid* g = nullptr;
-  PFX_TRY(grid_get(ctx, radius, 0, &g));
+  PFX_TRY(grid_for_radius(ctx, radius, &g));
   float* dout = out;
   if (mem == PFX_HOST_ASYNC) {
     if (lrf_in) return ctx->fail(PFX_E_INVALID, "pfx_shot352: PFX_HOST_ASYNC output with caller-supplied frames is not supported");
@@ -982,6 +986,15 @@ static bool match_use_tc(const Ctx* ctx, size_t na, size_t nb, int dim) {
   if (ctx->match_engine >= 0) return ctx->match_engine == 1;
   return (double)na * (double)nb * (double)dim >= 1.5e9;
 }
+
+namespace pfx {
+// device rows in, device results out: the engine choice of pfx_match_nn for the ring matcher (group.cu)
+int match_dispatch_dev(Ctx* ctx, const float* a, int na, int lda, const float* b, int nb, int ldb, int dim, int* idx,
+                       float* d2) {
+  if (match_use_tc(ctx, na, nb, dim)) return match_nn_tc(ctx, a, na, lda, b, nb, ldb, dim, idx, d2);
+  return match_nn_exact(ctx, a, na, lda, b, nb, ldb, dim, idx, d2);
+}
+}  // namespace pfx
 
 static int match_dispatch(Ctx* ctx, const float* a, int na, int lda, const float* b, int nb, int ldb, int dim,
                           int* idx, float* d2) {

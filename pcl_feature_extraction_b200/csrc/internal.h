@@ -36,6 +36,7 @@ namespace pfx {
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 struct Ctx;
+struct Group;
 
 // One voxel hash over the current surface (sorted copy of the points + cell table).
 struct Grid {
@@ -48,6 +49,9 @@ struct Grid {
   // build; the first consumer makes the main stream wait for it
   cudaEvent_t ready = nullptr;
   bool pending = false;
+  // read-back of the device-chosen parameters (pinned) and the event recorded behind the build
+  void* host_params = nullptr;
+  cudaEvent_t built = nullptr;
   int n = 0;
   uint32_t hmask = 0;
   DevBuf params, pts, inv_perm, keys, vals, keys2, vals2, ghist, cell_start, cell_key, hkeys, hvals,
@@ -71,6 +75,10 @@ struct Grid {
     for (DevBuf* b : {&params, &pts, &inv_perm, &keys, &vals, &keys2, &vals2, &ghist, &cell_start,
                       &cell_key, &hkeys, &hvals, &pt_cell, &cell_nbr, &bsum, &misc})
       b->release();
+    if (host_params) cudaFreeHost(host_params);
+    if (built) cudaEventDestroy(built);
+    host_params = nullptr;
+    built = nullptr;
   }
 };
 
@@ -109,6 +117,8 @@ struct Ctx {
   uint64_t qry_version = 0;
 
   std::vector<Grid*> grids;
+  double radius_hint = 0;  // pfx_prepare_radius before any hash of the surface exists (grid_prepare_async)
+  uint64_t radius_hint_version = 0;
 
   // kNN list cache (sorted-position indices + d2), valid for (grid, k, query version)
   DevBuf knn_idx, knn_d2;
@@ -162,6 +172,15 @@ struct Ctx {
   int st_k = 0;
   long long st_total = 0;
 
+  // multi-GPU (group.cu): NCCL group membership, slab surface, ring-match buffers
+  struct Group* group = nullptr;
+  DevBuf grp_tmp, slab_rows, slab_pack, slab_recv, slab_gid, ring_buf[2], ring_best, ring_res;
+  bool slab_active = false;
+  int slab_axis = 0;
+  size_t slab_owned = 0;
+  long long slab_total = 0;
+  double slab_lo = 0, slab_hi = 0;
+
   int match_engine = -1;  // -1 auto, 0 exact fp32 scan, 1 tcgen05 candidates + fp32 rescore
   TcOperand tc_ops[2];
   DevBuf tc_cand_d, tc_cand_j, tc_redo, tc_rows, tc_res;
@@ -211,6 +230,8 @@ struct Ctx {
 
 // ---- grid.cu
 int grid_get(Ctx* ctx, double radius, int knn_k, Grid** out);
+int grid_for_radius(Ctx* ctx, double radius, Grid** out);  // exact, or any grid of the surface whose edge covers the radius
+int grid_wait_built(Ctx* ctx, Grid* g);
 int grid_prepare_async(Ctx* ctx, double radius);  // build the radius grid on the auxiliary stream
 int grid_wait_pending(Ctx* ctx);                  // main stream waits for every build in flight
 void grid_free_all(Ctx* ctx);
@@ -286,6 +307,9 @@ int strict_normals(Ctx* ctx, Grid* g, double radius, int k, float4* out_query_or
 int harris_response_strict(Ctx* ctx, Grid* g, double radius, float* resp_dev_orig);
 int harris_refine_strict(Ctx* ctx, Grid* g, double radius, float* corners_dev, int nc);
 int fpfh_sorted(Ctx* ctx, Grid* g, double radius, const float* spfh_sorted_rows, float* out_dev, size_t stride_floats);
+
+// ---- group.cu
+void group_release(Ctx* ctx);
 
 // ---- helpers (capi.cu)
 int pfh_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t stride_floats);

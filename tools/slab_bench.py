@@ -1,103 +1,161 @@
-"""Slab-sharded dense FPFH33 + SHOT352 of ONE cloud over N GPUs (SURVEY.md §8e partitioning 2).
+"""Slab-sharded dense FPFH33 + SHOT352 of ONE cloud over N GPUs through the C ABI's group API (SURVEY.md §8e
+partitioning 2): pfx_group_join (NCCL inside the library), pfx_slab_distribute (device-resident all-to-all of slab +
+halo points, grouped ncclSend / ncclRecv), the unchanged dense stages on owned + halo points, owned rows kept.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
       tools/slab_bench.py [--side 1024] [--steps 5] [--verify]
 
-Each rank owns one slab (equal-count cut along the longest axis), receives its neighbours' halo points once over
-NCCL P2P, runs the unchanged dense path on (owned + halo) points and keeps its owned rows.  Prints one JSON line
-(rank 0): whole-cloud descriptors/s with the MAX over ranks of the device-timed step, the halo share, and with
---verify the comparison of the gathered rows against a single-GPU run of the whole cloud on rank 0."""
+torch.distributed is only the launcher-side plumbing here (broadcast of the 128-byte group id, the barrier and the
+gather of rows for --verify); every byte of the data path moves inside libpfx_b200.so.  Prints one JSON line (rank 0):
+whole-cloud descriptors/s with the MAX over ranks of the device-timed step, the halo share, and with --verify the
+comparison of the gathered rows against a single-GPU run of the whole cloud on rank 0.  `slab_record` is also what
+bench.py reports as its "slab" sub-record at N > 1."""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-import torch
-import torch.distributed as dist
-import pcl_feature_extraction_b200 as pfx
-from pcl_feature_extraction_b200 import sharding
-from pcl_feature_extraction_b200.synth import sheet_cloud
 
 K_NN, PITCH = 32, 0.004
 SHOT_RADIUS = 3.2 * PITCH
 
 
-def dense_step(ctx, d_pts, n, d_f, d_s):
-    ctx.set_surface_dev(d_pts.data_ptr(), n, 16)
+def dense_step(ctx, d_f, d_s):
     ctx.prepare_radius(SHOT_RADIUS)
     ctx.normals_dev(0.0, K_NN, None)
     ctx.fpfh_dev(0.0, K_NN, d_f.data_ptr())
     ctx.shot352_dev(SHOT_RADIUS, d_s.data_ptr())
 
 
+def join_group(ctx, dist, rank, world):
+    """rank 0 makes the NCCL id, the launcher's process group carries it to the others"""
+    box = [ctx.group_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    ctx.group_join(rank, world, box[0])
+
+
+def slab_record(pfx, ctx, torch, dist, dev, rank, world, side=1024, steps=5, warmup=2, verify=False, seed=20240601):
+    """one cloud, every rank starting from an arbitrary disjoint part of it (points rank, rank + world, ... of the
+    shuffled cloud) resident in ITS device memory.  A step = pfx_slab_distribute (device to device) + the dense
+    stages on owned + halo points."""
+    from pcl_feature_extraction_b200.synth import sheet_cloud
+    pts = sheet_cloud(side=side, pitch=PITCH, seed=seed)
+    n_total = len(pts)
+    ids = np.arange(rank, n_total, world, dtype=np.int32)
+    part = np.zeros((len(ids), 4), np.float32)
+    part[:, :3] = pts[ids]
+    d_part = torch.from_numpy(part).to(dev)
+    d_ids = torch.from_numpy(ids).to(dev)
+    ctx.set_viewpoint(0.0, 0.0, 0.0)
+
+    # support of the k-search chain (normals -> SPFH -> FPFH: 3 x the largest k-th neighbour distance over all
+    # ranks) and of SHOT (radius + one k-th distance for its normals): measured once on the owned points (halo 0)
+    ctx.slab_distribute((d_part.data_ptr(), len(ids)), 0.0, global_ids=d_ids.data_ptr(), mem=pfx.capi.DEVICE)
+    _, d2 = ctx.knn(K_NN)
+    dk = float(np.sqrt(d2[:, -1].max())) if len(d2) else 0.0
+    dk = ctx.group_allreduce([dk], "max")[0] * 1.05
+    halo = max(3.0 * dk, SHOT_RADIUS + dk)
+
+    def step():
+        return ctx.slab_distribute((d_part.data_ptr(), len(ids)), halo, global_ids=d_ids.data_ptr(), mem=pfx.capi.DEVICE)
+
+    n_owned, n_local = step()
+    d_f = torch.empty((n_local, 33), dtype=torch.float32, device=dev)
+    d_s = torch.empty((n_local, 361), dtype=torch.float32, device=dev)
+    for _ in range(warmup):
+        step()
+        dense_step(ctx, d_f, d_s)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    t_dist = 0.0
+    e0.record()
+    for _ in range(steps):
+        e1.record()
+        step()
+        e2.record()
+        dense_step(ctx, d_f, d_s)
+        torch.cuda.synchronize()
+        t_dist += e1.elapsed_time(e2)
+    e3 = torch.cuda.Event(enable_timing=True)
+    e3.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ctx.group_allreduce([e0.elapsed_time(e3) / steps], "max")[0]
+    ms_dist = ctx.group_allreduce([t_dist / steps], "max")[0]
+    halo_share = ctx.group_allreduce([(n_local - n_owned) / max(n_owned, 1)], "max")[0]
+    out = {"workload": f"one {side}x{side}-point cloud slab-sharded over {world} GPUs: pfx_slab_distribute (NCCL send/recv of "
+                       "slab + halo points, device to device) + dense normals k=32 + FPFH33 k=32 + SHOT352 r=12.8 mm on owned + halo points",
+           "n_gpus": world, "points": n_total, "value": 2.0 * n_total / (ms * 1e-3), "unit": "descriptors/s", "ms_per_cloud": ms,
+           "distribute_ms": ms_dist, "halo_m": halo, "halo_points_share_max": halo_share, "scaling": "strong"}
+    if verify:
+        gid = torch.from_numpy(ctx.slab_global_ids()[:n_owned].astype(np.int64)).to(dev)
+        rows = torch.cat([d_f[:n_owned], d_s[:n_owned]], 1)
+        if world > 1:
+            sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+            dist.all_gather(sizes, torch.tensor([n_owned], dtype=torch.int64, device=dev))
+            m = int(max(int(s.item()) for s in sizes))
+            pad_rows = torch.zeros((m, rows.shape[1]), dtype=torch.float32, device=dev)
+            pad_gid = torch.full((m,), -1, dtype=torch.int64, device=dev)
+            pad_rows[:n_owned] = rows
+            pad_gid[:n_owned] = gid
+            all_rows = [torch.empty_like(pad_rows) for _ in range(world)] if rank == 0 else None
+            all_gid = [torch.empty_like(pad_gid) for _ in range(world)] if rank == 0 else None
+            dist.gather(pad_rows, all_rows, dst=0)
+            dist.gather(pad_gid, all_gid, dst=0)
+        else:
+            all_rows, all_gid = [rows], [gid]
+        if rank == 0:
+            full = torch.zeros((n_total, 394), dtype=torch.float32, device=dev)
+            seen = torch.zeros(n_total, dtype=torch.int32, device=dev)
+            for r, g in zip(all_rows, all_gid):
+                keep = g >= 0
+                full[g[keep]] = r[keep]
+                seen[g[keep]] += 1
+            p4 = np.zeros((n_total, 4), np.float32)
+            p4[:, :3] = pts
+            dp = torch.from_numpy(p4).to(dev)
+            f1 = torch.empty((n_total, 33), dtype=torch.float32, device=dev)
+            s1 = torch.empty((n_total, 361), dtype=torch.float32, device=dev)
+            ctx.set_surface_dev(dp.data_ptr(), n_total, 16)
+            dense_step(ctx, f1, s1)
+            torch.cuda.synchronize()
+            ref = torch.cat([f1, s1], 1)
+            same = (full.view(torch.int32) == ref.view(torch.int32)) | (torch.isnan(full) & torch.isnan(ref))
+            diff = torch.nan_to_num((full - ref).abs(), nan=0.0)
+            out["verify"] = {"every_point_owned_once": bool((seen == 1).all().item()),
+                             "rows_bit_identical": float(same.all(1).float().mean().item()),
+                             "fpfh_rows_bit_identical": float(same[:, :33].all(1).float().mean().item()),
+                             "shot_rows_bit_identical": float(same[:, 33:].all(1).float().mean().item()),
+                             "fpfh_max_abs_diff": float(diff[:, :33].max().item()),
+                             "shot_max_abs_diff": float(diff[:, 33:385].max().item())}
+    return out
+
+
 def main():
+    import torch
+    import torch.distributed as dist
+    import pcl_feature_extraction_b200 as pfx
     ap = argparse.ArgumentParser()
     ap.add_argument("--side", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--verify", action="store_true")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    pts = sheet_cloud(side=args.side, pitch=PITCH, seed=20240601)  # every rank can read the cloud; it keeps its slab
-    n_total = len(pts)
     ctx = pfx.Context(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    ctx.set_viewpoint(0.0, 0.0, 0.0)
-
-    axis = sharding.longest_axis(pts.min(0), pts.max(0))
-    cuts = sharding.slab_cuts(pts[:, axis], world)
-    mine = np.where(sharding.slab_of(pts[:, axis], cuts) == rank)[0]
-    # support of the k-search chain: 3 x the largest k-th neighbour distance (all-reduce MAX), and SHOT's radius chain
-    ctx.set_surface(pts[mine])
-    _, d2 = ctx.knn(K_NN)
-    dk = float(np.sqrt(d2[:, -1].max()))
-    halo = max(sharding.knn_support_radius(dk * 1.05, 3, device=dev), SHOT_RADIUS + sharding.knn_support_radius(dk * 1.05, 1, device=dev))
-    owned = np.concatenate([pts[mine], mine[:, None].astype(np.float32)], 1).astype(np.float32)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    local_rows, n_owned = sharding.exchange_halo(owned, axis, cuts, rank, world, halo, device=dev)
-    e1.record(); torch.cuda.synchronize()
-    halo_ms = e0.elapsed_time(e1)
-    n_local = len(local_rows)
-    p4 = np.zeros((n_local, 4), np.float32); p4[:, :3] = local_rows[:, :3]
-    d_pts = torch.from_numpy(p4).to(dev)
-    d_f = torch.empty((n_local, 33), dtype=torch.float32, device=dev)
-    d_s = torch.empty((n_local, 361), dtype=torch.float32, device=dev)
-    for _ in range(args.warmup):
-        dense_step(ctx, d_pts, n_local, d_f, d_s)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        dense_step(ctx, d_pts, n_local, d_f, d_s)
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = sharding.max_over_ranks(e0.elapsed_time(e1) / args.steps, device=dev)
-    out = {"metric": "FPFH+SHOT descriptors/sec, one 1M-pt cloud slab-sharded", "n_gpus": world, "points": n_total,
-           "value": 2.0 * n_total / (ms * 1e-3), "unit": "descriptors/s", "ms_per_step": ms, "halo_m": halo,
-           "halo_points_share": (n_local - n_owned) / max(n_owned, 1), "halo_exchange_ms": halo_ms, "scaling": "strong"}
-    if args.verify:
-        rows = torch.cat([d_f[:n_owned], d_s[:n_owned]], 1).cpu().numpy()
-        full = sharding.gather_rows(rows, n_total, mine, rank, world, device=dev)
-        if rank == 0:
-            p4 = np.zeros((n_total, 4), np.float32); p4[:, :3] = pts
-            dp = torch.from_numpy(p4).to(dev)
-            f1 = torch.empty((n_total, 33), dtype=torch.float32, device=dev)
-            s1 = torch.empty((n_total, 361), dtype=torch.float32, device=dev)
-            dense_step(ctx, dp, n_total, f1, s1)
-            torch.cuda.synchronize()
-            ref = torch.cat([f1, s1], 1).cpu().numpy()
-            same = (full.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(full) & np.isnan(ref))
-            diff = np.nan_to_num(np.abs(full - ref), nan=0.0)
-            out["verify"] = {"rows_bit_identical": float(same.all(1).mean()), "fpfh_max_abs_diff": float(diff[:, :33].max()),
-                             "shot_max_abs_diff": float(diff[:, 33:385].max())}
+    join_group(ctx, dist, rank, world)
+    out = slab_record(pfx, ctx, torch, dist, dev, rank, world, side=args.side, steps=args.steps, warmup=args.warmup, verify=args.verify)
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    ctx.group_leave()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
