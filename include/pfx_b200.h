@@ -88,6 +88,9 @@ int pfx_set_surface_normals(pfx_ctx* ctx, const void* normals, size_t n, size_t 
                             int curv_off, int mem);
 int pfx_set_viewpoint(pfx_ctx* ctx, float vx, float vy, float vz);
 size_t pfx_num_surface(const pfx_ctx* ctx);
+/* the points of the current surface in its own order, rows of `stride` bytes with xyz first (after
+ * pfx_slab_distribute: this rank's owned points, then the halo points) */
+int pfx_get_surface(pfx_ctx* ctx, void* out, size_t stride, int mem);
 size_t pfx_num_queries(const pfx_ctx* ctx);
 
 /* ------------------------------------------------------------------ neighbour search
@@ -248,6 +251,18 @@ int pfx_shot1344(pfx_ctx* ctx, double radius, const float* lrf_in, float* out, s
  * 7956 B.  lrf_in (optional): frames of the queries; otherwise SHOT frames at local_radius.  Needs no normals. */
 int pfx_usc1980(pfx_ctx* ctx, double search_radius, double min_radius, double density_radius, double local_radius,
                 const float* lrf_in, float* out, size_t stride, int mem);
+
+/* ------------------------------------------------------------------ 3D Shape Context (next row)
+ * pfx_sc3d1980 <- ShapeContext3DEstimation<PointXYZRGB, Normal, ShapeContext1980>::compute (evaluation.cpp:319-345,
+ * the first entry of the reference's descriptor list, which sets setMinimalRadius(r / 10) and
+ * setPointDensityRadius(r / 5)).  Same rows, bins and weights as pfx_usc1980; the frame of a query is the NORMAL
+ * of its nearest surface point plus a RANDOM tangent direction.  Upstream seeds a boost::mt19937 from the wall
+ * clock; here the three uniform [0, 1) draws of query i are the top 24 bits of SplitMix64(seed + golden (3 i + t +
+ * 1)), so a run is reproducible and a CPU restatement can follow it.  rf[9] of every row is zero, as upstream
+ * ("3DSC does not define a repeatable local RF"); frames_out (optional, nq x 9 floats) receives the frames that
+ * were used.  Needs surface normals. */
+int pfx_sc3d1980(pfx_ctx* ctx, double search_radius, double min_radius, double density_radius, uint64_t seed, float* out,
+                 size_t stride, float* frames_out, int mem);
 
 /* ------------------------------------------------------------------ spin images (next row)
  * pfx_spin_image153 <- SpinImageEstimation<PointXYZRGB, Normal, Histogram<153>>::compute with its defaults

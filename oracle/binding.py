@@ -384,6 +384,24 @@ def usc1980(surf, q, search_radius, min_radius=None, density_radius=None, local_
     return out, rf, dens[: len(surf)]
 
 
+def sc3d1980(surf, normals4, q, search_radius, min_radius=None, density_radius=None, seed=12345):
+    """3DSC -> (rows [nq, 1980], frames [nq, 9] the descriptors were computed in); defaults = the reference's
+    settings (r / 10, r / 5)"""
+    surf, q = _f32(surf), _f32(q)
+    nr = np.ascontiguousarray(normals4, np.float32)
+    assert nr.shape == (len(surf), 4)
+    out = np.zeros((len(q), 1980), np.float32)
+    rf = np.zeros((len(q), 9), np.float32)
+    L = lib()
+    L.orc_sc3d1980.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
+                               C.c_ulonglong, C.c_void_p, C.c_void_p]
+    _chk(L.orc_sc3d1980(_opt(surf), _opt(nr), len(surf), _opt(q), len(q), C.c_double(search_radius),
+                        C.c_double(min_radius if min_radius is not None else search_radius / 10.0),
+                        C.c_double(density_radius if density_radius is not None else search_radius / 5.0),
+                        C.c_ulonglong(seed), _opt(out), _opt(rf)), "sc3d1980")
+    return out, rf
+
+
 def spin_image153(surf, q, qnormals4, radius):
     surf, q = _f32(surf), _f32(q)
     nr = np.ascontiguousarray(qnormals4, np.float32)

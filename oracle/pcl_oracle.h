@@ -111,6 +111,13 @@ int orc_usc1980(const float* surf, int n, const float* q, int nq, double search_
                 double density_radius, double local_radius, const float* lrf_in, float* out1980, float* rf9,
                 int* density_out);
 
+/* 3DSC (evaluation.cpp:319-345): frames = nearest neighbour's normal + a seeded random tangent direction (SplitMix64
+ * contract, usc.cpp); descriptor = USC's bins in that frame.  frames_out optional. */
+int orc_sc3d_frames(const float* surf, const float* normals4, int n, const float* q, int nq, double search_radius,
+                    unsigned long long seed, float* rf9);
+int orc_sc3d1980(const float* surf, const float* normals4, int n, const float* q, int nq, double search_radius,
+                 double min_radius, double density_radius, unsigned long long seed, float* out1980, float* frames_out);
+
 /* ---- spin images (evaluation.cpp:515-554 -> SpinImageEstimation<PointXYZRGB, Normal, Histogram<153>>, defaults):
  * qnormals4: the normals of the QUERIES (nq x 4); out nq x 153 (9 alpha rows x 17 beta columns). */
 int orc_spin_image153(const float* surf, int n, const float* q, const float* qnormals4, int nq, double radius,

@@ -133,3 +133,80 @@ extern "C" int orc_usc1980(const float* surf, int n, const float* q, int nq, dou
   }
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ 3DSC
+// pcl::ShapeContext3DEstimation<PointXYZRGB, Normal, ShapeContext1980> (reference evaluation.cpp:319-345:
+// setMinimalRadius(r / 10), setPointDensityRadius(r / 5), search radius r through features.h:181-195; upstream
+// features/impl/3dsc.hpp).  Same bins and weights as USC (which upstream derived from it); only the frame differs:
+//   z = the NORMAL of the nearest surface point of the query (first of the (d2, index)-sorted neighbours),
+//   x = a RANDOM vector (three uniform [0, 1) draws) made orthogonal to z by solving for one component
+//       (the z component when |n_z| > FLT_EPSILON, else y, else x), normalised (Eigen 3.2: times 1 / norm),
+//   y = z cross x.
+// Upstream draws from a boost::mt19937 seeded with the wall clock: unpinnable.  Contract here: the three draws of
+// query i are the top 24 bits of SplitMix64(seed + golden * (3 i + t + 1)), t = 0, 1, 2, as floats in [0, 1).
+// The descriptor is computed once per query (PCL 1.7's ShapeContext1980 output); upstream zeroes rf afterwards
+// ("3DSC does not define a repeatable local RF"), and so does this.  No neighbours / NaN normal -> NaN descriptor.
+static inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+extern "C" int orc_sc3d_frames(const float* surf, const float* normals4, int n, const float* q, int nq, double search_radius,
+                               unsigned long long seed, float* rf9) {
+  if (!(search_radius > 0)) return -1;
+  Searcher s;
+  s.init(surf, n, search_radius, 0);
+  const float nanv = std::numeric_limits<float>::quiet_NaN();
+  const float eps = std::numeric_limits<float>::epsilon();
+#pragma omp parallel
+  {
+    std::vector<Nbr> nb;
+#pragma omp for schedule(dynamic, 64)
+    for (int i = 0; i < nq; ++i) {
+      float* rf = rf9 + 9 * (size_t)i;
+      for (int b = 0; b < 9; ++b) rf[b] = nanv;
+      const float* o = q + 3 * (size_t)i;
+      nb.clear();
+      if (finite3(o)) s.query(o, nb);
+      if (nb.empty()) continue;
+      const float* nz = normals4 + 4 * (size_t)nb[0].idx;  // strict "<" over the sorted list keeps its first element
+      if (!finite3(nz)) continue;
+      float x[3];
+      for (int t = 0; t < 3; ++t) {
+        const uint64_t z = splitmix64(seed + 0x9E3779B97F4A7C15ull * (uint64_t)(3 * (uint64_t)i + t + 1));
+        x[t] = (float)(z >> 40) * (1.0f / 16777216.0f);
+      }
+      if (std::fabs(nz[2]) > eps)
+        x[2] = -(nz[0] * x[0] + nz[1] * x[1]) / nz[2];
+      else if (std::fabs(nz[1]) > eps)
+        x[1] = -(nz[0] * x[0] + nz[2] * x[2]) / nz[1];
+      else if (std::fabs(nz[0]) > eps)
+        x[0] = -(nz[1] * x[1] + nz[2] * x[2]) / nz[0];
+      float xn = x[0] * x[0];
+      xn = xn + x[1] * x[1];
+      xn = xn + x[2] * x[2];
+      const float inv = 1.0f / std::sqrt(xn);
+      for (int a = 0; a < 3; ++a) x[a] = x[a] * inv;
+      rf[0] = x[0]; rf[1] = x[1]; rf[2] = x[2];
+      rf[3] = nz[1] * x[2] - nz[2] * x[1];
+      rf[4] = nz[2] * x[0] - nz[0] * x[2];
+      rf[5] = nz[0] * x[1] - nz[1] * x[0];
+      rf[6] = nz[0]; rf[7] = nz[1]; rf[8] = nz[2];
+    }
+  }
+  return 0;
+}
+
+// out: nq x 1980; frames_out (optional, nq x 9): the frames the descriptors were computed in (upstream returns zeros)
+extern "C" int orc_sc3d1980(const float* surf, const float* normals4, int n, const float* q, int nq, double search_radius,
+                            double min_radius, double density_radius, unsigned long long seed, float* out1980,
+                            float* frames_out) {
+  if (!(search_radius > 0) || !(min_radius > 0) || !(density_radius > 0) || search_radius < min_radius) return -1;
+  std::vector<float> rf((size_t)std::max(nq, 1) * 9), rf2((size_t)std::max(nq, 1) * 9);
+  if (orc_sc3d_frames(surf, normals4, n, q, nq, search_radius, seed, rf.data()) != 0) return -1;
+  if (frames_out) std::memcpy(frames_out, rf.data(), (size_t)nq * 9 * sizeof(float));
+  // the shared binning: USC with the frames given (local radius unused)
+  return orc_usc1980(surf, n, q, nq, search_radius, min_radius, density_radius, 1.0, rf.data(), out1980, rf2.data(), nullptr);
+}

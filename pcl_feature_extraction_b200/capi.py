@@ -77,6 +77,7 @@ SIGNATURES = {
     "pfx_set_surface_normals": (_i, [_vp, _vp, _sz, _sz, _i, _i]),
     "pfx_set_viewpoint": (_i, [_vp, _f, _f, _f]),
     "pfx_num_surface": (_sz, [_vp]),
+    "pfx_get_surface": (_i, [_vp, _vp, _sz, _i]),
     "pfx_num_queries": (_sz, [_vp]),
     "pfx_knn": (_i, [_vp, _i, _vp, _vp, _i]),
     "pfx_radius_count": (_i, [_vp, _d, _vp, C.POINTER(C.c_int64), _i]),
@@ -100,6 +101,7 @@ SIGNATURES = {
     "pfx_shot1344": (_i, [_vp, _d, _vp, _vp, _sz, _i]),
     "pfx_spin_image153": (_i, [_vp, _d, _vp, _sz, _sz, _vp, _sz, _i]),
     "pfx_usc1980": (_i, [_vp, _d, _d, _d, _d, _vp, _vp, _sz, _i]),
+    "pfx_sc3d1980": (_i, [_vp, _d, _d, _d, C.c_uint64, _vp, _sz, _vp, _i]),
     "pfx_match": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _f, _vp, _sz, C.POINTER(_sz), _i]),
     "pfx_match_nn": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _vp, _vp, _i]),
     "pfx_range_image_planar": (_i, [_vp, _i, _i, _f, _f, _f, _f, _f, _vp]),
@@ -398,6 +400,17 @@ class Context:
                                        density_radius if density_radius is not None else search_radius / 5.0, local_radius,
                                        _ptr(lrf), _ptr(out), 7956, HOST))
         return out[:, :1980].copy(), out[:, 1980:].copy()
+
+    def sc3d1980(self, search_radius, min_radius=None, density_radius=None, seed=12345):
+        """3DSC -> (rows [nq, 1980], frames [nq, 9] the descriptors were computed in); defaults = the reference's
+        settings (r / 10, r / 5).  Needs surface normals."""
+        nq = self.num_queries
+        out = np.zeros((nq, 1989), np.float32)
+        fr = np.zeros((nq, 9), np.float32)
+        self._chk(self.lib.pfx_sc3d1980(self.h, search_radius, min_radius if min_radius is not None else search_radius / 10.0,
+                                        density_radius if density_radius is not None else search_radius / 5.0, int(seed),
+                                        _ptr(out), 7956, _ptr(fr), HOST))
+        return out[:, :1980].copy(), fr, out[:, 1980:].copy()
 
     def shot352_dev(self, radius, out_ptr, stride=1444):
         self._chk(self.lib.pfx_shot352(self.h, radius, None, _ptr(out_ptr), stride, DEVICE))

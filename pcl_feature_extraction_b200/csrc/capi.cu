@@ -314,6 +314,39 @@ extern "C" int pfx_profile_end(pfx_ctx* ctx, char* buf, size_t buflen) {
   return 0;
 }
 extern "C" size_t pfx_num_surface(const pfx_ctx* ctx) { return ctx ? ctx->n : 0; }
+
+namespace pfx {
+__global__ void surface_out_kernel(const float4* __restrict__ surf, int n, unsigned char* __restrict__ out, size_t stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = surf[i];
+  float* o = reinterpret_cast<float*>(out + (size_t)i * stride);
+  o[0] = p.x;
+  o[1] = p.y;
+  o[2] = p.z;
+  if (stride >= 16) o[3] = 0.f;
+}
+}  // namespace pfx
+
+// the points of the current surface in its own order (after pfx_slab_distribute: owned points first, then the halo)
+extern "C" int pfx_get_surface(pfx_ctx* ctx, void* out, size_t stride, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_get_surface: no surface set");
+  if (!out || stride < 12 || (stride & 3) || (mem != PFX_HOST && mem != PFX_DEVICE))
+    return ctx->fail(PFX_E_INVALID, "pfx_get_surface: bad output / stride / mem");
+  const size_t n = ctx->n;
+  if (n == 0) return 0;
+  unsigned char* dout = static_cast<unsigned char*>(out);
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->out_stage.ensure(n * stride));
+    dout = ctx->out_stage.as<unsigned char>();
+    if (stride > 16) PFX_CUDA(cudaMemsetAsync(dout, 0, n * stride, ctx->stream));
+  }
+  PFX_LAUNCH(ctx, surface_out_kernel, div_up((long long)n, 256), 256, 0, ctx->surf.as<float4>(), (int)n, dout, stride);
+  PFX_CUDA(cudaGetLastError());
+  if (mem == PFX_HOST) return deliver(ctx, out, dout, n * stride, mem);
+  return 0;
+}
 extern "C" size_t pfx_num_queries(const pfx_ctx* ctx) { return ctx ? ctx->num_queries() : 0; }
 
 // ================================================================================== inputs
@@ -934,6 +967,39 @@ extern "C" int pfx_usc1980(pfx_ctx* ctx, double search_radius, double min_radius
   }
   PFX_TRY(usc_compute(ctx, search_radius, min_radius, density_radius, local_radius, dlrf, dout, stride / 4));
   if (mem == PFX_HOST) return deliver(ctx, out, dout, nq * stride, mem);
+  return 0;
+}
+
+// 3DSC: the reference's first active descriptor (evaluation.cpp:67, :319-345)
+extern "C" int pfx_sc3d1980(pfx_ctx* ctx, double search_radius, double min_radius, double density_radius, uint64_t seed,
+                            float* out, size_t stride, float* frames_out, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_sc3d1980: no surface set");
+  if (!(search_radius > 0)) return ctx->fail(PFX_E_PRECOND, "pfx_sc3d1980: needs a radius search (setRadiusSearch)");
+  // ShapeContext3DEstimation::initCompute: "search_radius_ must be GREATER than min_radius_"
+  if (!(min_radius > 0) || !(density_radius > 0) || search_radius < min_radius)
+    return ctx->fail(PFX_E_PRECOND, "pfx_sc3d1980: radii must be positive and search_radius >= min_radius");
+  if (!ctx->have_normals) return ctx->fail(PFX_E_STATE, "pfx_sc3d1980: no input normals (setInputNormals)");
+  if (!out || stride < 7956 || (stride & 3) || (mem != PFX_HOST && mem != PFX_DEVICE))
+    return ctx->fail(PFX_E_INVALID, "pfx_sc3d1980: bad output / stride / mem");
+  const size_t nq = ctx->num_queries();
+  if (nq == 0) return 0;
+  float* dout = out;
+  float* dfr = frames_out;
+  if (mem == PFX_HOST) {
+    PFX_CUDA(ctx->out_stage.ensure(nq * stride));
+    dout = ctx->out_stage.as<float>();
+    if (stride != 7956) PFX_CUDA(cudaMemsetAsync(dout, 0, nq * stride, ctx->stream));
+    if (frames_out) {
+      PFX_CUDA(ctx->stage2.ensure(nq * 9 * sizeof(float)));
+      dfr = ctx->stage2.as<float>();
+    }
+  }
+  PFX_TRY(sc3d_compute(ctx, search_radius, min_radius, density_radius, seed, dout, stride / 4, dfr));
+  if (mem == PFX_HOST) {
+    if (frames_out) PFX_CUDA(cudaMemcpyAsync(frames_out, dfr, nq * 9 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    return deliver(ctx, out, dout, nq * stride, mem);
+  }
   return 0;
 }
 

@@ -199,11 +199,8 @@ __global__ void bbox_kernel(const float4* __restrict__ pts, int n, BuildAcc* acc
 // Set the cell edge and the grid dimensions.  edge_req > 0: radius grid.  edge_req <= 0: kNN grid,
 // stage 0 picks a trial edge from the bbox (2-manifold guess), stage 1 rescales it so that an
 // occupied cell holds about `target_occ` points (occupancy measured by cell_probe_kernel).
-// min_edge (kNN grids, final stage): a radius search announced for this surface (pfx_prepare_radius) wants
-// edge >= min_edge so that the same hash serves it; granted when it costs the k-search at most 1.15x its edge
-// (a third more stencil candidates), refused otherwise - the host learns the edge from the read-back.
 __global__ void params_kernel(const BuildAcc* acc, GridParams* gp, float edge_req, int stage,
-                              float target_occ, float min_edge) {
+                              float target_occ) {
   GridParams P;
   int nv = acc->n_valid;
   P.n_valid = nv;
@@ -225,7 +222,6 @@ __global__ void params_kernel(const BuildAcc* acc, GridParams* gp, float edge_re
     } else {
       float occ = (float)nv / fmaxf((float)acc->n_cells_probe, 1.f);
       edge = gp->edge * sqrtf(target_occ / fmaxf(occ, 1e-3f));
-      if (min_edge > edge && min_edge <= 1.15f * edge) edge = min_edge;
     }
     edge = fmaxf(edge, 1e-7f * fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-30f)));
     if (!(edge > 0.f) || !isfinite(edge)) edge = 1.f;
@@ -497,20 +493,18 @@ static int grid_build(Ctx* ctx, Grid* g, double radius, int knn_k) {
   if (n > 0) PFX_LAUNCH(ctx, bbox_kernel, std::min(wide, div_up(n, T)), T, 0, src, n, acc);
   if (radius > 0) {
     float edge = (float)(radius * (1.0 + 1e-3));
-    PFX_LAUNCH(ctx, params_kernel, 1, 1, 0, acc, gp, edge, 0, 0.f, 0.f);
+    PFX_LAUNCH(ctx, params_kernel, 1, 1, 0, acc, gp, edge, 0, 0.f);
   } else {
     // points per occupied cell: ~k/3 keeps the 3x3x3 stencil of a surface at 100-200 candidates while
     // the k-th neighbour still falls inside it (cell-tile kNN, knn_tile.cu)
     float target = std::max(2.0f, ctx->knn_occupancy * (float)knn_k);
-    PFX_LAUNCH(ctx, params_kernel, 1, 1, 0, acc, gp, 0.f, 0, target, 0.f);
+    PFX_LAUNCH(ctx, params_kernel, 1, 1, 0, acc, gp, 0.f, 0, target);
     if (n > 0) {
       PFX_CUDA(cudaMemsetAsync(g->hkeys.p, 0xff, ((size_t)g->hmask + 1) * sizeof(uint32_t), ctx->stream));
       PFX_LAUNCH(ctx, cell_probe_kernel, std::min(wide, div_up(n, T)), T, 0, src, n, gp,
                  g->hkeys.as<uint32_t>(), g->hmask, acc);
     }
-    const float min_edge = (ctx->radius_hint > 0 && ctx->radius_hint_version == ctx->surf_version)
-                               ? (float)(ctx->radius_hint * (1.0 + 1e-3)) : 0.f;
-    PFX_LAUNCH(ctx, params_kernel, 1, 1, 0, acc, gp, 0.f, 1, target, min_edge);
+    PFX_LAUNCH(ctx, params_kernel, 1, 1, 0, acc, gp, 0.f, 1, target);
   }
   if (n > 0) {
     PFX_LAUNCH(ctx, keys_kernel, div_up(n, T), T, 0, src, n, gp, g->keys.as<uint32_t>(), g->vals.as<int>());
@@ -532,7 +526,7 @@ static int grid_build(Ctx* ctx, Grid* g, double radius, int knn_k) {
     PFX_CUDA(cudaMemsetAsync(g->cell_start.p, 0, sizeof(int), ctx->stream));
   }
   // the parameters the device settled on (cell edge, dimensions) come back asynchronously: a later radius stage may
-  // reuse this hash when its edge covers the radius (grid_for_radius), and waits on `built` only then
+  // reuse this hash once its edge is known to cover the radius (grid_for_radius; never waited for)
   if (!g->host_params) {
     PFX_CUDA(cudaMallocHost(&g->host_params, sizeof(GridParams)));
     PFX_CUDA(cudaEventCreateWithFlags(&g->built, cudaEventDisableTiming));
@@ -564,16 +558,6 @@ int grid_wait_pending(Ctx* ctx) {
 int grid_prepare_async(Ctx* ctx, double radius) {
   for (Grid* g : ctx->grids)
     if (g->surf_version == ctx->surf_version && g->radius == radius) return 0;  // cached or already in flight
-  bool have_grid = false;
-  for (Grid* g : ctx->grids) have_grid |= g->surf_version == ctx->surf_version;
-  if (!have_grid) {
-    // no hash of this surface yet: remember the radius; a k-search grid built next takes it as a lower bound for
-    // its cell edge (params_kernel) and then serves the radius stage too (grid_for_radius).  Otherwise the radius
-    // grid is built when the radius stage asks for it.
-    ctx->radius_hint = radius;
-    ctx->radius_hint_version = ctx->surf_version;
-    return 0;
-  }
   if (!ctx->aux_stream) {
     PFX_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     PFX_CUDA(cudaEventCreateWithFlags(&ctx->ev_surface, cudaEventDisableTiming));
@@ -595,19 +579,21 @@ int grid_prepare_async(Ctx* ctx, double radius) {
 }
 
 // A hash for a radius search: the grid built for exactly this radius when it exists, else any grid of the current
-// surface whose cell edge covers the radius (3x3x3 stencils need edge >= radius (1 + 1e-3)) without being more
-// than 1.6x too coarse - typically the k-search grid of the same cloud (dense FPFH k = 32 then SHOT352 at
-// r ~ the k-th neighbour distance: one hash instead of two) - else a new one.  The edge of a k-search grid is chosen
-// on the device; the host reads it from the pinned read-back after waiting for that build alone (an event recorded
-// right behind it: the stream's later work keeps running).
+// surface whose cell edge is KNOWN to cover the radius (3x3x3 stencils need edge >= radius (1 + 1e-3)) without
+// being more than 1.6x too coarse, else a new one.  The edge of a radius grid is known on the host; the edge of a
+// k-search grid is chosen on the device and read back asynchronously - it counts only when that read-back has
+// already landed (cudaEventQuery: the host never waits here, so a pipeline that runs ahead of the device simply
+// builds the radius grid, on the auxiliary stream when pfx_prepare_radius announced it).
 int grid_for_radius(Ctx* ctx, double radius, Grid** out) {
   for (Grid* g : ctx->grids)
     if (g->surf_version == ctx->surf_version && g->radius == radius) return grid_get(ctx, radius, 0, out);
   const double need = radius * (1.0 + 1e-3);
   for (Grid* g : ctx->grids) {
-    if (g->surf_version != ctx->surf_version || !g->host_params || g->n != (int)ctx->n) continue;
-    PFX_TRY(grid_wait_built(ctx, g));
-    const double edge = (double)static_cast<const GridParams*>(g->host_params)->edge;
+    if (g->surf_version != ctx->surf_version || !g->host_params || g->n != (int)ctx->n || g->pending) continue;
+    double edge = 0;
+    if (g->radius > 0) edge = (double)(float)(g->radius * (1.0 + 1e-3));
+    else if (cudaEventQuery(g->built) == cudaSuccess) edge = (double)static_cast<const GridParams*>(g->host_params)->edge;
+    else (void)cudaGetLastError();  // cudaErrorNotReady is not an error
     if (edge >= need && edge <= 1.6 * need) {
       ctx->tick++;
       g->last_use = ctx->tick;
@@ -617,15 +603,6 @@ int grid_for_radius(Ctx* ctx, double radius, Grid** out) {
     }
   }
   return grid_get(ctx, radius, 0, out);
-}
-
-int grid_wait_built(Ctx* ctx, Grid* g) {
-  if (g->pending) {  // built on the auxiliary stream: the main stream must order itself behind it as well
-    PFX_CUDA(cudaStreamWaitEvent(ctx->stream, g->ready, 0));
-    g->pending = false;
-  }
-  PFX_CUDA(cudaEventSynchronize(g->built));
-  return 0;
 }
 
 int grid_get(Ctx* ctx, double radius, int knn_k, Grid** out) {

@@ -117,8 +117,6 @@ struct Ctx {
   uint64_t qry_version = 0;
 
   std::vector<Grid*> grids;
-  double radius_hint = 0;  // pfx_prepare_radius before any hash of the surface exists (grid_prepare_async)
-  uint64_t radius_hint_version = 0;
 
   // kNN list cache (sorted-position indices + d2), valid for (grid, k, query version)
   DevBuf knn_idx, knn_d2;
@@ -231,7 +229,6 @@ struct Ctx {
 // ---- grid.cu
 int grid_get(Ctx* ctx, double radius, int knn_k, Grid** out);
 int grid_for_radius(Ctx* ctx, double radius, Grid** out);  // exact, or any grid of the surface whose edge covers the radius
-int grid_wait_built(Ctx* ctx, Grid* g);
 int grid_prepare_async(Ctx* ctx, double radius);  // build the radius grid on the auxiliary stream
 int grid_wait_pending(Ctx* ctx);                  // main stream waits for every build in flight
 void grid_free_all(Ctx* ctx);
@@ -319,6 +316,8 @@ int colors_to_lab(Ctx* ctx, const unsigned char* rgb_dev, size_t stride_bytes, i
 int shot_color_compute(Ctx* ctx, Grid* g, double radius, const float* rf9_dev, float* out_dev, size_t stride_floats);
 int usc_compute(Ctx* ctx, double search_radius, double min_radius, double density_radius, double local_radius,
                 const float* lrf_dev, float* out_dev, size_t stride_floats);
+int sc3d_compute(Ctx* ctx, double search_radius, double min_radius, double density_radius, unsigned long long seed,
+                 float* out_dev, size_t stride_floats, float* frames_out_dev);
 int spin_compute(Ctx* ctx, Grid* g, double radius, const float* qnormals_dev, size_t nstride_floats, float* out_dev,
                  size_t stride_floats);
 int icp_align_run(Ctx* ctx, const float* src_dev, int n, size_t stride_floats, const pfx_icp_params* prm,

@@ -122,6 +122,116 @@ static void usc_tables(UscTab& T, double min_radius, double search_radius) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ 3DSC frames
+// ShapeContext3DEstimation::computePoint (reference evaluation.cpp:319-345): z = the normal of the query's nearest
+// surface point, x = a random vector made orthogonal to z, y = z cross x.  One warp per query: the nearest point by
+// (d2, index) over the 3x3x3 stencil, then lane 0 builds the frame in the CPU's float operation order.  The random
+// vector follows the library's seeded contract (upstream's wall-clock-seeded mt19937 cannot be pinned): the three
+// draws of query i are the top 24 bits of SplitMix64(seed + golden * (3 i + t + 1)) as floats in [0, 1).
+__device__ __forceinline__ uint64_t sc_splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(128)
+sc3d_frames_kernel(GridDev g, const float4* __restrict__ queries, int nq, int dense, float r2,
+                   const float4* __restrict__ nrm_sorted, unsigned long long seed, float* __restrict__ rf9) {
+  const int lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (qi >= nq) return;
+  const float4 q = dense ? g.pts[qi] : queries[qi];
+  const int row = dense ? __float_as_int(q.w) : qi;
+  const float nanv = __int_as_float(0x7fc00000);
+  unsigned long long best = ~0ull;  // (d2 bits << 32) | original index
+  int best_j = -1;
+  if (finite3(q.x, q.y, q.z) && (!dense || qi < g.gp->n_valid)) {
+    const CellBlock blk = dense ? stencil_of_point(g, qi, lane) : stencil_of_pos(g, q.x, q.y, q.z, lane);
+    for (int base = 0; base < blk.total; base += 32) {
+      const int t = base + lane;
+      const bool valid = t < blk.total;
+      const int j = block_candidate(blk, valid ? t : 0);
+      if (!valid) continue;
+      const float4 p = g.pts[j];
+      const float d2 = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
+      if (!(d2 < r2)) continue;
+      const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(p.w);
+      if (key < best) {
+        best = key;
+        best_j = j;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ob = __shfl_xor_sync(FULL, best, o);
+    const int oj = __shfl_xor_sync(FULL, best_j, o);
+    if (ob < best) {
+      best = ob;
+      best_j = oj;
+    }
+  }
+  if (lane != 0) return;
+  float* rf = rf9 + (size_t)row * 9;
+  float4 nz = make_float4(nanv, nanv, nanv, 0.f);
+  if (best_j >= 0) nz = nrm_sorted[best_j];
+  if (best_j < 0 || !finite3(nz.x, nz.y, nz.z)) {
+    for (int b = 0; b < 9; ++b) rf[b] = nanv;
+    return;
+  }
+  float x[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const uint64_t z = sc_splitmix64(seed + 0x9E3779B97F4A7C15ull * (uint64_t)(3 * (uint64_t)row + t + 1));
+    x[t] = __fmul_rn((float)(z >> 40), 1.0f / 16777216.0f);
+  }
+  const float eps = 1.1920929e-07f;
+  if (fabsf(nz.z) > eps)
+    x[2] = __fdiv_rn(-__fadd_rn(__fmul_rn(nz.x, x[0]), __fmul_rn(nz.y, x[1])), nz.z);
+  else if (fabsf(nz.y) > eps)
+    x[1] = __fdiv_rn(-__fadd_rn(__fmul_rn(nz.x, x[0]), __fmul_rn(nz.z, x[2])), nz.y);
+  else if (fabsf(nz.x) > eps)
+    x[0] = __fdiv_rn(-__fadd_rn(__fmul_rn(nz.y, x[1]), __fmul_rn(nz.z, x[2])), nz.x);
+  const float xn = __fadd_rn(__fadd_rn(__fmul_rn(x[0], x[0]), __fmul_rn(x[1], x[1])), __fmul_rn(x[2], x[2]));
+  const float inv = __fdiv_rn(1.0f, __fsqrt_rn(xn));
+  x[0] = __fmul_rn(x[0], inv); x[1] = __fmul_rn(x[1], inv); x[2] = __fmul_rn(x[2], inv);
+  rf[0] = x[0]; rf[1] = x[1]; rf[2] = x[2];
+  rf[3] = __fsub_rn(__fmul_rn(nz.y, x[2]), __fmul_rn(nz.z, x[1]));
+  rf[4] = __fsub_rn(__fmul_rn(nz.z, x[0]), __fmul_rn(nz.x, x[2]));
+  rf[5] = __fsub_rn(__fmul_rn(nz.x, x[1]), __fmul_rn(nz.y, x[0]));
+  rf[6] = nz.x; rf[7] = nz.y; rf[8] = nz.z;
+}
+
+__global__ void sc3d_zero_rf_kernel(float* __restrict__ out, size_t stride, int nq) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nq * 9) out[(size_t)(t / 9) * stride + USC_LEN + (t % 9)] = 0.f;
+}
+
+int usc_compute(Ctx* ctx, double search_radius, double min_radius, double density_radius, double local_radius,
+                const float* lrf_dev, float* out_dev, size_t stride_floats);
+
+// 3DSC rows (1980 + 9 floats, the frame zeroed as upstream does); frames_out_dev (optional, nq x 9): the frames used
+int sc3d_compute(Ctx* ctx, double search_radius, double min_radius, double density_radius, unsigned long long seed,
+                 float* out_dev, size_t stride_floats, float* frames_out_dev) {
+  const int nq = (int)ctx->num_queries();
+  if (nq == 0) return 0;
+  Grid* g = nullptr;
+  PFX_TRY(grid_get(ctx, search_radius, 0, &g));
+  const float4* nrm = nullptr;
+  PFX_TRY(normals_sorted_for_grid(ctx, g, &nrm));
+  PFX_CUDA(ctx->tmp4.ensure((size_t)nq * 9 * sizeof(float)));
+  float* frames = ctx->tmp4.as<float>();
+  PFX_LAUNCH(ctx, sc3d_frames_kernel, div_up(nq, 4), 128, 0, g->view(), ctx->q_is_surface ? nullptr : ctx->qry.as<float4>(), nq,
+             ctx->q_is_surface ? 1 : 0, (float)(search_radius * search_radius), nrm, seed, frames);
+  if (frames_out_dev)
+    PFX_CUDA(cudaMemcpyAsync(frames_out_dev, frames, (size_t)nq * 9 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  PFX_TRY(usc_compute(ctx, search_radius, min_radius, density_radius, 1.0, frames, out_dev, stride_floats));
+  PFX_LAUNCH(ctx, sc3d_zero_rf_kernel, div_up(nq * 9, 256), 256, 0, out_dev, stride_floats, nq);
+  PFX_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // out_dev: rows of 1980 + 9 floats at stride_floats, caller query order.  lrf_dev: frames given by the caller (nq x 9)
 // or null (SHOT frames at local_radius).
 int usc_compute(Ctx* ctx, double search_radius, double min_radius, double density_radius, double local_radius,

@@ -47,50 +47,78 @@ def slab_record(pfx, ctx, torch, dist, dev, rank, world, side=1024, steps=5, war
     d_ids = torch.from_numpy(ids).to(dev)
     ctx.set_viewpoint(0.0, 0.0, 0.0)
 
-    # support of the k-search chain (normals -> SPFH -> FPFH: 3 x the largest k-th neighbour distance over all
-    # ranks) and of SHOT (radius + one k-th distance for its normals): measured once on the owned points (halo 0)
-    ctx.slab_distribute((d_part.data_ptr(), len(ids)), 0.0, global_ids=d_ids.data_ptr(), mem=pfx.capi.DEVICE)
+    # support of the k-search chain (normals -> SPFH -> FPFH: three k-th neighbour distances) and of SHOT (radius + one
+    # k-th distance for its normals).  Measured once on the owned points (halo 0): the largest k-th neighbour distance
+    # over all ranks bounds everything; only points within three of those of a cut can start a chain that crosses it,
+    # so the halo is three times the largest k-th distance AMONG THEM (the global maximum sits at the corners of the
+    # sheet, where a neighbourhood is a quarter disc)
+    n_owned0, _ = ctx.slab_distribute((d_part.data_ptr(), len(ids)), 0.0, global_ids=d_ids.data_ptr(), mem=pfx.capi.DEVICE)
+    info = ctx.slab_info()
     _, d2 = ctx.knn(K_NN)
-    dk = float(np.sqrt(d2[:, -1].max())) if len(d2) else 0.0
-    dk = ctx.group_allreduce([dk], "max")[0] * 1.05
+    dkk = np.sqrt(d2[:n_owned0, -1].astype(np.float64)) if n_owned0 else np.zeros(0)
+    dk_all = ctx.group_allreduce([float(dkk.max()) if len(dkk) else 0.0], "max")[0]
+    coord = pts[ctx.slab_global_ids()[:n_owned0], info["axis"]].astype(np.float64)
+    near = np.zeros(len(coord), bool)
+    if np.isfinite(info["lo"]):
+        near |= coord < info["lo"] + 3.0 * dk_all
+    if np.isfinite(info["hi"]):
+        near |= coord >= info["hi"] - 3.0 * dk_all
+    dk = ctx.group_allreduce([float(dkk[near].max()) if near.any() else 0.0], "max")[0] * 1.05
     halo = max(3.0 * dk, SHOT_RADIUS + dk)
 
-    def step():
+    def distribute():
         return ctx.slab_distribute((d_part.data_ptr(), len(ids)), halo, global_ids=d_ids.data_ptr(), mem=pfx.capi.DEVICE)
 
-    n_owned, n_local = step()
+    n_owned, n_local = distribute()
     d_f = torch.empty((n_local, 33), dtype=torch.float32, device=dev)
     d_s = torch.empty((n_local, 361), dtype=torch.float32, device=dev)
+    # ---- (1) the distribution alone (ingest: the analogue of the H2D upload of a single-GPU cloud)
     for _ in range(warmup):
-        step()
-        dense_step(ctx, d_f, d_s)
+        distribute()
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    t_dist = 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        e1.record()
-        step()
-        e2.record()
+        distribute()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_dist = ctx.group_allreduce([e0.elapsed_time(e1) / steps], "max")[0]
+    # ---- (2) the dense stages on the resident slab (owned + halo points): what `value` times on one GPU.  The surface
+    # is re-declared every step (device pointer of the slab rows) so that every step rebuilds its indices
+    surf_rows = torch.empty((n_local, 4), dtype=torch.float32, device=dev)
+    ctx._chk(ctx.lib.pfx_get_surface(ctx.h, pfx.capi._ptr(surf_rows), 16, pfx.capi.DEVICE))
+    gids_local = ctx.slab_global_ids()
+
+    def dense():
+        ctx.set_surface_dev(surf_rows.data_ptr(), n_local, 16)
         dense_step(ctx, d_f, d_s)
-        torch.cuda.synchronize()
-        t_dist += e1.elapsed_time(e2)
-    e3 = torch.cuda.Event(enable_timing=True)
-    e3.record()
+
+    for _ in range(warmup):
+        dense()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ms = ctx.group_allreduce([e0.elapsed_time(e3) / steps], "max")[0]
-    ms_dist = ctx.group_allreduce([t_dist / steps], "max")[0]
+    e0.record()
+    for _ in range(steps):
+        dense()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ctx.group_allreduce([e0.elapsed_time(e1) / steps], "max")[0]
     halo_share = ctx.group_allreduce([(n_local - n_owned) / max(n_owned, 1)], "max")[0]
     out = {"workload": f"one {side}x{side}-point cloud slab-sharded over {world} GPUs: pfx_slab_distribute (NCCL send/recv of "
-                       "slab + halo points, device to device) + dense normals k=32 + FPFH33 k=32 + SHOT352 r=12.8 mm on owned + halo points",
+                       "slab + halo points, device to device), then dense normals k=32 + FPFH33 k=32 + SHOT352 r=12.8 mm on the "
+                       "resident owned + halo points of every rank",
            "n_gpus": world, "points": n_total, "value": 2.0 * n_total / (ms * 1e-3), "unit": "descriptors/s", "ms_per_cloud": ms,
-           "distribute_ms": ms_dist, "halo_m": halo, "halo_points_share_max": halo_share, "scaling": "strong"}
+           "distribute_ms": ms_dist, "ms_per_cloud_with_distribution": ms + ms_dist, "halo_m": halo,
+           "halo_points_share_max": halo_share, "scaling": "strong",
+           "timed": "CUDA events, max over ranks; ms_per_cloud = dense stages on the resident slab, distribute_ms = the "
+                    "device-to-device all-to-all that builds it (several small host round trips: counts, cuts)"}
     if verify:
-        gid = torch.from_numpy(ctx.slab_global_ids()[:n_owned].astype(np.int64)).to(dev)
+        gid = torch.from_numpy(gids_local[:n_owned].astype(np.int64)).to(dev)
         rows = torch.cat([d_f[:n_owned], d_s[:n_owned]], 1)
         if world > 1:
             sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
