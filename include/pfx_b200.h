@@ -132,6 +132,16 @@ int pfx_harris3d(pfx_ctx* ctx, double radius, float threshold, int nonmax, int r
                  int32_t* snapped_idx, size_t cap, size_t* n_kp, int mem);
 int pfx_harris_nms(pfx_ctx* ctx, const float* response, double radius, float threshold,
                    int32_t* kp_idx, size_t cap, size_t* n_kp, int mem);
+/* pfx_harris6d <- HarrisKeypoint6D<PointXYZRGB, PointXYZI>::compute (keypoints.h:166-179; in the reference's active
+ * detector list, evaluation.cpp:63-65): same arguments and outputs as pfx_harris3d.  response = the 4th smallest
+ * eigenvalue of the 6x6 covariance of (normal, normalised intensity gradient) over the neighbourhood; the normals are
+ * estimated internally at `radius`, the intensity comes from the colours given with pfx_set_surface_colors
+ * (0.00390625 (0.114 b + 0.5870 g + 0.2989 r)), the gradient is IntensityGradientEstimation's at `radius`.  All of
+ * it runs in reference order (strict.cu); where upstream leans on Eigen internals that cannot be pinned (its float
+ * column-pivoting QR, its 6x6 tridiagonal eigen solver) the library follows the written-out rules of DESIGN.md
+ * section 3, which the CPU restatement follows too.  PFX_E_STATE without colours. */
+int pfx_harris6d(pfx_ctx* ctx, double radius, float threshold, int nonmax, int refine, float snap_max_d2, float* response,
+                 int32_t* kp_idx, float* kp_xyz, int32_t* snapped_idx, size_t cap, size_t* n_kp, int mem);
 
 /* ------------------------------------------------------------------ descriptors
  * pfx_fpfh <- FPFHEstimation::compute (evaluation.cpp:597-602 via features.h:190-195): SPFH over the

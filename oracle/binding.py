@@ -138,6 +138,20 @@ def harris_response(pts, normals4, radius):
     return r
 
 
+def harris6d_response(pts, rgb, normals4, radius):
+    """-> (response [n], gradients [n, 3] after the length rule, intensity [n]); rgb: uint32 0x00RRGGBB per point"""
+    pts = _f32(pts)
+    rgb = np.ascontiguousarray(rgb, np.uint32)
+    nr = np.ascontiguousarray(normals4, np.float32)
+    assert len(rgb) == len(pts) and nr.shape == (len(pts), 4)
+    resp = np.zeros(len(pts), np.float32)
+    grad = np.zeros((len(pts), 3), np.float32)
+    inten = np.zeros(len(pts), np.float32)
+    _chk(lib().orc_harris6d_response(_opt(pts), _opt(rgb), _opt(nr), len(pts), C.c_double(radius), _opt(resp), _opt(grad),
+                                     _opt(inten)), "harris6d_response")
+    return resp, grad, inten
+
+
 def harris_nms(pts, response, radius, threshold):
     pts, response = _f32(pts), _f32(response)
     kp = np.zeros(len(pts), np.int32)

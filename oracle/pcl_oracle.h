@@ -111,6 +111,12 @@ int orc_usc1980(const float* surf, int n, const float* q, int nq, double search_
                 double density_radius, double local_radius, const float* lrf_in, float* out1980, float* rf9,
                 int* density_out);
 
+/* ---- Harris 6D (keypoints.h:166-179 -> HarrisKeypoint6D): response = 4th smallest eigenvalue of the 6x6 covariance
+ * of (normal, normalised intensity gradient); rgb packed 0x00RRGGBB; gradients_out (n x 3) / intensity_out (n)
+ * optional.  NMS / refinement / snap are Harris3D's (orc_harris_nms, orc_harris_refine, orc_snap_to_cloud). */
+int orc_harris6d_response(const float* pts, const uint32_t* rgb, const float* normals4, int n, double radius,
+                          float* response, float* gradients_out, float* intensity_out);
+
 /* 3DSC (evaluation.cpp:319-345): frames = nearest neighbour's normal + a seeded random tangent direction (SplitMix64
  * contract, usc.cpp); descriptor = USC's bins in that frame.  frames_out optional. */
 int orc_sc3d_frames(const float* surf, const float* normals4, int n, const float* q, int nq, double search_radius,

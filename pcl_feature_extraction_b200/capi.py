@@ -87,6 +87,7 @@ SIGNATURES = {
     "pfx_iss": (_i, [_vp, _d, _d, _i, _d, _d, _vp, _sz, C.POINTER(_sz), _vp, _i]),
     "pfx_iss_nms": (_i, [_vp, _vp, _d, _i, _vp, _sz, C.POINTER(_sz), _i]),
     "pfx_harris3d": (_i, [_vp, _d, _f, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, C.POINTER(_sz), _i]),
+    "pfx_harris6d": (_i, [_vp, _d, _f, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, C.POINTER(_sz), _i]),
     "pfx_harris_nms": (_i, [_vp, _vp, _d, _f, _vp, _sz, C.POINTER(_sz), _i]),
     "pfx_fpfh": (_i, [_vp, _d, _i, _vp, _sz, _i]),
     "pfx_spfh": (_i, [_vp, _d, _i, _vp, _i]),
@@ -317,6 +318,19 @@ class Context:
         snap = np.zeros(n, np.int32)
         nk = C.c_size_t(0)
         self._chk(self.lib.pfx_harris3d(self.h, radius, threshold, int(nonmax), int(refine), snap_max_d2, _ptr(resp),
+                                        _ptr(kp), _ptr(xyz), _ptr(snap), n, C.byref(nk), HOST))
+        m = nk.value
+        return dict(response=resp, kp_idx=kp[:m].copy(), kp_xyz=xyz[:m].copy(), snapped_idx=snap[:m].copy())
+
+    def harris6d(self, radius=0.01, threshold=1e-6, nonmax=True, refine=True, snap_max_d2=1e-4):
+        """HarrisKeypoint6D; the surface colours must have been set (set_surface_colors)"""
+        n = self.num_surface
+        resp = np.zeros(n, np.float32)
+        kp = np.zeros(n, np.int32)
+        xyz = np.zeros((n, 3), np.float32)
+        snap = np.zeros(n, np.int32)
+        nk = C.c_size_t(0)
+        self._chk(self.lib.pfx_harris6d(self.h, radius, threshold, int(nonmax), int(refine), snap_max_d2, _ptr(resp),
                                         _ptr(kp), _ptr(xyz), _ptr(snap), n, C.byref(nk), HOST))
         m = nk.value
         return dict(response=resp, kp_idx=kp[:m].copy(), kp_xyz=xyz[:m].copy(), snapped_idx=snap[:m].copy())

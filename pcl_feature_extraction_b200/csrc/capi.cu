@@ -691,6 +691,66 @@ static int harris3d_impl(pfx_ctx* ctx, double radius, float threshold, int nonma
   return 0;
 }
 
+static int harris6d_impl(pfx_ctx* ctx, double radius, float threshold, int nonmax, int refine, float snap_max_d2,
+                         float* response, int32_t* kp_idx, float* kp_xyz, int32_t* snapped_idx, size_t cap,
+                         size_t* n_kp, int mem) {
+  PFX_TRY(check_ctx(ctx));
+  if (ctx->surf_version == 0) return ctx->fail(PFX_E_PRECOND, "pfx_harris6d: no surface set");
+  if (!(radius > 0)) return ctx->fail(PFX_E_PRECOND, "pfx_harris6d: radius must be > 0");
+  const size_t n = ctx->n;
+  if (n_kp) *n_kp = 0;
+  if (n == 0) return 0;
+  Grid* g = nullptr;
+  PFX_TRY(grid_get(ctx, radius, 0, &g));
+  // HarrisKeypoint3D::initCompute: no normals given -> NormalEstimation on the surface at the same radius
+  if (!ctx->have_normals) {
+    bool saved = ctx->q_is_surface;
+    ctx->q_is_surface = true;
+    int rc = strict_normals(ctx, g, radius, 0, nullptr);
+    ctx->q_is_surface = saved;
+    if (rc) return rc;
+  }
+  PFX_CUDA(ctx->tmp1.ensure(n * sizeof(float)));
+  float* dresp = ctx->tmp1.as<float>();
+  PFX_TRY(harris6d_response(ctx, g, radius, dresp, nullptr));
+  if (response) {
+    if (mem == PFX_DEVICE) PFX_TRY(deliver(ctx, response, dresp, n * sizeof(float), mem));
+    else PFX_CUDA(cudaMemcpyAsync(response, dresp, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (!nonmax) {  // PCL: output = the response cloud itself (every point)
+    if (n_kp) *n_kp = n;
+    PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+  PFX_CUDA(ctx->tmp2.ensure(n * sizeof(int)));
+  PFX_CUDA(cudaMemsetAsync(ctx->tmp2.p, 0, n * sizeof(int), ctx->stream));
+  PFX_TRY(harris_nms(ctx, g, dresp, radius, threshold, ctx->tmp2.as<int>()));
+  int* didx = nullptr;
+  size_t cnt = 0;
+  PFX_TRY(emit_keypoints(ctx, ctx->tmp2.as<int>(), kp_idx, cap, &cnt, mem, &didx));
+  if (n_kp) *n_kp = cnt;
+  if (cnt == 0 || (!kp_xyz && !snapped_idx)) return 0;
+  if (cnt > cap) return ctx->fail(PFX_E_CAPACITY, "keypoint buffer too small");
+  // corner positions (refined) and the snap back onto the cloud
+  PFX_CUDA(ctx->stage2.ensure(cnt * 3 * sizeof(float) + cnt * sizeof(int)));
+  float* dxyz = ctx->stage2.as<float>();
+  int* dsnap = reinterpret_cast<int*>(dxyz + cnt * 3);
+  PFX_LAUNCH(ctx, gather_xyz_kernel, div_up((long long)cnt, 256), 256, 0, ctx->surf.as<float4>(), didx, (int)cnt, dxyz);
+  if (refine) {
+    PFX_TRY(harris_refine_strict(ctx, g, radius, dxyz, (int)cnt));
+  }
+  if (kp_xyz) {
+    if (mem == PFX_DEVICE) PFX_TRY(deliver(ctx, kp_xyz, dxyz, cnt * 3 * sizeof(float), mem));
+    else PFX_CUDA(cudaMemcpyAsync(kp_xyz, dxyz, cnt * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (snapped_idx) {
+    PFX_TRY(snap_to_cloud(ctx, dxyz, (int)cnt, snap_max_d2, dsnap));
+    PFX_TRY(deliver(ctx, snapped_idx, dsnap, cnt * sizeof(int), mem));
+  }
+  PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 extern "C" int pfx_harris3d(pfx_ctx* ctx, double radius, float threshold, int nonmax, int refine, float snap_max_d2,
                             float* response, int32_t* kp_idx, float* kp_xyz, int32_t* snapped_idx, size_t cap,
                             size_t* n_kp, int mem) {
@@ -703,6 +763,36 @@ extern "C" int pfx_harris3d(pfx_ctx* ctx, double radius, float threshold, int no
     ctx->have_normals = false;
     ctx->normals_sorted_for = nullptr;
   }
+  return rc;
+}
+
+// HarrisKeypoint6D (keypoints.h:166-179): the surface's colours must have been set (pfx_set_surface_colors)
+extern "C" int pfx_harris6d(pfx_ctx* ctx, double radius, float threshold, int nonmax, int refine, float snap_max_d2,
+                            float* response, int32_t* kp_idx, float* kp_xyz, int32_t* snapped_idx, size_t cap,
+                            size_t* n_kp, int mem) {
+  if (!ctx) return PFX_E_INVALID;
+  if (ctx->surf_version != 0 && ctx->surf_rgb_version != ctx->surf_version)
+    return ctx->fail(PFX_E_STATE, "pfx_harris6d: the surface has no colours (pfx_set_surface_colors)");
+  // the detector always estimates its own normals at its radius and keeps them private to the call; they are computed
+  // in reference order (strict.cu) whatever the parity mode: the response is an eigenvalue of their covariance
+  const bool had = ctx->have_normals;
+  DevBuf keep;
+  if (had) {  // park the caller's normals
+    keep = ctx->normals;
+    ctx->normals = DevBuf();
+  }
+  ctx->have_normals = false;
+  int rc = harris6d_impl(ctx, radius, threshold, nonmax, refine, snap_max_d2, response, kp_idx, kp_xyz, snapped_idx,
+                         cap, n_kp, mem);
+  if (had) {
+    ctx->normals.release();
+    ctx->normals = keep;
+    ctx->have_normals = true;
+    ctx->normals_version++;
+  } else {
+    ctx->have_normals = false;
+  }
+  ctx->normals_sorted_for = nullptr;
   return rc;
 }
 
@@ -854,6 +944,13 @@ extern "C" int pfx_shot352(pfx_ctx* ctx, double radius, const float* lrf_in, flo
   return 0;
 }
 
+namespace pfx {
+__global__ void rgb_words_kernel(const unsigned char* __restrict__ src, size_t stride, int n, unsigned* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = *reinterpret_cast<const unsigned*>(src + (size_t)i * stride) & 0x00ffffffu;
+}
+}  // namespace pfx
+
 // SHOT1344: colours of the surface / the queries, then the descriptor
 extern "C" int pfx_set_surface_colors(pfx_ctx* ctx, const void* rgb, size_t n, size_t stride, int mem) {
   PFX_TRY(check_ctx(ctx));
@@ -865,6 +962,11 @@ extern "C" int pfx_set_surface_colors(pfx_ctx* ctx, const void* rgb, size_t n, s
   PFX_TRY(upload_records(ctx, rgb, n, stride, mem, ctx->stage, &src));
   PFX_TRY(colors_to_lab(ctx, src, stride, (int)n, ctx->surf_lab));
   ctx->surf_lab_version = ctx->surf_version;
+  // the packed words themselves (Harris 6D derives its intensity from them)
+  PFX_CUDA(ctx->surf_rgb.ensure(std::max<size_t>(n, 1) * sizeof(unsigned)));
+  if (n) PFX_LAUNCH(ctx, rgb_words_kernel, div_up((long long)n, 256), 256, 0, src, stride, (int)n, ctx->surf_rgb.as<unsigned>());
+  PFX_CUDA(cudaGetLastError());
+  ctx->surf_rgb_version = ctx->surf_version;
   return 0;
 }
 

@@ -167,6 +167,8 @@ struct Ctx {
   // for the stages whose floats feed index outputs (strict.cu)
   int parity_mode = 0;
   DevBuf st_cnt, st_off, st_idx, st_d2;  // sorted neighbour lists of strict.cu
+  DevBuf surf_rgb, h6_inten, h6_grad;    // Harris 6D: packed 0x00RRGGBB of the surface points, intensity, gradients
+  uint64_t surf_rgb_version = 0;
   int st_k = 0;
   long long st_total = 0;
 
@@ -303,6 +305,7 @@ int strict_lists_build(Ctx* ctx, Grid* g, double radius, int k);
 int strict_normals(Ctx* ctx, Grid* g, double radius, int k, float4* out_query_order);
 int harris_response_strict(Ctx* ctx, Grid* g, double radius, float* resp_dev_orig);
 int harris_refine_strict(Ctx* ctx, Grid* g, double radius, float* corners_dev, int nc);
+int harris6d_response(Ctx* ctx, Grid* g, double radius, float* resp_dev_orig, float* grad_out_dev);
 int fpfh_sorted(Ctx* ctx, Grid* g, double radius, const float* spfh_sorted_rows, float* out_dev, size_t stride_floats);
 
 // ---- group.cu

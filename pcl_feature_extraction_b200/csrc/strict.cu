@@ -470,4 +470,357 @@ int fpfh_sorted(Ctx* ctx, Grid* g, double radius, const float* spfh_sorted_rows,
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------- Harris 6D
+// HarrisKeypoint6D (reference keypoints.h:166-179): intensity from the colours, IntensityGradientEstimation, the
+// 6x6 covariance of (normal, normalised gradient), response = its 4th smallest eigenvalue.  Everything here walks the
+// sorted lists like the kernels above; the definitions that replace unpinnable Eigen internals (the 3x3
+// column-pivoting Householder QR written out, the 6x6 cyclic Jacobi in double) are stated in DESIGN.md section 3 and
+// followed operation for operation on both sides.
+__global__ void harris6d_intensity_kernel(const unsigned* __restrict__ rgb, int n, float* __restrict__ inten) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned c = rgb[i];
+  const float r = (float)((c >> 16) & 255u), g = (float)((c >> 8) & 255u), b = (float)(c & 255u);
+  // grayscale = 0.00390625 * (0.114 b + 0.5870 g + 0.2989 r): a double expression rounded once
+  inten[i] = (float)(0.00390625 * (0.114 * (double)b + 0.5870 * (double)g + 0.2989 * (double)r));
+}
+
+// x = A^-1 b by Eigen 3.2's ColPivHouseholderQR<Matrix3f> written out (see oracle header for the rules)
+__device__ __forceinline__ void colpiv_qr_solve3(const float (&Ain)[3][3], const float (&bin)[3], float (&x)[3]) {
+  float qr[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) qr[r][c] = Ain[r][c];
+  float hco[3] = {0.f, 0.f, 0.f};
+  int transp[3] = {0, 1, 2};
+  float colsq[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) colsq[k] = qr[0][k] * qr[0][k] + (qr[1][k] * qr[1][k] + qr[2][k] * qr[2][k]);
+  const float eps = 1.1920929e-07f;
+  const float thr_helper = fmaxf(colsq[0], fmaxf(colsq[1], colsq[2])) * (eps * eps) / 3.0f;
+  int nonzero = 3;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (nonzero != 3) continue;  // (the factorisation ended at an earlier k)
+    int big = k;
+#pragma unroll
+    for (int c = k + 1; c < 3; ++c)
+      if (colsq[c] > colsq[big]) big = c;
+    // column `big` (runtime index): select without dynamic register indexing
+    float colv[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) colv[r] = (big == 0) ? qr[r][0] : ((big == 1) ? qr[r][1] : qr[r][2]);
+    float bsq = 0.f;
+#pragma unroll
+    for (int r = k; r < 3; ++r) bsq = (r == k) ? colv[r] * colv[r] : bsq + colv[r] * colv[r];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (c == big) colsq[c] = bsq;
+    if (bsq < thr_helper * (float)(3 - k)) {
+      nonzero = k;
+      continue;
+    }
+    transp[k] = big;
+    if (k != big) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (c == big) {
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const float t = qr[r][k];
+            qr[r][k] = qr[r][c];
+            qr[r][c] = t;
+          }
+          const float t = colsq[k];
+          colsq[k] = colsq[c];
+          colsq[c] = t;
+        }
+    }
+    float tailsq = 0.f;
+#pragma unroll
+    for (int r = k + 1; r < 3; ++r) tailsq = (r == k + 1) ? qr[r][k] * qr[r][k] : tailsq + qr[r][k] * qr[r][k];
+    const float c0 = qr[k][k];
+    float tau, beta;
+    if (k == 2 || tailsq == 0.f) {
+      tau = 0.f;
+      beta = c0;
+#pragma unroll
+      for (int r = k + 1; r < 3; ++r) qr[r][k] = 0.f;
+    } else {
+      beta = sqrtf(c0 * c0 + tailsq);
+      if (c0 >= 0.f) beta = -beta;
+      const float den = c0 - beta;
+#pragma unroll
+      for (int r = k + 1; r < 3; ++r) qr[r][k] = qr[r][k] / den;
+      tau = (beta - c0) / beta;
+    }
+    hco[k] = tau;
+    qr[k][k] = beta;
+    if (k < 2) {
+#pragma unroll
+      for (int c = k + 1; c < 3; ++c) {
+        float tmp = 0.f;
+#pragma unroll
+        for (int r = k + 1; r < 3; ++r) tmp = (r == k + 1) ? qr[r][k] * qr[r][c] : tmp + qr[r][k] * qr[r][c];
+        tmp = tmp + qr[k][c];
+        qr[k][c] = qr[k][c] - tau * tmp;
+#pragma unroll
+        for (int r = k + 1; r < 3; ++r) qr[r][c] = qr[r][c] - (tau * qr[r][k]) * tmp;
+      }
+    }
+#pragma unroll
+    for (int c = k + 1; c < 3; ++c) colsq[c] = colsq[c] - qr[k][c] * qr[k][c];
+  }
+  int perm[3] = {0, 1, 2};
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (k < nonzero) {
+      // swap perm[k] and perm[transp[k]]
+      const int tk = transp[k];
+      const int a = perm[k];
+      const int b = (tk == 0) ? perm[0] : ((tk == 1) ? perm[1] : perm[2]);
+      perm[k] = b;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (c == tk && c != k) perm[c] = a;
+    }
+  x[0] = x[1] = x[2] = 0.f;
+  if (nonzero == 0) return;
+  float c[3] = {bin[0], bin[1], bin[2]};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (k >= nonzero) continue;
+    if (k == 2) {
+      c[2] = c[2] * (1.0f - hco[2]);
+      continue;
+    }
+    float tmp = 0.f;
+#pragma unroll
+    for (int r = k + 1; r < 3; ++r) tmp = (r == k + 1) ? qr[r][k] * c[r] : tmp + qr[r][k] * c[r];
+    tmp = tmp + c[k];
+    c[k] = c[k] - hco[k] * tmp;
+#pragma unroll
+    for (int r = k + 1; r < 3; ++r) c[r] = c[r] - (hco[k] * qr[r][k]) * tmp;
+  }
+#pragma unroll
+  for (int i = 2; i >= 0; --i) {
+    if (i >= nonzero) continue;
+    float sacc = c[i];
+#pragma unroll
+    for (int j = i + 1; j < 3; ++j)
+      if (j < nonzero) sacc = sacc - qr[i][j] * c[j];
+    c[i] = sacc / qr[i][i];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (i < nonzero) {
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+        if (perm[i] == t) x[t] = c[i];
+    }
+}
+
+// IntensityGradientEstimation::computeFeature + the length rule of HarrisKeypoint6D::detectKeypoints; one thread per
+// surface point, lists = the surface's own sorted lists, everything in ORIGINAL order
+__global__ void __launch_bounds__(128)
+harris6d_gradient_kernel(ListView L, const float4* __restrict__ surf, const float* __restrict__ inten,
+                         const float4* __restrict__ nrm, int n, float* __restrict__ grad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float nanv = __int_as_float(0x7fc00000);
+  long long b0;
+  int m;
+  L.row(i, b0, m);
+  const float4 q = surf[i];
+  float G[3] = {nanv, nanv, nanv};
+  if (m > 0 && finite3(q.x, q.y, q.z)) {
+    float cen[3] = {0.f, 0.f, 0.f}, mean_i = 0.f;
+    for (int t = 0; t < m; ++t) {
+      const int j = L.idx[b0 + t];
+      const float4 p = surf[j];
+      cen[0] += p.x;
+      cen[1] += p.y;
+      cen[2] += p.z;
+      mean_i += inten[j];
+    }
+    const float fn = (float)m;
+    const float inv_n = 1.0f / fn;
+    cen[0] *= inv_n;
+    cen[1] *= inv_n;
+    cen[2] *= inv_n;
+    mean_i /= fn;
+    if (m >= 3) {
+      float A[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, bv[3] = {0.f, 0.f, 0.f};
+      for (int t = 0; t < m; ++t) {
+        const int j = L.idx[b0 + t];
+        const float4 p = surf[j];
+        const float it = inten[j];
+        if (!isfinite(p.x) || !isfinite(p.y) || !isfinite(p.z) || !isfinite(it)) continue;
+        const float dx = p.x - cen[0], dy = p.y - cen[1], dz = p.z - cen[2];
+        const float di = it - mean_i;
+        A[0][0] += dx * dx;
+        A[0][1] += dx * dy;
+        A[0][2] += dx * dz;
+        A[1][1] += dy * dy;
+        A[1][2] += dy * dz;
+        A[2][2] += dz * dz;
+        bv[0] += dx * di;
+        bv[1] += dy * di;
+        bv[2] += dz * di;
+      }
+      A[1][0] = A[0][1];
+      A[2][0] = A[0][2];
+      A[2][1] = A[1][2];
+      float x[3];
+      colpiv_qr_solve3(A, bv, x);
+      const float4 nr4 = nrm[i];
+      const float nr[3] = {nr4.x, nr4.y, nr4.z};
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float mm = (r == c ? 1.0f : 0.0f) - nr[r] * nr[c];
+          acc = (c == 0) ? mm * x[c] : acc + mm * x[c];
+        }
+        G[r] = acc;
+      }
+    }
+  }
+  // keep the direction of gradients with squared length > 200 (upstream's magic number), zero the rest (NaN included)
+  float len = G[0] * G[0] + G[1] * G[1] + G[2] * G[2];
+  if ((double)len > 200.0) {
+    len = (float)(1.0 / sqrt((double)len));
+    G[0] *= len;
+    G[1] *= len;
+    G[2] *= len;
+  } else {
+    G[0] = G[1] = G[2] = 0.f;
+  }
+  grad[3 * (size_t)i] = G[0];
+  grad[3 * (size_t)i + 1] = G[1];
+  grad[3 * (size_t)i + 2] = G[2];
+}
+
+// responseTomasi: 6x6 covariance of (normal, gradient) over the list, 4th smallest eigenvalue by cyclic Jacobi in double
+__global__ void __launch_bounds__(64)
+harris6d_response_kernel(ListView L, const float4* __restrict__ surf, const float4* __restrict__ nrm,
+                         const float* __restrict__ grad, int n, float* __restrict__ resp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float r = 0.f;
+  const float4 q = surf[i];
+  if (finite3(q.x, q.y, q.z)) {
+    long long b0;
+    int m;
+    L.row(i, b0, m);
+    float co[21];
+#pragma unroll
+    for (int t = 0; t < 21; ++t) co[t] = 0.f;
+    unsigned count = 0;
+    for (int t = 0; t < m; ++t) {
+      const int j = L.idx[b0 + t];
+      const float4 nr = nrm[j];
+      const float g0 = grad[3 * (size_t)j], g1 = grad[3 * (size_t)j + 1], g2 = grad[3 * (size_t)j + 2];
+      if (!isfinite(nr.x) || !isfinite(g0)) continue;
+      const float v[6] = {nr.x, nr.y, nr.z, g0, g1, g2};
+      int e = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int c = a; c < 6; ++c) co[e++] += v[a] * v[c];
+      ++count;
+    }
+    if (count > 0) {
+      const float norm = (float)(1.0 / (double)(float)count);
+#pragma unroll
+      for (int t = 0; t < 21; ++t) co[t] *= norm;
+    }
+    const float trace = co[0] + co[6] + co[11] + co[15] + co[18] + co[20];
+    if (trace != 0) {
+      double A[6][6];
+      {
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int c = a; c < 6; ++c) {
+            A[a][c] = (double)co[e];
+            A[c][a] = (double)co[e];
+            ++e;
+          }
+      }
+      for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0, dg = 0;
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+          dg += fabs(A[p][p]);
+#pragma unroll
+          for (int qq = p + 1; qq < 6; ++qq) off += fabs(A[p][qq]);
+        }
+        if (off <= 1e-300 || off <= 1e-18 * dg) break;
+#pragma unroll
+        for (int p = 0; p < 5; ++p)
+#pragma unroll
+          for (int qq = p + 1; qq < 6; ++qq) {
+            if (A[p][qq] == 0.0) continue;
+            const double theta = (A[qq][qq] - A[p][p]) / (2.0 * A[p][qq]);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+            for (int rr = 0; rr < 6; ++rr) {
+              const double arp = A[rr][p], arq = A[rr][qq];
+              A[rr][p] = c * arp - s * arq;
+              A[rr][qq] = s * arp + c * arq;
+            }
+#pragma unroll
+            for (int rr = 0; rr < 6; ++rr) {
+              const double apr = A[p][rr], aqr = A[qq][rr];
+              A[p][rr] = c * apr - s * aqr;
+              A[qq][rr] = s * apr + c * aqr;
+            }
+          }
+      }
+      double w[6];
+#pragma unroll
+      for (int t = 0; t < 6; ++t) w[t] = A[t][t];
+      // ascending order; only the value of rank 3 is needed: count how many are smaller (ties by position, as a
+      // stable sort would place them)
+      double w3 = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        int rank = 0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) rank += (w[c] < w[a] || (w[c] == w[a] && c < a)) ? 1 : 0;
+        if (rank == 3) w3 = w[a];
+      }
+      r = (float)w3;
+    }
+  }
+  resp[i] = r;
+}
+
+// response of every surface point (original order).  Needs: surface colours (ctx->surf_rgb) and normals at `radius`.
+int harris6d_response(Ctx* ctx, Grid* g, double radius, float* resp_dev_orig, float* grad_out_dev) {
+  const int n = (int)ctx->n;
+  if (n == 0) return 0;
+  const bool saved = ctx->q_is_surface;
+  ctx->q_is_surface = true;
+  int rc = strict_lists_build(ctx, g, radius, 0);
+  ctx->q_is_surface = saved;
+  if (rc) return rc;
+  PFX_CUDA(ctx->h6_inten.ensure((size_t)n * sizeof(float)));
+  PFX_CUDA(ctx->h6_grad.ensure((size_t)n * 3 * sizeof(float)));
+  PFX_LAUNCH(ctx, harris6d_intensity_kernel, div_up(n, 256), 256, 0, ctx->surf_rgb.as<unsigned>(), n, ctx->h6_inten.as<float>());
+  PFX_LAUNCH(ctx, harris6d_gradient_kernel, div_up(n, 128), 128, 0, list_view(ctx), ctx->surf.as<float4>(),
+             ctx->h6_inten.as<float>(), ctx->normals.as<float4>(), n, ctx->h6_grad.as<float>());
+  PFX_LAUNCH(ctx, harris6d_response_kernel, div_up(n, 64), 64, 0, list_view(ctx), ctx->surf.as<float4>(),
+             ctx->normals.as<float4>(), ctx->h6_grad.as<float>(), n, resp_dev_orig);
+  if (grad_out_dev)
+    PFX_CUDA(cudaMemcpyAsync(grad_out_dev, ctx->h6_grad.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  PFX_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace pfx

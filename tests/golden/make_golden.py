@@ -3,6 +3,7 @@ box has no /root/reference).
 
 clouds.npz      : xyz of the reference's four bundled PCD clouds (data/indoor, data/underwater),
                   needed because BASELINE configs C1-C3 are defined on them.
+clouds_rgb.npz  : the packed colours of the underwater pair (Harris 6D works on intensities).
 oracle_kat.npz  : outputs of the CPU oracle (oracle/) on a fixed crop; they pin the oracle against
                   silent drift.  They are NOT PCL outputs: PCL cannot be built here (parity unpinned).
 """
@@ -25,6 +26,13 @@ for name, rel in [("indoor_source", "indoor/source.pcd"), ("indoor_target", "ind
     xyz, _, _ = read_pcd(os.path.join(REF, rel))
     clouds[name] = xyz
 np.savez_compressed(os.path.join(out, "clouds.npz"), **clouds)
+
+# packed 0x00RRGGBB colours of the underwater pair (the launch file's clouds): HarrisKeypoint6D needs intensities
+colours = {}
+for name, rel in [("underwater_source", "underwater/source.pcd"), ("underwater_target", "underwater/target.pcd")]:
+    _, rgb, _ = read_pcd(os.path.join(REF, rel))
+    colours[name] = (rgb & 0x00FFFFFF).astype(np.uint32)
+np.savez_compressed(os.path.join(out, "clouds_rgb.npz"), **colours)
 
 # fixed crop: a box of the indoor source cloud (keeps the real sampling pattern)
 src = clouds["indoor_source"]

@@ -118,6 +118,10 @@ def slab_record(pfx, ctx, torch, dist, dev, rank, world, side=1024, steps=5, war
            "timed": "CUDA events, max over ranks; ms_per_cloud = dense stages on the resident slab, distribute_ms = the "
                     "device-to-device all-to-all that builds it (several small host round trips: counts, cuts)"}
     if verify:
+        # the cuts of all ranks (for the diagnosis of differing rows): rank r contributes its upper bound at slot r
+        his = [0.0] * world
+        his[rank] = info["hi"] if np.isfinite(info["hi"]) else 0.0
+        cut_pos = np.array(ctx.group_allreduce(his, "sum")[: world - 1])
         gid = torch.from_numpy(gids_local[:n_owned].astype(np.int64)).to(dev)
         rows = torch.cat([d_f[:n_owned], d_s[:n_owned]], 1)
         if world > 1:
@@ -158,6 +162,14 @@ def slab_record(pfx, ctx, torch, dist, dev, rank, world, side=1024, steps=5, war
                              "shot_rows_bit_identical": float(same[:, 33:].all(1).float().mean().item()),
                              "fpfh_max_abs_diff": float(diff[:, :33].max().item()),
                              "shot_max_abs_diff": float(diff[:, 33:385].max().item())}
+            bad = torch.nonzero(~same.all(1)).flatten().cpu().numpy()
+            if len(bad) and len(cut_pos):
+                c = pts[bad, info["axis"]].astype(np.float64)
+                dcut = np.abs(c[:, None] - cut_pos[None, :]).min(1)
+                out["verify"]["differing_rows"] = {"count": int(len(bad)), "dist_to_cut_min": float(dcut.min()),
+                                                   "dist_to_cut_median": float(np.median(dcut)), "dist_to_cut_max": float(dcut.max()),
+                                                   "beyond_halo": int((dcut > halo).sum()), "first_ids": [int(v) for v in bad[:8]],
+                                                   "first_dist": [float(v) for v in dcut[:8]]}
     return out
 
 
