@@ -79,6 +79,19 @@ int pfx_profile_end(pfx_ctx* ctx, char* buf, size_t buflen);
  * pfx_set_surface_normals <- FeatureFromNormals::setInputNormals (features.h:188)
  * pfx_set_viewpoint <- cloud.sensor_origin_ used by flipNormalTowardsViewpoint (default 0,0,0) */
 int pfx_set_surface(pfx_ctx* ctx, const void* pts, size_t n, size_t stride, int mem);
+/* Reuse of unchanged HOST inputs (default on).  The reference announces the same cloud to every Feature object,
+ * builds a fresh kd-tree for it and recomputes the normals of the whole cloud per descriptor type
+ * (features.h:186-193, inside the loops of evaluation.cpp:272,302).  Here a PFX_HOST cloud whose fingerprint
+ * (pointer, size, stride, hash of every record up to 262144 points, of 8192 evenly spaced ones beyond) equals the
+ * resident surface's is NOT uploaded
+ * again: its voxel hashes, kNN lists and normals stay.  pfx_normals with the parameters of the resident dense normals
+ * only delivers them; pfx_set_surface_normals of the very buffer pfx_normals filled (or of one uploaded before) is a
+ * no-op.  A cloud of more than 262144 points edited IN PLACE between two calls must be announced with reuse switched
+ * off (pfx_set_reuse(ctx, 0)) or after a call with n = 0.  pfx_reuse_info out6: surface uploads, surface announcements answered from the resident
+ * copy, dense normals passes, pfx_normals calls answered from the resident normals, normals uploads, normals
+ * uploads skipped. */
+int pfx_set_reuse(pfx_ctx* ctx, int enable);
+int pfx_reuse_info(const pfx_ctx* ctx, uint64_t* out6);
 int pfx_set_queries(pfx_ctx* ctx, const void* pts, size_t n, size_t stride, int mem);
 /* Optional hint: build the search index of `radius` now, on an auxiliary stream, behind the surface upload.  A
  * later radius stage with the same radius (pfx_shot352, pfx_fpfh, pfx_radius_*, ...) finds it ready instead of

@@ -56,6 +56,8 @@ SIGNATURES = {
     "pfx_last_error": (C.c_char_p, [_vp]),
     "pfx_set_stream": (_i, [_vp, _vp]),
     "pfx_set_parity_mode": (_i, [_vp, _i]),
+    "pfx_set_reuse": (_i, [_vp, _i]),
+    "pfx_reuse_info": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "pfx_group_unique_id": (_i, [_vp]),
     "pfx_group_join": (_i, [_vp, _i, _i, _vp]),
     "pfx_group_leave": (_i, [_vp]),
@@ -606,6 +608,15 @@ class Context:
         """both sides sharded over the group's ranks, device buffers; idx = GLOBAL target rows"""
         self._chk(self.lib.pfx_match_ring(self.h, _ptr(a_ptr), na, stride_a or dim * 4, _ptr(b_ptr), nb, stride_b or dim * 4,
                                           dim, int(b_offset), _ptr(idx_ptr), _ptr(d2_ptr), DEVICE))
+
+    def set_reuse(self, enable):
+        self._chk(self.lib.pfx_set_reuse(self.h, 1 if enable else 0))
+
+    def reuse_info(self):
+        a = (C.c_uint64 * 6)()
+        self._chk(self.lib.pfx_reuse_info(self.h, a))
+        return dict(surface_uploads=int(a[0]), surface_reused=int(a[1]), normals_passes=int(a[2]), normals_reused=int(a[3]),
+                    normals_uploads=int(a[4]), normals_upload_skipped=int(a[5]))
 
     def set_parity_mode(self, strict):
         """True: reference-order arithmetic for normals / Harris3D / radius-search FPFH (bit-identical to the CPU

@@ -130,6 +130,34 @@ static int async_deliver(Ctx* ctx, int s, void* dst, size_t bytes) {
   return 0;
 }
 
+// fingerprint of a host buffer of n records: every record up to 262144 of them (the reference's clouds: an edit in
+// place cannot go unnoticed), 8192 evenly spaced ones beyond
+static Ctx::HostFp host_fingerprint(const void* p, size_t n, size_t stride, size_t rec_bytes) {
+  Ctx::HostFp f;
+  f.ptr = p;
+  f.n = n;
+  f.stride = stride;
+  uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)n ^ ((uint64_t)stride << 40);
+  const unsigned char* b = static_cast<const unsigned char*>(p);
+  const size_t samples = n <= 262144 ? n : 8192;
+  const size_t words = rec_bytes / 4;
+  for (size_t s = 0; s < samples; ++s) {
+    const size_t i = (samples == n) ? s : (size_t)(((unsigned __int128)s * (n - 1)) / (samples - 1));
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(b + i * stride);
+    for (size_t t = 0; t < words; ++t) {
+      h ^= w[t];
+      h *= 0xBF58476D1CE4E5B9ull;
+      h ^= h >> 29;
+    }
+  }
+  f.hash = h;
+  f.valid = true;
+  return f;
+}
+static bool same_fp(const Ctx::HostFp& a, const Ctx::HostFp& b) {
+  return a.valid && b.valid && a.ptr == b.ptr && a.n == b.n && a.stride == b.stride && a.hash == b.hash;
+}
+
 static int check_ctx(pfx_ctx* ctx) {
   if (!ctx) return PFX_E_INVALID;
   cudaError_t e = cudaSetDevice(ctx->device);
@@ -354,6 +382,26 @@ extern "C" int pfx_set_surface(pfx_ctx* ctx, const void* pts, size_t n, size_t s
   PFX_TRY(check_ctx(ctx));
   if ((n && !pts) || stride < 12 || (stride & 3) || n > 0x7fffffffull)
     return ctx->fail(PFX_E_INVALID, "pfx_set_surface: bad pointer / stride / size");
+  Ctx::HostFp fp;
+  if (mem == PFX_HOST && ctx->reuse && n > 0) {
+    // the same host cloud announced again (the reference does so for every Feature object, features.h:190-193):
+    // the device copy, its voxel hashes, kNN lists and normals stay
+    fp = host_fingerprint(pts, n, stride, 12);
+    if (ctx->surf_version != 0 && !ctx->slab_active && same_fp(fp, ctx->surf_fp)) {
+      // the visible state is that of a fresh surface (queries = the surface, no input normals); the normals stay
+      // RESIDENT and come back into force when pfx_normals asks for the same ones or pfx_set_surface_normals hands in
+      // the buffer they were delivered to
+      ctx->stat_surface_reused++;
+      ctx->q_is_surface = true;
+      ctx->nq = 0;
+      ctx->qry_version++;
+      ctx->have_normals = false;
+      return 0;
+    }
+  }
+  ctx->surf_fp = fp;
+  ctx->nrm_fp.valid = false;
+  ctx->stat_surface_uploads++;
   const unsigned char* src = nullptr;
   PFX_TRY(grid_wait_pending(ctx));  // a build in flight on the auxiliary stream still reads the old surface
   PFX_TRY(upload_records(ctx, pts, n, stride, mem, ctx->stage, &src));
@@ -399,6 +447,19 @@ extern "C" int pfx_set_surface_normals(pfx_ctx* ctx, const void* normals, size_t
   if (n != ctx->n) return ctx->fail(PFX_E_PRECOND, "pfx_set_surface_normals: the number of normals differs from the surface size");
   if (stride < 16 || (stride & 3) || curv_off < 3 || (size_t)(curv_off + 1) * 4 > stride)
     return ctx->fail(PFX_E_INVALID, "pfx_set_surface_normals: bad stride / curvature offset");
+  Ctx::HostFp fp;
+  if (mem == PFX_HOST && ctx->reuse && n > 0) {
+    // normals the library itself delivered into this very buffer (pfx_normals), or uploaded from it before, for this
+    // surface: the device copy is current (features.h:187-188 hands the normals of the whole cloud back for every
+    // descriptor type)
+    fp = host_fingerprint(normals, n, stride, ((size_t)curv_off + 1) * 4);
+    if (ctx->nrm_fp_surf == ctx->surf_version && ctx->nrm_fp_version == ctx->normals_version && same_fp(fp, ctx->nrm_fp)) {
+      ctx->stat_normals_upload_skipped++;
+      ctx->have_normals = true;
+      return 0;
+    }
+  }
+  ctx->stat_normals_uploads++;
   const unsigned char* src = nullptr;
   PFX_TRY(upload_records(ctx, normals, n, stride, mem, ctx->stage, &src));
   PFX_CUDA(ctx->normals.ensure(std::max<size_t>(n, 1) * sizeof(float4)));
@@ -406,6 +467,9 @@ extern "C" int pfx_set_surface_normals(pfx_ctx* ctx, const void* normals, size_t
   PFX_CUDA(cudaGetLastError());
   ctx->have_normals = true;
   ctx->normals_version++;
+  ctx->nrm_fp = fp;
+  ctx->nrm_fp_surf = ctx->surf_version;
+  ctx->nrm_fp_version = ctx->normals_version;
   return 0;
 }
 
@@ -516,9 +580,41 @@ extern "C" int pfx_normals(pfx_ctx* ctx, double radius, int k, void* out, size_t
     rows = ctx->tmp0.as<float4>();
   }
   if (!out && !ctx->q_is_surface) return 0;
-  if (ctx->parity_mode == PFX_PARITY_STRICT) PFX_TRY(strict_normals(ctx, g, radius, k, rows));
-  else PFX_TRY(normals_compute(ctx, g, radius, k, rows));
+  // dense normals computed before with the same parameters for this surface are still resident: the reference
+  // recomputes the normals of the whole cloud for every descriptor type (features.h:186-188)
+  const bool dense = ctx->q_is_surface;
+  const Ctx::NrmKey& K = ctx->nrm_key;
+  const bool cached = dense && ctx->reuse && K.surf == ctx->surf_version && K.version == ctx->normals_version && K.version != 0 &&
+                      K.radius == radius && K.k == k && K.parity == ctx->parity_mode && K.vp[0] == ctx->vp[0] &&
+                      K.vp[1] == ctx->vp[1] && K.vp[2] == ctx->vp[2];
+  if (cached) {
+    ctx->stat_normals_reused++;
+    ctx->have_normals = true;
+    rows = ctx->normals.as<float4>();  // original order = caller order of dense queries
+  } else {
+    if (ctx->parity_mode == PFX_PARITY_STRICT) PFX_TRY(strict_normals(ctx, g, radius, k, rows));
+    else PFX_TRY(normals_compute(ctx, g, radius, k, rows));
+    if (dense) {
+      ctx->stat_normals_passes++;
+      ctx->nrm_key.surf = ctx->surf_version;
+      ctx->nrm_key.version = ctx->normals_version;
+      ctx->nrm_key.radius = radius;
+      ctx->nrm_key.k = k;
+      ctx->nrm_key.parity = ctx->parity_mode;
+      for (int a = 0; a < 3; ++a) ctx->nrm_key.vp[a] = ctx->vp[a];
+      ctx->nrm_fp.valid = false;
+    }
+  }
   if (!out || nq == 0) return 0;
+  struct RecordFp {  // host delivery of dense normals: remember the buffer, a later setInputNormals of it is a no-op
+    Ctx* c; const void* out; size_t n, stride; int curv_off; bool on;
+    ~RecordFp() {
+      if (!on) return;
+      c->nrm_fp = host_fingerprint(out, n, stride, ((size_t)curv_off + 1) * 4);
+      c->nrm_fp_surf = c->surf_version;
+      c->nrm_fp_version = c->normals_version;
+    }
+  } record{ctx, out, nq, stride, curv_off, dense && mem == PFX_HOST && ctx->reuse};
   if (mem == PFX_DEVICE) {
     if (stride == 16 && curv_off == 3) return deliver(ctx, out, rows, nq * sizeof(float4), mem);
     PFX_LAUNCH(ctx, normals_out_kernel, div_up((long long)nq, 256), 256, 0, rows, (int)nq, static_cast<unsigned char*>(out), stride, curv_off);
@@ -1178,6 +1274,27 @@ extern "C" int pfx_match_info(pfx_ctx* ctx, double* out4) {
   out4[1] = (double)ctx->match_rows;
   out4[2] = (double)ctx->match_redo;
   out4[3] = 0;
+  return 0;
+}
+
+extern "C" int pfx_set_reuse(pfx_ctx* ctx, int enable) {
+  if (!ctx) return PFX_E_INVALID;
+  ctx->reuse = enable != 0;
+  ctx->surf_fp.valid = false;
+  ctx->nrm_fp.valid = false;
+  return 0;
+}
+
+// out6: surface uploads, surface announcements answered from the resident copy, dense normals passes, pfx_normals
+// calls answered from the resident normals, normals uploads, normals uploads skipped
+extern "C" int pfx_reuse_info(const pfx_ctx* ctx, uint64_t* out6) {
+  if (!ctx || !out6) return PFX_E_INVALID;
+  out6[0] = ctx->stat_surface_uploads;
+  out6[1] = ctx->stat_surface_reused;
+  out6[2] = ctx->stat_normals_passes;
+  out6[3] = ctx->stat_normals_reused;
+  out6[4] = ctx->stat_normals_uploads;
+  out6[5] = ctx->stat_normals_upload_skipped;
   return 0;
 }
 

@@ -163,6 +163,28 @@ struct Ctx {
   DevBuf lab_tab, surf_lab, qry_lab;
   uint64_t surf_lab_version = 0, qry_lab_version = 0;
 
+  // reuse of HOST inputs that are announced again unchanged (the reference re-submits the same cloud, and recomputes
+  // its normals, for every descriptor type: features.h:186-193): fingerprint = pointer, size, stride and a hash of
+  // the records
+  struct HostFp {
+    const void* ptr = nullptr;
+    size_t n = 0, stride = 0;
+    uint64_t hash = 0;
+    bool valid = false;
+  };
+  bool reuse = true;
+  HostFp surf_fp, nrm_fp;
+  uint64_t nrm_fp_surf = 0, nrm_fp_version = 0;  // surface / normals version the normals fingerprint belongs to
+  // what the resident dense normals were computed with (pfx_normals); valid while normals_version == nrm_key_version
+  struct NrmKey {
+    uint64_t surf = 0, version = 0;
+    double radius = 0;
+    int k = 0, parity = 0;
+    float vp[3] = {0, 0, 0};
+  } nrm_key;
+  uint64_t stat_surface_uploads = 0, stat_surface_reused = 0, stat_normals_passes = 0, stat_normals_reused = 0,
+           stat_normals_uploads = 0, stat_normals_upload_skipped = 0;
+
   // parity mode (pfx_set_parity_mode): 0 fast kernels (tolerance contract), 1 strict = reference-order arithmetic
   // for the stages whose floats feed index outputs (strict.cu)
   int parity_mode = 0;

@@ -4,7 +4,7 @@
 // reference's column meaning (evaluation.cpp:190-206), preceded by the direct ICP of the two clouds
 // (evaluation.cpp:246-266) and, per detector, the ICP of the keypoint clouds (evaluation.cpp:289-293).
 //
-//   evaluation_b200 <source.pcd> <target.pcd> [feat_radius=0.08] [normal_radius=0.05] [dump_dir]
+//   evaluation_b200 <source.pcd> <target.pcd> [feat_radius=0.08] [normal_radius=0.05] [dump_dir] [strict=1]
 //
 // With dump_dir, raw results are written (kp indices are implied by the keypoint clouds) so that
 // tests/test_host_shim.py can compare this C++ path with the Python-bound C ABI and the oracle.
@@ -95,6 +95,8 @@ int main(int argc, char** argv) {
     return 1;
   }
   if (!pcl::b200::ctx()) return 3;
+  // the reference's pipeline takes index decisions on floats: run it in reference-order arithmetic unless told not to
+  pcl::b200::set_parity_strict(!(argc > 6 && std::atoi(argv[6]) == 0));
   std::printf("Keypoint name, Descriptor name, Source cloud size, Target cloud size, Source keypoints size, "
               "Target keypoints size, Source features size, Target features size, Correspondences, "
               "Filtered correspondences, Keypoints runtime, Features runtime, Correspondences runtime\n");
@@ -106,7 +108,7 @@ int main(int argc, char** argv) {
     icpAlign(source, target, icp_tf, score, convergence);
     print_icp("direct ICP", icp_tf, now_s() - t0, score, convergence, dump_dir, "direct_icp.bin");
   }
-  const std::string keypoints_list[] = {KP_HARRIS_3D, KP_ISS};
+  const std::string keypoints_list[] = {KP_HARRIS_3D, KP_HARRIS_6D, KP_ISS};  // the active list of evaluation.cpp:63-65
   for (const std::string& kp_type : keypoints_list) {
     PointCloudRGB::Ptr skp(new PointCloudRGB), tkp(new PointCloudRGB);
     double t0 = now_s();
@@ -126,6 +128,15 @@ int main(int argc, char** argv) {
     }
     dump(dump_dir, kp_type + "_src_kp.bin", skp->points);
     dump(dump_dir, kp_type + "_tgt_kp.bin", tkp->points);
+    {  // evaluation.cpp:319-345, the first entry of the descriptor list
+      pcl::ShapeContext3DEstimation<PointRGB, pcl::Normal, pcl::ShapeContext1980>::Ptr sc(
+          new pcl::ShapeContext3DEstimation<PointRGB, pcl::Normal, pcl::ShapeContext1980>);
+      sc->setMinimalRadius(feat_r / 10.0);
+      sc->setPointDensityRadius(feat_r / 5.0);
+      pcl::Feature<PointRGB, pcl::ShapeContext1980>::Ptr ex(sc);
+      run_descriptor<pcl::ShapeContext1980>(kp_type, DESC_SHAPE_CONTEXT, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime,
+                                            dump_dir);
+    }
     {
       pcl::Feature<PointRGB, pcl::FPFHSignature33>::Ptr ex(new pcl::FPFHEstimation<PointRGB, pcl::Normal, pcl::FPFHSignature33>);
       run_descriptor<pcl::FPFHSignature33>(kp_type, DESC_FPFH, ex, source, target, skp, tkp, feat_r, normal_r, kp_runtime, dump_dir);
@@ -238,6 +249,15 @@ int main(int argc, char** argv) {
       dump(dump_dir, "Narf_NARF_corr.bin", corr);
     }
   }
-  pfx_destroy(pcl::b200::ctx());
-  return 0;
+  {
+    // what the reference's redundancy (the same cloud and its normals re-submitted per descriptor type,
+    // features.h:186-193) cost here: uploads and normals passes actually performed vs answered from resident state
+    unsigned long long r[6];
+    pcl::b200::reuse_totals(r);
+    std::printf("# reuse: surface uploads %llu (reused %llu), dense normals passes %llu (reused %llu), normals uploads %llu "
+                "(skipped %llu)\n", r[0], r[1], r[2], r[3], r[4], r[5]);
+    std::vector<unsigned long long> v(r, r + 6);
+    dump(dump_dir, "reuse.bin", v);
+  }
+  return 0;  // the thread's contexts are released with its pool
 }

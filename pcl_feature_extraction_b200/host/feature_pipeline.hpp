@@ -18,6 +18,7 @@ typedef pcl::PointCloud<PointRGB> PointCloudRGB;
 typedef pcl::PointCloud<pcl::PointXYZI> PointCloudXYZI;
 
 static const std::string KP_HARRIS_3D = "Harris3D";
+static const std::string KP_HARRIS_6D = "Harris6D";
 static const std::string KP_ISS = "Iss";
 static const std::string KP_NARF = "Narf";
 static const std::string DESC_NARF = "NARF";
@@ -26,6 +27,7 @@ static const std::string DESC_SHOT = "SHOT";
 static const std::string DESC_SHOT_COLOR = "SHOTColor";
 static const std::string DESC_SPIN_IMAGE = "SpinImage";
 static const std::string DESC_USC = "USC";
+static const std::string DESC_SHAPE_CONTEXT = "ShapeContext";
 static const std::string DESC_MOMENT_INV = "MomentInvariants";
 static const std::string DESC_PFH = "PFH";
 static const std::string DESC_PPAL_CURV = "PrincipalCurvatures";
@@ -62,7 +64,7 @@ class Keypoints {
   Keypoints(const std::string kp_type, double normal_radius_search)
       : kp_type_(kp_type), normal_radius_search_(normal_radius_search) {}
 
-  // keypoints.h:102-291 (Harris3D and ISS branches)
+  // keypoints.h:102-291 (Harris3D, Harris6D, ISS and NARF branches)
   void compute(const PointCloudRGB::Ptr& cloud, PointCloudRGB::Ptr& cloud_keypoints) {
     if (kp_type_ == KP_HARRIS_3D) {
       pcl::HarrisKeypoint3D<PointRGB, pcl::PointXYZI> harris3d;
@@ -75,6 +77,18 @@ class Keypoints {
       // already done on the device by pfx_harris3d
       cloud_keypoints.reset(new PointCloudRGB);
       for (int s : harris3d.getSnappedIndices())
+        if (s >= 0) cloud_keypoints->push_back(cloud->points[s]);
+      return;
+    }
+    if (kp_type_ == KP_HARRIS_6D) {  // keypoints.h:166-179
+      pcl::HarrisKeypoint6D<PointRGB, pcl::PointXYZI> harris6d;
+      PointCloudXYZI::Ptr keypoints(new PointCloudXYZI);
+      harris6d.setNonMaxSupression(true);
+      harris6d.setInputCloud(cloud);
+      harris6d.setThreshold(1e-6f);
+      harris6d.compute(*keypoints);
+      cloud_keypoints.reset(new PointCloudRGB);
+      for (int s : harris6d.getSnappedIndices())
         if (s >= 0) cloud_keypoints->push_back(cloud->points[s]);
       return;
     }
@@ -119,7 +133,7 @@ class Keypoints {
 
   // keypoints.h:401-428.  batched: one device-side 2-NN pass + reduction instead of N tree queries
   double computeCloudResolution(const PointCloudRGB::Ptr& cloud) {
-    pfx_ctx* c = pcl::b200::ctx();
+    pfx_ctx* c = pcl::b200::use(cloud.get());  // the context bound to this cloud
     double res = 0.0;
     if (!c) return res;
     if (!pcl::b200::ok(pfx_set_surface(c, cloud->points.data(), cloud->size(), sizeof(PointRGB), PFX_HOST), "Keypoints")) return 0.0;

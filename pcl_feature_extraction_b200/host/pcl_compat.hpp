@@ -100,27 +100,112 @@ template <typename T> inline bool isFinite(const T& p) { return std::isfinite(p.
 
 // ------------------------------------------------------------------------------- context
 namespace b200 {
-inline pfx_ctx*& ctx_slot() { static pfx_ctx* c = nullptr; return c; }
-// one context per process (device 0 unless set_device() was called first); PCL objects are not
-// thread-safe either, the shim keeps that contract
-inline int& device_slot() { static int d = 0; return d; }
-inline void set_device(int d) { device_slot() = d; }
-inline pfx_ctx* ctx() {
-  pfx_ctx*& c = ctx_slot();
-  if (!c) {
-    int rc = pfx_create(device_slot(), &c);
-    if (rc != 0) {
-      std::fprintf(stderr, "[pcl::b200] pfx_create(%d) failed with %d: an sm_100 GPU is required (no CPU fallback)\n",
-                   device_slot(), rc);
+// Contexts.  A pfx_ctx holds ONE resident surface with its voxel hashes and normals; the reference alternates between
+// its source and target cloud inside the detector x descriptor loops (evaluation.cpp:272,302) and re-announces the
+// same cloud to every Feature object (features.h:186-193).  The shim therefore keeps a small pool of contexts per
+// (thread, device) and binds each CLOUD OBJECT to one of them: use(cloud) makes that context current, so a cloud that
+// comes back finds its device copy, hashes and normals (the C ABI recognises an unchanged host cloud, pfx_set_reuse).
+// PCL objects are not thread-safe; the pools are thread-local, so every thread works on its own contexts,
+// on the device it chose with set_device() (default 0).
+constexpr int POOL = 4;
+struct Pool {
+  int device = 0;
+  pfx_ctx* ctx[POOL] = {nullptr, nullptr, nullptr, nullptr};
+  const void* key[POOL] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned long long used[POOL] = {0, 0, 0, 0};
+  unsigned long long tick = 0;
+  int current = 0;
+  ~Pool() {
+    for (pfx_ctx*& c : ctx) {
+      if (c) pfx_destroy(c);
       c = nullptr;
     }
   }
-  return c;
+};
+inline Pool& pool() { static thread_local Pool p; return p; }
+// the device of this thread's contexts; changing it releases the contexts of the previous device
+inline void set_device(int d) {
+  Pool& p = pool();
+  if (p.device == d) return;
+  for (int i = 0; i < POOL; ++i) {
+    if (p.ctx[i]) pfx_destroy(p.ctx[i]);
+    p.ctx[i] = nullptr;
+    p.key[i] = nullptr;
+    p.used[i] = 0;
+  }
+  p.device = d;
+  p.current = 0;
+}
+inline bool& strict_flag() { static thread_local bool s = false; return s; }
+inline pfx_ctx* make_ctx(Pool& p, int slot) {
+  if (!p.ctx[slot]) {
+    int rc = pfx_create(p.device, &p.ctx[slot]);
+    if (rc == 0 && strict_flag()) pfx_set_parity_mode(p.ctx[slot], PFX_PARITY_STRICT);
+    if (rc != 0) {
+      std::fprintf(stderr, "[pcl::b200] pfx_create(%d) failed with %d: an sm_100 GPU is required (no CPU fallback)\n",
+                   p.device, rc);
+      p.ctx[slot] = nullptr;
+    }
+  }
+  return p.ctx[slot];
+}
+// PFX_PARITY_STRICT (reference-order arithmetic, include/pfx_b200.h) for this thread's contexts, present and future
+inline void set_parity_strict(bool strict) {
+  strict_flag() = strict;
+  Pool& p = pool();
+  for (int i = 0; i < POOL; ++i)
+    if (p.ctx[i]) pfx_set_parity_mode(p.ctx[i], strict ? PFX_PARITY_STRICT : PFX_PARITY_FAST);
+}
+// the current context (the one bound to the cloud announced last)
+inline pfx_ctx* ctx() {
+  Pool& p = pool();
+  return make_ctx(p, p.current);
+}
+// bind `cloud` (its address is the key) to a context and make it current: the context that already holds it, else a
+// free one, else the least recently used
+inline pfx_ctx* use(const void* cloud) {
+  Pool& p = pool();
+  int slot = -1;
+  for (int i = 0; i < POOL; ++i)
+    if (p.key[i] == cloud && p.ctx[i]) slot = i;
+  if (slot < 0)
+    for (int i = 0; i < POOL && slot < 0; ++i)
+      if (!p.key[i]) slot = i;
+  if (slot < 0) {
+    slot = 0;
+    for (int i = 1; i < POOL; ++i)
+      if (p.used[i] < p.used[slot]) slot = i;
+  }
+  p.key[slot] = cloud;
+  p.used[slot] = ++p.tick;
+  p.current = slot;
+  return make_ctx(p, slot);
+}
+// make a context obtained earlier current again (objects that own device state: RangeImage)
+inline void use_ctx(pfx_ctx* c) {
+  Pool& p = pool();
+  for (int i = 0; i < POOL; ++i)
+    if (p.ctx[i] == c && c) {
+      p.current = i;
+      p.used[i] = ++p.tick;
+    }
 }
 inline bool ok(int rc, const char* who) {
   if (rc == 0) return true;
-  std::fprintf(stderr, "[pcl::%s] %s (code %d)\n", who, ctx_slot() ? pfx_last_error(ctx_slot()) : "no context", rc);
+  pfx_ctx* c = pool().ctx[pool().current];
+  std::fprintf(stderr, "[pcl::%s] %s (code %d)\n", who, c ? pfx_last_error(c) : "no context", rc);
   return false;
+}
+// counters of the current thread's contexts (pfx_reuse_info summed): what the reference's redundancy costs here
+inline void reuse_totals(unsigned long long out6[6]) {
+  for (int k = 0; k < 6; ++k) out6[k] = 0;
+  Pool& p = pool();
+  for (int i = 0; i < POOL; ++i)
+    if (p.ctx[i]) {
+      uint64_t v[6];
+      if (pfx_reuse_info(p.ctx[i], v) == 0)
+        for (int k = 0; k < 6; ++k) out6[k] += v[k];
+    }
 }
 }  // namespace b200
 
@@ -135,7 +220,7 @@ struct KdTree {
   void setInputCloud(const typename PointCloud<PointT>::ConstPtr& c) { input_ = c; }
   // batched form of the per-point loop at keypoints.h:411-424
   int nearestKSearchAll(int k, std::vector<int>& idx, std::vector<float>& d2) const {
-    pfx_ctx* c = b200::ctx();
+    pfx_ctx* c = b200::use(input_.get());  // the context bound to this cloud
     if (!c || !input_) return 0;
     idx.assign(input_->size() * k, -1);
     d2.assign(input_->size() * k, 0.f);
@@ -244,7 +329,7 @@ class Feature {
   }
   // surface + queries to the device; dense when input and surface are the same cloud
   bool upload() {
-    pfx_ctx* c = b200::ctx();
+    pfx_ctx* c = b200::use(surface_.get());  // the context bound to this cloud
     if (!b200::ok(pfx_set_surface(c, surface_->points.data(), surface_->size(), sizeof(PointInT), PFX_HOST), name())) return false;
     pfx_set_viewpoint(c, surface_->sensor_origin_[0], surface_->sensor_origin_[1], surface_->sensor_origin_[2]);
     if (input_.get() == surface_.get()) return b200::ok(pfx_set_queries(c, nullptr, 0, 0, PFX_HOST), name());
@@ -411,6 +496,43 @@ class UniqueShapeContext : public Feature<PointInT, PointOutT> {
   }
   typename PointCloud<PointRFT>::ConstPtr frames_;
   double min_radius_ = 0.1, point_density_radius_ = 0.2, local_radius_ = 2.5;  // PCL's defaults
+};
+
+// ------------------------------------------------------------------------------- 3D Shape Context
+// pcl::ShapeContext3DEstimation<PointXYZRGB, Normal, ShapeContext1980> as configured at evaluation.cpp:319-345
+// (setMinimalRadius, setPointDensityRadius; radius through Features<T>::compute).  The random tangent direction of
+// every frame follows the library's seeded contract (pfx_sc3d1980); setSeed() is an addition of this shim.
+template <typename PointInT, typename PointNT, typename PointOutT = ShapeContext1980>
+class ShapeContext3DEstimation : public FeatureFromNormals<PointInT, PointNT, PointOutT> {
+ public:
+  typedef std::shared_ptr<ShapeContext3DEstimation<PointInT, PointNT, PointOutT>> Ptr;
+  void setMinimalRadius(double r) { min_radius_ = r; }
+  double getMinimalRadius() const { return min_radius_; }
+  void setPointDensityRadius(double r) { point_density_radius_ = r; }
+  double getPointDensityRadius() const { return point_density_radius_; }
+  void setSeed(unsigned long long seed) { seed_ = seed; }
+
+ protected:
+  const char* name() const override { return "ShapeContext3DEstimation"; }
+  bool initCompute() override {
+    if (!FeatureFromNormals<PointInT, PointNT, PointOutT>::initCompute()) return false;
+    if (this->search_radius_ < min_radius_) {
+      std::fprintf(stderr, "[pcl::%s::initCompute] search_radius_ must be GREATER than min_radius_.\n", name());
+      return false;
+    }
+    return true;
+  }
+  bool computeFeature(PointCloud<PointOutT>& output) override {
+    if (!this->uploadWithNormals()) return false;
+    int rc = pfx_sc3d1980(b200::ctx(), this->search_radius_, min_radius_, point_density_radius_, seed_,
+                          reinterpret_cast<float*>(output.points.data()), sizeof(PointOutT), nullptr, PFX_HOST);
+    if (!b200::ok(rc, name())) return false;
+    for (const auto& p : output.points)
+      if (!std::isfinite(p.descriptor[0])) { output.is_dense = false; break; }
+    return true;
+  }
+  double min_radius_ = 0.1, point_density_radius_ = 0.2;  // PCL's defaults
+  unsigned long long seed_ = 12345;
 };
 
 // ------------------------------------------------------------------------------- MomentInvariants (no normals)
@@ -594,7 +716,7 @@ class ISSKeypoint3D : public Keypoint<PointInT, PointOutT> {
 
  protected:
   void detectKeypoints(PointCloud<PointOutT>& output) override {
-    pfx_ctx* c = b200::ctx();
+    pfx_ctx* c = b200::use(this->input_.get());  // the context bound to this cloud
     if (border_radius_ > 0) {
       std::fprintf(stderr, "[pcl::ISSKeypoint3D] border estimation (border_radius > 0) is outside the reference's path\n");
       return;
@@ -636,7 +758,7 @@ class HarrisKeypoint3D : public Keypoint<PointInT, PointOutT> {
 
  protected:
   void detectKeypoints(PointCloud<PointOutT>& output) override {
-    pfx_ctx* c = b200::ctx();
+    pfx_ctx* c = b200::use(this->input_.get());  // the context bound to this cloud
     const auto& in = *this->input_;
     if (!b200::ok(pfx_set_surface(c, in.points.data(), in.size(), sizeof(PointInT), PFX_HOST), "HarrisKeypoint3D")) return;
     pfx_set_viewpoint(c, in.sensor_origin_[0], in.sensor_origin_[1], in.sensor_origin_[2]);
@@ -673,6 +795,57 @@ class HarrisKeypoint3D : public Keypoint<PointInT, PointOutT> {
   std::vector<int> snapped_;
 };
 
+// pcl::HarrisKeypoint6D<PointXYZRGB, PointXYZI> as driven at keypoints.h:166-179 (setNonMaxSupression, setThreshold,
+// radius left at 0.01, refinement left on).  The colours of the input cloud supply the intensity.
+template <typename PointInT, typename PointOutT, typename NormalT = Normal>
+class HarrisKeypoint6D : public Keypoint<PointInT, PointOutT> {
+ public:
+  explicit HarrisKeypoint6D(float radius = 0.01f, float threshold = 0.0f) : threshold_(threshold) { this->search_radius_ = radius; }
+  void setRadius(float r) { this->search_radius_ = r; }
+  void setThreshold(float t) { threshold_ = t; }
+  void setNonMaxSupression(bool b) { nonmax_ = b; }
+  void setRefine(bool b) { refine_ = b; }
+  void setNumberOfThreads(unsigned) {}
+  const std::vector<int>& getSnappedIndices() const { return snapped_; }
+
+ protected:
+  void detectKeypoints(PointCloud<PointOutT>& output) override {
+    pfx_ctx* c = b200::use(this->input_.get());
+    const auto& in = *this->input_;
+    if (!c) return;
+    if (!b200::ok(pfx_set_surface(c, in.points.data(), in.size(), sizeof(PointInT), PFX_HOST), "HarrisKeypoint6D")) return;
+    pfx_set_viewpoint(c, in.sensor_origin_[0], in.sensor_origin_[1], in.sensor_origin_[2]);
+    if (!b200::ok(pfx_set_surface_colors(c, &in.points.data()->rgba, in.size(), sizeof(PointInT), PFX_HOST), "HarrisKeypoint6D")) return;
+    const size_t cap = in.size();
+    std::vector<float> resp(cap), xyz(cap * 3);
+    std::vector<int> idx(cap);
+    snapped_.assign(cap, -1);
+    size_t n = 0;
+    int rc = pfx_harris6d(c, this->search_radius_, threshold_, nonmax_ ? 1 : 0, refine_ ? 1 : 0, 1e-4f, resp.data(),
+                          idx.data(), xyz.data(), snapped_.data(), cap, &n, PFX_HOST);
+    if (!b200::ok(rc, "HarrisKeypoint6D")) return;
+    if (!nonmax_) {
+      output.points.resize(in.size());
+      for (size_t i = 0; i < in.size(); ++i) {
+        output.points[i].x = in.points[i].x; output.points[i].y = in.points[i].y; output.points[i].z = in.points[i].z;
+        output.points[i].intensity = resp[i];
+      }
+      snapped_.clear();
+      return;
+    }
+    output.points.resize(n);
+    snapped_.resize(n);
+    this->keypoints_indices_->indices.assign(idx.begin(), idx.begin() + n);
+    for (size_t i = 0; i < n; ++i) {
+      output.points[i].x = xyz[3 * i]; output.points[i].y = xyz[3 * i + 1]; output.points[i].z = xyz[3 * i + 2];
+      output.points[i].intensity = resp[idx[i]];
+    }
+  }
+  float threshold_;
+  bool nonmax_ = true, refine_ = true;
+  std::vector<int> snapped_;
+};
+
 // ------------------------------------------------------------------------------- filters
 // pcl::VoxelGrid (config C1 ingest): setInputCloud / setLeafSize / filter.  Centroids of xyz in ascending
 // voxel-index order; colour is not carried (downsample_all_data for rgb is outside the path).
@@ -684,7 +857,7 @@ class VoxelGrid {
   void filter(PointCloud<PointT>& output) {
     output.points.clear();
     output.width = output.height = 0;
-    pfx_ctx* c = b200::ctx();
+    pfx_ctx* c = b200::use(input_.get());  // the context bound to this cloud
     if (!c || !input_) return;
     if (!uniform_) {
       std::fprintf(stderr, "[pcl::VoxelGrid] only cubic leaves are implemented\n");
@@ -735,7 +908,7 @@ class RangeImage {
                             const std::array<float, 16>* /*sensor_pose: identity*/ = nullptr,
                             CoordinateFrame frame = CAMERA_FRAME, float noise_level = 0.0f, float min_range = 0.0f,
                             int border_size = 0) {
-    pfx_ctx* c = b200::ctx();
+    pfx_ctx* c = b200::use(&cloud);  // the context bound to this cloud
     valid_ = false;
     if (!c || frame != CAMERA_FRAME || noise_level != 0.0f) {
       std::fprintf(stderr, "[pcl::RangeImage] only CAMERA_FRAME with noise_level 0 is implemented\n");
@@ -781,7 +954,7 @@ class RangeImagePlanar : public RangeImage {
                                          const PoseT& /*sensor_pose: identity for the bundled clouds*/,
                                          CoordinateFrame frame = CAMERA_FRAME, float noise_level = 0.0f,
                                          float min_range = 0.0f) {
-    pfx_ctx* c = b200::ctx();
+    pfx_ctx* c = b200::use(&cloud);  // the context bound to this cloud
     valid_ = false;
     if (!c || frame != CAMERA_FRAME || noise_level != 0.0f) {
       std::fprintf(stderr, "[pcl::RangeImagePlanar] only CAMERA_FRAME with noise_level 0 is implemented\n");
@@ -975,7 +1148,7 @@ class IterativeClosestPoint {
     res_ = pfx_icp_result();
     final_ = guess;
     res_.fitness = std::numeric_limits<double>::max();
-    pfx_ctx* c = b200::ctx();
+    pfx_ctx* c = b200::use(target_.get());  // the context bound to this cloud
     if (!c || !source_ || !target_) return;
     output = *source_;
     if (!b200::ok(pfx_set_surface(c, target_->points.data(), target_->size(), sizeof(PointTarget), PFX_HOST),

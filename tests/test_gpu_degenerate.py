@@ -118,3 +118,64 @@ def test_two_contexts_side_by_side(ctx):
         assert np.array_equal(m1, m2)
     finally:
         other.close()
+
+
+@pytest.mark.gpu
+def test_host_input_reuse_keeps_grids_and_normals(ctx, orc, clouds):
+    """the reference announces the same cloud (and hands back the same normals) for every descriptor type
+    (features.h:186-193): an unchanged PFX_HOST cloud is not uploaded again, its normals are not recomputed, and
+    the results are the bits of a fresh run; an edit in place is noticed"""
+    import pcl_feature_extraction_b200 as pfx
+    pts = np.ascontiguousarray(clouds["underwater_source"][:30000]).copy()
+    q = np.ascontiguousarray(pts[::50])
+    ctx.set_reuse(True)
+    ctx.set_viewpoint(0, 0, 0)
+    ctx.set_surface(pts)
+    i0 = ctx.reuse_info()
+    nbuf = np.zeros((len(pts), 4), np.float32)
+
+    def normals_into(buf):
+        ctx._chk(ctx.lib.pfx_normals(ctx.h, 0.03, 0, pfx.capi._ptr(buf), 16, 3, pfx.capi.HOST))
+
+    normals_into(nbuf)
+    ctx.set_surface_normals(nbuf)          # the buffer pfx_normals just filled: no upload
+    ctx.set_queries(q)
+    f1 = ctx.fpfh(radius=0.05)
+    l1 = ctx.launches
+    # the reference's next descriptor type: same cloud, normals recomputed, same keypoints
+    ctx.set_surface(pts)
+    with pytest.raises(pfx.PfxError):       # a fresh surface has no input normals yet (FeatureFromNormals::initCompute)
+        ctx.set_queries(q)
+        ctx.fpfh(radius=0.05)
+    ctx.set_queries(None)
+    nbuf2 = np.zeros_like(nbuf)
+    normals_into(nbuf2)                     # answered from the resident normals
+    assert np.array_equal(nbuf2.view(np.uint32), nbuf.view(np.uint32))
+    ctx.set_surface_normals(nbuf2)
+    ctx.set_queries(q)
+    l2 = ctx.launches
+    f2 = ctx.fpfh(radius=0.05)
+    assert np.array_equal(f1.view(np.uint32), f2.view(np.uint32))
+    i1 = ctx.reuse_info()
+    assert i1["surface_uploads"] - i0["surface_uploads"] == 0 and i1["surface_reused"] - i0["surface_reused"] == 1
+    assert i1["normals_passes"] - i0["normals_passes"] == 1 and i1["normals_reused"] - i0["normals_reused"] == 1
+    assert i1["normals_upload_skipped"] - i0["normals_upload_skipped"] == 2
+    # the second FPFH found its radius grid: it launched far fewer kernels than the first descriptor pass did
+    assert ctx.launches - l2 < 12
+    # an edit in place is a different cloud
+    pts[123] += np.float32(0.5)
+    ctx.set_surface(pts)
+    i2 = ctx.reuse_info()
+    assert i2["surface_uploads"] - i1["surface_uploads"] == 1
+    normals_into(nbuf2)
+    ref, _, gap = orc.normals(pts, radius=0.03)
+    ok = gap > 1e-3
+    assert np.abs(nbuf2[ok, :3] - ref[ok, :3]).max() < 1e-4        # recomputed for the edited cloud
+    assert ctx.reuse_info()["normals_passes"] - i2["normals_passes"] == 1
+    # switched off: every announcement uploads
+    ctx.set_reuse(False)
+    ctx.set_surface(pts)
+    ctx.set_surface(pts)
+    assert ctx.reuse_info()["surface_uploads"] - i2["surface_uploads"] == 2
+    ctx.set_reuse(True)
+    ctx.set_queries(None)

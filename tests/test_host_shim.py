@@ -28,7 +28,9 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     tgt_rgb = rng.integers(0, 1 << 24, len(tgt)).astype(np.uint32)
     write_pcd(tmp_path / "s.pcd", src, src_rgb)
     write_pcd(tmp_path / "t.pcd", tgt, tgt_rgb)
-    r = subprocess.run([BIN, str(tmp_path / "s.pcd"), str(tmp_path / "t.pcd"), "0.05", "0.03", str(tmp_path)],
+    # (last argument 0: the throughput kernels, which is what the Python context of this test runs too; the driver's
+    # default, reference-order arithmetic, is covered by test_evaluation_driver_strict_and_reuse)
+    r = subprocess.run([BIN, str(tmp_path / "s.pcd"), str(tmp_path / "t.pcd"), "0.05", "0.03", str(tmp_path), "0"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     lines = r.stdout.strip().splitlines()
@@ -36,7 +38,8 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     assert sum(l.startswith("# direct ICP") for l in lines) == 1
     byname = {(x[0], x[1]): x for x in rows}
     for kp_name in ("Harris3D", "Iss"):
-        for d_name in ("FPFH", "SHOT", "SHOTColor", "SpinImage", "USC", "MomentInvariants", "PFH", "PrincipalCurvatures"):
+        for d_name in ("ShapeContext", "FPFH", "SHOT", "SHOTColor", "SpinImage", "USC", "MomentInvariants", "PFH",
+                       "PrincipalCurvatures"):
             assert (kp_name, d_name) in byname
     # NARF row (present when both clouds yield keypoints): the shim's RangeImagePlanar / NarfKeypoint /
     # NarfDescriptor objects against the C ABI called from Python on the same cloud
@@ -155,3 +158,53 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     ctx.set_queries(kq)
     assert np.array_equal(sp_shim, ctx.spin_image153(0.05, np.ascontiguousarray(sp_nrm[:, :4])), equal_nan=True)
     ctx.set_queries(None)
+
+
+@pytest.mark.gpu
+def test_evaluation_driver_strict_and_reuse(tmp_path, clouds, orc):
+    """the driver's default mode on the bundled underwater pair WITH its colours: reference-order arithmetic
+    (PFX_PARITY_STRICT), so the Harris3D / Harris6D keypoints and the FPFH rows equal the oracle's bit for bit, the
+    3DSC row is there, and the reference's redundancy (the same cloud and its normals re-submitted for every
+    descriptor type, features.h:186-193) costs one upload per cloud and one normals pass per cloud and detector"""
+    from pcl_feature_extraction_b200.pcd import write_pcd
+    rgbz = np.load(os.path.join(ROOT, "tests", "golden", "clouds_rgb.npz"))
+    src = np.ascontiguousarray(clouds["underwater_source"])
+    tgt = np.ascontiguousarray(clouds["underwater_target"])
+    write_pcd(tmp_path / "s.pcd", src, rgbz["underwater_source"])
+    write_pcd(tmp_path / "t.pcd", tgt, rgbz["underwater_target"])
+    r = subprocess.run([BIN, str(tmp_path / "s.pcd"), str(tmp_path / "t.pcd"), "0.05", "0.03", str(tmp_path)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    rows = {(x[0], x[1]): x for x in (l.split(", ") for l in lines[1:] if not l.startswith("#"))}
+    for kp_name in ("Harris3D", "Harris6D", "Iss"):
+        for d_name in ("ShapeContext", "FPFH", "SHOT", "USC"):
+            assert (kp_name, d_name) in rows, (kp_name, d_name, r.stdout[-2000:])
+
+    def kp_xyz(name):
+        return np.ascontiguousarray(np.fromfile(tmp_path / name, dtype=np.float32).reshape(-1, 8)[:, :3])
+
+    # Harris3D: the oracle's whole chain (normals r = 1 cm, response, NMS, refinement, 1 cm snap)
+    nr1, _, _ = orc.normals(src, radius=0.01)
+    resp = orc.harris_response(src, nr1, 0.01)
+    kp = orc.harris_nms(src, resp, 0.01, 1e-6)
+    sn = orc.snap_to_cloud(src, orc.harris_refine(src, nr1, 0.01, src[kp].copy()), 1e-4)
+    assert np.array_equal(kp_xyz("Harris3D_src_kp.bin"), src[sn[sn >= 0]])
+    # Harris6D likewise, with the intensity gradient
+    resp6, _, _ = orc.harris6d_response(src, rgbz["underwater_source"], nr1, 0.01)
+    kp6 = orc.harris_nms(src, resp6, 0.01, 1e-6)
+    sn6 = orc.snap_to_cloud(src, orc.harris_refine(src, nr1, 0.01, src[kp6].copy()), 1e-4)
+    assert np.array_equal(kp_xyz("Harris6D_src_kp.bin"), src[sn6[sn6 >= 0]])
+    assert int(rows[("Harris6D", "FPFH")][4]) == int((sn6 >= 0).sum()) > 20
+    # FPFH at the Harris3D keypoints: bit for bit the oracle's rows, hence the same correspondences
+    nr, _, _ = orc.normals(src, radius=0.03)
+    f_or = orc.fpfh(src, nr, src[sn[sn >= 0]], radius=0.05)
+    f_shim = np.fromfile(tmp_path / "Harris3D_FPFH_src.bin", dtype=np.float32).reshape(-1, 33)
+    assert np.array_equal(f_shim.view(np.uint32), f_or.view(np.uint32))
+    # reuse: 2 big clouds -> 2 uploads of them; everything else is keypoint clouds (spin-image normals, ICP)
+    reuse = np.fromfile(tmp_path / "reuse.bin", dtype=np.uint64)
+    up, reused, passes, p_reused, n_up, n_skip = (int(v) for v in reuse)
+    print(r.stdout.strip().splitlines()[-1])
+    assert reused >= 3 * 2 * 8          # 3 detectors x 2 clouds x (>= 8 descriptor types announce the cloud again)
+    assert p_reused >= 3 * 2 * 4        # ... and at least 4 of them ask for its normals again
+    assert passes <= 3 * 2 + 3 * 2      # one pass per big cloud and detector, one per keypoint cloud (spin images)
