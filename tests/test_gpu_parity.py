@@ -115,10 +115,11 @@ def test_radius_search_dense_sets(ctx, orc, clouds):
     assert np.array_equal(off, ooff)
     # unsorted lists: compare as sets per row through a (row, idx) sort
     rows = np.repeat(np.arange(len(xyz)), np.diff(off))
-    assert np.array_equal(np.lexsort((idx, rows)), np.lexsort((idx, rows)))
     a = np.stack([rows, idx], 1)
     b = np.stack([rows, oidx], 1)
-    assert np.array_equal(a[np.lexsort((a[:, 1], a[:, 0]))], b[np.lexsort((b[:, 1], b[:, 0]))])
+    oa, ob = np.lexsort((a[:, 1], a[:, 0])), np.lexsort((b[:, 1], b[:, 0]))
+    assert np.array_equal(a[oa], b[ob])
+    assert np.array_equal(d2[oa].view(np.uint32), od2[ob].view(np.uint32))   # and the same FLANN distances
 
 
 def test_radius_empty_and_outside_queries(ctx, orc):
@@ -229,10 +230,10 @@ def test_spfh_same_normals(ctx, orc, clouds):
     s = ctx.spfh(radius=0.05)
     ref = orc.spfh(xyz, nr, np.arange(len(xyz), dtype=np.int32), radius=0.05)
     d = np.abs(s - ref).max(1)
-    # identical inputs: rows are bit-identical except where one pair sits on a bin boundary
+    # identical inputs: rows are bit-identical; a pair whose f1 sits within 2e-5 bins of a bin edge takes the correctly
+    # rounded atan2 (pair_features.cuh), so at most a libm-vs-correct-rounding ulp can still move a vote
     exact = (d == 0).mean()
-    assert exact > 0.97, exact
-    assert (d > 1e-3).mean() < 0.03
+    assert exact >= 0.999, exact
     # a moved vote changes two bins by 100/(n-1) each; nothing larger may happen
     off, _, _ = orc.radius_search(xyz, xyz, 0.05)
     n = np.diff(off)
@@ -259,10 +260,10 @@ def test_fpfh_dense_same_normals(ctx, orc, clouds, sheet, mode):
     ok = ~np.isnan(f[:, 0])
     sums = f[ok].reshape(-1, 3, 11).sum(2)
     assert np.abs(sums - 100).max() < 1e-2
-    # tolerance: 1e-4 of the histogram scale (100) for >= 98 % of rows; the rest are rows that
-    # inherit a moved SPFH vote (bounded by one vote of one neighbour)
-    assert (d <= 1e-2).mean() >= 0.98, ((d <= 1e-2).mean(), d.max())
-    assert d.max() < 12.0, d.max()
+    # tolerance: 1e-5 of the histogram scale (100) for >= 99.9 % of rows (float vs fixed-point / double summation);
+    # a row may carry at most one moved SPFH vote of one neighbour
+    assert (d <= 1e-3).mean() >= 0.999, ((d <= 1e-3).mean(), d.max())
+    assert d.max() < 4.0, d.max()
     assert np.median(d) < 1e-4
 
 
@@ -278,7 +279,8 @@ def test_fpfh_keypoint_queries(ctx, orc, clouds):
     ref = orc.fpfh(xyz, nr, q, radius=0.05)
     assert np.isnan(f[-1]).all()
     d = _fpfh_compare(f, ref)
-    assert (d <= 1e-2).mean() >= 0.97 and d.max() < 12.0
+    # (516 queries: at most one row may carry a moved vote)
+    assert (d > 1e-3).sum() <= max(1, int(0.001 * len(d))) and d.max() < 4.0
 
 
 def test_fpfh_plane_known_answer(ctx):
@@ -305,8 +307,11 @@ def test_fpfh_end_to_end_gpu_normals(ctx, orc, sheet):
     nr, _, _ = orc.normals(sheet, k=32)
     ref = orc.fpfh(sheet, nr, k=32)
     d = _fpfh_compare(f, ref)
-    assert np.median(d) < 1e-3
-    assert (d <= 1e-2).mean() >= 0.9, (d <= 1e-2).mean()
+    # the two sets of normals differ by ~1e-7: a pair feature that sits that close to a bin edge moves one vote of one
+    # SPFH row, which reaches the ~32 FPFH rows that gather it with ~0.1 each; everything else agrees to 1e-3
+    assert np.median(d) < 1e-4
+    assert (d <= 1e-3).mean() >= 0.97, ((d <= 1e-3).mean(), (d <= 1e-2).mean())
+    assert d.max() < 4.0
 
 
 # ------------------------------------------------------------------------------------ SHOT
@@ -612,10 +617,27 @@ def test_golden_kat(ctx):
     assert np.array_equal(off, z["rad_off"]) and np.array_equal(ridx, z["rad_idx"]) and np.array_equal(rd2, z["rad_d2"])
     ctx.set_queries(None)
     assert abs(ctx.cloud_resolution() - z["resolution"][0]) < 1e-12
+    res = ctx.cloud_resolution()
+    kp, sal = ctx.iss(6 * res, 4 * res)
+    assert np.array_equal(kp, z["iss_kp"])
+    assert np.abs(sal - z["iss_sal"]).max() <= 1e-13
+    ctx.set_parity_mode(True)   # reference-order arithmetic: Harris3D response and keypoints are the fixture's bits
+    try:
+        h = ctx.harris3d(0.01, 1e-6)
+    finally:
+        ctx.set_parity_mode(False)
+    assert np.array_equal(h["response"].view(np.uint32), z["harris_resp"].view(np.uint32))
+    assert np.array_equal(h["kp_idx"], z["harris_kp"])
     ctx.set_surface_normals(z["normals"])
     ctx.set_queries(q)
     f = ctx.fpfh(radius=0.05)
-    assert (np.abs(f - z["fpfh"]).max(1) <= 1e-2).mean() > 0.97
+    assert np.abs(f - z["fpfh"]).max() <= 1e-3
+    ctx.set_parity_mode(True)
+    try:
+        f_strict = ctx.fpfh(radius=0.05)
+    finally:
+        ctx.set_parity_mode(False)
+    assert np.array_equal(f_strict.view(np.uint32), z["fpfh"].view(np.uint32))
     s, _ = ctx.shot352(0.05, lrf_in=z["shot_rf"])
     ok = ~np.isnan(z["shot"][:, 0])
     assert np.abs(s[ok] - z["shot"][ok]).max() <= 1e-4
