@@ -334,8 +334,8 @@ int pfx_icp_align(pfx_ctx* ctx, const void* src, size_t n_src, size_t stride_src
 /* ------------------------------------------------------------------ range image, NARF keypoints, Narf36
  * pfx_range_image_planar <- RangeImagePlanar::createFromPointCloudWithFixedSize (keypoints.h:204-216,
  * tools.h:65-76); pfx_range_image_spherical <- RangeImage::createFromPointCloud (config C3).  Both project
- * the current surface with the sensor at the origin of the cloud frame (CAMERA_FRAME, identity pose: what
- * the reference passes for the bundled clouds), noise_level 0.  The image (height x width pixels of
+ * the current surface through the sensor pose set with pfx_range_image_set_pose (default: the sensor at the origin
+ * of the cloud frame, what the reference passes for the bundled clouds), CAMERA_FRAME, noise_level 0.  The image (height x width pixels of
  * x, y, z, range = pcl::PointWithRange without padding; unobserved: NaN xyz, range -inf) stays in the
  * context; desc_out receives its geometry (the spherical image is cropped to the observed box + border). */
 typedef struct {
@@ -348,6 +348,13 @@ int pfx_range_image_planar(pfx_ctx* ctx, int width, int height, float cx, float 
                            float min_range, pfx_range_image_desc* desc_out);
 int pfx_range_image_spherical(pfx_ctx* ctx, float ang_res, float max_angle_width, float max_angle_height,
                               float min_range, int border, pfx_range_image_desc* desc_out);
+/* Sensor pose (keypoints.h:207-210 builds it as translation(sensor_origin_) * rotation(sensor_orientation_)):
+ * pose16 = row-major 4x4, world <- sensor, NULL = identity (what the bundled clouds carry).  It applies to the
+ * images built or set after the call: points are projected with its inverse (PCL's to_range_image_system), the
+ * image handed out by pfx_range_image_get, the keypoint positions and the Narf36 poses are in world coordinates,
+ * Narf36's upright frame uses the world's y axis.  Internally the image lives in the sensor frame, so the border
+ * and interest stages are those of the identity pose. */
+int pfx_range_image_set_pose(pfx_ctx* ctx, const float* pose16);
 /* use a caller-supplied image (height*width*4 floats) / read the current one back */
 int pfx_range_image_set(pfx_ctx* ctx, const pfx_range_image_desc* desc, const float* img, int mem);
 int pfx_range_image_get(pfx_ctx* ctx, pfx_range_image_desc* desc_out, float* img, int mem);

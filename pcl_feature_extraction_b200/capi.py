@@ -109,6 +109,7 @@ SIGNATURES = {
     "pfx_match_nn": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _vp, _vp, _i]),
     "pfx_range_image_planar": (_i, [_vp, _i, _i, _f, _f, _f, _f, _f, _vp]),
     "pfx_range_image_spherical": (_i, [_vp, _f, _f, _f, _f, _i, _vp]),
+    "pfx_range_image_set_pose": (_i, [_vp, _vp]),
     "pfx_range_image_set": (_i, [_vp, _vp, _vp, _i]),
     "pfx_range_image_get": (_i, [_vp, _vp, _vp, _i]),
     "pfx_narf_borders": (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
@@ -445,6 +446,11 @@ class Context:
         d = RangeImageDesc()
         self._chk(self.lib.pfx_range_image_planar(self.h, width, height, cx, cy, fx, fy, min_range, C.byref(d)))
         return d
+
+    def range_image_set_pose(self, pose4x4=None):
+        """sensor pose (world <- sensor, 4x4) of the range images built next; None = identity"""
+        p = None if pose4x4 is None else np.ascontiguousarray(pose4x4, np.float32).reshape(16)
+        self._chk(self.lib.pfx_range_image_set_pose(self.h, _ptr(p)))
 
     def range_image_spherical(self, ang_res, max_angle_w=2 * np.pi, max_angle_h=np.pi, min_range=0.0, border=0):
         d = RangeImageDesc()

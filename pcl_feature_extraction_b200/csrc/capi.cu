@@ -1520,6 +1520,40 @@ extern "C" int pfx_range_image_set(pfx_ctx* ctx, const pfx_range_image_desc* des
   ctx->ri = *desc;
   ctx->ri_valid = true;
   ctx->ri_stage = 0;
+  // with a sensor pose the caller's image is in world coordinates; the library works in the sensor frame, where the
+  // xyz of a pixel follows from (pixel, range) exactly
+  if (ctx->ri_has_pose) PFX_TRY(range_image_import_world(ctx));
+  return 0;
+}
+
+// Sensor pose of the range image (keypoints.h:207-210: translation(sensor_origin_) * rotation(sensor_orientation_)):
+// pose16 = row-major 4x4, world <- sensor; NULL = identity.  Applies to the images built or set AFTER the call.
+extern "C" int pfx_range_image_set_pose(pfx_ctx* ctx, const float* pose16) {
+  PFX_TRY(check_ctx(ctx));
+  bool identity = true;
+  if (pose16) {
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) {
+        const float v = pose16[4 * r + c];
+        if (!std::isfinite(v)) return ctx->fail(PFX_E_INVALID, "pfx_range_image_set_pose: non-finite pose");
+        if (v != (r == c ? 1.f : 0.f)) identity = false;
+      }
+    // a rigid pose: R R^T = I to float accuracy
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        double d = 0;
+        for (int k = 0; k < 3; ++k) d += (double)pose16[4 * a + k] * pose16[4 * b + k];
+        if (std::fabs(d - (a == b ? 1.0 : 0.0)) > 1e-4)
+          return ctx->fail(PFX_E_INVALID, "pfx_range_image_set_pose: the rotation part is not orthonormal");
+      }
+  }
+  ctx->ri_has_pose = !identity;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) ctx->ri_R[3 * r + c] = identity ? (r == c ? 1.f : 0.f) : pose16[4 * r + c];
+    ctx->ri_t[r] = identity ? 0.f : pose16[4 * r + 3];
+  }
+  ctx->ri_valid = false;  // an image built under another pose is no longer current
+  ctx->ri_stage = 0;
   return 0;
 }
 
@@ -1527,8 +1561,13 @@ extern "C" int pfx_range_image_get(pfx_ctx* ctx, pfx_range_image_desc* desc_out,
   PFX_TRY(check_ctx(ctx));
   if (!ctx->ri_valid) return ctx->fail(PFX_E_STATE, "pfx_range_image_get: no range image");
   if (desc_out) *desc_out = ctx->ri;
-  if (img) return deliver(ctx, img, ctx->ri_img.p, (size_t)ctx->ri.width * ctx->ri.height * sizeof(float4), mem);
-  return 0;
+  if (!img) return 0;
+  const size_t bytes = (size_t)ctx->ri.width * ctx->ri.height * sizeof(float4);
+  if (!ctx->ri_has_pose || bytes == 0) return deliver(ctx, img, ctx->ri_img.p, bytes, mem);
+  // pcl::RangeImage::points are WORLD coordinates
+  PFX_CUDA(ctx->tmp1.ensure(bytes));
+  PFX_TRY(range_image_export_world(ctx, ctx->tmp1.as<float4>()));
+  return deliver(ctx, img, ctx->tmp1.p, bytes, mem);
 }
 
 namespace pfx {

@@ -150,6 +150,10 @@ struct Ctx {
 
   // range image + NARF state (narf.cu)
   pfx_range_image_desc ri = {};
+  // sensor pose of the range image (pfx_range_image_set_pose): world <- sensor, rotation rows + translation.  The
+  // image and every NARF stage live in the SENSOR frame; inputs / outputs are mapped from / to the world frame
+  float ri_R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, ri_t[3] = {0, 0, 0};
+  bool ri_has_pose = false;
   DevBuf ri_img, nb_surf, nb_scores, nb_shadow, nb_traits, nb_dir, nb_change, nk_interest;
   bool ri_valid = false;
   int ri_stage = 0;  // 0 image only, 1 borders extracted, 2 interest image for ri_support
@@ -312,6 +316,8 @@ bool match_tc_fits(int dim);  // the resident A tile + two ring stages fit in sh
 int range_image_build(Ctx* ctx, const pfx_range_image_desc* want, float max_angle_w, float max_angle_h, float min_range,
                       int border);
 int narf_prepare(Ctx* ctx, int stage, float support_size);
+int range_image_export_world(Ctx* ctx, float4* out_dev);
+int range_image_import_world(Ctx* ctx);
 int narf_keypoints(Ctx* ctx, float support_size, int** kp_dev, int* n_kp);
 int narf_keypoint_attrs(Ctx* ctx, const int* kp_dev, int n, float* xyz, float* val, int mem);
 int narf36_compute(Ctx* ctx, const int* kp_dev, int n_kp, float support_size, int rotation_invariant,

@@ -55,7 +55,26 @@ struct RiDev {
   int w, h, planar;
   float cx, cy, fx, fy, ares;
   int offx, offy;
-  const float4* px;  // x, y, z, range (unobserved: NaN xyz, range -inf)
+  const float4* px;  // x, y, z, range (unobserved: NaN xyz, range -inf), SENSOR frame
+  // sensor pose (world <- sensor): rows of R and t; identity unless pfx_range_image_set_pose was called
+  int has_pose;
+  float R[9], t[3];
+  __device__ __forceinline__ F3 to_sensor(F3 p) const {  // R^T (p - t)
+    if (!has_pose) return p;
+    const F3 d = f3(p.x - t[0], p.y - t[1], p.z - t[2]);
+    return f3(R[0] * d.x + R[3] * d.y + R[6] * d.z, R[1] * d.x + R[4] * d.y + R[7] * d.z, R[2] * d.x + R[5] * d.y + R[8] * d.z);
+  }
+  __device__ __forceinline__ F3 rot_to_world(F3 v) const {  // R v
+    if (!has_pose) return v;
+    return f3(R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z, R[6] * v.x + R[7] * v.y + R[8] * v.z);
+  }
+  __device__ __forceinline__ F3 to_world(F3 p) const {  // R p + t
+    if (!has_pose) return p;
+    const F3 r = rot_to_world(p);
+    return f3(r.x + t[0], r.y + t[1], r.z + t[2]);
+  }
+  // the world's y axis (the "up" of pcl::Narf's upright frame) seen from the sensor frame: R^T e_y
+  __device__ __forceinline__ F3 world_up() const { return has_pose ? f3(R[3], R[4], R[5]) : f3(0.0f, 1.0f, 0.0f); }
   __device__ __forceinline__ bool in_image(int x, int y) const { return x >= 0 && x < w && y >= 0 && y < h; }
   __device__ __forceinline__ float range(int x, int y) const { return in_image(x, y) ? px[y * w + x].w : -CUDART_INF_F; }
   __device__ __forceinline__ bool valid(int x, int y) const { return in_image(x, y) && isfinite(px[y * w + x].w); }
@@ -156,7 +175,7 @@ __global__ void ri_project_kernel(const float4* __restrict__ pts, int n, RiDev r
   float4 p = pts[i];
   if (!finite3(p.x, p.y, p.z)) return;
   float fx_, fy_, r;
-  ri.project(f3(p.x, p.y, p.z), fx_, fy_, r);
+  ri.project(ri.to_sensor(f3(p.x, p.y, p.z)), fx_, fy_, r);  // to_range_image_system = (sensor pose)^-1
   if (!isfinite(fx_) || !isfinite(fy_)) return;
   int x = (int)lrintf(fx_), y = (int)lrintf(fy_);
   if (r < min_range || !ri.in_image(x, y)) return;
@@ -810,7 +829,8 @@ __global__ void nk_gather_kernel(RiDev ri, const int* __restrict__ kp, int n, co
   if (i >= n) return;
   float4 p = ri.px[kp[i]];
   if (xyz) {
-    xyz[3 * i] = p.x; xyz[3 * i + 1] = p.y; xyz[3 * i + 2] = p.z;
+    const F3 w = ri.to_world(f3(p.x, p.y, p.z));
+    xyz[3 * i] = w.x; xyz[3 * i + 1] = w.y; xyz[3 * i + 2] = w.z;
   }
   if (val) val[i] = interest[kp[i]];
 }
@@ -939,7 +959,7 @@ narf36_kernel(RiDev ri, const int* __restrict__ kp_px, int n_kp, float support, 
       F3 mean = va.mean(pos);
       if (fdot(normal, fnormalized(mean)) < 0.0f) normal = -1.0f * normal;
       F3 on_plane = (fdot(normal, mean) - fdot(normal, pos)) * normal + pos;
-      F3 ydir = f3(0.0f, 1.0f, 0.0f);
+      F3 ydir = ri.world_up();
       T.r0 = fnormalized(fcross(ydir, normal));
       T.r1 = fnormalized(fcross(normal, T.r0));
       T.r2 = fnormalized(normal);
@@ -1164,11 +1184,13 @@ narf36_kernel(RiDev ri, const int* __restrict__ kp_px, int n_kp, float support, 
       for (int d = lane; d < N36_DS; d += 32) o[6 + d] = S->desc[d];
     }
     if (lane == 0) {
-      const F3 p = Tr.apply_inv(f3(0.f, 0.f, 0.f));
+      // the feature frame in WORLD coordinates: position R p + t, axes R r_i
+      const F3 p = ri.to_world(Tr.apply_inv(f3(0.f, 0.f, 0.f)));
+      const F3 w0 = ri.rot_to_world(Tr.r0), w1 = ri.rot_to_world(Tr.r1), w2 = ri.rot_to_world(Tr.r2);
       o[0] = p.x; o[1] = p.y; o[2] = p.z;
-      o[3] = atan2f(Tr.r1.z, Tr.r2.z);
-      o[4] = asinf(-Tr.r0.z);
-      o[5] = atan2f(Tr.r0.y, Tr.r0.x);
+      o[3] = atan2f(w1.z, w2.z);
+      o[4] = asinf(-w0.z);
+      o[5] = atan2f(w0.y, w0.x);
     }
     __syncwarp();
   }
@@ -1195,6 +1217,9 @@ static RiDev ri_view(const Ctx* ctx) {
   r.cx = ctx->ri.cx; r.cy = ctx->ri.cy; r.fx = ctx->ri.fx; r.fy = ctx->ri.fy;
   r.ares = ctx->ri.ang_res; r.offx = ctx->ri.off_x; r.offy = ctx->ri.off_y;
   r.px = ctx->ri_img.as<float4>();
+  r.has_pose = ctx->ri_has_pose ? 1 : 0;
+  for (int i = 0; i < 9; ++i) r.R[i] = ctx->ri_R[i];
+  for (int i = 0; i < 3; ++i) r.t[i] = ctx->ri_t[i];
   return r;
 }
 
@@ -1351,6 +1376,44 @@ int narf_keypoints(Ctx* ctx, float support_size, int** kp_dev, int* n_kp) {
   PFX_TRY(compact_flags(ctx, flags, np, ctx->tmp3.as<int>(), &cnt));
   *kp_dev = ctx->tmp3.as<int>();
   *n_kp = cnt;
+  return 0;
+}
+
+// the image in WORLD coordinates (what pcl::RangeImage::points holds) from the sensor-frame image, and back:
+// xyz of an image pixel is a function of (pixel, range) alone, so the way back re-derives it exactly
+__global__ void ri_to_world_kernel(RiDev ri, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ri.w * ri.h) return;
+  const float4 p = ri.px[i];
+  float4 o = p;
+  if (isfinite(p.w)) {
+    const F3 w = ri.to_world(f3(p.x, p.y, p.z));
+    o.x = w.x; o.y = w.y; o.z = w.z;
+  }
+  out[i] = o;
+}
+__global__ void ri_from_ranges_kernel(RiDev ri, float4* __restrict__ img) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ri.w * ri.h) return;
+  const float r = img[i].w;
+  if (!isfinite(r)) return;
+  const int y = i / ri.w, x = i - y * ri.w;
+  const F3 v = ri.point3d((float)x, (float)y, r);
+  img[i] = make_float4(v.x, v.y, v.z, r);
+}
+
+int range_image_export_world(Ctx* ctx, float4* out_dev) {
+  const RiDev ri = ri_view(ctx);
+  const int np = ri.w * ri.h;
+  if (np > 0) PFX_LAUNCH(ctx, ri_to_world_kernel, div_up(np, 256), 256, 0, ri, out_dev);
+  PFX_CUDA(cudaGetLastError());
+  return 0;
+}
+int range_image_import_world(Ctx* ctx) {  // ctx->ri_img holds a world-frame image: make it the sensor-frame one
+  RiDev ri = ri_view(ctx);
+  const int np = ri.w * ri.h;
+  if (np > 0) PFX_LAUNCH(ctx, ri_from_ranges_kernel, div_up(np, 256), 256, 0, ri, ctx->ri_img.as<float4>());
+  PFX_CUDA(cudaGetLastError());
   return 0;
 }
 

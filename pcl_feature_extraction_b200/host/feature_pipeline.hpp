@@ -51,9 +51,10 @@ class Tools {
     float center_x = (640.0f / 2.0f), center_y = (480.0f / 2.0f);
     float focal_length_x = 525.0f;
     float noise_level = 0.0f, minimum_range = 0.0f;
-    const int sensor_pose_identity = 0;  // translation(sensor_origin) * rotation(sensor_orientation) = identity here
+    // keypoints.h:207-210: translation(sensor_origin_) * rotation(sensor_orientation_) (identity for the bundled clouds)
+    const pcl::Affine3f sensor_pose = pcl::poseFromOriginAndOrientation(cloud->sensor_origin_, cloud->sensor_orientation_);
     range_image.createFromPointCloudWithFixedSize(*cloud, image_size_x, image_size_y, center_x, center_y, focal_length_x,
-                                                  focal_length_x, sensor_pose_identity, pcl::RangeImage::CAMERA_FRAME,
+                                                  focal_length_x, sensor_pose, pcl::RangeImage::CAMERA_FRAME,
                                                   noise_level, minimum_range);
   }
 };
@@ -244,6 +245,8 @@ inline int loadPCDFile(const std::string& path, PointCloudRGB& cloud) {
       ss >> n;
     } else if (key == "VIEWPOINT") {
       ss >> cloud.sensor_origin_[0] >> cloud.sensor_origin_[1] >> cloud.sensor_origin_[2];
+      float q[4];  // qw qx qy qz
+      if (ss >> q[0] >> q[1] >> q[2] >> q[3]) std::memcpy(cloud.sensor_orientation_, q, sizeof(q));
     } else if (key == "DATA") {
       std::string mode;
       ss >> mode;

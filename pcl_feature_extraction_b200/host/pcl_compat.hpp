@@ -896,20 +896,36 @@ class VoxelGrid {
 // the reference drives (keypoints.h:204-224, tools.h:65-76, evaluation.cpp:629-637).  The image itself
 // lives in the library's context; these objects hold its geometry and re-install it before use, so several
 // RangeImage objects may coexist like in the reference.
+// row-major 4x4 rigid transform, the shim's stand-in for Eigen::Affine3f (sensor pose: world <- sensor)
+typedef std::array<float, 16> Affine3f;
+inline Affine3f identityPose() { return Affine3f{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}; }
+// Eigen::Affine3f(Eigen::Translation3f(origin)) * Eigen::Affine3f(orientation) as built at keypoints.h:207-210;
+// origin = cloud.sensor_origin_ (x y z), q = cloud.sensor_orientation_ (w x y z)
+inline Affine3f poseFromOriginAndOrientation(const float origin[4], const float q[4]) {
+  const float w = q[0], x = q[1], y = q[2], z = q[3];
+  return Affine3f{1 - 2 * (y * y + z * z), 2 * (x * y - z * w),     2 * (x * z + y * w),     origin[0],
+                  2 * (x * y + z * w),     1 - 2 * (x * x + z * z), 2 * (y * z - x * w),     origin[1],
+                  2 * (x * z - y * w),     2 * (y * z + x * w),     1 - 2 * (x * x + y * y), origin[2],
+                  0, 0, 0, 1};
+}
+
 class RangeImage {
  public:
   enum CoordinateFrame { CAMERA_FRAME = 0, LASER_FRAME = 1 };
   virtual ~RangeImage() {}
   uint32_t width = 0, height = 0;
-  std::vector<PointWithRange> points;
+  std::vector<PointWithRange> points;  // world coordinates, as in PCL
+  const Affine3f& getSensorPose() const { return pose_; }
   // RangeImage::createFromPointCloud (config C3): spherical projection, cropped.  sensor pose: identity.
   template <typename CloudT>
   void createFromPointCloud(const CloudT& cloud, float angular_resolution, float max_angle_width, float max_angle_height,
-                            const std::array<float, 16>* /*sensor_pose: identity*/ = nullptr,
+                            const Affine3f* sensor_pose = nullptr,
                             CoordinateFrame frame = CAMERA_FRAME, float noise_level = 0.0f, float min_range = 0.0f,
                             int border_size = 0) {
     pfx_ctx* c = b200::use(&cloud);  // the context bound to this cloud
     valid_ = false;
+    pose_ = sensor_pose ? *sensor_pose : identityPose();
+    if (c && !b200::ok(pfx_range_image_set_pose(c, pose_.data()), "RangeImage")) return;
     if (!c || frame != CAMERA_FRAME || noise_level != 0.0f) {
       std::fprintf(stderr, "[pcl::RangeImage] only CAMERA_FRAME with noise_level 0 is implemented\n");
       return;
@@ -924,6 +940,7 @@ class RangeImage {
   bool install() const {
     pfx_ctx* c = b200::ctx();
     if (!c || !valid_) return false;
+    if (!b200::ok(pfx_range_image_set_pose(c, pose_.data()), "RangeImage")) return false;
     return b200::ok(pfx_range_image_set(c, &desc_, raw_.data(), PFX_HOST), "RangeImage");
   }
   const pfx_range_image_desc& desc() const { return desc_; }
@@ -940,8 +957,11 @@ class RangeImage {
     }
     valid_ = true;
   }
+  static Affine3f poseOf(const Affine3f& p) { return p; }
+  template <typename T> static Affine3f poseOf(const T&) { return identityPose(); }  // (any other type: identity)
   pfx_range_image_desc desc_ = {};
   std::vector<float> raw_;
+  Affine3f pose_ = identityPose();
   bool valid_ = false;
 };
 
@@ -951,11 +971,12 @@ class RangeImagePlanar : public RangeImage {
   template <typename CloudT, typename PoseT>
   void createFromPointCloudWithFixedSize(const CloudT& cloud, int di_width, int di_height, float di_center_x,
                                          float di_center_y, float di_focal_length_x, float di_focal_length_y,
-                                         const PoseT& /*sensor_pose: identity for the bundled clouds*/,
-                                         CoordinateFrame frame = CAMERA_FRAME, float noise_level = 0.0f,
-                                         float min_range = 0.0f) {
+                                         const PoseT& sensor_pose, CoordinateFrame frame = CAMERA_FRAME,
+                                         float noise_level = 0.0f, float min_range = 0.0f) {
     pfx_ctx* c = b200::use(&cloud);  // the context bound to this cloud
     valid_ = false;
+    pose_ = poseOf(sensor_pose);  // pcl::Affine3f (identity for the bundled clouds)
+    if (c && !b200::ok(pfx_range_image_set_pose(c, pose_.data()), "RangeImagePlanar")) return;
     if (!c || frame != CAMERA_FRAME || noise_level != 0.0f) {
       std::fprintf(stderr, "[pcl::RangeImagePlanar] only CAMERA_FRAME with noise_level 0 is implemented\n");
       return;

@@ -145,3 +145,64 @@ def test_narf_end_to_end_c3(ctx, orc, indoor):
     assert f.shape == of.shape
     if len(of):
         assert np.abs(f[:, 6:] - of[:, 6:]).max() <= 1e-4
+
+
+def _pose(axis, angle, t):
+    axis = np.asarray(axis, np.float64) / np.linalg.norm(axis)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    R = np.eye(3) + np.sin(angle) * K + (1 - np.cos(angle)) * (K @ K)
+    P = np.eye(4)
+    P[:3, :3], P[:3, 3] = R, t
+    return P
+
+
+@pytest.mark.parametrize("planar", [True, False])
+def test_sensor_pose_moves_the_world_not_the_image(ctx, indoor, planar):
+    """keypoints.h:207-210 hands RangeImage the pose translation(sensor_origin_) * rotation(sensor_orientation_).  A
+    cloud moved rigidly together with its sensor must give the image of the unmoved cloud under the identity pose:
+    the same ranges (up to the float rounding of the transform), the image points, keypoint positions and Narf36
+    poses moved by the pose, the same descriptor values."""
+    P = _pose([0.3, -1.0, 0.5], 0.7, [0.4, -1.1, 2.0])
+    R, t = P[:3, :3], P[:3, 3]
+    moved = (indoor.astype(np.float64) @ R.T + t).astype(np.float32)
+
+    def run(cloud, pose):
+        ctx.set_surface(cloud)
+        ctx.range_image_set_pose(pose)
+        if planar:
+            ctx.range_image_planar(W, H, W / 2, H / 2, F, F)
+        else:
+            ctx.range_image_spherical(float(np.deg2rad(0.5)))
+        d, img = ctx.range_image_get()
+        kp, xyz, val, _ = ctx.narf_keypoints(0.2)
+        f = ctx.narf36(kp, 0.2, True)
+        return d, img, kp, xyz, f
+
+    try:
+        d0, img0, kp0, xyz0, f0 = run(indoor, None)
+        d1, img1, kp1, xyz1, f1 = run(moved, P)
+    finally:
+        ctx.range_image_set_pose(None)
+    assert (d0.width, d0.height, d0.off_x, d0.off_y) == (d1.width, d1.height, d1.off_x, d1.off_y)
+    r0, r1 = img0[..., 3], img1[..., 3]
+    both = np.isfinite(r0) & np.isfinite(r1)
+    assert (np.isfinite(r0) == np.isfinite(r1)).mean() > 0.999
+    # the moved cloud lands in the sensor frame within ~1e-6 m of the original: ranges agree to that, except where a
+    # point sat on a pixel boundary and now feeds the neighbouring pixel
+    close = np.abs(r0[both] - r1[both]) <= 2e-5
+    assert close.mean() > 0.995, close.mean()
+    # image points are world coordinates: those of the unmoved image, moved
+    want = img0[..., :3][both].astype(np.float64) @ R.T + t
+    good = np.abs(r0[both] - r1[both]) <= 2e-5
+    assert np.abs(img1[..., :3][both][good] - want[good]).max() < 1e-4
+    # keypoints: (almost) the same pixels, positions moved by the pose, descriptors unchanged
+    common = np.intersect1d(kp0, kp1)
+    assert len(common) >= 0.8 * max(len(kp0), 1) and len(kp0) > 5
+    i0 = np.searchsorted(kp0, common)
+    i1 = np.searchsorted(kp1, common)
+    assert np.abs(xyz1[i1] - (xyz0[i0].astype(np.float64) @ R.T + t)).max() < 1e-4
+    assert abs(len(f0) - len(f1)) <= max(2, 0.2 * len(f0))
+    # descriptors of keypoints that yield one orientation each in both runs: same values, positions moved
+    if len(f0) == len(f1) and np.array_equal(kp0, kp1):
+        assert np.abs(f1[:, :3] - (f0[:, :3].astype(np.float64) @ R.T + t)).max() < 1e-3
+        assert np.median(np.abs(f1[:, 6:] - f0[:, 6:]).max(1)) < 1e-3
