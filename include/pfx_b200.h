@@ -200,14 +200,17 @@ int pfx_match_info(pfx_ctx* ctx, double* out4);
  * pfx_group_unique_id   fills 128 bytes (ncclUniqueId) on one rank; hand them to all ranks
  * pfx_group_join        ncclCommInitRank for this context's device
  * pfx_slab_distribute   the ranks hold arbitrary disjoint parts of one cloud (records of `stride` bytes, xyz first;
- *                       global_ids optional int32 per point, default = position in the concatenation of the parts
- *                       in rank order).  The cloud is cut into `world` slabs along its longest axis at equal-count
- *                       cuts; on return the surface of this context = the points of its slab (rows 0 .. n_owned-1)
- *                       followed by every point within `halo` of the slab (n_local rows in all), moved device to
- *                       device by grouped ncclSend / ncclRecv.  With halo >= the support of the stage chain
+ *                       global_ids optional int32 per point, unique, default = position in the concatenation of the
+ *                       parts in rank order).  The cloud is cut into `world` slabs along its longest axis at
+ *                       equal-count cuts; on return the surface of this context = the n_owned points of its slab and
+ *                       every point within `halo` of it (n_local rows in all), moved device to device by grouped
+ *                       ncclSend / ncclRecv and held in ASCENDING GLOBAL-ID order, so that every (distance, index)
+ *                       tie-break of the stages resolves as it does on one GPU and sharded rows equal single-GPU rows
+ *                       bit for bit.  With halo >= the support of the stage chain
  *                       (normals r_n; FPFH 2 r_f + r_n; SHOT r_s + r_n; k-searches: multiples of the largest k-th
  *                       neighbour distance) the dense stages give every owned point the rows it gets on one GPU.
- * pfx_slab_global_ids   int32 [n_local]: the global id of every local surface point
+ * pfx_slab_owned_rows   int32 [n_owned]: the local rows (ascending) that belong to this rank's slab
+ * pfx_slab_global_ids   int32 [n_local]: the global id of every local surface point (ascending)
  * pfx_match_ring        exact 1-NN with both descriptor sets sharded: every rank passes its query rows `a` and its
  *                       target block `b` (first global row b_offset); target blocks rotate around the ring under the
  *                       match; nn_idx = GLOBAL target row (-1 none), ties -> lowest global row, as pfx_match_nn.
@@ -220,6 +223,7 @@ int pfx_group_info(const pfx_ctx* ctx, int* rank, int* world);
 int pfx_group_allreduce(pfx_ctx* ctx, double* vals, int n, int op);
 int pfx_slab_distribute(pfx_ctx* ctx, const void* part, size_t n_part, size_t stride, const int32_t* global_ids, int mem,
                         double halo, size_t* n_owned, size_t* n_local);
+int pfx_slab_owned_rows(pfx_ctx* ctx, int32_t* out, int mem);
 int pfx_slab_global_ids(pfx_ctx* ctx, int32_t* out, int mem);
 /* info6: [0] axis, [1] n_owned, [2] n_local, [3] points over all ranks, [4] / [5] lower / upper bound of the slab */
 int pfx_slab_info(const pfx_ctx* ctx, double* info6);

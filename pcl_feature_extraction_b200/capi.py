@@ -64,6 +64,7 @@ SIGNATURES = {
     "pfx_group_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
     "pfx_group_allreduce": (_i, [_vp, C.POINTER(_d), _i, _i]),
     "pfx_slab_distribute": (_i, [_vp, _vp, _sz, _sz, _vp, _i, _d, C.POINTER(_sz), C.POINTER(_sz)]),
+    "pfx_slab_owned_rows": (_i, [_vp, _vp, _i]),
     "pfx_slab_global_ids": (_i, [_vp, _vp, _i]),
     "pfx_slab_info": (_i, [_vp, C.POINTER(_d)]),
     "pfx_match_ring": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _i, _i, _vp, _vp, _i]),
@@ -598,6 +599,13 @@ class Context:
         no, nl = C.c_size_t(0), C.c_size_t(0)
         self._chk(self.lib.pfx_slab_distribute(self.h, ptr, n, st, gid, mem, float(halo), C.byref(no), C.byref(nl)))
         return no.value, nl.value
+
+    def slab_owned_rows(self):
+        """local rows (ascending) of this rank's own points"""
+        info = self.slab_info()
+        out = np.zeros(info["n_owned"], np.int32)
+        self._chk(self.lib.pfx_slab_owned_rows(self.h, _ptr(out), HOST))
+        return out
 
     def slab_global_ids(self):
         info = self.slab_info()

@@ -370,6 +370,21 @@ static int radix_sort_pairs(Ctx* ctx, Grid* g, int n) {
   return 0;  // 4 passes: result is back in keys / vals
 }
 
+// ascending sort of n (uint32 key, int value) pairs held in the scratch buffers of ctx->vg_scratch (keys / vals):
+// used by the slab distribution (group.cu) to order the local points by global id
+int sort_pairs_scratch(Ctx* ctx, int n, uint32_t** keys, int** vals) {
+  Grid* g = &ctx->vg_scratch;
+  const size_t nn = (size_t)std::max(n, 1);
+  PFX_CUDA(g->keys.ensure(nn * sizeof(uint32_t)));
+  PFX_CUDA(g->keys2.ensure(nn * sizeof(uint32_t)));
+  PFX_CUDA(g->vals.ensure(nn * sizeof(int)));
+  PFX_CUDA(g->vals2.ensure(nn * sizeof(int)));
+  *keys = g->keys.as<uint32_t>();
+  *vals = g->vals.as<int>();
+  return 0;
+}
+int sort_pairs_scratch_run(Ctx* ctx, int n) { return n > 1 ? radix_sort_pairs(ctx, &ctx->vg_scratch, n) : 0; }
+
 // ------------------------------------------------------------------------------- post-sort stages
 __global__ void gather_kernel(const float4* __restrict__ pts, const int* __restrict__ vals, int n,
                               float4* __restrict__ sorted, int* __restrict__ inv_perm) {

@@ -5,9 +5,10 @@
 //                         axis (equal-count cuts from an all-reduced histogram) and every rank receives the points of
 //                         its slab plus a halo of the given width: a device-side pack per peer (stable stream
 //                         compaction), the count matrix by ncclAllGather, the payload by grouped ncclSend / ncclRecv
-//                         (NVLink P2P), then owned-first partition.  The surface of the context becomes
-//                         owned + halo points; the unchanged dense stages run on it and the first n_owned rows are
-//                         this rank's results.  (SURVEY.md section 8e partitioning 2.)
+//                         (NVLink P2P), then a sort by global id.  The surface of the context becomes the owned +
+//                         halo points in ascending global-id order (so that index tie-breaks resolve as on one
+//                         GPU); the unchanged dense stages run on it and pfx_slab_owned_rows lists the rows that
+//                         are this rank's results.  (SURVEY.md section 8e partitioning 2.)
 //   pfx_match_ring        exact 1-NN with BOTH descriptor sets sharded: target blocks rotate around the ring on a
 //                         second stream (ncclSend / ncclRecv) while the current block is matched (tcgen05 engine or
 //                         exact scan); each rank keeps the packed (d2 bits << 32 | global index) minimum of its own
@@ -179,12 +180,24 @@ __global__ void slab_pack_kernel(const float4* __restrict__ pts, const int* __re
   if (i < n && flags[i]) out[pos[i]] = pts[i];
 }
 
-// owned-first partition of the received rows: flags = 1 for rows inside my slab
-__global__ void slab_owned_kernel(const float4* __restrict__ pts, int n, int axis, float lo, float hi, int i_am_first,
-                                  int want_owned, int* __restrict__ flags) {
+// sort keys of the received rows: the global id (unique), value = position in the receive buffer
+__global__ void slab_keys_kernel(const float4* __restrict__ rows, int n, uint32_t* __restrict__ keys, int* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float4 p = pts[i];
+  keys[i] = (uint32_t)__float_as_int(rows[i].w);
+  vals[i] = i;
+}
+
+// local point j = the received row of j-th smallest global id: surface (w = local index), global ids, and the flag
+// "inside my slab" (non-finite points belong to slab 0)
+__global__ void slab_commit_kernel(const float4* __restrict__ rows, const int* __restrict__ order, int n, int axis, float lo,
+                                   float hi, int i_am_first, float4* __restrict__ surf, int* __restrict__ gid,
+                                   int* __restrict__ own_flag) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const float4 p = rows[order[j]];
+  surf[j] = make_float4(p.x, p.y, p.z, __int_as_float(j));
+  gid[j] = __float_as_int(p.w);
   int own;
   if (!finite3(p.x, p.y, p.z)) {
     own = i_am_first;
@@ -192,18 +205,12 @@ __global__ void slab_owned_kernel(const float4* __restrict__ pts, int n, int axi
     const float c = coord_of(p, axis);
     own = (c >= lo && c < hi) ? 1 : 0;
   }
-  flags[i] = (own == want_owned) ? 1 : 0;
+  own_flag[j] = own;
 }
 
-// rows -> surface (w = local index) + global ids
-__global__ void slab_commit_kernel(const float4* __restrict__ rows, const int* __restrict__ flags, const int* __restrict__ pos,
-                                   int n, int base, float4* __restrict__ surf, int* __restrict__ gid) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !flags[i]) return;
-  const int j = base + pos[i];
-  const float4 p = rows[i];
-  surf[j] = make_float4(p.x, p.y, p.z, __int_as_float(j));
-  gid[j] = __float_as_int(p.w);
+__global__ void slab_own_list_kernel(const int* __restrict__ flags, const int* __restrict__ pos, int n, int* __restrict__ list) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n && flags[j]) list[pos[j]] = j;
 }
 
 // ------------------------------------------------------------------------------------------- ring match
@@ -474,28 +481,31 @@ extern "C" int pfx_slab_distribute(pfx_ctx* ctx, const void* part, size_t n_part
     PFX_CUDA(cudaMemcpyAsync(recv.as<float4>() + recv_off[rank], pack.as<float4>() + send_off[rank],
                              (size_t)send_count[rank] * sizeof(float4), cudaMemcpyDeviceToDevice, st));
 
-  // ---- owned first, halo after (both stable: the local order is a function of the global order of the parts)
+  // ---- local order = ascending GLOBAL id, owned and halo points alike.  Every (d2, index) tie-break of the stages
+  // (the k-th neighbour of a k-search, the median fallback of the SHOT frame) then resolves exactly as it does when
+  // the whole cloud is described on one GPU, where the index IS the global id: sharded rows equal single-GPU rows bit
+  // for bit.  The rows of this rank's own points are listed in ctx->slab_own (ascending).
   PFX_CUDA(ctx->surf.ensure(std::max<size_t>(n_local, 1) * sizeof(float4)));
   PFX_CUDA(ctx->slab_gid.ensure(std::max<size_t>(n_local, 1) * sizeof(int)));
+  PFX_CUDA(ctx->slab_own.ensure(std::max<size_t>(n_local, 1) * sizeof(int)));
   int n_owned = 0;
   if (n_local > 0) {
+    uint32_t* skeys = nullptr;
+    int* svals = nullptr;
+    PFX_TRY(sort_pairs_scratch(ctx, n_local, &skeys, &svals));
+    PFX_LAUNCH(ctx, slab_keys_kernel, div_up(n_local, 256), 256, 0, recv.as<float4>(), n_local, skeys, svals);
+    PFX_TRY(sort_pairs_scratch_run(ctx, n_local));
     PFX_CUDA(ctx->tmp1.ensure((size_t)n_local * sizeof(int)));
     PFX_CUDA(ctx->tmp2.ensure((size_t)n_local * sizeof(int)));
     flags = ctx->tmp1.as<int>();
     pos = ctx->tmp2.as<int>();
     int* d_total = d_counts + 40;
-    PFX_LAUNCH(ctx, slab_owned_kernel, div_up(n_local, 256), 256, 0, recv.as<float4>(), n_local, axis, cuts[rank], cuts[rank + 1],
-               rank == 0 ? 1 : 0, 1, flags);
+    PFX_LAUNCH(ctx, slab_commit_kernel, div_up(n_local, 256), 256, 0, recv.as<float4>(), svals, n_local, axis, cuts[rank],
+               cuts[rank + 1], rank == 0 ? 1 : 0, ctx->surf.as<float4>(), ctx->slab_gid.as<int>(), flags);
     PFX_TRY(scan_exclusive_i32(ctx, flags, pos, n_local, d_total, ctx->scanbuf));
-    PFX_LAUNCH(ctx, slab_commit_kernel, div_up(n_local, 256), 256, 0, recv.as<float4>(), flags, pos, n_local, 0,
-               ctx->surf.as<float4>(), ctx->slab_gid.as<int>());
+    PFX_LAUNCH(ctx, slab_own_list_kernel, div_up(n_local, 256), 256, 0, flags, pos, n_local, ctx->slab_own.as<int>());
     PFX_CUDA(cudaMemcpyAsync(&n_owned, d_total, sizeof(int), cudaMemcpyDeviceToHost, st));
     PFX_CUDA(cudaStreamSynchronize(st));
-    PFX_LAUNCH(ctx, slab_owned_kernel, div_up(n_local, 256), 256, 0, recv.as<float4>(), n_local, axis, cuts[rank], cuts[rank + 1],
-               rank == 0 ? 1 : 0, 0, flags);
-    PFX_TRY(scan_exclusive_i32(ctx, flags, pos, n_local, nullptr, ctx->scanbuf));
-    PFX_LAUNCH(ctx, slab_commit_kernel, div_up(n_local, 256), 256, 0, recv.as<float4>(), flags, pos, n_local, n_owned,
-               ctx->surf.as<float4>(), ctx->slab_gid.as<int>());
   }
   PFX_CUDA(cudaGetLastError());
   // ---- the context's surface is now owned + halo
@@ -517,7 +527,20 @@ extern "C" int pfx_slab_distribute(pfx_ctx* ctx, const void* part, size_t n_part
   return 0;
 }
 
-// global ids of the local surface points (first n_owned: this rank's own), int32 [n_local]
+// local row numbers (ascending) of this rank's own points, int32 [n_owned]
+extern "C" int pfx_slab_owned_rows(pfx_ctx* ctx, int32_t* out, int mem) {
+  if (!ctx) return PFX_E_INVALID;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return ctx->fail(PFX_E_STATE, "cudaSetDevice failed");
+  if (!ctx->slab_active) return ctx->fail(PFX_E_STATE, "pfx_slab_owned_rows: no slab surface (pfx_slab_distribute)");
+  if (!out || (mem != PFX_HOST && mem != PFX_DEVICE)) return ctx->fail(PFX_E_INVALID, "pfx_slab_owned_rows: bad arguments");
+  if (ctx->slab_owned == 0) return 0;
+  PFX_CUDA(cudaMemcpyAsync(out, ctx->slab_own.p, ctx->slab_owned * sizeof(int),
+                           mem == PFX_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
+  if (mem == PFX_HOST) PFX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// global ids of the local surface points (ascending), int32 [n_local]
 extern "C" int pfx_slab_global_ids(pfx_ctx* ctx, int32_t* out, int mem) {
   if (!ctx) return PFX_E_INVALID;
   if (cudaSetDevice(ctx->device) != cudaSuccess) return ctx->fail(PFX_E_STATE, "cudaSetDevice failed");

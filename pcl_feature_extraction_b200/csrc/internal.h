@@ -200,7 +200,7 @@ struct Ctx {
 
   // multi-GPU (group.cu): NCCL group membership, slab surface, ring-match buffers
   struct Group* group = nullptr;
-  DevBuf grp_tmp, slab_rows, slab_pack, slab_recv, slab_gid, ring_buf[2], ring_best, ring_res;
+  DevBuf grp_tmp, slab_rows, slab_pack, slab_recv, slab_gid, slab_own, ring_buf[2], ring_best, ring_res;
   bool slab_active = false;
   int slab_axis = 0;
   size_t slab_owned = 0;
@@ -256,6 +256,8 @@ struct Ctx {
 
 // ---- grid.cu
 int grid_get(Ctx* ctx, double radius, int knn_k, Grid** out);
+int sort_pairs_scratch(Ctx* ctx, int n, uint32_t** keys, int** vals);  // scratch (key, value) buffers ...
+int sort_pairs_scratch_run(Ctx* ctx, int n);                           // ... sorted ascending by key in place
 int grid_for_radius(Ctx* ctx, double radius, Grid** out);  // exact, or any grid of the surface whose edge covers the radius
 int grid_prepare_async(Ctx* ctx, double radius);  // build the radius grid on the auxiliary stream
 int grid_wait_pending(Ctx* ctx);                  // main stream waits for every build in flight

@@ -118,9 +118,8 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
         }
         // ---- find tau with count(d2 <= tau) == k.  The first sweep counts at two thresholds around the density
         // estimate (0.8 / 1.25 tau0), which usually brackets rank k at once; interpolation narrows a wide bracket
-        // (the count is nearly linear in tau on a surface); as soon as at most XCAP candidates lie between the
-        // bracket ends they are written to shared memory and the (k - clo)-th smallest of them is picked by rank
-        // counting - one step, however close the k-th and (k+1)-th distances are.
+        // (the count is nearly linear in tau on a surface); once at most XCAP candidates lie between the bracket ends
+        // the (k - clo)-th smallest of them is picked by rank counting.
         float lo = -1.f, hi = INF, tau = tau0;
         int clo = 0, chi = M;
         bool done = !active, fail = false;
@@ -141,8 +140,48 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
           if (!done && ca == k) { tau = ta; done = true; }
           if (!done && cb == k) { tau = tb; done = true; }
         }
+        // The four queries of a pass narrow their brackets TOGETHER (a compare-and-count pass over registers per step,
+        // idle for the queries that are already there) until every one of them is exact or holds at most XCAP
+        // candidates between its bracket ends; the rank extraction then runs ONCE for the whole warp.  (Extracting as
+        // soon as any query was ready ran the extraction block two to four times per pass: the queries of a warp reach
+        // their brackets at different steps.)
         for (int it = 0; it < 40; ++it) {
-          if (__all_sync(FULL, done || fail)) break;
+          const bool ready = done || fail || (hi != INF && (chi - clo) <= XCAP);
+          if (__all_sync(FULL, ready)) break;
+          const bool want_c = !ready;
+          if (want_c) {
+            float t;
+            if (hi == INF) {
+              t = lo * fmaxf(1.25f, ((float)k + 1.f) / ((float)clo + 0.5f));
+            } else if (lo < 0.f) {
+              t = hi * ((float)k / ((float)chi + 0.5f));
+            } else if ((it & 3) != 3) {
+              t = lo + (hi - lo) * (((float)(k - clo) + 0.5f) / (float)(chi - clo + 1));
+            } else {
+              t = 0.5f * lo + 0.5f * hi;
+            }
+            const float lo_next = (lo < 0.f) ? 0.f : __uint_as_float(__float_as_uint(lo) + 1u);
+            if (!(t > lo)) t = lo_next;
+            if (!(t < hi)) t = __uint_as_float(__float_as_uint(hi) - 1u);
+            if (!(t > lo) || !(t < hi)) fail = true;  // adjacent floats around many equal distances
+            tau = t;
+          }
+          int c = 0;
+#pragma unroll
+          for (int r = 0; r < TR; ++r) {
+            if ((r & 3) == 0 && r * 8 >= M) break;
+            c += (d2[r] <= tau) ? 1 : 0;
+          }
+          c = group_sum8(c);
+          if (want_c && !fail) {
+            if (c == k) done = true;
+            else if (c < k) { lo = tau; clo = c; }
+            else { hi = tau; chi = c; }
+          }
+        }
+        {
+          // ---- rank extraction: the candidates between the bracket ends go to shared memory and the (k - clo)-th
+          // smallest of them is picked by rank counting - one step, however close the k-th and (k+1)-th distances are
           const bool want_x = !(done || fail) && hi != INF && (chi - clo) <= XCAP;
           if (__any_sync(FULL, want_x)) {
             unsigned mask = 0;
@@ -185,37 +224,6 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
               else { tau = cand; done = true; }
             }
             __syncwarp();
-          }
-          const bool want_c = !(done || fail);
-          if (!__any_sync(FULL, want_c)) continue;
-          if (want_c) {
-            float t;
-            if (hi == INF) {
-              t = lo * fmaxf(1.25f, ((float)k + 1.f) / ((float)clo + 0.5f));
-            } else if (lo < 0.f) {
-              t = hi * ((float)k / ((float)chi + 0.5f));
-            } else if ((it & 3) != 3) {
-              t = lo + (hi - lo) * (((float)(k - clo) + 0.5f) / (float)(chi - clo + 1));
-            } else {
-              t = 0.5f * lo + 0.5f * hi;
-            }
-            const float lo_next = (lo < 0.f) ? 0.f : __uint_as_float(__float_as_uint(lo) + 1u);
-            if (!(t > lo)) t = lo_next;
-            if (!(t < hi)) t = __uint_as_float(__float_as_uint(hi) - 1u);
-            if (!(t > lo) || !(t < hi)) fail = true;  // adjacent floats around many equal distances
-            tau = t;
-          }
-          int c = 0;
-#pragma unroll
-          for (int r = 0; r < TR; ++r) {
-            if ((r & 3) == 0 && r * 8 >= M) break;
-            c += (d2[r] <= tau) ? 1 : 0;
-          }
-          c = group_sum8(c);
-          if (want_c && !fail) {
-            if (c == k) done = true;
-            else if (c < k) { lo = tau; clo = c; }
-            else { hi = tau; chi = c; }
           }
         }
         if (!done) fail = true;

@@ -36,7 +36,7 @@ def join_group(ctx, dist, rank, world):
 def slab_record(pfx, ctx, torch, dist, dev, rank, world, side=1024, steps=5, warmup=2, verify=False, seed=20240601):
     """one cloud, every rank starting from an arbitrary disjoint part of it (points rank, rank + world, ... of the
     shuffled cloud) resident in ITS device memory.  A step = pfx_slab_distribute (device to device) + the dense
-    stages on owned + halo points."""
+    stages on owned + halo points; the rows pfx_slab_owned_rows lists are this rank's results."""
     from pcl_feature_extraction_b200.synth import sheet_cloud
     pts = sheet_cloud(side=side, pitch=PITCH, seed=seed)
     n_total = len(pts)
@@ -90,6 +90,7 @@ def slab_record(pfx, ctx, torch, dist, dev, rank, world, side=1024, steps=5, war
     surf_rows = torch.empty((n_local, 4), dtype=torch.float32, device=dev)
     ctx._chk(ctx.lib.pfx_get_surface(ctx.h, pfx.capi._ptr(surf_rows), 16, pfx.capi.DEVICE))
     gids_local = ctx.slab_global_ids()
+    own_rows = ctx.slab_owned_rows()      # local rows (ascending global id) of this rank's own points
 
     def dense():
         ctx.set_surface_dev(surf_rows.data_ptr(), n_local, 16)
@@ -122,8 +123,9 @@ def slab_record(pfx, ctx, torch, dist, dev, rank, world, side=1024, steps=5, war
         his = [0.0] * world
         his[rank] = info["hi"] if np.isfinite(info["hi"]) else 0.0
         cut_pos = np.array(ctx.group_allreduce(his, "sum")[: world - 1])
-        gid = torch.from_numpy(gids_local[:n_owned].astype(np.int64)).to(dev)
-        rows = torch.cat([d_f[:n_owned], d_s[:n_owned]], 1)
+        own_t = torch.from_numpy(own_rows.astype(np.int64)).to(dev)
+        gid = torch.from_numpy(gids_local[own_rows].astype(np.int64)).to(dev)
+        rows = torch.cat([d_f[own_t], d_s[own_t]], 1)
         if world > 1:
             sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
             dist.all_gather(sizes, torch.tensor([n_owned], dtype=torch.int64, device=dev))
