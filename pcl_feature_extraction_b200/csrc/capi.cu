@@ -396,6 +396,8 @@ extern "C" int pfx_set_surface(pfx_ctx* ctx, const void* pts, size_t n, size_t s
       ctx->nq = 0;
       ctx->qry_version++;
       ctx->have_normals = false;
+      ctx->surf_lab_version = 0;  // colours are cheap to hand in again: a fresh surface has none
+      ctx->surf_rgb_version = 0;
       return 0;
     }
   }

@@ -101,6 +101,65 @@ match_exact_kernel(const float* __restrict__ A, int na, int lda, const unsigned 
   }
 }
 
+// A FEW query rows against all targets (the rows the tensor-core matcher could not certify: a handful per call).  The
+// tiled kernel above would spend a 64-row tile on them; here one THREAD owns one target row and keeps the distances
+// to up to FEW_R query rows (staged in shared memory) in registers, walking its row once - the target matrix is read
+// once per group of FEW_R query rows.  Same sequential float sum, same (d2, index) merge; a target row holding a
+// non-finite value is skipped.
+constexpr int FEW_R = 8, FEW_THREADS = 128, FEW_MAX_ROWS = 64, FEW_MAX_DIM = 1024;
+
+__global__ void __launch_bounds__(FEW_THREADS)
+match_few_kernel(const float* __restrict__ A, int na, int lda, const unsigned char* __restrict__ aok,
+                 const float* __restrict__ B, int nb, int ldb, int dim, unsigned long long* __restrict__ best) {
+  extern __shared__ float few_as[];  // [FEW_R][dim]
+  __shared__ unsigned long long wbest[FEW_THREADS / 32][FEW_R];
+  const int j = blockIdx.x * FEW_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int r0 = 0; r0 < na; r0 += FEW_R) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < FEW_R * dim; e += FEW_THREADS) {
+      const int i = e / dim, d = e - i * dim;
+      few_as[e] = (r0 + i < na) ? A[(size_t)(r0 + i) * lda + d] : 0.f;
+    }
+    __syncthreads();
+    float acc[FEW_R];
+#pragma unroll
+    for (int i = 0; i < FEW_R; ++i) acc[i] = 0.f;
+    bool good = j < nb;
+    if (good) {
+      const float* brow = B + (size_t)j * ldb;
+      for (int d = 0; d < dim; ++d) {
+        const float bv = brow[d];
+        good = good && isfinite(bv);
+#pragma unroll
+        for (int i = 0; i < FEW_R; ++i) {
+          const float df = __fsub_rn(few_as[i * dim + d], bv);
+          acc[i] = __fadd_rn(acc[i], __fmul_rn(df, df));
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < FEW_R; ++i) {
+      unsigned long long key = good ? (((unsigned long long)__float_as_uint(acc[i]) << 32) | (unsigned)j) : PACK_NONE;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(FULL, key, o);
+        key = other < key ? other : key;
+      }
+      if (lane == 0) wbest[wid][i] = key;
+    }
+    __syncthreads();
+    if (threadIdx.x < FEW_R) {
+      const int i = threadIdx.x;
+      unsigned long long key = wbest[0][i];
+#pragma unroll
+      for (int w = 1; w < FEW_THREADS / 32; ++w) key = wbest[w][i] < key ? wbest[w][i] : key;
+      const int ai = r0 + i;
+      if (ai < na && aok[ai] && key != PACK_NONE) atomicMin(&best[ai], key);
+    }
+  }
+}
+
 __global__ void unpack_kernel(const unsigned long long* __restrict__ best, int n, int* __restrict__ idx,
                               float* __restrict__ d2) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -121,9 +180,13 @@ int match_nn_exact(Ctx* ctx, const float* a, int na, int lda, const float* b, in
   unsigned char* aok = flags.as<unsigned char>();
   unsigned char* bok = aok + na;
   PFX_LAUNCH(ctx, row_finite_kernel, div_up(na, 8), 256, 0, a, na, lda, dim, aok);
-  if (nb > 0) PFX_LAUNCH(ctx, row_finite_kernel, div_up(nb, 8), 256, 0, b, nb, ldb, dim, bok);
   PFX_LAUNCH(ctx, pack_init_kernel, div_up(na, 256), 256, 0, best.as<unsigned long long>(), na);
-  if (nb > 0) {
+  if (nb > 0 && na <= FEW_MAX_ROWS && dim <= FEW_MAX_DIM && nb >= 4096) {
+    // a handful of query rows: one thread per target row (finite check of the targets inline)
+    PFX_LAUNCH(ctx, match_few_kernel, div_up(nb, FEW_THREADS), FEW_THREADS, (size_t)FEW_R * dim * sizeof(float), a, na, lda,
+               aok, b, nb, ldb, dim, best.as<unsigned long long>());
+  } else if (nb > 0) {
+    PFX_LAUNCH(ctx, row_finite_kernel, div_up(nb, 8), 256, 0, b, nb, ldb, dim, bok);
     const int nat = div_up(na, MT), nbt = div_up(nb, MT);
     // enough blocks for ~4 waves of the machine, never more splits than B tiles
     int splits = std::max(1, std::min(nbt, (ctx->sm_count * 4 + nat - 1) / nat));

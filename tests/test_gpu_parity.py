@@ -483,6 +483,31 @@ def test_match_bit_exact(ctx, orc, dim, na, nb):
     assert np.array_equal(c["distance"].view(np.uint32), dist.view(np.uint32))
 
 
+@pytest.mark.parametrize("dim,na,nb", [(33, 5, 5000), (352, 64, 4500), (36, 1, 4096), (352, 9, 20000)])
+def test_match_few_query_rows(ctx, orc, dim, na, nb):
+    """a handful of query rows against many targets takes the one-thread-per-target kernel (the redo path of the
+    tensor-core matcher): same bits as the oracle, NaN / inf target rows skipped, ties to the lowest index"""
+    rng = np.random.default_rng(dim + na + nb)
+    a = rng.uniform(0, 1, (na, dim)).astype(np.float32)
+    b = rng.uniform(0, 1, (nb, dim)).astype(np.float32)
+    b[100] = a[0]
+    b[200] = a[0]            # an exact tie: index 100 must win
+    b[50, 3] = np.nan
+    b[51, 0] = np.inf
+    if na > 2:
+        a[2, 1] = np.nan     # a query row that can never match
+    ctx.set_match_engine(0)
+    try:
+        idx, d2 = ctx.match_nn(a, b)
+    finally:
+        ctx.set_match_engine(-1)
+    oidx, od2 = orc.match_nn(a, b)
+    assert np.array_equal(idx, oidx) and idx[0] == 100
+    ok = oidx >= 0
+    assert np.array_equal(d2[ok].view(np.uint32), od2[ok].view(np.uint32))
+    assert (idx != 50).all() and (idx != 51).all()
+
+
 def test_match_ties_and_nan_rows(ctx, orc):
     rng = np.random.default_rng(11)
     a = rng.integers(0, 3, (300, 33)).astype(np.float32)  # many exact ties
