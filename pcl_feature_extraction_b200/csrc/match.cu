@@ -128,7 +128,24 @@ match_few_kernel(const float* __restrict__ A, int na, int lda, const unsigned ch
     bool good = j < nb;
     if (good) {
       const float* brow = B + (size_t)j * ldb;
-      for (int d = 0; d < dim; ++d) {
+      int d = 0;
+      if ((((size_t)brow) & 15) == 0) {  // 16-byte loads of the target row when it allows them
+        const float4* b4 = reinterpret_cast<const float4*>(brow);
+        for (; d + 4 <= dim; d += 4) {
+          const float4 bq = b4[d >> 2];
+          const float bv[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            good = good && isfinite(bv[e]);
+#pragma unroll
+            for (int i = 0; i < FEW_R; ++i) {
+              const float df = __fsub_rn(few_as[i * dim + d + e], bv[e]);
+              acc[i] = __fadd_rn(acc[i], __fmul_rn(df, df));
+            }
+          }
+        }
+      }
+      for (; d < dim; ++d) {
         const float bv = brow[d];
         good = good && isfinite(bv);
 #pragma unroll

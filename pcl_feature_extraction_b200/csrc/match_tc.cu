@@ -119,53 +119,99 @@ constexpr uint32_t TC_IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32
                                    ((uint32_t)(TC_TILE >> 4) << 24);
 
 // ------------------------------------------------------------------------------------------ prep
-// one warp per (padded) row: operand tile order + |x~|^2 + |x - x~| (+ max of the latter two over the rows).
+// fp32 rows -> operand tiles + |x~|^2 + |x - x~| (+ the maxima of the latter two over the rows).  A block of 8 warps
+// converts EIGHT rows (one row octet of a 128-row tile): lane = (row of the octet, quarter of a 16-byte K chunk), warp
+// w takes the chunks w, w + 8, ...  The eight rows' 16-byte pieces of one chunk are 128 contiguous bytes of the tile
+// (core-matrix order), so every warp store is one full line; loads are 32-byte row segments.  A row holding a
+// non-finite value becomes zeros with an infinite norm (never a candidate).  Sums are combined in a fixed order.
 // TF32 = false: bf16 elements (8 per 16-byte chunk); true: tf32 = fp32 with a 10-bit mantissa (4 per chunk).
 template <bool TF32>
-__global__ void tc_prep_kernel(const float* __restrict__ X, int n, int ld, int dim, int dpad, int npad,
-                               unsigned char* __restrict__ Xt, float* __restrict__ norm, float* __restrict__ err,
-                               unsigned* __restrict__ maxima /* [0] max err bits, [1] max finite norm bits */) {
+__global__ void __launch_bounds__(256)
+tc_prep_kernel(const float* __restrict__ X, int n, int ld, int dim, int dpad, int npad, unsigned char* __restrict__ Xt,
+               float* __restrict__ norm, float* __restrict__ err,
+               unsigned* __restrict__ maxima /* [0] max err bits, [1] max finite norm bits */) {
   constexpr int EPC = TF32 ? 4 : 8;  // elements per 16-byte K chunk
-  const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= npad) return;
-  bool fin = r < n;
-  if (fin) {
-    bool good = true;
-    for (int k = lane; k < dim; k += 32) good = good && isfinite(X[(size_t)r * ld + k]);
-    fin = __all_sync(FULL, good);
+  constexpr int EPT = EPC / 4;       // elements per thread and chunk
+  __shared__ int s_bad[8];
+  __shared__ float s_s2[8][8], s_e2[8][8];  // [warp][row]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int ro = lane >> 2, part = lane & 3;
+  const int r = blockIdx.x * 8 + ro;  // npad is a multiple of 128: r < npad
+  const int nchunk = dpad / EPC;
+  if (threadIdx.x < 8) s_bad[threadIdx.x] = 0;
+  __syncthreads();
+  const float* row = X + (size_t)r * ld;
+  bool bad = false;
+  if (r < n) {
+    for (int c = w; c < nchunk; c += 8) {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int k = c * EPC + part * EPT + e;
+        if (k < dim) bad = bad || !isfinite(row[k]);
+      }
+    }
   }
-  const size_t tile_base = (size_t)(r >> 7) * (size_t)(dpad / EPC) * TC_SLAB;  // bytes
+  if (bad) s_bad[ro] = 1;
+  __syncthreads();
+  const bool fin = r < n && !s_bad[ro];
+  const size_t tile_base = (size_t)(r >> 7) * (size_t)nchunk * TC_SLAB;  // bytes
   const int rr = r & 127;
   const size_t row_off = (size_t)(rr >> 3) * 128 + (size_t)(rr & 7) * 16;
   float s2 = 0.f, e2 = 0.f;
-  for (int k = lane; k < dpad; k += 32) {
-    float v = (fin && k < dim) ? X[(size_t)r * ld + k] : 0.f;
-    float vr;
-    unsigned char* dst = Xt + tile_base + (size_t)(k / EPC) * TC_SLAB + row_off;
+  for (int c = w; c < nchunk; c += 8) {
+    float v[EPT], vr[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int k = c * EPC + part * EPT + e;
+      v[e] = (fin && k < dim) ? row[k] : 0.f;
+    }
+    unsigned char* dst = Xt + tile_base + (size_t)c * TC_SLAB + row_off + (size_t)part * 4;
     if (TF32) {
       uint32_t bits;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bits) : "f"(v));
-      vr = __uint_as_float(bits);
-      reinterpret_cast<float*>(dst)[k % EPC] = vr;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bits) : "f"(v[0]));
+      vr[0] = __uint_as_float(bits);
+      *reinterpret_cast<float*>(dst) = vr[0];
     } else {
-      __nv_bfloat16 h = __float2bfloat16_rn(v);
-      vr = __bfloat162float(h);
-      reinterpret_cast<__nv_bfloat16*>(dst)[k % EPC] = h;
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[EPT - 1]);
+      vr[0] = __bfloat162float(h0);
+      vr[EPT - 1] = __bfloat162float(h1);
+      __nv_bfloat162 pair;
+      pair.x = h0;
+      pair.y = h1;
+      *reinterpret_cast<__nv_bfloat162*>(dst) = pair;
     }
-    s2 = fmaf(vr, vr, s2);
-    float dv = v - vr;
-    e2 = fmaf(dv, dv, e2);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      s2 = fmaf(vr[e], vr[e], s2);
+      const float dv = v[e] - vr[e];
+      e2 = fmaf(dv, dv, e2);
+    }
   }
-  s2 = warp_sum(s2);
-  e2 = warp_sum(e2);
-  if (lane == 0) {
-    float e = fin ? sqrtf(e2) * 1.001f + 1e-30f : 0.f;
-    norm[r] = fin ? s2 : TC_BIG;
-    err[r] = e;
-    if (fin) {
+  // the four lanes of a row, then the eight warps in a fixed order
+  s2 += __shfl_xor_sync(FULL, s2, 1);
+  s2 += __shfl_xor_sync(FULL, s2, 2);
+  e2 += __shfl_xor_sync(FULL, e2, 1);
+  e2 += __shfl_xor_sync(FULL, e2, 2);
+  if (part == 0) {
+    s_s2[w][ro] = s2;
+    s_e2[w][ro] = e2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    const int rw = blockIdx.x * 8 + threadIdx.x;
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) {
+      a += s_s2[ww][threadIdx.x];
+      b += s_e2[ww][threadIdx.x];
+    }
+    const bool f = rw < n && !s_bad[threadIdx.x];
+    const float e = f ? sqrtf(b) * 1.001f + 1e-30f : 0.f;
+    norm[rw] = f ? a : TC_BIG;
+    err[rw] = e;
+    if (f) {
       atomicMax(&maxima[0], __float_as_uint(e));
-      atomicMax(&maxima[1], __float_as_uint(s2));
+      atomicMax(&maxima[1], __float_as_uint(a));
     }
   }
 }
@@ -444,81 +490,119 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
 }
 
 // ------------------------------------------------------------------------------------------ rescore
-// one warp per A row: exact distances of the candidates that can still win, argmin by (d2, j), certificate
-__global__ void __launch_bounds__(256)
+// A block of 8 warps takes 8 A rows.  (1) One warp per row reads its candidate lists, forms the bounds and decides which
+// candidates can still win (usually one to three of 18).  (2) The surviving (row, candidate) pairs of the block are
+// pooled in shared memory and ONE THREAD PER PAIR takes the exact distance (FLANN's sequential float sum, no FMA:
+// 352 dependent additions - with a lane per candidate of its own row a warp ran that loop for two or three busy
+// lanes); the best (d2, j) key per row is kept with a shared-memory atomicMin.  (3) Lane 0 of each row's warp checks
+// the certificate.
+constexpr int RS_ROWS = 8, RS_MAXPAIRS = 512;
+
+__device__ __forceinline__ float tc_exact_d2(const float* __restrict__ a, const float* __restrict__ b, int dim) {
+  float acc = 0.f;
+  int d = 0;
+  // 16-byte loads when both rows allow it (the sum stays sequential over d: FLANN's order)
+  if ((((size_t)a | (size_t)b) & 15) == 0) {
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    for (; d + 4 <= dim; d += 4) {
+      const float4 av = a4[d >> 2], bv = b4[d >> 2];
+      const float d0 = __fsub_rn(av.x, bv.x), d1 = __fsub_rn(av.y, bv.y), d2_ = __fsub_rn(av.z, bv.z), d3 = __fsub_rn(av.w, bv.w);
+      acc = __fadd_rn(acc, __fmul_rn(d0, d0));
+      acc = __fadd_rn(acc, __fmul_rn(d1, d1));
+      acc = __fadd_rn(acc, __fmul_rn(d2_, d2_));
+      acc = __fadd_rn(acc, __fmul_rn(d3, d3));
+    }
+  }
+  for (; d < dim; ++d) {
+    const float df = __fsub_rn(a[d], b[d]);
+    acc = __fadd_rn(acc, __fmul_rn(df, df));
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(RS_ROWS * 32)
 tc_rescore_kernel(const float* __restrict__ A, int na, int lda, const float* __restrict__ B, int nb, int ldb, int dim,
                   const float* __restrict__ cand_d, const int* __restrict__ cand_j, int nlists /* nsplit * TC_LISTS */,
                   const float* __restrict__ norm_a, const float* __restrict__ err_a,
                   const unsigned* __restrict__ maxima_b, int* __restrict__ nn_idx, float* __restrict__ nn_d2,
                   int* __restrict__ redo_list, int* __restrict__ redo_count) {
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= na) return;
-  const float nai = norm_a[i];
-  if (!(nai < 0.5f * TC_BIG)) {  // non-finite query row: never matched
-    if (lane == 0) {
-      nn_idx[i] = -1;
-      if (nn_d2) nn_d2[i] = CUDART_INF_F;
-    }
-    return;
-  }
+  __shared__ unsigned long long s_best[RS_ROWS];
+  __shared__ int s_pair_j[RS_MAXPAIRS];
+  __shared__ unsigned char s_pair_row[RS_MAXPAIRS];
+  __shared__ int s_npairs;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int i = blockIdx.x * RS_ROWS + wid;
+  if (threadIdx.x == 0) s_npairs = 0;
+  if (lane == 0) s_best[wid] = 0xffffffffffffffffull;
+  __syncthreads();
+  const bool row_ok = i < na;
+  const float nai = row_ok ? norm_a[i] : TC_BIG;
+  const bool finite_row = row_ok && nai < 0.5f * TC_BIG;  // a non-finite query row is never matched
   const float eb_max = __uint_as_float(maxima_b[0]), nb_max = __uint_as_float(maxima_b[1]);
-  const float eps = err_a[i] + eb_max;
+  const float eps = (finite_row ? err_a[i] : 0.f) + eb_max;
   // slack of the approximate squared distances themselves: fp32 accumulation of `dim` exact bf16 products,
   // the cancellation in na + nb - 2 dot, and the column number stored in the 7 low mantissa bits of a key
   const float delta2 = 2.4e-7f * (float)dim * sqrtf(nai * nb_max) + 2e-6f * (nai + nb_max);
   const float REL = 2e-5f;
   const int ncand = nlists * TC_KS;
-  const float* cd = cand_d + (size_t)i * ncand;
-  const int* cj = cand_j + (size_t)i * ncand;
-  // outside bound: per list, the bound slot (keys never offered) and, when the list is full, its last entry
-  // (keys offered but rejected or evicted are >= it)
-  float kth = CUDART_INF_F, dmin = CUDART_INF_F;
-  for (int c = lane; c < ncand; c += 32) {
-    const int slot = c % TC_KS;
-    const float d = cd[c];
-    if (slot == TC_K) kth = fminf(kth, d);
-    else if (cj[c] >= 0) {
-      if (slot == TC_K - 1) kth = fminf(kth, d);
-      dmin = fminf(dmin, d);
+  float kth = CUDART_INF_F;
+  if (finite_row) {
+    const float* cd = cand_d + (size_t)i * ncand;
+    const int* cj = cand_j + (size_t)i * ncand;
+    // outside bound: per list, the bound slot (keys never offered) and, when the list is full, its last entry
+    // (keys offered but rejected or evicted are >= it)
+    float dmin = CUDART_INF_F;
+    for (int c = lane; c < ncand; c += 32) {
+      const int slot = c % TC_KS;
+      const float d = cd[c];
+      if (slot == TC_K) kth = fminf(kth, d);
+      else if (cj[c] >= 0) {
+        if (slot == TC_K - 1) kth = fminf(kth, d);
+        dmin = fminf(dmin, d);
+      }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    kth = fminf(kth, __shfl_xor_sync(FULL, kth, o));
-    dmin = fminf(dmin, __shfl_xor_sync(FULL, dmin, o));
-  }
-  // a candidate can only win if its lower bound is below the upper bound of the approximate best
-  const float win_hi = sqrtf(fmaxf(dmin + delta2 + REL * fabsf(dmin), 0.f)) + eps;
-  unsigned long long best = 0xffffffffffffffffull;
-  for (int c0 = 0; c0 < ncand; c0 += 32) {
-    const int c = c0 + lane;
-    unsigned long long key = 0xffffffffffffffffull;
-    if (c < ncand && (c % TC_KS) != TC_K) {
+    for (int o = 16; o > 0; o >>= 1) {
+      kth = fminf(kth, __shfl_xor_sync(FULL, kth, o));
+      dmin = fminf(dmin, __shfl_xor_sync(FULL, dmin, o));
+    }
+    // a candidate can only win if its lower bound is below the upper bound of the approximate best
+    const float win_hi = sqrtf(fmaxf(dmin + delta2 + REL * fabsf(dmin), 0.f)) + eps;
+    for (int c = lane; c < ncand; c += 32) {
+      if ((c % TC_KS) == TC_K) continue;
       const int j = cj[c];
       const float dc = cd[c];
       if (j >= 0 && j < nb && dc < 0.5f * TC_BIG) {
         const float lo = sqrtf(fmaxf(dc - delta2 - REL * fabsf(dc), 0.f)) - eps;
         if (lo <= win_hi) {
-          const float* a = A + (size_t)i * lda;
-          const float* b = B + (size_t)j * ldb;
-          float acc = 0.f;
-          for (int d = 0; d < dim; ++d) {
-            float df = __fsub_rn(a[d], b[d]);
-            acc = __fadd_rn(acc, __fmul_rn(df, df));
+          const int slot = atomicAdd(&s_npairs, 1);
+          if (slot < RS_MAXPAIRS) {
+            s_pair_j[slot] = j;
+            s_pair_row[slot] = (unsigned char)wid;
+          } else {  // (more survivors than the pool holds: take this one here)
+            const float acc = tc_exact_d2(A + (size_t)i * lda, B + (size_t)j * ldb, dim);
+            atomicMin(&s_best[wid], ((unsigned long long)__float_as_uint(acc) << 32) | (unsigned)j);
           }
-          key = ((unsigned long long)__float_as_uint(acc) << 32) | (unsigned)j;
         }
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      unsigned long long other = __shfl_xor_sync(FULL, key, o);
-      key = other < key ? other : key;
-    }
-    best = key < best ? key : best;
   }
-  if (lane == 0) {
+  __syncthreads();
+  const int npairs = min(s_npairs, RS_MAXPAIRS);
+  for (int t = threadIdx.x; t < npairs; t += RS_ROWS * 32) {
+    const int rw = s_pair_row[t], j = s_pair_j[t];
+    const float acc = tc_exact_d2(A + (size_t)(blockIdx.x * RS_ROWS + rw) * lda, B + (size_t)j * ldb, dim);
+    atomicMin(&s_best[rw], ((unsigned long long)__float_as_uint(acc) << 32) | (unsigned)j);
+  }
+  __syncthreads();
+  if (lane == 0 && row_ok) {
+    if (!finite_row) {
+      nn_idx[i] = -1;
+      if (nn_d2) nn_d2[i] = CUDART_INF_F;
+      return;
+    }
+    const unsigned long long best = s_best[wid];
     bool certified = false;
     int j = -1;
     float d2 = CUDART_INF_F;
