@@ -28,8 +28,11 @@ normals_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2, 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int limit = worklist ? *wl_count : nq;
   const int n_valid = g.gp->n_valid;
-  for (int qbase = (blockIdx.x * NWPB + wid) * 32; qbase < limit; qbase += gridDim.x * NWPB * 32) {
-    const int qend = min(32, limit - qbase);
+  // queries per warp before the lanes solve: 32 fills the SIMT width of the eigen solve; a work list (a few hundred
+  // queries the tile path handed back) is spread four to a warp instead, so that it does not end on a few busy warps
+  const int qpw = worklist ? 4 : 32;
+  for (int qbase = (blockIdx.x * NWPB + wid) * qpw; qbase < limit; qbase += gridDim.x * NWPB * qpw) {
+    const int qend = min(qpw, limit - qbase);
     Moments mine;
 #pragma unroll
     for (int i = 0; i < 9; ++i) mine.s[i] = 0.0;

@@ -17,6 +17,7 @@ def pytest_sessionstart(session):
     Existing artefacts are left alone - a snapshot copied to a GPU box must not trigger a rebuild there."""
     needed = [os.path.join(ROOT, "pcl_feature_extraction_b200", "lib", "libpfx_b200.so"),
               os.path.join(ROOT, "pcl_feature_extraction_b200", "lib", "evaluation_b200"),
+              os.path.join(ROOT, "pcl_feature_extraction_b200", "lib", "group_threads_demo"),
               os.path.join(ROOT, "oracle", "liboracle_pcl.so")]
     if not all(os.path.exists(p) for p in needed):
         import __graft_entry__

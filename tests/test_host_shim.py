@@ -208,3 +208,17 @@ def test_evaluation_driver_strict_and_reuse(tmp_path, clouds, orc):
     assert reused >= 3 * 2 * 8          # 3 detectors x 2 clouds x (>= 8 descriptor types announce the cloud again)
     assert p_reused >= 3 * 2 * 4        # ... and at least 4 of them ask for its normals again
     assert passes <= 3 * 2 + 3 * 2      # one pass per big cloud and detector, one per keypoint cloud (spin images)
+
+
+@pytest.mark.gpu
+def test_group_api_from_one_cpp_process_with_a_thread_per_gpu():
+    """the multi-GPU group API (pfx_group_join, pfx_slab_distribute, pfx_slab_owned_rows, pfx_group_allreduce) driven
+    from C++ threads of ONE process, no launcher: as many ranks as the box has GPUs (a group of one on a single-GPU box
+    still goes through NCCL and the whole distribution path); the gathered owned rows must equal the single-GPU rows"""
+    import torch
+    demo = os.path.join(ROOT, "pcl_feature_extraction_b200", "lib", "group_threads_demo")
+    assert os.path.exists(demo), "run __graft_entry__.build()"
+    n = min(torch.cuda.device_count(), 4)
+    r = subprocess.run([demo, str(n), "192"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"n_gpus={n}" in r.stdout and "rows_bit_identical=1" in r.stdout

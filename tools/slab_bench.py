@@ -65,6 +65,21 @@ def slab_record(pfx, ctx, torch, dist, dev, rank, world, side=1024, steps=5, war
         near |= coord >= info["hi"] - 3.0 * dk_all
     dk = ctx.group_allreduce([float(dkk[near].max()) if near.any() else 0.0], "max")[0] * 1.05
     halo = max(3.0 * dk, SHOT_RADIUS + dk)
+    # second look: on the halo-0 surface a point next to a cut misses the neighbours beyond it, so its k-th distance is
+    # overestimated (a half disc).  With the provisional halo in place the k-th distances of the owned points near the
+    # cuts are the true ones: measure them again and shrink the halo to three of those
+    n_own1, n_loc1 = ctx.slab_distribute((d_part.data_ptr(), len(ids)), halo, global_ids=d_ids.data_ptr(), mem=pfx.capi.DEVICE)
+    own1 = ctx.slab_owned_rows()
+    _, d2 = ctx.knn(K_NN)
+    dkk = np.sqrt(d2[own1, -1].astype(np.float64)) if n_own1 else np.zeros(0)
+    coord = pts[ctx.slab_global_ids()[own1], info["axis"]].astype(np.float64)
+    near = np.zeros(len(coord), bool)
+    if np.isfinite(info["lo"]):
+        near |= coord < info["lo"] + halo
+    if np.isfinite(info["hi"]):
+        near |= coord >= info["hi"] - halo
+    dk_true = ctx.group_allreduce([float(dkk[near].max()) if near.any() else 0.0], "max")[0] * 1.05
+    halo = min(halo, max(3.0 * dk_true, SHOT_RADIUS + dk_true))
 
     def distribute():
         return ctx.slab_distribute((d_part.data_ptr(), len(ids)), halo, global_ids=d_ids.data_ptr(), mem=pfx.capi.DEVICE)
