@@ -113,11 +113,21 @@ def c3(gpu, planar):
     return T.ms, {"image": shape, "keypoints": len(kp), "descriptors": len(f)}, kp
 
 
-def report(name, fn, *args):
+def report(name, fn, *args, strict_too=False):
     fn(True, *args)  # warm-up (allocations, first-use costs)
     g_ms, g_info, g_idx = fn(True, *args)
     c_ms, c_info, c_idx = fn(False, *args)
-    out = {"config": name, "gpu_ms": {k: round(v, 3) for k, v in g_ms.items()}, "gpu_total_ms": round(sum(g_ms.values()), 3),
+    strict = None
+    if strict_too:  # PFX_PARITY_STRICT: reference-order arithmetic, index outputs equal to the CPU path's
+        ctx.set_parity_mode(True)
+        try:
+            fn(True, *args)
+            s_ms, s_info, s_idx = fn(True, *args)
+        finally:
+            ctx.set_parity_mode(False)
+        strict = {"gpu_ms": {k: round(v, 3) for k, v in s_ms.items()}, "gpu_total_ms": round(sum(s_ms.values()), 3), "gpu": s_info,
+                  "index_outputs_equal_cpu": s_info == c_info}
+    out = {"config": name, "gpu_strict": strict, "gpu_ms": {k: round(v, 3) for k, v in g_ms.items()}, "gpu_total_ms": round(sum(g_ms.values()), 3),
            "cpu_ms": {k: round(v, 1) for k, v in c_ms.items()}, "cpu_total_ms": round(sum(c_ms.values()), 1),
            "cpu_threads": orc.num_threads(), "gpu": g_info, "cpu": c_info,
            "note": "GPU: C ABI with host buffers (H2D/D2H included), wall clock after a warm-up pass; CPU: restated-PCL oracle, OpenMP"}
@@ -125,8 +135,8 @@ def report(name, fn, *args):
 
 
 if __name__ == "__main__":
-    report("C1 indoor pair: VoxelGrid 1cm + normals r=3cm + ISS + FPFH33 r=5cm + reciprocal matching", c1)
-    report("C2 underwater pair: Harris3D + SHOT352 r=5cm (normals r=3cm) + reciprocal matching", c2)
+    report("C1 indoor pair: VoxelGrid 1cm + normals r=3cm + ISS + FPFH33 r=5cm + reciprocal matching", c1, strict_too=True)
+    report("C2 underwater pair: Harris3D + SHOT352 r=5cm (normals r=3cm) + reciprocal matching", c2, strict_too=True)
     report("C3 indoor source: spherical range image 0.5 deg + NARF keypoints (support 0.2) + Narf36", c3, False)
     report("C3' indoor source: planar 640x480 f=525 range image (the reference's geometry) + NARF + Narf36", c3, True)
     ctx.close()
