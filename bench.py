@@ -72,8 +72,12 @@ def whole_step_bytes(nbar):
 def ncu_traffic(kernel_key):
     """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/), or None"""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return json.load(f).get(kernel_key)
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            path = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(path):
+                with open(path) as f:
+                    return json.load(f).get(kernel_key)
+        return None
     except Exception:
         return None
 
@@ -379,7 +383,7 @@ def main():
 
     def step_device(i):
         ctx.set_surface_dev(devs[i & 1].data_ptr(), n, 16)
-        ctx.prepare_radius(SHOT_RADIUS)  # the SHOT index is built on the auxiliary stream, under the kNN / FPFH stages
+        # (no radius index: dense SHOT takes its neighbourhoods from the k-search rows that normals / FPFH left resident)
         ctx.normals_dev(0.0, K_NN, None)
         ctx.fpfh_dev(0.0, K_NN, d_fpfh.data_ptr())
         ctx.shot352_dev(SHOT_RADIUS, d_shot.data_ptr())
@@ -421,7 +425,6 @@ def main():
 
     def step_on(c, bufs, i):
         c.set_surface_dev(devs[i & 1].data_ptr(), n, 16)
-        c.prepare_radius(SHOT_RADIUS)
         c.normals_dev(0.0, K_NN, None)
         c.fpfh_dev(0.0, K_NN, bufs[0].data_ptr())
         c.shot352_dev(SHOT_RADIUS, bufs[1].data_ptr())
@@ -524,7 +527,6 @@ def main():
         def step_host(i):
             h = hosts[i & 1]
             ctx._chk(ctx.lib.pfx_set_surface(ctx.h, pfx.capi._ptr(h), n, 16, HOST))
-            ctx.prepare_radius(SHOT_RADIUS)
             ctx._chk(ctx.lib.pfx_normals(ctx.h, 0.0, K_NN, None, 16, 3, HOST))
             ctx._chk(ctx.lib.pfx_fpfh(ctx.h, 0.0, K_NN, pfx.capi._ptr(h_fpfh[i & 1]), 132, ASYNC))
             ctx._chk(ctx.lib.pfx_shot352(ctx.h, SHOT_RADIUS, None, pfx.capi._ptr(h_shot[i & 1]), 1444, ASYNC))
@@ -550,16 +552,21 @@ def main():
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
+        # the dominant kernel may run as more than one launch per cloud (shot_fused_kernel: the pass over the k-search
+        # rows + the pass over the rows it could not close); together they produce the n rows the bytes are counted for
         cnt_dom = sum(c for nm, (c, _) in dom_prof.items())
         ms_dom = sum(m for nm, (_, m) in dom_prof.items())
-        per_launch_s = (ms_dom / max(cnt_dom, 1)) * 1e-3
+        launches_per_cloud = max(1, round(cnt_dom / max(args.steps, 1)))
+        per_launch_s = (ms_dom / max(args.steps, 1)) * 1e-3
         alg = ALG_BYTES[dom_key](nbar) * n
         wsb = whole_step_bytes(nbar_radius)
         achieved = alg / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": dom_key, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm_gbs"], "peak_kind": peak_kind + " (burst copy)", "traffic": ncu_traffic(dom_key) if n == (1 << 20) else None,
                     "alg_bytes_per_point": ALG_BYTES[dom_key](nbar), "points_per_launch": n, "mean_neighbours": nbar,
-                    "launch_ms": per_launch_s * 1e3, "timed": "CUDA events on the launching stream over the single-cloud timed region (kernel alone on the GPU)",
+                    "launch_ms": per_launch_s * 1e3, "launches_per_cloud": launches_per_cloud,
+                    "timed": "CUDA events on the launching stream over the single-cloud timed region (kernel alone on the GPU); "
+                             "launch_ms = all launches of this kernel for one cloud",
                     "kernel_shares_of_step": shares,
                     "whole_step": {"alg_bytes_per_point": wsb, "mean_neighbours_radius_stages": nbar_radius,
                                    "achieved_GBps": wsb * n * args.steps / (total_ms * 1e-3) / 1e9,

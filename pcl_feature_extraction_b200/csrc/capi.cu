@@ -2,6 +2,8 @@
 // conversion (strided AoS records <-> the float4 SoA rows the kernels use) and stage sequencing.
 #include <cstring>
 
+#include <cstdlib>
+
 #include "internal.h"
 #include "seqsum.h"
 
@@ -195,6 +197,7 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
   pfx_ctx* c = new pfx_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("PFX_SHOT_ROWS")) c->shot_from_rows = atoi(e) != 0;
   *out = c;
   return 0;
 }
@@ -235,6 +238,10 @@ extern "C" int pfx_destroy(pfx_ctx* ctx) {
     cudaEventDestroy(r.e1);
   }
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->rows_stat.host) {
+    cudaFreeHost(ctx->rows_stat.host);
+    cudaEventDestroy(ctx->rows_stat.ev);
+  }
   delete ctx;
   return 0;
 }
@@ -1015,7 +1022,8 @@ extern "C" int pfx_shot352(pfx_ctx* ctx, double radius, const float* lrf_in, flo
   const size_t nq = ctx->num_queries();
   if (nq == 0) return 0;
   Grid* g = nullptr;
-  PFX_TRY(grid_for_radius(ctx, radius, &g));
+  // frames estimated here + the dense k-search rows of this surface resident: no radius index at all (shot_fused.cu)
+  if (lrf_in || !shot_rows_available(ctx, radius)) PFX_TRY(grid_for_radius(ctx, radius, &g));
   float* dout = out;
   if (mem == PFX_HOST_ASYNC) {
     if (lrf_in) return ctx->fail(PFX_E_INVALID, "pfx_shot352: PFX_HOST_ASYNC output with caller-supplied frames is not supported");

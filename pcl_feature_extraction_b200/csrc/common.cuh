@@ -209,6 +209,37 @@ __device__ __forceinline__ CellBlock stencil_of_pos(const GridDev& g, float x, f
   return make_block(g, c, lane);
 }
 
+// ---- searches on a grid whose cells are SMALLER than the radius (a k-search grid serving a radius stage): m rings of
+// cells around the query's cell, (2m+1)^3 cells visited in chunks of 32.  `need` = radius (1 + 1e-3), the margin a radius
+// grid's own edge carries, so m == 1 exactly when the grid was built for the radius (or a larger one).
+__device__ __forceinline__ int stencil_rings(const GridParams& P, float need) {
+  int m = max(1, (int)ceilf(need * P.inv_e));
+  while ((float)m * P.edge < need) ++m;
+  return m;
+}
+__device__ __forceinline__ int stencil_chunks(int m) {
+  return m == 1 ? 1 : ((2 * m + 1) * (2 * m + 1) * (2 * m + 1) + 31) / 32;
+}
+// chunk ch of the (2m+1)^3 stencil around position (x, y, z): lane l probes cell 32 ch + l
+__device__ __forceinline__ CellBlock stencil_chunk(const GridDev& g, float x, float y, float z, int m, int ch, int lane) {
+  const GridParams& P = *g.gp;
+  const int cx = cell_coord(x, P.ox, P.inv_e, P.nx), cy = cell_coord(y, P.oy, P.inv_e, P.ny),
+            cz = cell_coord(z, P.oz, P.inv_e, P.nz);
+  const int side = 2 * m + 1, l = ch * 32 + lane;
+  int c = -1;
+  if (l < side * side * side) {
+    const int x2 = cx + l % side - m, y2 = cy + (l / side) % side - m, z2 = cz + l / (side * side) - m;
+    if (x2 >= 0 && x2 < P.nx && y2 >= 0 && y2 < P.ny && z2 >= 0 && z2 < P.nz) c = hash_lookup(g, morton3(x2, y2, z2));
+  }
+  return make_block(g, c, lane);
+}
+// the stencil of a query as a sequence of CellBlocks: one block (adjacency row or 27 probes) when m == 1
+template <bool DENSE>
+__device__ __forceinline__ CellBlock stencil_block(const GridDev& g, int qi, float4 q, int m, int ch, int lane) {
+  if (m == 1) return DENSE ? stencil_of_point(g, qi, lane) : stencil_of_pos(g, q.x, q.y, q.z, lane);
+  return stencil_chunk(g, q.x, q.y, q.z, m, ch, lane);
+}
+
 // ---- symmetric 3x3 eigen decomposition by cyclic Jacobi (T = float or double).
 // a = (xx, xy, xz, yy, yz, zz).  Eigenvalues ascending in w, eigenvectors in the columns v[r][c].
 template <typename T>

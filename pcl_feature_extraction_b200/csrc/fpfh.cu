@@ -32,6 +32,53 @@ __device__ __forceinline__ bool pair_bins(float4 q, float4 nq, float4 p, float4 
   return true;
 }
 
+// The same three bins with a third of the arithmetic: reciprocal square roots instead of the two IEEE square roots and
+// five IEEE divisions, float bin coordinates instead of double.  Every approximation is a few ulp, i.e. at most 1e-4
+// of a bin; a pair whose result could differ from the reference arithmetic - a bin coordinate within 2.5e-4 of an
+// edge, the source / target swap decided by less than 1e-5, an ill-conditioned atan2 (|(sn, cs)| < 0.03), anything
+// non-finite - is recomputed by pair_bins, so the bins are ALWAYS those of the exact path (about 1 pair in 800 is).
+__device__ __forceinline__ bool pair_bins_fast(float4 q, float4 nq, float4 p, float4 nj, int& b1, int& b2, int& b3) {
+  float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+  const float s4 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  if (!(s4 > 1e-30f)) return pair_bins(q, nq, p, nj, b1, b2, b3);  // coincident (or denormal distance): exact path decides
+  const float inv4 = rsqrtf(s4);
+  const float a1 = fmaf(nq.z, dz, fmaf(nq.y, dy, nq.x * dx)) * inv4;
+  const float a2 = fmaf(nj.z, dz, fmaf(nj.y, dy, nj.x * dx)) * inv4;
+  const float m1 = fabsf(a1), m2 = fabsf(a2);
+  const bool swap = (m1 < m2) && (m2 <= 1.0f);
+  bool risky = fabsf(m1 - m2) < 1e-5f || fabsf(m2 - 1.0f) < 1e-5f;
+  float ux, uy, uz, tx, ty, tz, f3;
+  if (swap) {
+    ux = nj.x; uy = nj.y; uz = nj.z;
+    tx = nq.x; ty = nq.y; tz = nq.z;
+    dx = -dx; dy = -dy; dz = -dz;
+    f3 = -a2;
+  } else {
+    ux = nq.x; uy = nq.y; uz = nq.z;
+    tx = nj.x; ty = nj.y; tz = nj.z;
+    f3 = a1;
+  }
+  float vx = dy * uz - dz * uy, vy = dz * ux - dx * uz, vz = dx * uy - dy * ux;
+  const float vs = fmaf(vz, vz, fmaf(vy, vy, vx * vx));
+  const float vinv = rsqrtf(vs);
+  vx *= vinv; vy *= vinv; vz *= vinv;
+  const float wx = uy * vz - uz * vy, wy = uz * vx - ux * vz, wz = ux * vy - uy * vx;
+  const float f2 = fmaf(vz, tz, fmaf(vy, ty, vx * tx));
+  const float sn = fmaf(wz, tz, fmaf(wy, ty, wx * tx));
+  const float cs = fmaf(uz, tz, fmaf(uy, ty, ux * tx));
+  const float f1 = fast_atan2f(sn, cs);
+  const float u1 = (f1 + 3.14159274f) * (11.0f * 0.159154943f);
+  const float u2 = (f2 + 1.0f) * 5.5f, u3 = (f3 + 1.0f) * 5.5f;
+  const float e1 = fabsf(u1 - rintf(u1)), e2 = fabsf(u2 - rintf(u2)), e3 = fabsf(u3 - rintf(u3));
+  // (a NaN / Inf normal makes f2 and sn non-finite; vs == 0 makes vinv infinite: all caught by the last test)
+  risky = risky || fminf(e1, fminf(e2, e3)) < 2.5e-4f || fmaf(sn, sn, cs * cs) < 1e-3f || !(fabsf(f2) + fabsf(sn) < 1e30f);
+  if (risky) return pair_bins(q, nq, p, nj, b1, b2, b3);
+  b1 = min(max((int)floorf(u1), 0), 10);
+  b2 = 11 + min(max((int)floorf(u2), 0), 10);
+  b3 = 22 + min(max((int)floorf(u3), 0), 10);
+  return true;
+}
+
 // T[c] = c sequential float additions of incr (PCL's hist += hist_incr), c = 0..32
 __device__ __forceinline__ void build_incr_table(float* T, int n_nb, int lane) {
   float incr = (n_nb > 1) ? __fdiv_rn(100.0f, (float)(n_nb - 1)) : 0.f;
@@ -73,7 +120,7 @@ spfh_kernel(GridDev g, const float4* __restrict__ nrm, float r2, const int* __re
   auto consume = [&](int j, bool valid) {
     int b1 = -1, b2 = -1, b3 = -1;
     if (valid && j != i && nq_ok) {
-      if (!pair_bins(q, nq, g.pts[j], nrm[j], b1, b2, b3)) b1 = b2 = b3 = -1;
+      if (!pair_bins_fast(q, nq, g.pts[j], nrm[j], b1, b2, b3)) b1 = b2 = b3 = -1;
     }
     unsigned m1 = __match_any_sync(FULL, b1);
     unsigned m2 = __match_any_sync(FULL, b2);
@@ -296,14 +343,16 @@ fpfh_list_kernel(GridDev g, const float4* __restrict__ queries, int nq, const in
       if (ok && sidx < 32) {
         myj[t] = lj[sidx];
         const float d2 = ldd[sidx];
-        if (myj[t] >= 0 && d2 != 0.f) myw[t] = __frcp_rn(d2);  // "minus the query point itself": dists == 0 skipped
+        // "minus the query point itself": dists == 0 skipped.  The weights only enter through their 24-bit quantised
+        // ratios to the largest one: the reciprocal unit (1 ulp, deterministic) is as good as the IEEE reciprocal
+        if (myj[t] >= 0 && d2 != 0.f) myw[t] = __fdividef(1.0f, d2);
       }
       n_nb += (myj[t] >= 0) ? 1 : 0;
     }
     n_nb = (int)group9_sum((unsigned)n_nb, c9, grp);
     const float wl = fmaxf(fmaxf(myw[0], myw[1]), fmaxf(myw[2], myw[3]));
     const float wmax = group9_max(wl, c9, grp);
-    const float inv = (wmax > 0.f) ? __frcp_rn(wmax) * 16777216.0f : 0.f;
+    const float inv = (wmax > 0.f) ? __fdividef(16777216.0f, wmax) : 0.f;
     unsigned qv[4], wsum = 0;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {

@@ -1,11 +1,13 @@
 // grid.cu — GPU voxel hash built with sort-and-scan (replaces the kd-tree / FLANN index that the
 // reference builds at features.h:192-193, tools.h:29-30, keypoints.h:186-187,371-372,408-409).
 //
-// build: bbox -> cell edge -> 30-bit Morton keys -> hand-written LSD radix sort (8-bit digits,
-// stable) -> physically permuted float4 points -> cell heads + scan -> cell table -> open-addressing
-// hash of occupied cells -> 27-neighbour adjacency table.  Nothing synchronises with the host: the
-// grid description (GridParams) lives in device memory and every kernel that depends on a
-// data-dependent count uses a grid-stride loop over a device-side bound.
+// build (9 launches): bbox -> [occupied-cell probe at a trial edge, k-search grids] -> 30-bit Morton keys + the digit
+// histograms of all four radix passes -> 4 x one-sweep LSD radix pass (8-bit digits, stable, chained scan with
+// decoupled look-back: one read and one write of the pairs per pass) -> ONE kernel that finds the cell heads, scans
+// them (decoupled look-back again), writes the cell table and the per-point cell ids, inserts the cells into the
+// open-addressing hash and gathers the points into sorted order -> 27-neighbour adjacency table.  Nothing
+// synchronises with the host: the grid description (GridParams) lives in device memory and every kernel that depends
+// on a data-dependent count uses a grid-stride loop over a device-side bound.
 #include "internal.h"
 
 namespace pfx {
@@ -124,8 +126,8 @@ int scan_exclusive_i64(Ctx* ctx, const int* in, long long* out, int n, DevBuf& b
 }
 
 // ------------------------------------------------------------------------------------------ bbox
-struct BuildAcc {
-  uint32_t mn[3], mx[3];
+struct BuildAcc {  // all-zero initial state (one memset): the minima are kept as the complement of their ordered key
+  uint32_t mn_inv[3], mx[3];
   int n_valid;
   int n_cells_probe;  // occupied cells counted at the trial edge (kNN density estimate)
 };
@@ -136,15 +138,6 @@ __device__ __forceinline__ uint32_t f2ord(float f) {
 }
 __device__ __forceinline__ float ord2f(uint32_t u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-}
-
-__global__ void acc_init_kernel(BuildAcc* a) {
-  for (int i = 0; i < 3; ++i) {
-    a->mn[i] = 0xffffffffu;
-    a->mx[i] = 0u;
-  }
-  a->n_valid = 0;
-  a->n_cells_probe = 0;
 }
 
 __global__ void bbox_kernel(const float4* __restrict__ pts, int n, BuildAcc* acc) {
@@ -189,18 +182,19 @@ __global__ void bbox_kernel(const float4* __restrict__ pts, int n, BuildAcc* acc
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int a = 0; a < 3; ++a) {
-      atomicMin(&acc->mn[a], s_mn[a]);
+      atomicMax(&acc->mn_inv[a], ~s_mn[a]);
       atomicMax(&acc->mx[a], s_mx[a]);
     }
     atomicAdd(&acc->n_valid, s_cnt);
   }
 }
 
-// Set the cell edge and the grid dimensions.  edge_req > 0: radius grid.  edge_req <= 0: kNN grid,
-// stage 0 picks a trial edge from the bbox (2-manifold guess), stage 1 rescales it so that an
-// occupied cell holds about `target_occ` points (occupancy measured by cell_probe_kernel).
-__global__ void params_kernel(const BuildAcc* acc, GridParams* gp, float edge_req, int stage,
-                              float target_occ) {
+// The cell edge and the grid dimensions.  edge_req > 0: radius grid.  edge_req <= 0: k-search grid, stage 0 picks a
+// trial edge from the bbox (2-manifold guess), stage 1 rescales it (prev_edge) so that an occupied cell holds about
+// `target_occ` points (occupancy measured by cell_probe_kernel).  A pure function of the accumulator: every kernel
+// that needs the parameters before they are stored recomputes them.
+__device__ __forceinline__ GridParams make_params(const BuildAcc* acc, float edge_req, int stage, float target_occ,
+                                                   float prev_edge) {
   GridParams P;
   int nv = acc->n_valid;
   P.n_valid = nv;
@@ -208,7 +202,7 @@ __global__ void params_kernel(const BuildAcc* acc, GridParams* gp, float edge_re
   if (nv == 0) {
     P.mnx = P.mny = P.mnz = P.mxx = P.mxy = P.mxz = 0.f;
   } else {
-    P.mnx = ord2f(acc->mn[0]); P.mny = ord2f(acc->mn[1]); P.mnz = ord2f(acc->mn[2]);
+    P.mnx = ord2f(~acc->mn_inv[0]); P.mny = ord2f(~acc->mn_inv[1]); P.mnz = ord2f(~acc->mn_inv[2]);
     P.mxx = ord2f(acc->mx[0]); P.mxy = ord2f(acc->mx[1]); P.mxz = ord2f(acc->mx[2]);
   }
   float ex = P.mxx - P.mnx, ey = P.mxy - P.mny, ez = P.mxz - P.mnz;
@@ -221,7 +215,7 @@ __global__ void params_kernel(const BuildAcc* acc, GridParams* gp, float edge_re
       edge = sqrtf(area * target_occ / fmaxf((float)nv, 1.f));
     } else {
       float occ = (float)nv / fmaxf((float)acc->n_cells_probe, 1.f);
-      edge = gp->edge * sqrtf(target_occ / fmaxf(occ, 1e-3f));
+      edge = prev_edge * sqrtf(target_occ / fmaxf(occ, 1e-3f));
     }
     edge = fmaxf(edge, 1e-7f * fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-30f)));
     if (!(edge > 0.f) || !isfinite(edge)) edge = 1.f;
@@ -237,7 +231,17 @@ __global__ void params_kernel(const BuildAcc* acc, GridParams* gp, float edge_re
   P.nx = min(1024, (int)floorf(ex * P.inv_e) + 1);
   P.ny = min(1024, (int)floorf(ey * P.inv_e) + 1);
   P.nz = min(1024, (int)floorf(ez * P.inv_e) + 1);
-  *gp = P;
+  return P;
+}
+// the final parameters of a grid: radius grid (edge_req > 0) or the rescaled k-search grid
+__device__ __forceinline__ GridParams final_params(const BuildAcc* acc, float edge_req, float target_occ) {
+  if (edge_req > 0.f) return make_params(acc, edge_req, 0, 0.f, 0.f);
+  const GridParams trial = make_params(acc, 0.f, 0, target_occ, 0.f);
+  return make_params(acc, 0.f, 1, target_occ, trial.edge);
+}
+
+__global__ void empty_params_kernel(const BuildAcc* acc, GridParams* gp, float edge_req, float target_occ) {
+  *gp = final_params(acc, edge_req, target_occ);  // an empty cloud: zero counts, unit dimensions
 }
 
 __device__ __forceinline__ uint32_t point_key(const GridParams& P, float x, float y, float z) {
@@ -247,9 +251,12 @@ __device__ __forceinline__ uint32_t point_key(const GridParams& P, float x, floa
 }
 
 // count distinct occupied cells at the trial edge with a hash set (kNN density estimate)
-__global__ void cell_probe_kernel(const float4* __restrict__ pts, int n, const GridParams* gp,
+__global__ void cell_probe_kernel(const float4* __restrict__ pts, int n, float target_occ,
                                   uint32_t* hset, uint32_t hmask, BuildAcc* acc) {
-  const GridParams P = *gp;
+  __shared__ GridParams sP;
+  if (threadIdx.x == 0) sP = make_params(acc, 0.f, 0, target_occ, 0.f);  // (n_cells_probe is not read at stage 0)
+  __syncthreads();
+  const GridParams P = sP;
   int local = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 p = pts[i];
@@ -267,50 +274,101 @@ __global__ void cell_probe_kernel(const float4* __restrict__ pts, int n, const G
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(&acc->n_cells_probe, local);
 }
 
-__global__ void keys_kernel(const float4* __restrict__ pts, int n, const GridParams* gp,
-                            uint32_t* __restrict__ keys, int* __restrict__ vals) {
-  const GridParams P = *gp;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4 p = pts[i];
-  keys[i] = point_key(P, p.x, p.y, p.z);
-  vals[i] = i;
+// digit histograms of the four radix passes, accumulated per block in shared memory
+__device__ __forceinline__ void hist4_add(unsigned (*h)[256], uint32_t key) {
+  atomicAdd(&h[0][key & 255u], 1u);
+  atomicAdd(&h[1][(key >> 8) & 255u], 1u);
+  atomicAdd(&h[2][(key >> 16) & 255u], 1u);
+  atomicAdd(&h[3][key >> 24], 1u);
+}
+__device__ __forceinline__ void hist4_flush(unsigned (*h)[256], unsigned* __restrict__ ghist) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+    const unsigned c = (&h[0][0])[i];
+    if (c) atomicAdd(&ghist[i], c);
+  }
+}
+
+// Morton keys of the points under the grid's final parameters (computed here from the accumulator and stored by
+// block 0), the identity permutation, and the digit histograms of the sort that follows
+__global__ void __launch_bounds__(256)
+keys_hist_kernel(const float4* __restrict__ pts, int n, const BuildAcc* acc, float edge_req, float target_occ,
+                 GridParams* gp, uint32_t* __restrict__ keys, int* __restrict__ vals, unsigned* __restrict__ ghist) {
+  __shared__ GridParams sP;
+  __shared__ unsigned h[4][256];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&h[0][0])[i] = 0u;
+  if (threadIdx.x == 0) {
+    sP = final_params(acc, edge_req, target_occ);
+    if (blockIdx.x == 0) *gp = sP;
+  }
+  __syncthreads();
+  const GridParams P = sP;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = pts[i];
+    const uint32_t key = point_key(P, p.x, p.y, p.z);
+    keys[i] = key;
+    vals[i] = i;
+    hist4_add(h, key);
+  }
+  hist4_flush(h, ghist);
+}
+
+// the histograms alone, for keys made elsewhere (VoxelGrid ids, slab global ids)
+__global__ void __launch_bounds__(256)
+rs_hist4_kernel(const uint32_t* __restrict__ keys, int n, unsigned* __restrict__ ghist) {
+  __shared__ unsigned h[4][256];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&h[0][0])[i] = 0u;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) hist4_add(h, keys[i]);
+  hist4_flush(h, ghist);
 }
 
 // ------------------------------------------------------------------------------------ radix sort
-// LSD, 8-bit digits, stable.  Tile = 8 warps x 8 rounds x 32 lanes = 2048 keys; warp w owns the
-// contiguous chunk [w*256, w*256+256) of the tile so that (block, warp, round, lane) is the input
-// order.  Ranking inside a warp uses __match_any_sync (no shared-memory atomics on the hot path).
+// LSD, 8-bit digits, stable, ONE-SWEEP: the digit histograms of all four passes are taken up front (with the keys),
+// so a pass reads its tile of pairs once, ranks them, learns where its digits start in the output from the tiles
+// before it through a chained scan with decoupled look-back (a status word per (tile, digit): 2 flag bits + 30-bit
+// count; tiles are handed out by an atomic ticket, so every predecessor of a running tile is itself running), and
+// writes the pairs once.  Tile = 8 warps x 8 rounds x 32 lanes = 2048 pairs; warp w owns the contiguous chunk
+// [w*256, w*256+256) of the tile so that (tile, warp, round, lane) is the input order.  Ranking inside a warp uses
+// __match_any_sync (no shared-memory atomics on the hot path); the tile is staged in shared memory in sorted order so
+// that the global writes of one digit are contiguous.
 constexpr int RS_THREADS = 256;
 constexpr int RS_ROUNDS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;
+constexpr unsigned LB_AGG = 1u << 30, LB_INCL = 2u << 30, LB_FLAGS = 3u << 30, LB_VALUE = (1u << 30) - 1u;
 
-__global__ void __launch_bounds__(RS_THREADS)
-rs_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift, int nblk, int* __restrict__ ghist) {
-  __shared__ int cnt[256];
-  cnt[threadIdx.x] = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int base = blockIdx.x * RS_TILE + wid * (RS_ROUNDS * 32);
-#pragma unroll
-  for (int r = 0; r < RS_ROUNDS; ++r) {
-    int i = base + r * 32 + lane;
-    if (i < n) atomicAdd(&cnt[(keys[i] >> shift) & 255u], 1);
-  }
-  __syncthreads();
-  ghist[threadIdx.x * nblk + blockIdx.x] = cnt[threadIdx.x];
+__device__ __forceinline__ unsigned ld_status(const unsigned* p) {
+  return *reinterpret_cast<const volatile unsigned*>(p);
 }
+__device__ __forceinline__ void st_status(unsigned* p, unsigned v) { *reinterpret_cast<volatile unsigned*>(p) = v; }
+
+// layout of the sort's control block (zeroed by one memset per sort): tickets, histograms, status words
+struct SortCtl {
+  unsigned ticket[4];
+  unsigned pad[60];
+  unsigned ghist[4][256];
+};
+static size_t sort_ctl_bytes(int ntiles) { return sizeof(SortCtl) + (size_t)4 * ntiles * 256 * sizeof(unsigned); }
 
 __global__ void __launch_bounds__(RS_THREADS)
-rs_scatter_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ vals, int n, int shift,
-                  int nblk, const int* __restrict__ ghist, uint32_t* __restrict__ okeys,
-                  int* __restrict__ ovals) {
+rs_onesweep_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ vals, int n, int pass,
+                   SortCtl* __restrict__ ctl, unsigned* __restrict__ status /* [ntiles][256] of this pass */,
+                   uint32_t* __restrict__ okeys, int* __restrict__ ovals) {
   __shared__ int wcnt[8][256];
+  __shared__ uint32_t skey[RS_TILE];
+  __shared__ int sval[RS_TILE];
+  __shared__ unsigned sdst[256];
+  __shared__ unsigned scan_sm[9];
+  __shared__ int s_tile;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ctl->ticket[pass], 1u);
   for (int i = threadIdx.x; i < 8 * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
   __syncthreads();
+  const int tile = s_tile;
+  const int shift = pass * 8;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  const int base = blockIdx.x * RS_TILE + wid * (RS_ROUNDS * 32);
+  const int tbase = tile * RS_TILE;
+  const int base = tbase + wid * (RS_ROUNDS * 32);
   uint32_t k[RS_ROUNDS];
   int v[RS_ROUNDS], rk[RS_ROUNDS];
 #pragma unroll
@@ -319,6 +377,10 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ val
     bool ok = i < n;
     k[r] = ok ? keys[i] : 0u;
     v[r] = ok ? vals[i] : 0;
+  }
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+    bool ok = base + r * 32 + lane < n;
     int d = ok ? (int)((k[r] >> shift) & 255u) : 256;  // 256: padding lanes group together
     unsigned m = __match_any_sync(FULL, d);
     int old = ok ? wcnt[wid][d] : 0;
@@ -328,41 +390,83 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ val
     __syncwarp();
   }
   __syncthreads();
-  {  // per digit: exclusive prefix over the 8 warps, offset by the global base of (digit, block)
-    int d = threadIdx.x;
-    int run = ghist[d * nblk + blockIdx.x];
+  // thread d owns digit d: counts of the 8 warps -> exclusive prefix, tile total
+  const int d = threadIdx.x;
+  int run = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      int t = wcnt[w][d];
-      wcnt[w][d] = run;
-      run += t;
-    }
+  for (int w = 0; w < 8; ++w) {
+    int t = wcnt[w][d];
+    wcnt[w][d] = run;
+    run += t;
   }
+  unsigned* st = status + (size_t)tile * 256 + d;
+  st_status(st, (tile == 0 ? LB_INCL : LB_AGG) | (unsigned)run);
+  // where digit d starts in the output (all tiles) and inside this tile
+  const unsigned gbase = block_excl_scan<unsigned>(ctl->ghist[pass][d], scan_sm, nullptr);
+  const unsigned lstart = block_excl_scan<unsigned>((unsigned)run, scan_sm, nullptr);
+  unsigned excl = 0;
+  if (tile > 0) {
+    for (int t = tile - 1;; --t) {
+      unsigned sv;
+      do {
+        sv = ld_status(status + (size_t)t * 256 + d);
+      } while ((sv & LB_FLAGS) == 0u);
+      excl += sv & LB_VALUE;
+      if (sv & LB_INCL) break;
+    }
+    st_status(st, LB_INCL | (excl + (unsigned)run));
+  }
+  sdst[d] = gbase + excl - lstart;  // + position inside the sorted tile = position in the output
+#pragma unroll
+  for (int w = 0; w < 8; ++w) wcnt[w][d] += (int)lstart;
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; ++r) {
-    int i = base + r * 32 + lane;
-    if (i < n) {
-      int dst = wcnt[wid][(k[r] >> shift) & 255u] + rk[r];
-      okeys[dst] = k[r];
-      ovals[dst] = v[r];
+    if (base + r * 32 + lane < n) {
+      const int pos = wcnt[wid][(k[r] >> shift) & 255u] + rk[r];
+      skey[pos] = k[r];
+      sval[pos] = v[r];
+    }
+  }
+  __syncthreads();
+  const int tile_n = min(RS_TILE, n - tbase);
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+    const int i = r * RS_THREADS + threadIdx.x;
+    if (i < tile_n) {
+      const uint32_t key = skey[i];
+      const unsigned dst = sdst[(key >> shift) & 255u] + (unsigned)i;
+      okeys[dst] = key;
+      ovals[dst] = sval[i];
     }
   }
 }
 
-static int radix_sort_pairs(Ctx* ctx, Grid* g, int n) {
-  int nblk = div_up(n, RS_TILE);
-  PFX_CUDA(g->ghist.ensure((size_t)256 * nblk * sizeof(int)));
+// sorts the pairs in g->keys / g->vals (result back in the same buffers).  have_hist: the control block was zeroed and
+// the histograms were taken by the kernel that made the keys.
+static int sort_ctl_prepare(Ctx* ctx, Grid* g, int n) {
+  const int ntiles = div_up(n, RS_TILE);
+  PFX_CUDA(g->ghist.ensure(sort_ctl_bytes(ntiles)));
+  PFX_CUDA(cudaMemsetAsync(g->ghist.p, 0, sort_ctl_bytes(ntiles), ctx->stream));
+  return 0;
+}
+
+static int radix_sort_pairs(Ctx* ctx, Grid* g, int n, bool have_hist = false) {
+  const int ntiles = div_up(n, RS_TILE);
   uint32_t* k0 = g->keys.as<uint32_t>();
   uint32_t* k1 = g->keys2.as<uint32_t>();
   int* v0 = g->vals.as<int>();
   int* v1 = g->vals2.as<int>();
+  if (!have_hist) {
+    PFX_TRY(sort_ctl_prepare(ctx, g, n));
+    PFX_LAUNCH(ctx, rs_hist4_kernel, std::min(ctx->sm_count * 4, div_up(n, 256)), 256, 0, k0, n,
+               &g->ghist.as<SortCtl>()->ghist[0][0]);
+  }
+  SortCtl* ctl = g->ghist.as<SortCtl>();
+  unsigned* status = reinterpret_cast<unsigned*>(ctl + 1);
   for (int pass = 0; pass < 4; ++pass) {
-    int shift = pass * 8;
-    PFX_LAUNCH(ctx, rs_hist_kernel, nblk, RS_THREADS, 0, k0, n, shift, nblk, g->ghist.as<int>());
-    PFX_TRY(scan_exclusive_i32(ctx, g->ghist.as<int>(), g->ghist.as<int>(), 256 * nblk, nullptr, g->bsum));
-    PFX_LAUNCH(ctx, rs_scatter_kernel, nblk, RS_THREADS, 0, k0, v0, n, shift, nblk,
-               g->ghist.as<int>(), k1, v1);
+    PFX_LAUNCH(ctx, rs_onesweep_kernel, ntiles, RS_THREADS, 0, k0, v0, n, pass, ctl,
+               status + (size_t)pass * ntiles * 256, k1, v1);
     std::swap(k0, k1);
     std::swap(v0, v1);
   }
@@ -386,17 +490,6 @@ int sort_pairs_scratch(Ctx* ctx, int n, uint32_t** keys, int** vals) {
 int sort_pairs_scratch_run(Ctx* ctx, int n) { return n > 1 ? radix_sort_pairs(ctx, &ctx->vg_scratch, n) : 0; }
 
 // ------------------------------------------------------------------------------- post-sort stages
-__global__ void gather_kernel(const float4* __restrict__ pts, const int* __restrict__ vals, int n,
-                              float4* __restrict__ sorted, int* __restrict__ inv_perm) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int o = vals[i];
-  float4 p = pts[o];
-  p.w = __int_as_float(o);
-  sorted[i] = p;
-  inv_perm[o] = i;
-}
-
 __global__ void heads_kernel(const uint32_t* __restrict__ keys, int n, int* __restrict__ heads) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -404,42 +497,105 @@ __global__ void heads_kernel(const uint32_t* __restrict__ keys, int n, int* __re
   heads[i] = (k != KEY_INVALID && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
 }
 
-// pt_cell holds the exclusive scan of heads on entry; turn it into the cell id of every point and
-// emit the cell table
-__global__ void cells_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ heads, int n,
-                             int* __restrict__ pt_cell, uint32_t* __restrict__ cell_key,
-                             int* __restrict__ cell_start, const int* __restrict__ total_cells,
-                             GridParams* gp) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) {
-    int nc = *total_cells;
-    gp->ncells = nc;
-    cell_start[nc] = gp->n_valid;
-  }
-  if (i >= n) return;
-  int ex = pt_cell[i];
-  int h = heads[i];
-  if (h) {
-    cell_key[ex] = keys[i];
-    cell_start[ex] = i;
-  }
-  pt_cell[i] = (keys[i] == KEY_INVALID) ? -1 : (ex + h - 1);
-}
+// Everything between the sort and the adjacency table in ONE pass over the sorted pairs: cell heads (a key that
+// differs from its predecessor), their exclusive scan across tiles (single-value chained scan with decoupled look-back,
+// tiles handed out by an atomic ticket), the cell table (cell_key / cell_start), the cell id of every point, the
+// insertion of each new cell into the open-addressing hash, and the gather of the points into sorted order
+// (w = original index) with the inverse permutation.  The tile that holds the last pair also stores the cell count
+// and the end sentinel of cell_start.
+constexpr int CF_THREADS = 256;
+constexpr int CF_ITEMS = 8;
+constexpr int CF_TILE = CF_THREADS * CF_ITEMS;
 
-__global__ void hash_insert_kernel(const uint32_t* __restrict__ cell_key, const GridParams* gp,
-                                   uint32_t* hkeys, int* hvals, uint32_t hmask) {
-  int nc = gp->ncells;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
-    uint32_t key = cell_key[c];
-    uint32_t h = (hash_key(key) >> 7) & hmask;
-    for (;;) {
-      uint32_t prev = atomicCAS(&hkeys[h], KEY_INVALID, key);
-      if (prev == KEY_INVALID) {
-        hvals[h] = c;
-        break;
+struct CellsCtl {
+  unsigned ticket;
+  unsigned pad[15];
+};
+
+__global__ void __launch_bounds__(CF_THREADS)
+cells_fused_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ vals, const float4* __restrict__ pts,
+                   int n, CellsCtl* __restrict__ ctl, unsigned* __restrict__ status /* [ntiles] */,
+                   float4* __restrict__ sorted, int* __restrict__ inv_perm, int* __restrict__ pt_cell,
+                   uint32_t* __restrict__ cell_key, int* __restrict__ cell_start, uint32_t* __restrict__ hkeys,
+                   int* __restrict__ hvals, uint32_t hmask, GridParams* gp) {
+  __shared__ int sm[9];
+  __shared__ int s_tile, s_excl;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ctl->ticket, 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  const int base = tile * CF_TILE + threadIdx.x * CF_ITEMS;
+  uint32_t k[CF_ITEMS];
+  uint32_t prev = KEY_INVALID;  // (the first pair of the cloud is a head whenever its key is valid)
+  if (base > 0 && base < n) prev = keys[base - 1];
+  int heads = 0;
+  unsigned hmask_bits = 0;
+#pragma unroll
+  for (int i = 0; i < CF_ITEMS; ++i) {
+    k[i] = (base + i < n) ? keys[base + i] : KEY_INVALID;
+    const bool h = k[i] != KEY_INVALID && (base + i == 0 || k[i] != prev);
+    prev = k[i];
+    hmask_bits |= (h ? 1u : 0u) << i;
+    heads += h ? 1 : 0;
+  }
+  int tile_total;
+  const int thread_excl = block_excl_scan<int>(heads, sm, &tile_total);
+  // exclusive prefix of this tile: warp 0 looks back over its predecessors, 32 at a time
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    if (lane == 0) st_status(status + tile, (tile == 0 ? LB_INCL : LB_AGG) | (unsigned)tile_total);
+    unsigned excl = 0;
+    for (int t0 = tile - 1; t0 >= 0; t0 -= 32) {
+      const int t = t0 - lane;
+      unsigned sv = LB_INCL;  // before tile 0: an inclusive prefix of zero
+      if (t >= 0) {
+        do {
+          sv = ld_status(status + t);
+        } while ((sv & LB_FLAGS) == 0u);
       }
-      h = (h + 1) & hmask;
+      const unsigned incl = __ballot_sync(FULL, (sv & LB_INCL) != 0u);
+      const int first = incl ? __ffs(incl) - 1 : 31;  // nearest predecessor that holds an inclusive prefix
+      unsigned add = (lane <= first) ? (sv & LB_VALUE) : 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(FULL, add, o);
+      excl += add;
+      if (incl) break;
     }
+    if (lane == 0) {
+      if (tile > 0) st_status(status + tile, LB_INCL | (excl + (unsigned)tile_total));
+      s_excl = (int)excl;
+    }
+  }
+  __syncthreads();
+  int ex = s_excl + thread_excl;  // cells that start before my first pair
+#pragma unroll
+  for (int i = 0; i < CF_ITEMS; ++i) {
+    const int idx = base + i;
+    if (idx >= n) break;
+    const bool h = (hmask_bits >> i) & 1u;
+    if (h) {
+      cell_key[ex] = k[i];
+      cell_start[ex] = idx;
+      uint32_t slot = (hash_key(k[i]) >> 7) & hmask;
+      for (;;) {
+        const uint32_t was = atomicCAS(&hkeys[slot], KEY_INVALID, k[i]);
+        if (was == KEY_INVALID) {
+          hvals[slot] = ex;
+          break;
+        }
+        slot = (slot + 1) & hmask;
+      }
+      ++ex;
+    }
+    pt_cell[idx] = (k[i] == KEY_INVALID) ? -1 : ex - 1;
+    const int o = vals[idx];
+    float4 p = pts[o];
+    p.w = __int_as_float(o);
+    sorted[idx] = p;
+    inv_perm[o] = idx;
+  }
+  if (threadIdx.x == CF_THREADS - 1 && (tile + 1) * CF_TILE >= n) {  // the tile with the last pair: ex = all cells
+    gp->ncells = ex;
+    cell_start[ex] = gp->n_valid;
   }
 }
 
@@ -504,40 +660,34 @@ static int grid_build(Ctx* ctx, Grid* g, double radius, int knn_k) {
   const float4* src = ctx->surf.as<float4>();
   const int T = 256;
   const int wide = ctx->sm_count * 4;
-  PFX_LAUNCH(ctx, acc_init_kernel, 1, 1, 0, acc);
-  if (n > 0) PFX_LAUNCH(ctx, bbox_kernel, std::min(wide, div_up(n, T)), T, 0, src, n, acc);
-  if (radius > 0) {
-    float edge = (float)(radius * (1.0 + 1e-3));
-    PFX_LAUNCH(ctx, params_kernel, 1, 1, 0, acc, gp, edge, 0, 0.f);
-  } else {
-    // points per occupied cell: ~k/3 keeps the 3x3x3 stencil of a surface at 100-200 candidates while
-    // the k-th neighbour still falls inside it (cell-tile kNN, knn_tile.cu)
-    float target = std::max(2.0f, ctx->knn_occupancy * (float)knn_k);
-    PFX_LAUNCH(ctx, params_kernel, 1, 1, 0, acc, gp, 0.f, 0, target);
-    if (n > 0) {
-      PFX_CUDA(cudaMemsetAsync(g->hkeys.p, 0xff, ((size_t)g->hmask + 1) * sizeof(uint32_t), ctx->stream));
-      PFX_LAUNCH(ctx, cell_probe_kernel, std::min(wide, div_up(n, T)), T, 0, src, n, gp,
-                 g->hkeys.as<uint32_t>(), g->hmask, acc);
-    }
-    PFX_LAUNCH(ctx, params_kernel, 1, 1, 0, acc, gp, 0.f, 1, target);
-  }
+  const float edge_req = radius > 0 ? (float)(radius * (1.0 + 1e-3)) : 0.f;
+  // points per occupied cell of a k-search grid: ~k/3 keeps the 3x3x3 stencil of a surface at 100-200 candidates
+  // while the k-th neighbour still falls inside it (cell-tile kNN, knn_tile.cu)
+  const float target = radius > 0 ? 0.f : std::max(2.0f, ctx->knn_occupancy * (float)knn_k);
+  PFX_CUDA(cudaMemsetAsync(acc, 0, sizeof(BuildAcc) + 64, ctx->stream));
   if (n > 0) {
-    PFX_LAUNCH(ctx, keys_kernel, div_up(n, T), T, 0, src, n, gp, g->keys.as<uint32_t>(), g->vals.as<int>());
-    PFX_TRY(radix_sort_pairs(ctx, g, n));
-    PFX_LAUNCH(ctx, gather_kernel, div_up(n, T), T, 0, src, g->vals.as<int>(), n, g->pts.as<float4>(),
-               g->inv_perm.as<int>());
-    // heads -> exclusive scan (into pt_cell) -> cell table; vals2 is free after the sort
-    int* heads = g->vals2.as<int>();
-    int* total_cells = reinterpret_cast<int*>(g->misc.as<char>() + sizeof(BuildAcc));
-    PFX_LAUNCH(ctx, heads_kernel, div_up(n, T), T, 0, g->keys.as<uint32_t>(), n, heads);
-    PFX_TRY(scan_exclusive_i32(ctx, heads, g->pt_cell.as<int>(), n, total_cells, g->bsum));
-    PFX_LAUNCH(ctx, cells_kernel, div_up(n, T), T, 0, g->keys.as<uint32_t>(), heads, n,
-               g->pt_cell.as<int>(), g->cell_key.as<uint32_t>(), g->cell_start.as<int>(), total_cells, gp);
+    PFX_LAUNCH(ctx, bbox_kernel, std::min(wide, div_up(n, T)), T, 0, src, n, acc);
+    if (!(radius > 0)) {
+      PFX_CUDA(cudaMemsetAsync(g->hkeys.p, 0xff, ((size_t)g->hmask + 1) * sizeof(uint32_t), ctx->stream));
+      PFX_LAUNCH(ctx, cell_probe_kernel, std::min(wide, div_up(n, T)), T, 0, src, n, target, g->hkeys.as<uint32_t>(),
+                 g->hmask, acc);
+    }
+    PFX_TRY(sort_ctl_prepare(ctx, g, n));
+    PFX_LAUNCH(ctx, keys_hist_kernel, std::min(wide, div_up(n, T)), T, 0, src, n, acc, edge_req, target, gp,
+               g->keys.as<uint32_t>(), g->vals.as<int>(), &g->ghist.as<SortCtl>()->ghist[0][0]);
+    PFX_TRY(radix_sort_pairs(ctx, g, n, true));
+    const int ntiles = div_up(n, CF_TILE);
+    PFX_CUDA(g->bsum.ensure(sizeof(CellsCtl) + (size_t)ntiles * sizeof(unsigned)));
+    PFX_CUDA(cudaMemsetAsync(g->bsum.p, 0, sizeof(CellsCtl) + (size_t)ntiles * sizeof(unsigned), ctx->stream));
     PFX_CUDA(cudaMemsetAsync(g->hkeys.p, 0xff, ((size_t)g->hmask + 1) * sizeof(uint32_t), ctx->stream));
-    PFX_LAUNCH(ctx, hash_insert_kernel, std::min(wide, div_up(n, T)), T, 0, g->cell_key.as<uint32_t>(), gp,
-               g->hkeys.as<uint32_t>(), g->hvals.as<int>(), g->hmask);
+    CellsCtl* cctl = g->bsum.as<CellsCtl>();
+    PFX_LAUNCH(ctx, cells_fused_kernel, ntiles, CF_THREADS, 0, g->keys.as<uint32_t>(), g->vals.as<int>(), src, n, cctl,
+               reinterpret_cast<unsigned*>(cctl + 1), g->pts.as<float4>(), g->inv_perm.as<int>(), g->pt_cell.as<int>(),
+               g->cell_key.as<uint32_t>(), g->cell_start.as<int>(), g->hkeys.as<uint32_t>(), g->hvals.as<int>(), g->hmask,
+               gp);
     PFX_LAUNCH(ctx, adjacency_kernel, wide * 2, T, 0, g->view(), g->cell_nbr.as<int>());
   } else {
+    PFX_LAUNCH(ctx, empty_params_kernel, 1, 1, 0, acc, gp, edge_req, target);
     PFX_CUDA(cudaMemsetAsync(g->cell_start.p, 0, sizeof(int), ctx->stream));
   }
   // the parameters the device settled on (cell edge, dimensions) come back asynchronously: a later radius stage may
@@ -724,7 +874,7 @@ int voxel_grid_run(Ctx* ctx, float leaf, float* out_dev, size_t cap, size_t* n_o
   BuildAcc* acc = g->misc.as<BuildAcc>();
   const float4* src = ctx->surf.as<float4>();
   const int T = 256;
-  PFX_LAUNCH(ctx, acc_init_kernel, 1, 1, 0, acc);
+  PFX_CUDA(cudaMemsetAsync(acc, 0, sizeof(BuildAcc) + 64, ctx->stream));
   PFX_LAUNCH(ctx, bbox_kernel, std::min(ctx->sm_count * 4, div_up(n, T)), T, 0, src, n, acc);
   BuildAcc h;
   PFX_CUDA(cudaMemcpyAsync(&h, acc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
@@ -739,7 +889,7 @@ int voxel_grid_run(Ctx* ctx, float leaf, float* out_dev, size_t cap, size_t* n_o
   const float inv = 1.0f / leaf;
   long long minb[3], divb[3];
   for (int a = 0; a < 3; ++a) {
-    float mn = ord2f_host(h.mn[a]), mx = ord2f_host(h.mx[a]);
+    float mn = ord2f_host(~h.mn_inv[a]), mx = ord2f_host(h.mx[a]);
     minb[a] = (long long)floorf(mn * inv);
     divb[a] = (long long)floorf(mx * inv) - minb[a] + 1;
   }

@@ -212,6 +212,17 @@ struct Ctx {
   DevBuf tc_cand_d, tc_cand_j, tc_redo, tc_rows, tc_res;
   long long match_rows = 0, match_redo = 0, match_tc_calls = 0;  // statistics of the tensor-core matcher
   float knn_occupancy = 0.4f;  // target points per occupied cell of a kNN grid, as a fraction of k
+  // dense SHOT takes its radius neighbourhoods from the resident k-search rows when it can (shot_fused.cu);
+  // PFX_SHOT_ROWS=0 in the environment keeps the stencil walk on a radius grid (A/B measurements)
+  bool shot_from_rows = true;
+  struct RowsStat {  // share of the k-search rows the last rows-based SHOT call could not close (asynchronous read-back)
+    int* host = nullptr;
+    cudaEvent_t ev = nullptr;
+    bool pending = false;
+    double radius = 0, open_frac = 0;
+    int k = 0;
+    size_t n = 0;
+  } rows_stat;
   Grid* last_grid = nullptr;
 
   // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg)
@@ -290,7 +301,8 @@ int shot_lrf_compute(Ctx* ctx, Grid* g, double radius, float* rf9_dev, int* nval
 int shot_compute(Ctx* ctx, Grid* g, double radius, const float* rf9_dev, float* out_dev,
                  size_t stride_floats);
 // ---- shot_fused.cu
-int shot_fused_compute(Ctx* ctx, Grid* g, double radius, float* out_dev, size_t stride_floats);
+int shot_fused_compute(Ctx* ctx, Grid* g, double radius, float* out_dev, size_t stride_floats);  // g may be null
+bool shot_rows_available(Ctx* ctx, double radius);
 
 // ---- keypoints.cu
 int cloud_resolution(Ctx* ctx, double* res);

@@ -279,9 +279,11 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
 #pragma unroll
           for (int i = 0; i < 9; ++i) m9[i] = group_sum8(m9[i]);
           if (good && sl == 0) {
-            double* dst = mom_out + (size_t)qi * 9;
+            // nine planes of n doubles: the four queries of a pass are consecutive, so each store is one sector,
+            // and normals_from_moments_kernel reads every plane coalesced
+            double* dst = mom_out + qi;
 #pragma unroll
-            for (int i = 0; i < 9; ++i) dst[i] = m9[i];
+            for (int i = 0; i < 9; ++i) dst[(size_t)i * g.n] = m9[i];
           }
         }
       }
@@ -297,7 +299,7 @@ __global__ void normals_from_moments_kernel(GridDev g, const double* __restrict_
   if (i >= g.gp->n_valid || qflag[i]) return;
   double s[9];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) s[t] = mom[(size_t)i * 9 + t];
+  for (int t = 0; t < 9; ++t) s[t] = mom[(size_t)t * g.n + i];
   const float4 q = g.pts[i];
   const float4 r = solve_normal_m9(s, k, q.x, q.y, q.z, vx, vy, vz);
   nrm_sorted[i] = r;

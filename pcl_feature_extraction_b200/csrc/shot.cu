@@ -51,9 +51,8 @@ constexpr int WTIE_CAP = 512;  // valid neighbours a warp can rank in shared mem
 
 // collect the keys (d2 bits << 32 | original index) of the valid neighbours into `keys`
 __device__ __forceinline__ int lrf_collect_keys(const GridDev& g, const CellBlock& blk, float4 q, float r2,
-                                                int lane, unsigned long long* keys, int cap) {
+                                                int lane, unsigned long long* keys, int cap, int n) {
   const unsigned lt = (1u << lane) - 1u;
-  int n = 0;
   for (int base = 0; base < blk.total; base += 32) {
     int c = base + lane;
     bool valid = c < blk.total;
@@ -70,7 +69,6 @@ __device__ __forceinline__ int lrf_collect_keys(const GridDev& g, const CellBloc
     if (valid && pos < cap) keys[pos] = key;
     n += __popc(m);
   }
-  __syncwarp();
   return n;
 }
 
@@ -117,13 +115,14 @@ template <bool DENSE>
 __global__ void __launch_bounds__(SWPB * 32)
 lrf_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2, double R, float* __restrict__ rf9,
            TieItem* __restrict__ tie_list, int* __restrict__ tie_count, int tie_cap, const int* __restrict__ qmap,
-           const int* __restrict__ qcount, int qpw /* queries per warp, 1..32 */) {
+           const int* __restrict__ qcount, int qpw /* queries per warp, 1..32 */, float need) {
   __shared__ unsigned long long skeys[SWPB][WTIE_CAP];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int qbase = (blockIdx.x * SWPB + wid) * qpw;
   const int limit = qmap ? min(*qcount, nq) : nq;  // qmap: work list of query numbers (optional)
   if (qbase >= limit) return;
   const int n_valid = g.gp->n_valid;
+  const int rings = stencil_rings(*g.gp, need), nch = stencil_chunks(rings);  // 1 / 1 on a grid built for the radius
   const int qend = min(qpw, limit - qbase);
   LrfAcc mine;
 #pragma unroll
@@ -139,8 +138,10 @@ lrf_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2, doub
     a.sw = 0.0;
     a.nvalid = 0;
     if (finite3(q.x, q.y, q.z) && (!DENSE || qi < n_valid)) {
-      CellBlock blk = DENSE ? stencil_of_point(g, qi, lane) : stencil_of_pos(g, q.x, q.y, q.z, lane);
-      lrf_scan_pass1(g, blk, q, r2, R, lane, a);
+      for (int ch = 0; ch < nch; ++ch) {
+        CellBlock blk = stencil_block<DENSE>(g, qi, q, rings, ch, lane);
+        lrf_scan_pass1(g, blk, q, r2, R, lane, a);
+      }
 #pragma unroll
       for (int i = 0; i < 6; ++i) a.m[i] = warp_sum(a.m[i]);
       a.sw = warp_sum(a.sw);
@@ -175,19 +176,21 @@ lrf_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2, doub
       zs[i] = __shfl_sync(FULL, z[i], t);
     }
     float4 q = DENSE ? g.pts[qi] : queries[qi];
-    CellBlock blk = DENSE ? stencil_of_point(g, qi, lane) : stencil_of_pos(g, q.x, q.y, q.z, lane);
     int px = 0, pz = 0;
-    for (int base = 0; base < blk.total; base += 32) {
-      int c = base + lane;
-      bool valid = c < blk.total;
-      int j = block_candidate(blk, valid ? c : 0);
-      if (valid) {
-        float4 p = g.pts[j];
-        float d2 = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
-        if (d2 < r2 && !(p.x == q.x && p.y == q.y && p.z == q.z)) {
-          double vx = (double)__fsub_rn(p.x, q.x), vy = (double)__fsub_rn(p.y, q.y), vz = (double)__fsub_rn(p.z, q.z);
-          if (vx * xs[0] + vy * xs[1] + vz * xs[2] >= 0) ++px;
-          if (vx * zs[0] + vy * zs[1] + vz * zs[2] >= 0) ++pz;
+    for (int ch = 0; ch < nch; ++ch) {
+      CellBlock blk = stencil_block<DENSE>(g, qi, q, rings, ch, lane);
+      for (int base = 0; base < blk.total; base += 32) {
+        int c = base + lane;
+        bool valid = c < blk.total;
+        int j = block_candidate(blk, valid ? c : 0);
+        if (valid) {
+          float4 p = g.pts[j];
+          float d2 = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
+          if (d2 < r2 && !(p.x == q.x && p.y == q.y && p.z == q.z)) {
+            double vx = (double)__fsub_rn(p.x, q.x), vy = (double)__fsub_rn(p.y, q.y), vz = (double)__fsub_rn(p.z, q.z);
+            if (vx * xs[0] + vy * xs[1] + vz * xs[2] >= 0) ++px;
+            if (vx * zs[0] + vy * zs[1] + vz * zs[2] >= 0) ++pz;
+          }
         }
       }
     }
@@ -197,7 +200,12 @@ lrf_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2, doub
     bool fx = votex < 0, fz = votez < 0;
     if (votex == 0 || votez == 0) {
       if (nv <= WTIE_CAP) {
-        int n = lrf_collect_keys(g, blk, q, r2, lane, skeys[wid], WTIE_CAP);
+        int n = 0;
+        for (int ch = 0; ch < nch; ++ch) {
+          CellBlock blk = stencil_block<DENSE>(g, qi, q, rings, ch, lane);
+          n = lrf_collect_keys(g, blk, q, r2, lane, skeys[wid], WTIE_CAP, n);
+        }
+        __syncwarp();
         int plx, plz;
         lrf_median_votes(g, q, skeys[wid], n, xs, zs, lane, plx, plz);
         if (votex == 0) fx = plx < 3;
@@ -246,12 +254,13 @@ template <bool DENSE>
 __global__ void __launch_bounds__(128)
 lrf_tie_kernel(GridDev g, const float4* __restrict__ queries, float r2, float* __restrict__ rf9,
                const TieItem* __restrict__ tie_list, const int* __restrict__ tie_count, int tie_cap,
-               int* __restrict__ overflow) {
+               int* __restrict__ overflow, float need) {
   __shared__ unsigned long long keys[TIE_CAP];
   __shared__ int cnt, plus_x, plus_z;
   const int total = min(*tie_count, tie_cap);
   if (*tie_count > tie_cap && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(overflow, 1);
   const GridParams P = *g.gp;
+  const int rings = stencil_rings(P, need), side = 2 * rings + 1;
   for (int e = blockIdx.x; e < total; e += gridDim.x) {
     const TieItem it = tie_list[e];
     const int qi = it.qi;
@@ -266,8 +275,8 @@ lrf_tie_kernel(GridDev g, const float4* __restrict__ queries, float r2, float* _
     __syncthreads();
     int cx = cell_coord(q.x, P.ox, P.inv_e, P.nx), cy = cell_coord(q.y, P.oy, P.inv_e, P.ny),
         cz = cell_coord(q.z, P.oz, P.inv_e, P.nz);
-    for (int l = 0; l < 27; ++l) {
-      int x2 = cx + l % 3 - 1, y2 = cy + (l / 3) % 3 - 1, z2 = cz + l / 9 - 1;
+    for (int l = 0; l < side * side * side; ++l) {
+      int x2 = cx + l % side - rings, y2 = cy + (l / side) % side - rings, z2 = cz + l / (side * side) - rings;
       if (x2 < 0 || x2 >= P.nx || y2 < 0 || y2 >= P.ny || z2 < 0 || z2 >= P.nz) continue;
       int c = hash_lookup(g, morton3(x2, y2, z2));
       if (c < 0) continue;
@@ -326,6 +335,7 @@ static int lrf_run(Ctx* ctx, Grid* g, double radius, float* rf9_dev, const int* 
   if (nq == 0) return 0;
   const bool dense = ctx->q_is_surface;
   const float r2 = (float)(radius * radius);
+  const float need = (float)(radius * (1.0 + 1e-3));  // the edge of a radius grid: one ring of cells on such a grid
   const int tie_cap = 65536;
   PFX_CUDA(ctx->tmp1.ensure((size_t)tie_cap * sizeof(TieItem)));
   PFX_CUDA(ctx->small.ensure(256));
@@ -338,14 +348,14 @@ static int lrf_run(Ctx* ctx, Grid* g, double radius, float* rf9_dev, const int* 
   const int blocks = div_up(nq, SWPB * qpw);
   if (dense) {
     PFX_LAUNCH(ctx, lrf_kernel<true>, blocks, SWPB * 32, 0, g->view(), nullptr, nq, r2, radius, rf9_dev, tl, flags,
-               tie_cap, qmap, qcount, qpw);
+               tie_cap, qmap, qcount, qpw, need);
     PFX_LAUNCH(ctx, lrf_tie_kernel<true>, ctx->sm_count, 128, 0, g->view(), nullptr, r2, rf9_dev, tl, flags, tie_cap,
-               flags + 1);
+               flags + 1, need);
   } else {
     PFX_LAUNCH(ctx, lrf_kernel<false>, blocks, SWPB * 32, 0, g->view(), ctx->qry.as<float4>(), nq, r2, radius,
-               rf9_dev, tl, flags, tie_cap, qmap, qcount, qpw);
+               rf9_dev, tl, flags, tie_cap, qmap, qcount, qpw, need);
     PFX_LAUNCH(ctx, lrf_tie_kernel<false>, ctx->sm_count, 128, 0, g->view(), ctx->qry.as<float4>(), r2, rf9_dev, tl,
-               flags, tie_cap, flags + 1);
+               flags, tie_cap, flags + 1, need);
   }
   PFX_CUDA(cudaGetLastError());
   return 0;
@@ -360,8 +370,9 @@ template <bool DENSE>
 __device__ __forceinline__ void shot_one_query(const GridDev& g, const float4* __restrict__ queries, int qi,
                                                const float4* __restrict__ nrm, float r2, double R,
                                                const float* __restrict__ rf9, float* __restrict__ out, size_t stride,
-                                               int* h, int lane) {
+                                               int* h, int lane, float need) {
   const int n_valid = g.gp->n_valid;
+  const int rings = stencil_rings(*g.gp, need), nch = stencil_chunks(rings);  // 1 / 1 on a grid built for the radius
   for (int c = lane; c < 352; c += 32) h[c] = 0;
   __syncwarp();
   float4 q = DENSE ? g.pts[qi] : queries[qi];
@@ -374,20 +385,20 @@ __device__ __forceinline__ void shot_one_query(const GridDev& g, const float4* _
   bool ok = finite3(q.x, q.y, q.z) && (!DENSE || qi < n_valid) && isfinite(rf[0]) && isfinite(rf[3]) &&
             isfinite(rf[6]);
   int n_nb = 0;
-  CellBlock blk;
-  blk.total = 0;
   if (ok) {
-    blk = DENSE ? stencil_of_point(g, qi, lane) : stencil_of_pos(g, q.x, q.y, q.z, lane);
     // neighbour count first: it fixes the fixed-point scale (and the < 5 rule)
-    for (int base = 0; base < blk.total; base += 32) {
-      int c = base + lane;
-      bool valid = c < blk.total;
-      int j = block_candidate(blk, valid ? c : 0);
-      if (valid) {
-        float4 p = g.pts[j];
-        valid = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z) < r2;
+    for (int ch = 0; ch < nch; ++ch) {
+      const CellBlock blk = stencil_block<DENSE>(g, qi, q, rings, ch, lane);
+      for (int base = 0; base < blk.total; base += 32) {
+        int c = base + lane;
+        bool valid = c < blk.total;
+        int j = block_candidate(blk, valid ? c : 0);
+        if (valid) {
+          float4 p = g.pts[j];
+          valid = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z) < r2;
+        }
+        n_nb += __popc(__ballot_sync(FULL, valid));
       }
-      n_nb += __popc(__ballot_sync(FULL, valid));
     }
   }
   if (!ok || n_nb == 0) {
@@ -406,6 +417,8 @@ __device__ __forceinline__ void shot_one_query(const GridDev& g, const float4* _
   const double r12 = R / 2, r14 = R / 4, r34 = 3 * R / 4;
   const float RAD45 = 0.78539816339744830962f, RAD90 = 1.57079632679489661923f, RAD135 = 2.35619449019234492885f,
               RAD_PI_7_8 = 2.7488935718910690836f;
+  for (int ch = 0; ch < nch; ++ch) {
+  const CellBlock blk = stencil_block<DENSE>(g, qi, q, rings, ch, lane);
   for (int base = 0; base < blk.total; base += 32) {
     int c = base + lane;
     bool valid = c < blk.total;
@@ -496,6 +509,7 @@ __device__ __forceinline__ void shot_one_query(const GridDev& g, const float4* _
     }
     shot_add(h, vol + step, w, scale);
   }
+  }
   __syncwarp();
   // normalise: h / sqrt(sum h^2)
   const float inv_scale = 1.0f / scale;
@@ -512,12 +526,12 @@ __device__ __forceinline__ void shot_one_query(const GridDev& g, const float4* _
 template <bool DENSE>
 __global__ void __launch_bounds__(SWPB * 32)
 shot_kernel(GridDev g, const float4* __restrict__ queries, int nq, const float4* __restrict__ nrm, float r2,
-            double R, const float* __restrict__ rf9, float* __restrict__ out, size_t stride) {
+            double R, const float* __restrict__ rf9, float* __restrict__ out, size_t stride, float need) {
   __shared__ int hist[SWPB][352];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int qi = blockIdx.x * SWPB + wid;
   if (qi >= nq) return;
-  shot_one_query<DENSE>(g, queries, qi, nrm, r2, R, rf9, out, stride, hist[wid], lane);
+  shot_one_query<DENSE>(g, queries, qi, nrm, r2, R, rf9, out, stride, hist[wid], lane, need);
 }
 
 // persistent variant over a device-side work list (queries the fused kernel handed back)
@@ -525,12 +539,12 @@ template <bool DENSE>
 __global__ void __launch_bounds__(SWPB * 32)
 shot_worklist_kernel(GridDev g, const float4* __restrict__ queries, const int* __restrict__ wl,
                      const int* __restrict__ wl_count, const float4* __restrict__ nrm, float r2, double R,
-                     const float* __restrict__ rf9, float* __restrict__ out, size_t stride) {
+                     const float* __restrict__ rf9, float* __restrict__ out, size_t stride, float need) {
   __shared__ int hist[SWPB][352];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int count = *wl_count;
   for (int w = blockIdx.x * SWPB + wid; w < count; w += gridDim.x * SWPB) {
-    shot_one_query<DENSE>(g, queries, wl[w], nrm, r2, R, rf9, out, stride, hist[wid], lane);
+    shot_one_query<DENSE>(g, queries, wl[w], nrm, r2, R, rf9, out, stride, hist[wid], lane, need);
     __syncwarp();
   }
 }
@@ -538,14 +552,15 @@ shot_worklist_kernel(GridDev g, const float4* __restrict__ queries, const int* _
 int shot_worklist(Ctx* ctx, Grid* g, double radius, const float* rf9_dev, float* out_dev, size_t stride_floats,
                   const int* wl, const int* wl_count) {
   const float r2 = (float)(radius * radius);
+  const float need = (float)(radius * (1.0 + 1e-3));
   const float4* nrm = nullptr;
   PFX_TRY(normals_sorted_for_grid(ctx, g, &nrm));
   if (ctx->q_is_surface)
     PFX_LAUNCH(ctx, shot_worklist_kernel<true>, ctx->sm_count * 4, SWPB * 32, 0, g->view(), nullptr, wl, wl_count, nrm,
-               r2, radius, rf9_dev, out_dev, stride_floats);
+               r2, radius, rf9_dev, out_dev, stride_floats, need);
   else
     PFX_LAUNCH(ctx, shot_worklist_kernel<false>, ctx->sm_count * 4, SWPB * 32, 0, g->view(), ctx->qry.as<float4>(), wl,
-               wl_count, nrm, r2, radius, rf9_dev, out_dev, stride_floats);
+               wl_count, nrm, r2, radius, rf9_dev, out_dev, stride_floats, need);
   PFX_CUDA(cudaGetLastError());
   return 0;
 }
@@ -554,15 +569,16 @@ int shot_compute(Ctx* ctx, Grid* g, double radius, const float* rf9_dev, float* 
   const int nq = (int)ctx->num_queries();
   if (nq == 0) return 0;
   const float r2 = (float)(radius * radius);
+  const float need = (float)(radius * (1.0 + 1e-3));
   const float4* nrm = nullptr;
   PFX_TRY(normals_sorted_for_grid(ctx, g, &nrm));
   const int blocks = div_up(nq, SWPB);
   if (ctx->q_is_surface)
     PFX_LAUNCH(ctx, shot_kernel<true>, blocks, SWPB * 32, 0, g->view(), nullptr, nq, nrm, r2, radius, rf9_dev,
-               out_dev, stride_floats);
+               out_dev, stride_floats, need);
   else
     PFX_LAUNCH(ctx, shot_kernel<false>, blocks, SWPB * 32, 0, g->view(), ctx->qry.as<float4>(), nq, nrm, r2, radius,
-               rf9_dev, out_dev, stride_floats);
+               rf9_dev, out_dev, stride_floats, need);
   PFX_CUDA(cudaGetLastError());
   return 0;
 }

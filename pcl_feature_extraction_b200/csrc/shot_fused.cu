@@ -11,19 +11,28 @@
 // memory, order-independent => bit-reproducible), L2 normalisation and the coalesced 1444-byte row.
 // Neighbouring queries read the same cells at the same time, so phase A's loads are warp broadcasts or
 // L1 hits.  Queries with more than NCAP neighbours go to the generic kernels (shot.cu) over a work list.
+//
+// ROWS variant: when the dense k-search of the same surface is resident (normals / FPFH ran with k <= 32), phase A
+// does not search at all.  A k-NN row that holds an entry with d2 >= r^2 contains EVERY point nearer than r (the
+// set is closed under "nearer than its farthest member"), so the radius neighbourhood is the row filtered by
+// d2 < r^2: the warp reads the 32 rows of its queries as one contiguous block and compacts them with a ballot.  Rows
+// without such an entry (32 or more points inside the radius, ~3 % of the 2^20-point sheet) go to a work list that
+// the stencil variant walks on the k-search grid itself, so no second voxel hash is built for the radius.
 #include "internal.h"
 #include "shot_common.cuh"
 
 namespace pfx {
 
-constexpr int NCAP = 48;
+constexpr int NCAP = 48;       // neighbours a query may have in the stencil variants
+constexpr int NCAP_ROWS = 32;  // ... and in the rows variant (k <= 32): a smaller table, more warps per SM
 constexpr int FS_WPB = 4;
 constexpr int NPAD = 33;  // row pitch of the neighbour table: [position][query lane], conflict-free both ways
 
+template <int CAP>
 struct FusedSmem {
-  int nbr[NCAP][NPAD];
+  int nbr[CAP][NPAD];
   int hist[352];
-  unsigned long long keys[NCAP];
+  unsigned long long keys[CAP];
 };
 
 // cell id of stencil slot l (0..26) of a query: adjacency row for surface points, hash probe otherwise
@@ -36,13 +45,23 @@ __device__ __forceinline__ int stencil_cell(const GridDev& g, const GridParams& 
   return hash_lookup(g, morton3(x2, y2, z2));
 }
 
-template <bool DENSE>
+// ROWS: neighbour sets from the resident k-search rows (rows_idx / rows_d2, k entries per sorted query).
+// qmap / qcount: optional device-side list of the queries to process (sorted positions when DENSE).
+// need = radius (1 + 1e-3): the stencil variant walks 3x3x3 cells, which covers the radius only on a grid whose edge
+// is at least that; on a finer grid it hands every query to the generic kernels (m-ring stencils).
+// COOP (work-list passes): phase A scans each query's stencil with the whole warp (coalesced candidates, ballot
+// compaction) instead of one lane per query - a short list of scattered queries is latency-bound, not issue-bound.
+template <bool DENSE, bool ROWS, bool COOP>
 __global__ void __launch_bounds__(FS_WPB * 32)
 shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const float4* __restrict__ nrm, float r2,
-                  double R, float* __restrict__ out, size_t stride, int* __restrict__ wl_count, int* __restrict__ wl) {
+                  double R, float* __restrict__ out, size_t stride, int* __restrict__ wl_count, int* __restrict__ wl,
+                  const int* __restrict__ rows_idx, const float* __restrict__ rows_d2, int k,
+                  const int* __restrict__ qmap, const int* __restrict__ qcount, float need,
+                  int qpw /* queries per warp: 32, fewer for a short work list (more warps in flight) */) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  FusedSmem* S = reinterpret_cast<FusedSmem*>(smem_raw) + wid;
+  constexpr int CAP = ROWS ? NCAP_ROWS : NCAP;
+  FusedSmem<CAP>* S = reinterpret_cast<FusedSmem<CAP>*>(smem_raw) + wid;
   const GridParams P = *g.gp;
   const int n_valid = P.n_valid;
   const float nanv = __int_as_float(0x7fc00000);
@@ -52,17 +71,73 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
 #pragma unroll
   for (int i = 0; i < 11; ++i) S->hist[lane + 32 * i] = 0;
   __syncwarp();
-  for (int qbase = (blockIdx.x * FS_WPB + wid) * 32; qbase < nq; qbase += gridDim.x * FS_WPB * 32) {
+  const int limit = qmap ? min(*qcount, nq) : nq;
+  const bool covers = ROWS || P.edge >= need;
+  for (int qbase = (blockIdx.x * FS_WPB + wid) * qpw; qbase < limit; qbase += gridDim.x * FS_WPB * qpw) {
     // ---------------- phase A (lane = query): one pass over the 3x3x3 stencil builds the neighbour list
     // in shared memory and the (R - d)-weighted scatter matrix of getLocalRF in double
-    const int qi = qbase + lane;
-    const bool have_q = qi < nq;
+    const bool have_q = lane < qpw && qbase + lane < limit;
+    const int qi = have_q ? (qmap ? qmap[qbase + lane] : qbase + lane) : 0;
     const float4 q = have_q ? (DENSE ? g.pts[qi] : queries[qi]) : make_float4(0.f, 0.f, 0.f, 0.f);
     const bool q_ok = have_q && finite3(q.x, q.y, q.z) && (!DENSE || qi < n_valid) && n_valid > 0;
     double m6[6] = {0, 0, 0, 0, 0, 0};
     double msw = 0.0;
     int n_all = 0, n_val = 0;
-    if (q_ok) {
+    bool handoff = q_ok && !covers;  // not answered here: goes to the work list
+    if (ROWS) {
+      // the rows of the warp's 32 queries are one contiguous block: query t's row is read by the whole warp (lane =
+      // slot), filtered by d2 < r2 and compacted into column t of the neighbour table
+      const int qend_a = min(qpw, limit - qbase);
+      for (int t = 0; t < qend_a; ++t) {
+        int cnt = 0;
+        bool closed = false;
+        for (int s0 = 0; s0 < k; s0 += 32) {
+          const int s = s0 + lane;
+          int j = -1;
+          float d2 = CUDART_INF_F;
+          if (s < k) {
+            j = rows_idx[(size_t)(qbase + t) * k + s];
+            d2 = rows_d2[(size_t)(qbase + t) * k + s];
+          }
+          const bool in = j >= 0 && d2 < r2;
+          const unsigned m = __ballot_sync(FULL, in);
+          if (in) S->nbr[cnt + __popc(m & lt)][t] = j;
+          cnt += __popc(m);
+          // an entry at or beyond the radius (or an unfilled slot: the cloud has fewer than k points) closes the set
+          closed |= __ballot_sync(FULL, s < k && !in) != 0u;
+        }
+        if (lane == t) {
+          n_all = cnt;
+          handoff = q_ok && !closed;
+        }
+      }
+      __syncwarp();
+    } else if (COOP) {
+      const int qend_a = min(qpw, limit - qbase);
+      for (int t = 0; t < qend_a; ++t) {
+        if (!__shfl_sync(FULL, (int)(q_ok && covers), t)) continue;
+        const int qi_t = __shfl_sync(FULL, qi, t);
+        const float qx = __shfl_sync(FULL, q.x, t), qy = __shfl_sync(FULL, q.y, t), qz = __shfl_sync(FULL, q.z, t);
+        const CellBlock blk = DENSE ? stencil_of_point(g, qi_t, lane) : stencil_of_pos(g, qx, qy, qz, lane);
+        int cnt = 0;
+        for (int base = 0; base < blk.total; base += 32) {  // same candidate order as the lane-serial walk below
+          const int c = base + lane;
+          const bool valid = c < blk.total;
+          const int j = block_candidate(blk, valid ? c : 0);
+          bool in = false;
+          if (valid) {
+            const float4 p = g.pts[j];
+            in = dist2_flann(qx, qy, qz, p.x, p.y, p.z) < r2;
+          }
+          const unsigned m = __ballot_sync(FULL, in);
+          const int pos = cnt + __popc(m & lt);
+          if (in && pos < CAP) S->nbr[pos][t] = j;
+          cnt += __popc(m);
+        }
+        if (lane == t) n_all = cnt;
+      }
+      __syncwarp();
+    } else if (q_ok && covers) {
       const int* adj = nullptr;
       int cx = 0, cy = 0, cz = 0;
       if (DENSE) {
@@ -80,13 +155,15 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
           const float4 p = g.pts[j];
           const float d2 = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
           if (d2 < r2) {
-            if (n_all < NCAP) S->nbr[n_all][lane] = j;
+            if (n_all < CAP) S->nbr[n_all][lane] = j;
             ++n_all;
           }
         }
       }
+    }
+    {
       // scatter matrix from the compact list (uniform trip counts: no lanes idle on rejected candidates)
-      const int n_list = min(n_all, NCAP);
+      const int n_list = (q_ok && !handoff) ? min(n_all, CAP) : 0;
       for (int c = 0; c < n_list; ++c) {
         const float4 p = g.pts[S->nbr[c][lane]];
         if (!(p.x == q.x && p.y == q.y && p.z == q.z)) {
@@ -105,7 +182,7 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
         }
       }
     }
-    const bool overflow = n_all > NCAP;  // handed to the generic kernels
+    const bool overflow = handoff || n_all > CAP;  // handed to the work list (ROWS: the stencil variant; else the generic kernels)
     // ---------------- phase B: every lane solves its own 3x3 eigen problem
     double x[3] = {0, 0, 0}, z[3] = {0, 0, 0};
     bool good = false;
@@ -191,7 +268,7 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
       lrf_to_float9(x, z, rf);
     }
     // ---------------- phase D (warp per query, lane = neighbour): 352-bin histogram, normalise, write the row
-    const int qend = min(32, nq - qbase);
+    const int qend = min(qpw, limit - qbase);
     for (int t = 0; t < qend; ++t) {
       const int n_t = __shfl_sync(FULL, n_all, t);
       const bool ok_t = __shfl_sync(FULL, (int)q_ok, t);
@@ -199,10 +276,11 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
       const bool gd = __shfl_sync(FULL, (int)good, t);
       const float4 qt = make_float4(__shfl_sync(FULL, q.x, t), __shfl_sync(FULL, q.y, t), __shfl_sync(FULL, q.z, t),
                                     __shfl_sync(FULL, q.w, t));
-      const size_t row = DENSE ? (size_t)__float_as_int(qt.w) : (size_t)(qbase + t);
+      const int qi_t = __shfl_sync(FULL, qi, t);
+      const size_t row = DENSE ? (size_t)__float_as_int(qt.w) : (size_t)qi_t;
       float* o = out + row * stride;
       if (of_t) {
-        if (lane == 0) wl[atomicAdd(wl_count, 1)] = qbase + t;
+        if (lane == 0) wl[atomicAdd(wl_count, 1)] = qi_t;
         continue;
       }
       if (!ok_t || n_t <= 0 || !gd) {  // non-finite query, no neighbours, or NaN frame: all-NaN row
@@ -253,11 +331,37 @@ int shot_worklist(Ctx* ctx, Grid* g, double radius, const float* rf9_dev, float*
                   const int* wl, const int* wl_count);
 
 // Fused LRF + SHOT352 for the current queries; neighbourhoods larger than NCAP go through the
-// generic kernels (shot.cu) over a device-side work list.
+// generic kernels (shot.cu) over a device-side work list.  g == nullptr: the caller has no grid for the radius yet -
+// the dense k-search rows serve when they are resident (shot_rows_available), else the radius grid is fetched here.
+bool shot_rows_available(Ctx* ctx, double radius) {
+  if (!(ctx->shot_from_rows && ctx->q_is_surface && ctx->knn_dense && ctx->knn_grid &&
+        ctx->knn_grid->surf_version == ctx->surf_version && ctx->knn_sversion == ctx->surf_version &&
+        ctx->knn_k >= 8 && ctx->knn_k <= 32 && ctx->n >= (size_t)ctx->sm_count * 512))
+    return false;
+  // The rows pay off while most of them close (the k-th neighbour lies beyond the radius).  What the previous call with
+  // this (radius, k) handed to the stencil pass is read back asynchronously and never waited for: when more than a
+  // quarter of the rows stayed open, the radius is too large for this k and a radius grid serves better.
+  Ctx::RowsStat& st = ctx->rows_stat;
+  if (st.host && st.radius == radius && st.k == ctx->knn_k && st.n > 0) {
+    if (st.pending && cudaEventQuery(st.ev) == cudaSuccess) {
+      st.open_frac = (double)st.host[0] / (double)st.n;
+      st.pending = false;
+    } else if (st.pending) {
+      (void)cudaGetLastError();  // cudaErrorNotReady is not an error
+    }
+    if (st.open_frac > 0.25) return false;
+  }
+  return true;
+}
+
 int shot_fused_compute(Ctx* ctx, Grid* g, double radius, float* out_dev, size_t stride_floats) {
   const int nq = (int)ctx->num_queries();
   if (nq == 0) return 0;
   const float r2 = (float)(radius * radius);
+  const float need = (float)(radius * (1.0 + 1e-3));
+  const bool rows = (g == nullptr) && shot_rows_available(ctx, radius);
+  if (rows) g = const_cast<Grid*>(ctx->knn_grid);
+  if (!g) PFX_TRY(grid_for_radius(ctx, radius, &g));
   const float4* nrm = nullptr;
   PFX_TRY(normals_sorted_for_grid(ctx, g, &nrm));
   if (!ctx->q_is_surface && nq < ctx->sm_count * 512) {
@@ -267,28 +371,57 @@ int shot_fused_compute(Ctx* ctx, Grid* g, double radius, float* out_dev, size_t 
     PFX_TRY(shot_lrf_compute(ctx, g, radius, ctx->tmp2.as<float>(), nullptr));
     return shot_compute(ctx, g, radius, ctx->tmp2.as<float>(), out_dev, stride_floats);
   }
-  PFX_CUDA(ctx->worklist2.ensure(((size_t)nq + 16) * sizeof(int)));
-  int* wl_count = ctx->worklist2.as<int>();
-  int* wl = wl_count + 16;
-  PFX_CUDA(cudaMemsetAsync(wl_count, 0, 16 * sizeof(int), ctx->stream));
-  const size_t smem = sizeof(FusedSmem) * FS_WPB;
+  // two device-side work lists: A = rows the k-search could not close (ROWS only), B = neighbourhoods beyond NCAP
+  PFX_CUDA(ctx->worklist2.ensure(2 * ((size_t)nq + 16) * sizeof(int)));
+  int* wlA_count = ctx->worklist2.as<int>();
+  int* wlB_count = wlA_count + 8;
+  int* wlA = wlA_count + 16;
+  int* wlB = wlA + nq + 16;
+  PFX_CUDA(cudaMemsetAsync(wlA_count, 0, 16 * sizeof(int), ctx->stream));
+  const size_t smem = sizeof(FusedSmem<NCAP>) * FS_WPB, smem_rows = sizeof(FusedSmem<NCAP_ROWS>) * FS_WPB;
   if (!ctx->smem_attr_shot_fused) {
-    PFX_CUDA(cudaFuncSetAttribute(shot_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PFX_CUDA(cudaFuncSetAttribute(shot_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PFX_CUDA(cudaFuncSetAttribute(shot_fused_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PFX_CUDA(cudaFuncSetAttribute(shot_fused_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PFX_CUDA(cudaFuncSetAttribute(shot_fused_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+    PFX_CUDA(cudaFuncSetAttribute(shot_fused_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ctx->smem_attr_shot_fused = true;
   }
   const int blocks = std::min(div_up(nq, FS_WPB * 32), ctx->sm_count * 16);
-  if (ctx->q_is_surface)
-    PFX_LAUNCH(ctx, shot_fused_kernel<true>, blocks, FS_WPB * 32, smem, g->view(), nullptr, nq, nrm, r2, radius, out_dev,
-               stride_floats, wl_count, wl);
-  else
-    PFX_LAUNCH(ctx, shot_fused_kernel<false>, blocks, FS_WPB * 32, smem, g->view(), ctx->qry.as<float4>(), nq, nrm, r2,
-               radius, out_dev, stride_floats, wl_count, wl);
+  if (rows) {
+    PFX_LAUNCH(ctx, (shot_fused_kernel<true, true, false>), blocks, FS_WPB * 32, smem_rows, g->view(), nullptr, nq, nrm, r2, radius,
+               out_dev, stride_floats, wlA_count, wlA, ctx->knn_idx.as<int>(), ctx->knn_d2.as<float>(), ctx->knn_k,
+               nullptr, nullptr, need, 32);
+    // the rows the k-search could not close: stencil walk on the k-search grid (a persistent launch over list A,
+    // 8 queries per warp: the list is short, more warps in flight hide its latency)
+    PFX_LAUNCH(ctx, (shot_fused_kernel<true, false, true>), ctx->sm_count * 8, FS_WPB * 32, smem, g->view(), nullptr, nq, nrm, r2,
+               radius, out_dev, stride_floats, wlB_count, wlB, nullptr, nullptr, 0, wlA, wlA_count, need, 8);
+    Ctx::RowsStat& st = ctx->rows_stat;
+    if (!st.host) {
+      PFX_CUDA(cudaMallocHost(reinterpret_cast<void**>(&st.host), 16 * sizeof(int)));
+      PFX_CUDA(cudaEventCreateWithFlags(&st.ev, cudaEventDisableTiming));
+    }
+    if (!(st.radius == radius && st.k == ctx->knn_k)) st.open_frac = 0.0;  // another configuration: no history yet
+    if (!st.pending) {  // (a read-back still in flight keeps its slot)
+      PFX_CUDA(cudaMemcpyAsync(st.host, wlA_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      PFX_CUDA(cudaEventRecord(st.ev, ctx->stream));
+      st.pending = true;
+      st.n = (size_t)nq;
+    }
+    st.radius = radius;
+    st.k = ctx->knn_k;
+  } else if (ctx->q_is_surface) {
+    PFX_LAUNCH(ctx, (shot_fused_kernel<true, false, false>), blocks, FS_WPB * 32, smem, g->view(), nullptr, nq, nrm, r2, radius,
+               out_dev, stride_floats, wlB_count, wlB, nullptr, nullptr, 0, nullptr, nullptr, need, 32);
+  } else {
+    PFX_LAUNCH(ctx, (shot_fused_kernel<false, false, false>), blocks, FS_WPB * 32, smem, g->view(), ctx->qry.as<float4>(), nq, nrm,
+               r2, radius, out_dev, stride_floats, wlB_count, wlB, nullptr, nullptr, 0, nullptr, nullptr, need, 32);
+  }
   PFX_CUDA(cudaGetLastError());
-  // neighbourhoods beyond NCAP: frames then descriptors with the generic kernels, work-list driven
+  // neighbourhoods beyond NCAP (or every query of list A when the grid's cells are finer than the radius): frames then
+  // descriptors with the generic kernels, work-list driven
   PFX_CUDA(ctx->tmp2.ensure((size_t)nq * 9 * sizeof(float)));
-  PFX_TRY(shot_lrf_worklist(ctx, g, radius, ctx->tmp2.as<float>(), wl, wl_count));
-  PFX_TRY(shot_worklist(ctx, g, radius, ctx->tmp2.as<float>(), out_dev, stride_floats, wl, wl_count));
+  PFX_TRY(shot_lrf_worklist(ctx, g, radius, ctx->tmp2.as<float>(), wlB, wlB_count));
+  PFX_TRY(shot_worklist(ctx, g, radius, ctx->tmp2.as<float>(), out_dev, stride_floats, wlB, wlB_count));
   return 0;
 }
 

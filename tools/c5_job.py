@@ -58,7 +58,6 @@ def main():
     def describe(L, c, slot):
         k = L["ctx"]
         k.set_surface_dev(clouds[c].data_ptr(), n, 16)
-        k.prepare_radius(R_SHOT)
         k.normals_dev(0.0, K, None)
         k.fpfh_dev(0.0, K, L["f"][slot].data_ptr())
         k.shot352_dev(R_SHOT, L["s"][slot].data_ptr())

@@ -25,7 +25,7 @@ def ev():
 for it in range(3):
     t = [ev()]
     ctx.set_surface_dev(d_pts.data_ptr(), n, 16)
-    if not os.environ.get("PFX_NO_HINT"):
+    if os.environ.get("PFX_HINT"):  # only useful with PFX_SHOT_ROWS=0 (SHOT on its own radius grid)
         ctx.prepare_radius(0.0128)
     t.append(ev())
     ctx.normals_dev(0.0, 32, None); t.append(ev())
@@ -37,7 +37,7 @@ for it in range(3):
     print(it, " ".join(f"{nm}={m:.3f}ms" for nm, m in zip(names, ms)), f"total={sum(ms):.3f}ms launches={ctx.launches}")
 ctx.profile_begin(None)
 ctx.set_surface_dev(d_pts.data_ptr(), n, 16)
-if not os.environ.get("PFX_NO_HINT"):
+if os.environ.get("PFX_HINT"):
     ctx.prepare_radius(0.0128)
 ctx.normals_dev(0.0, 32, None)
 ctx.fpfh_dev(0.0, 32, d_f.data_ptr())

@@ -19,7 +19,6 @@ SHOT_RADIUS = 3.2 * PITCH
 
 
 def dense_step(ctx, d_f, d_s):
-    ctx.prepare_radius(SHOT_RADIUS)
     ctx.normals_dev(0.0, K_NN, None)
     ctx.fpfh_dev(0.0, K_NN, d_f.data_ptr())
     ctx.shot352_dev(SHOT_RADIUS, d_s.data_ptr())

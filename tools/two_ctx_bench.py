@@ -25,7 +25,6 @@ for s in streams:
 def step(i):
     c = ctxs[i % NCTX]; f, s = outs[i % NCTX]
     c.set_surface_dev(clouds[i & 1].data_ptr(), n, 16)
-    c.prepare_radius(0.0128)
     c.normals_dev(0.0, 32, None)
     c.fpfh_dev(0.0, 32, f.data_ptr())
     c.shot352_dev(0.0128, s.data_ptr())
