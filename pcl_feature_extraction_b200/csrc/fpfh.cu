@@ -97,7 +97,7 @@ __device__ __forceinline__ void build_incr_table(float* T, int n_nb, int lane) {
 // rows in the sorted order of grid g.  COUNTS (list mode): 36-byte count rows; else 33 floats.
 // flags / only (optional): restrict to marked points.
 template <bool USE_LIST>
-__global__ void __launch_bounds__(FWPB * 32)
+__global__ void __launch_bounds__(FWPB * 32, 6)
 spfh_kernel(GridDev g, const float4* __restrict__ nrm, float r2, const int* __restrict__ lists, int k,
             const int* __restrict__ flags, const unsigned char* __restrict__ only, float* __restrict__ spfh,
             unsigned char* __restrict__ rows8) {

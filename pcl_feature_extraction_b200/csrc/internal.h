@@ -140,6 +140,7 @@ struct Ctx {
 
   // kernels that need > 48 KB of dynamic shared memory get the attribute once per context (= per device;
   // cudaFuncSetAttribute is a per-device setting, and a process may hold contexts on several devices)
+  int knn_tile_blocks_per_sm = 0, shot_fused_blocks_per_sm[2] = {0, 0};  // resident blocks per SM (occupancy API, cached)
   bool smem_attr_knn_tile = false, smem_attr_shot_fused = false, smem_attr_match_tc = false, smem_attr_narf = false;
   Grid vg_scratch;  // sort buffers of pfx_voxel_grid
 

@@ -66,7 +66,6 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
   const int sub = lane >> 3, sl = lane & 7;
   KnnTileSmem* S = reinterpret_cast<KnnTileSmem*>(smem_raw) + wid;
   const GridParams P = *g.gp;
-  const int total_warps = gridDim.x * TWPB;
   const float INF = CUDART_INF_F;
   // non-finite points sit after n_valid in sorted order and belong to no cell: the generic kernels
   // give them their rows
@@ -75,7 +74,13 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
       qflag[i] = 1;
       wl[atomicAdd(wl_count, 1)] = i;
     }
-  for (int cell = blockIdx.x * TWPB + wid; cell < P.ncells; cell += total_warps) {
+  // cells are handed out by a ticket (wl_count[8], zeroed with the work-list counter): stencils differ by a factor of
+  // two in size, and a static split leaves the last blocks running alone
+  for (;;) {
+    int cell = 0;
+    if (lane == 0) cell = atomicAdd(wl_count + 8, 1);
+    cell = __shfl_sync(FULL, cell, 0);
+    if (cell >= P.ncells) break;
     __syncwarp();
     const int M = tile_setup(g, cell, lane, &S->tab);
     const int q0 = S->tab.start[13];
@@ -333,7 +338,14 @@ int knn_tile_lists(Ctx* ctx, Grid* g, int k, bool with_normals) {
     PFX_CUDA(cudaFuncSetAttribute(knn_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ctx->smem_attr_knn_tile = true;
   }
-  const int blocks = ctx->sm_count * 3;
+  // one wave of resident blocks (the kernel is persistent over a cell ticket)
+  if (!ctx->knn_tile_blocks_per_sm) {
+    int b0 = 0, b1 = 0;
+    PFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, knn_tile_kernel<true>, TWPB * 32, smem));
+    PFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, knn_tile_kernel<false>, TWPB * 32, smem));
+    ctx->knn_tile_blocks_per_sm = std::max(1, std::min(b0, b1));
+  }
+  const int blocks = ctx->sm_count * ctx->knn_tile_blocks_per_sm;
   if (with_normals) {
     PFX_CUDA(ctx->tmp4.ensure((size_t)n * 9 * sizeof(double)));
     PFX_LAUNCH(ctx, knn_tile_kernel<true>, blocks, TWPB * 32, smem, g->view(), k, ctx->knn_idx.as<int>(),

@@ -52,12 +52,13 @@ __device__ __forceinline__ int stencil_cell(const GridDev& g, const GridParams& 
 // COOP (work-list passes): phase A scans each query's stencil with the whole warp (coalesced candidates, ballot
 // compaction) instead of one lane per query - a short list of scattered queries is latency-bound, not issue-bound.
 template <bool DENSE, bool ROWS, bool COOP>
-__global__ void __launch_bounds__(FS_WPB * 32)
+__global__ void __launch_bounds__(FS_WPB * 32, ROWS ? 8 : 6)
 shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const float4* __restrict__ nrm, float r2,
                   double R, float* __restrict__ out, size_t stride, int* __restrict__ wl_count, int* __restrict__ wl,
                   const int* __restrict__ rows_idx, const float* __restrict__ rows_d2, int k,
                   const int* __restrict__ qmap, const int* __restrict__ qcount, float need,
-                  int qpw /* queries per warp: 32, fewer for a short work list (more warps in flight) */) {
+                  int qpw /* queries per warp: 32, fewer for a short work list (more warps in flight) */,
+                  int* __restrict__ ticket /* zeroed: batches of qpw queries are handed out dynamically */) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   constexpr int CAP = ROWS ? NCAP_ROWS : NCAP;
@@ -73,7 +74,11 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
   __syncwarp();
   const int limit = qmap ? min(*qcount, nq) : nq;
   const bool covers = ROWS || P.edge >= need;
-  for (int qbase = (blockIdx.x * FS_WPB + wid) * qpw; qbase < limit; qbase += gridDim.x * FS_WPB * qpw) {
+  for (;;) {
+    int qbase = 0;
+    if (lane == 0) qbase = atomicAdd(ticket, 1) * qpw;
+    qbase = __shfl_sync(FULL, qbase, 0);
+    if (qbase >= limit) break;
     // ---------------- phase A (lane = query): one pass over the 3x3x3 stencil builds the neighbour list
     // in shared memory and the (R - d)-weighted scatter matrix of getLocalRF in double
     const bool have_q = lane < qpw && qbase + lane < limit;
@@ -386,15 +391,25 @@ int shot_fused_compute(Ctx* ctx, Grid* g, double radius, float* out_dev, size_t 
     PFX_CUDA(cudaFuncSetAttribute(shot_fused_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ctx->smem_attr_shot_fused = true;
   }
-  const int blocks = std::min(div_up(nq, FS_WPB * 32), ctx->sm_count * 16);
+  if (!ctx->shot_fused_blocks_per_sm[0]) {
+    int b = 0;
+    PFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, shot_fused_kernel<true, false, false>, FS_WPB * 32, smem));
+    ctx->shot_fused_blocks_per_sm[0] = std::max(1, b);
+    PFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, shot_fused_kernel<true, true, false>, FS_WPB * 32, smem_rows));
+    ctx->shot_fused_blocks_per_sm[1] = std::max(1, b);
+  }
+  // persistent over a ticket: one wave of resident blocks
+  const int blocks = std::min(div_up(nq, FS_WPB * 32), ctx->sm_count * ctx->shot_fused_blocks_per_sm[rows ? 1 : 0]);
+  int* ticket0 = wlA_count + 4;
+  int* ticket1 = wlA_count + 12;
   if (rows) {
     PFX_LAUNCH(ctx, (shot_fused_kernel<true, true, false>), blocks, FS_WPB * 32, smem_rows, g->view(), nullptr, nq, nrm, r2, radius,
                out_dev, stride_floats, wlA_count, wlA, ctx->knn_idx.as<int>(), ctx->knn_d2.as<float>(), ctx->knn_k,
-               nullptr, nullptr, need, 32);
+               nullptr, nullptr, need, 32, ticket0);
     // the rows the k-search could not close: stencil walk on the k-search grid (a persistent launch over list A,
-    // 8 queries per warp: the list is short, more warps in flight hide its latency)
+    // 16 queries per warp: the list is short, more warps in flight hide its latency)
     PFX_LAUNCH(ctx, (shot_fused_kernel<true, false, true>), ctx->sm_count * 8, FS_WPB * 32, smem, g->view(), nullptr, nq, nrm, r2,
-               radius, out_dev, stride_floats, wlB_count, wlB, nullptr, nullptr, 0, wlA, wlA_count, need, 8);
+               radius, out_dev, stride_floats, wlB_count, wlB, nullptr, nullptr, 0, wlA, wlA_count, need, 16, ticket1);
     Ctx::RowsStat& st = ctx->rows_stat;
     if (!st.host) {
       PFX_CUDA(cudaMallocHost(reinterpret_cast<void**>(&st.host), 16 * sizeof(int)));
@@ -411,10 +426,10 @@ int shot_fused_compute(Ctx* ctx, Grid* g, double radius, float* out_dev, size_t 
     st.k = ctx->knn_k;
   } else if (ctx->q_is_surface) {
     PFX_LAUNCH(ctx, (shot_fused_kernel<true, false, false>), blocks, FS_WPB * 32, smem, g->view(), nullptr, nq, nrm, r2, radius,
-               out_dev, stride_floats, wlB_count, wlB, nullptr, nullptr, 0, nullptr, nullptr, need, 32);
+               out_dev, stride_floats, wlB_count, wlB, nullptr, nullptr, 0, nullptr, nullptr, need, 32, ticket0);
   } else {
     PFX_LAUNCH(ctx, (shot_fused_kernel<false, false, false>), blocks, FS_WPB * 32, smem, g->view(), ctx->qry.as<float4>(), nq, nrm,
-               r2, radius, out_dev, stride_floats, wlB_count, wlB, nullptr, nullptr, 0, nullptr, nullptr, need, 32);
+               r2, radius, out_dev, stride_floats, wlB_count, wlB, nullptr, nullptr, 0, nullptr, nullptr, need, 32, ticket0);
   }
   PFX_CUDA(cudaGetLastError());
   // neighbourhoods beyond NCAP (or every query of list A when the grid's cells are finer than the radius): frames then
