@@ -783,7 +783,12 @@ int grid_get(Ctx* ctx, double radius, int knn_k, Grid** out) {
       return 0;
     }
   }
-  if (ctx->grids.size() < 4) {
+  // a grid of an earlier surface is of no use any more: recycle its buffers before allocating another set (a new
+  // cloud per step must not reach cudaMalloc in the steady state)
+  for (Grid* g : ctx->grids)
+    if (g->surf_version != ctx->surf_version && (!victim || g->last_use < victim->last_use)) victim = g;
+  if (victim) {
+  } else if (ctx->grids.size() < 4) {
     victim = new Grid();
     ctx->grids.push_back(victim);
   } else {
