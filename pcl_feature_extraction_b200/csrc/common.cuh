@@ -275,6 +275,9 @@ __device__ __forceinline__ void eig_sym3(const T a_in[6], T w[3], T (&v)[3][3], 
   for (int s = 0; s < sweeps; ++s) {
     T off = fabs(xy) + fabs(xz) + fabs(yz);
     if (off == T(0)) break;
+    // float: rotations by less than 1e-9 of the diagonal change nothing at 24 bits - stop there (the float solves are
+    // refined in double by their callers); a surface neighbourhood is there after 3-4 of the 8 sweeps
+    if (sizeof(T) == 4 && off <= T(1e-9) * (fabs(xx) + fabs(yy) + fabs(zz))) break;
     jacobi_rot<T>(xx, yy, xy, xz, yz, v, 0, 1);  // (p,q) = (0,1); third index 2: a[2][0], a[2][1]
     jacobi_rot<T>(xx, zz, xz, xy, yz, v, 0, 2);  // (0,2); third index 1: a[1][0], a[1][2]
     jacobi_rot<T>(yy, zz, yz, xy, xz, v, 1, 2);  // (1,2); third index 0: a[0][1], a[0][2]
