@@ -160,7 +160,8 @@ __device__ __forceinline__ void shot_accumulate_neighbor_f(int* h, float scale, 
   bd -= (float)step;
   float w = 1.0f - fabsf(bd);
   {
-    const int nb_step = (bd > 0.f) ? ((step + 1) % 10) : ((step + 9) % 10);
+    int nb_step = (bd > 0.f) ? step + 1 : step + 9;  // (step +- 1) mod 10, step in 0..10
+    nb_step -= (nb_step >= 10) ? 10 : 0;
     atomicAdd(&h[vol + nb_step], __float2int_rn(fabsf(bd) * scale));
   }
   if (outer) {

@@ -93,27 +93,45 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
       // the rows of the warp's 32 queries are one contiguous block: query t's row is read by the whole warp (lane =
       // slot), filtered by d2 < r2 and compacted into column t of the neighbour table
       const int qend_a = min(qpw, limit - qbase);
-      for (int t = 0; t < qend_a; ++t) {
-        int cnt = 0;
-        bool closed = false;
-        for (int s0 = 0; s0 < k; s0 += 32) {
-          const int s = s0 + lane;
-          int j = -1;
-          float d2 = CUDART_INF_F;
-          if (s < k) {
-            j = rows_idx[(size_t)(qbase + t) * k + s];
-            d2 = rows_d2[(size_t)(qbase + t) * k + s];
-          }
+      if (k == 32) {
+        // k = 32: one slot per lane, two coalesced 128-byte loads per query
+        const int* ri = rows_idx + (size_t)qbase * 32 + lane;
+        const float* rd = rows_d2 + (size_t)qbase * 32 + lane;
+#pragma unroll 4
+        for (int t = 0; t < qend_a; ++t) {
+          const int j = ri[t * 32];
+          const float d2 = rd[t * 32];
           const bool in = j >= 0 && d2 < r2;
           const unsigned m = __ballot_sync(FULL, in);
-          if (in) S->nbr[cnt + __popc(m & lt)][t] = j;
-          cnt += __popc(m);
-          // an entry at or beyond the radius (or an unfilled slot: the cloud has fewer than k points) closes the set
-          closed |= __ballot_sync(FULL, s < k && !in) != 0u;
+          if (in) S->nbr[__popc(m & lt)][t] = j;
+          if (lane == t) {
+            n_all = __popc(m);
+            handoff = q_ok && m == FULL;  // no entry at or beyond the radius: the set is open
+          }
         }
-        if (lane == t) {
-          n_all = cnt;
-          handoff = q_ok && !closed;
+      } else {
+        for (int t = 0; t < qend_a; ++t) {
+          int cnt = 0;
+          bool closed = false;
+          for (int s0 = 0; s0 < k; s0 += 32) {
+            const int s = s0 + lane;
+            int j = -1;
+            float d2 = CUDART_INF_F;
+            if (s < k) {
+              j = rows_idx[(size_t)(qbase + t) * k + s];
+              d2 = rows_d2[(size_t)(qbase + t) * k + s];
+            }
+            const bool in = j >= 0 && d2 < r2;
+            const unsigned m = __ballot_sync(FULL, in);
+            if (in) S->nbr[cnt + __popc(m & lt)][t] = j;
+            cnt += __popc(m);
+            // an entry at or beyond the radius (or an unfilled slot: the cloud has fewer than k points) closes the set
+            closed |= __ballot_sync(FULL, s < k && !in) != 0u;
+          }
+          if (lane == t) {
+            n_all = cnt;
+            handoff = q_ok && !closed;
+          }
         }
       }
       __syncwarp();
