@@ -532,7 +532,24 @@ def main():
             ctx._chk(ctx.lib.pfx_shot352(ctx.h, SHOT_RADIUS, None, pfx.capi._ptr(h_shot[i & 1]), 1444, ASYNC))
 
         k2 = max(3, min(args.steps, 10))
-        for i in range(2):
+        if os.environ.get("PFX_BENCH_DEBUG"):  # development aid: host time of every call of a step, synchronised
+            for i in range(6):
+                h, tt = hosts[i & 1], [time.perf_counter()]
+                for call in (lambda: ctx.lib.pfx_set_surface(ctx.h, pfx.capi._ptr(h), n, 16, HOST),
+                             lambda: ctx.lib.pfx_normals(ctx.h, 0.0, K_NN, None, 16, 3, HOST),
+                             lambda: ctx.lib.pfx_fpfh(ctx.h, 0.0, K_NN, pfx.capi._ptr(h_fpfh[i & 1]), 132, ASYNC),
+                             lambda: ctx.lib.pfx_shot352(ctx.h, SHOT_RADIUS, None, pfx.capi._ptr(h_shot[i & 1]), 1444, ASYNC)):
+                    ctx._chk(call())
+                    tt.append(time.perf_counter())
+                    if os.environ["PFX_BENCH_DEBUG"] == "1":
+                        ctx._chk(ctx.lib.pfx_sync(ctx.h))
+                    tt.append(time.perf_counter())
+                print("e2e debug step", i, [round(1e3 * (tt[j + 1] - tt[j]), 2) for j in range(8)], file=sys.stderr)
+            ctx.profile_begin(None)
+            step_host(0)
+            for nm, (c, ms_k) in sorted(ctx.profile_end().items(), key=lambda kv: -kv[1][1])[:8]:
+                print(f"e2e debug   {nm:45s} x{c:2d} {ms_k:8.3f} ms", file=sys.stderr)
+        for i in range(4):  # warm-up: staging slots, and one pass over every cached voxel hash of the context
             step_host(i)
         ctx._chk(ctx.lib.pfx_sync(ctx.h))
         barrier()

@@ -784,9 +784,15 @@ int grid_get(Ctx* ctx, double radius, int knn_k, Grid** out) {
     }
   }
   // a grid of an earlier surface is of no use any more: recycle its buffers before allocating another set (a new
-  // cloud per step must not reach cudaMalloc in the steady state)
-  for (Grid* g : ctx->grids)
-    if (g->surf_version != ctx->surf_version && (!victim || g->last_use < victim->last_use)) victim = g;
+  // cloud per step must not reach cudaMalloc in the steady state); among the stale ones a grid whose buffers already
+  // hold this many points comes first (small clouds described in between leave small grids behind: growing them one
+  // per step would put a cudaFree - a device-wide synchronisation - into each of the next steps), then the oldest
+  const size_t need_bytes = std::max<size_t>(ctx->n, 1) * sizeof(float4);
+  for (Grid* g : ctx->grids) {
+    if (g->surf_version == ctx->surf_version) continue;
+    const bool fits = g->pts.cap >= need_bytes, vfits = victim && victim->pts.cap >= need_bytes;
+    if (!victim || (fits && !vfits) || (fits == vfits && g->last_use < victim->last_use)) victim = g;
+  }
   if (victim) {
   } else if (ctx->grids.size() < 4) {
     victim = new Grid();
