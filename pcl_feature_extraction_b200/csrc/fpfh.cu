@@ -178,6 +178,82 @@ spfh_kernel(GridDev g, const float4* __restrict__ nrm, float r2, const int* __re
   }
 }
 
+// ------------------------------------------------------------------------------ SPFH from kNN rows, k <= 32
+// The k-search rows of every surface point (one list entry per lane).  A warp describes SPFH_NP consecutive points
+// and keeps two loads ahead of its arithmetic: while point i is binned, the neighbour points / normals of point i + 1
+// are in flight and so is the list entry of point i + 2.  (One point per warp left the warp idle through two
+// dependent global latencies - list entry, then the gathers - and a block lived for a single point.)
+#ifndef PFX_SPFH_NP
+#define PFX_SPFH_NP 8
+#endif
+#ifndef PFX_SPFH_MINB
+#define PFX_SPFH_MINB 4
+#endif
+constexpr int SPFH_NP = PFX_SPFH_NP;
+__global__ void __launch_bounds__(FWPB * 32, PFX_SPFH_MINB)
+spfh_list32_kernel(GridDev g, const float4* __restrict__ nrm, const int* __restrict__ lists, int k,
+                   unsigned char* __restrict__ rows8) {
+  __shared__ __align__(16) int hist[FWPB][36];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n_valid = g.gp->n_valid;
+  const int i0 = (blockIdx.x * FWPB + wid) * SPFH_NP;
+  if (i0 >= n_valid) return;
+  const int iend = min(i0 + SPFH_NP, n_valid);
+  int* h = hist[wid];
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int j_cur = (lane < k) ? lists[(size_t)i0 * k + lane] : -1;
+  int j_nxt = (i0 + 1 < iend && lane < k) ? lists[(size_t)(i0 + 1) * k + lane] : -1;
+  float4 p_cur = zero4, n_cur = zero4;
+  if (j_cur >= 0) {
+    p_cur = g.pts[j_cur];
+    n_cur = nrm[j_cur];
+  }
+  float4 q = g.pts[i0], nq = nrm[i0];
+  for (int i = i0; i < iend; ++i) {
+    // ---- loads of the points ahead
+    float4 p_nxt = zero4, n_nxt = zero4, q_nxt = zero4, nq_nxt = zero4;
+    if (i + 1 < iend) {
+      if (j_nxt >= 0) {
+        p_nxt = g.pts[j_nxt];
+        n_nxt = nrm[j_nxt];
+      }
+      q_nxt = g.pts[i + 1];
+      nq_nxt = nrm[i + 1];
+    }
+    const int j_nn = (i + 2 < iend && lane < k) ? lists[(size_t)(i + 2) * k + lane] : -1;
+    // ---- point i
+    h[lane] = 0;
+    if (lane < 4) h[32 + lane] = 0;
+    __syncwarp();
+    int b1 = -1, b2 = -1, b3 = -1;
+    if (j_cur >= 0 && j_cur != i && finite3(nq.x, nq.y, nq.z)) {
+      if (!pair_bins_fast(q, nq, p_cur, n_cur, b1, b2, b3)) b1 = b2 = b3 = -1;
+    }
+    const unsigned m1 = __match_any_sync(FULL, b1);
+    const unsigned m2 = __match_any_sync(FULL, b2);
+    const unsigned m3 = __match_any_sync(FULL, b3);
+    if (b1 >= 0) {  // the three sub-histograms occupy disjoint slots; one leader per distinct bin
+      if (lane == __ffs(m1) - 1) h[b1] = __popc(m1);
+      if (lane == __ffs(m2) - 1) h[b2] = __popc(m2);
+      if (lane == __ffs(m3) - 1) h[b3] = __popc(m3);
+    }
+    __syncwarp();
+    if (lane < 9) {
+      const int4 c4 = (lane < 8) ? *reinterpret_cast<const int4*>(h + 4 * lane) : make_int4(h[32], 0, 0, 0);
+      const unsigned w = (unsigned)(c4.x & 255) | ((unsigned)(c4.y & 255) << 8) | ((unsigned)(c4.z & 255) << 16) |
+                         ((unsigned)(c4.w & 255) << 24);
+      reinterpret_cast<unsigned*>(rows8 + (size_t)i * SROW)[lane] = w;
+    }
+    __syncwarp();
+    j_cur = j_nxt;
+    j_nxt = j_nn;
+    p_cur = p_nxt;
+    n_cur = n_nxt;
+    q = q_nxt;
+    nq = nq_nxt;
+  }
+}
+
 // mark the union of the queries' neighbourhoods (radius search, keypoint queries)
 __global__ void __launch_bounds__(FWPB * 32)
 mark_kernel(GridDev g, const float4* __restrict__ queries, int nq, float r2, int* __restrict__ flags) {
@@ -306,28 +382,58 @@ __device__ __forceinline__ float group9_max(float v, int c9, int grp) {
   return __shfl_sync(FULL, v, grp * 9);
 }
 
+#ifndef PFX_FL_NB
+#define PFX_FL_NB 2
+#endif
+#ifndef PFX_FL_MINB
+#define PFX_FL_MINB 4
+#endif
+constexpr int FL_NB = PFX_FL_NB;  // batches of three queries per warp
 template <bool DENSE, bool K32>
-__global__ void __launch_bounds__(FWPB * 32)
+__global__ void __launch_bounds__(FWPB * 32, PFX_FL_MINB)
 fpfh_list_kernel(GridDev g, const float4* __restrict__ queries, int nq, const int* __restrict__ lists,
                  const float* __restrict__ ld2, int k_rt, int wbits, const unsigned char* __restrict__ rows8,
                  float* __restrict__ out, size_t stride) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int grp = lane / 9, c9 = lane - grp * 9;
-  const int qi = (blockIdx.x * FWPB + wid) * 3 + grp;
   const int k = K32 ? 32 : k_rt;
+  const int n_valid = g.gp->n_valid;
+  const unsigned* rows32 = reinterpret_cast<const unsigned*>(rows8);
+  // A warp describes FL_NB batches of three queries.  K32: the list entries of the next batch (and its query points)
+  // are loaded while the rows of the current one are gathered, so a batch waits for one global latency, not two.
+  const int qwarp = (blockIdx.x * FWPB + wid) * (3 * FL_NB);
+  int pj[4] = {-1, -1, -1, -1};
+  float pd[4] = {0.f, 0.f, 0.f, 0.f};
+  float4 pq = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto prefetch = [&](int qn) {  // list entries c9 + 9 t and the point of query qn (K32 only)
+    const bool mem = grp < 3 && qn < nq;
+    const int qsn = mem ? qn : 0;
+    pq = DENSE ? g.pts[qsn] : queries[qsn];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int sidx = c9 + 9 * t;
+      pj[t] = -1;
+      pd[t] = 0.f;
+      if (mem && sidx < 32) {
+        pj[t] = lists[(size_t)qsn * 32 + sidx];
+        pd[t] = ld2[(size_t)qsn * 32 + sidx];
+      }
+    }
+  };
+  if (K32) prefetch(qwarp + grp);
+  for (int batch = 0; batch < FL_NB; ++batch) {
+  const int qi = qwarp + batch * 3 + grp;
   // every shuffle below names all 32 lanes (a compile-time full mask: no collective-sync sequences); lanes 27..31
   // and the groups past the last query idle through them
   const bool member = grp < 3 && qi < nq;
   if (__all_sync(FULL, !member)) return;
-  const int n_valid = g.gp->n_valid;
   const int qs = member ? qi : 0;
-  const float4 q = DENSE ? g.pts[qs] : queries[qs];
+  const float4 q = K32 ? pq : (DENSE ? g.pts[qs] : queries[qs]);
   const size_t row = DENSE ? (size_t)__float_as_int(q.w) : (size_t)qs;
   float* o = out + row * stride;
   const bool ok = member && finite3(q.x, q.y, q.z) && (!DENSE || qi < n_valid);
   const int* lj = lists + (size_t)qs * k;
   const float* ldd = ld2 + (size_t)qs * k;
-  const unsigned* rows32 = reinterpret_cast<const unsigned*>(rows8);
   unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;
   int n_nb = 0;
 
@@ -337,18 +443,14 @@ fpfh_list_kernel(GridDev g, const float4* __restrict__ queries, int nq, const in
     float myw[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const int sidx = c9 + 9 * t;
-      myj[t] = -1;
+      myj[t] = ok ? pj[t] : -1;
       myw[t] = 0.f;
-      if (ok && sidx < 32) {
-        myj[t] = lj[sidx];
-        const float d2 = ldd[sidx];
-        // "minus the query point itself": dists == 0 skipped.  The weights only enter through their 24-bit quantised
-        // ratios to the largest one: the reciprocal unit (1 ulp, deterministic) is as good as the IEEE reciprocal
-        if (myj[t] >= 0 && d2 != 0.f) myw[t] = __fdividef(1.0f, d2);
-      }
+      // "minus the query point itself": dists == 0 skipped.  The weights only enter through their 24-bit quantised
+      // ratios to the largest one: the reciprocal unit (1 ulp, deterministic) is as good as the IEEE reciprocal
+      if (myj[t] >= 0 && pd[t] != 0.f) myw[t] = __fdividef(1.0f, pd[t]);
       n_nb += (myj[t] >= 0) ? 1 : 0;
     }
+    if (batch + 1 < FL_NB) prefetch(qi + 3);
     n_nb = (int)group9_sum((unsigned)n_nb, c9, grp);
     const float wl = fmaxf(fmaxf(myw[0], myw[1]), fmaxf(myw[2], myw[3]));
     const float wmax = group9_max(wl, c9, grp);
@@ -424,13 +526,15 @@ fpfh_list_kernel(GridDev g, const float4* __restrict__ queries, int nq, const in
   s2 = group9_sum(s2, c9, grp);
   const float k0 = s0 ? __fdiv_rn(100.0f, (float)s0) : 0.f, k1 = s1 ? __fdiv_rn(100.0f, (float)s1) : 0.f,
               k2 = s2 ? __fdiv_rn(100.0f, (float)s2) : 0.f;
-  if (!member) return;
   const float nanv = __int_as_float(0x7fc00000);
+  if (member) {
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    const int bin = c9 * 4 + b;
-    if (bin < 33) o[bin] = nan_row ? nanv : __fmul_rn((float)v[b], bin < 11 ? k0 : (bin < 22 ? k1 : k2));
+    for (int b = 0; b < 4; ++b) {
+      const int bin = c9 * 4 + b;
+      if (bin < 33) o[bin] = nan_row ? nanv : __fmul_rn((float)v[b], bin < 11 ? k0 : (bin < 22 ? k1 : k2));
+    }
   }
+  }  // batch
 }
 
 __global__ void spfh_export_kernel(GridDev g, const float* __restrict__ spfh, const unsigned char* __restrict__ rows8,
@@ -482,13 +586,17 @@ int fpfh_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t
       ctx->knn_grid = nullptr;
     }
     PFX_TRY(knn_tile_lists(ctx, g, k, false));
-    PFX_LAUNCH(ctx, spfh_kernel<true>, div_up(n, FWPB), FWPB * 32, 0, g->view(), nrm, r2, ctx->knn_idx.as<int>(), k,
-               nullptr, nullptr, nullptr, rows8.as<unsigned char>());
+    if (k <= 32)
+      PFX_LAUNCH(ctx, spfh_list32_kernel, div_up(n, FWPB * SPFH_NP), FWPB * 32, 0, g->view(), nrm, ctx->knn_idx.as<int>(), k,
+                 rows8.as<unsigned char>());
+    else
+      PFX_LAUNCH(ctx, spfh_kernel<true>, div_up(n, FWPB), FWPB * 32, 0, g->view(), nrm, r2, ctx->knn_idx.as<int>(), k,
+                 nullptr, nullptr, nullptr, rows8.as<unsigned char>());
     if (spfh_out_dev)
       PFX_LAUNCH(ctx, spfh_export_kernel, div_up((long long)n * 33, 256), 256, 0, g->view(), nullptr,
                  rows8.as<unsigned char>(), n, k, spfh_out_dev);
     if (out_dev && nq > 0) {
-      const int blocks = div_up(nq, FWPB * 3);  // three queries per warp
+      const int blocks = div_up(nq, FWPB * 3 * FL_NB);  // three queries per warp and batch
       int kb = 0;  // bits of k - 1: a bin holds at most k - 1 votes of a neighbour row
       while ((1 << kb) <= std::max(k - 1, 1)) ++kb;
       const int wbits = 31 - kb;
