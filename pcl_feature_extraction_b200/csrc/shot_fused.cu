@@ -74,6 +74,12 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
   __syncwarp();
   const int limit = qmap ? min(*qcount, nq) : nq;
   const bool covers = ROWS || P.edge >= need;
+  if (COOP) {
+    // a work list is short and its queries are scattered: the pass is bound by the chain of dependent loads of a
+    // query, not by issue slots, so the list is spread over every resident warp (at least four queries each)
+    const int slots = gridDim.x * FS_WPB;
+    qpw = max(4, min(qpw, (limit + slots - 1) / slots));
+  }
   for (;;) {
     int qbase = 0;
     if (lane == 0) qbase = atomicAdd(ticket, 1) * qpw;
