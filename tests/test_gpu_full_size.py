@@ -107,7 +107,9 @@ def test_full_size_sampled_rows_against_the_oracle(ctx, orc, full):
     # FPFH with the GPU's own normals as input normals on both sides
     of = orc.fpfh(pts, nr, q, k=K)
     d = np.abs(of - full["f"][rows]).max(1)
-    assert (d <= 1e-2).mean() >= 0.97 and np.median(d) < 1e-4 and d.max() < 12.0
+    # (measured, tools/full_size_diag.py: every one of the 600 rows within 3.9e-5; a row beyond 1e-3 would carry a pair
+    # moved across a bin edge, which the exact-path certificate of the pair bins rules out up to an ulp of atan2)
+    assert (d <= 1e-3).mean() >= 0.995 and np.median(d) < 1e-4 and d.max() < 4.0
     # SHOT with the oracle's frames given to both sides: the descriptor stage alone
     os_, orf = orc.shot352(pts, nr, q, R_SHOT)
     ctx.set_surface(pts)
@@ -118,8 +120,15 @@ def test_full_size_sampled_rows_against_the_oracle(ctx, orc, full):
     ok = ~np.isnan(os_[:, 0])
     assert np.array_equal(np.isnan(s[:, 0]), ~ok)
     assert np.abs(s[ok] - os_[ok]).max() <= 1e-4
-    # and end to end (frames from the dense fused kernel) where the frame is well defined
+    # the dense fused kernel's rows in ITS OWN frames: every sampled row, whatever the eigen-gap of its frame
+    og, _ = orc.shot352(pts, nr, q, R_SHOT, lrf_in=full["rf"][rows])
+    assert np.array_equal(np.isnan(full["s"][rows][:, 0]), ~ok)
+    assert np.abs(full["s"][rows][ok] - og[ok]).max() <= 1e-5
+    # and end to end (frames from the dense fused kernel): frames to 1e-5 wherever the oracle's eigen-gap exceeds
+    # 1e-3 (measured: 100 % of the sampled rows; 99.8 % exceed 1e-2), rows to 1e-4 on (nearly) all rows
     _, gap2 = orc.shot_lrf(pts, q, R_SHOT)
-    clear = ok & (gap2.min(1) > 1e-2)
-    assert clear.mean() > 0.5
-    assert (np.abs(full["s"][rows][clear] - os_[clear]).max(1) <= 1e-4).mean() > 0.99
+    clear = ok & (gap2.min(1) > 1e-3)
+    assert clear.mean() > 0.99
+    assert np.abs(full["rf"][rows][clear] - orf[clear]).max() <= 1e-5
+    assert np.abs(full["s"][rows][clear] - os_[clear]).max() <= 1e-4
+    assert (np.abs(full["s"][rows][ok] - os_[ok]).max(1) <= 1e-4).mean() >= 0.995
