@@ -716,7 +716,7 @@ def test_config_c1_pipeline(ctx, orc, clouds):
         ctx.set_queries(xyz[kp])
         f = ctx.fpfh(radius=0.05)
         of = orc.fpfh(xyz, nr, q=xyz[okp], radius=0.05)
-        assert (np.abs(f - of).max(1) <= 1e-2).mean() > 0.97
+        assert (np.abs(f - of).max(1) <= 1e-3).mean() >= 0.99   # same normals on both sides
         ctx.set_queries(None)
         feats.append(f)
     c = ctx.match(feats[0], feats[1], reciprocal=True)

@@ -77,7 +77,7 @@ def test_evaluation_driver_matches_c_abi_and_oracle(tmp_path, clouds, ctx, orc):
     f_abi = ctx.fpfh(radius=0.05)
     assert np.array_equal(f_shim, f_abi)
     f_or = orc.fpfh(src, nr, src[kp], radius=0.05)
-    assert (np.abs(f_shim - f_or).max(1) <= 1e-2).mean() > 0.97
+    assert (np.abs(f_shim - f_or).max(1) <= 1e-3).mean() >= 0.99
     # SHOT rows carry descriptor[352] + rf[9]
     s_shim = np.fromfile(tmp_path / "Iss_SHOT_src.bin", dtype=np.float32).reshape(-1, 361)
     s_abi, rf_abi = ctx.shot352(0.05)
