@@ -198,6 +198,7 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("PFX_SHOT_ROWS")) c->shot_from_rows = atoi(e) != 0;
+  if (const char* e = getenv("PFX_TC_PAIR")) c->tc_pair = atoi(e);
   *out = c;
   return 0;
 }

@@ -31,10 +31,14 @@ constexpr int TC_TILE = 128;              // rows per operand tile (= UMMA M, an
 constexpr int TC_K = 8;                   // candidates kept per (row, column split)
 constexpr int TC_SLAB = TC_TILE * 16;     // bytes of one K-slab (8 bf16 of K for 128 rows)
 constexpr int TC_STAGE = 2 * 4 * TC_SLAB; // a stage = 2 half tiles x 4 slabs (K = 32)
-constexpr int TC_EPI_WARPS = 8;           // epilogue warps: (TMEM lane quarter) x (half of the 256 columns)
+#ifndef PFX_TC_EPI_WARPS
+#define PFX_TC_EPI_WARPS 8
+#endif
+constexpr int TC_EPI_WARPS = PFX_TC_EPI_WARPS;  // epilogue warps: (TMEM lane quarter) x (half or quarter of the 256 columns)
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = 128 + TC_EPI_THREADS;
-constexpr int TC_LISTS = 2;               // top-K lists per (row, split): one per column half
+constexpr int TC_LISTS = TC_EPI_WARPS / 4;      // top-K lists per (row, split): one per column group of a thread
+constexpr int TC_COLS = 256 / TC_LISTS;         // columns of a pair per epilogue thread
 constexpr int TC_KS = TC_K + 1;           // list stride in the candidate arrays: K entries + the bound slot
 constexpr float TC_BIG = 1e30f;           // |x~|^2 of a row that must never match (non-finite / padding)
 
@@ -84,6 +88,60 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: one thread of the LEADER CTA issues an MMA of M = 256 (128 rows from each
+// CTA's A tile) x N = 256 (128 columns from each CTA's B stage); both CTAs' TMEM receive their own 128 rows.
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the address of one of my shared-memory objects in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a local barrier whose arrivals come from the other CTA of the pair
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -117,6 +175,10 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T
 // slab / stage / descriptor geometry in BYTES is the same as for bf16
 constexpr uint32_t TC_IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_TILE >> 3) << 17) |
                                    ((uint32_t)(TC_TILE >> 4) << 24);
+
+// CTA pair: M = 256, N = 256
+constexpr uint32_t TC_IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+constexpr uint32_t TC_IDESC2_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 // ------------------------------------------------------------------------------------------ prep
 // fp32 rows -> operand tiles + |x~|^2 + |x - x~| (+ the maxima of the latter two over the rows).  A block of 8 warps
@@ -251,15 +313,31 @@ struct TcArgs {
   int nsplit;           // column splits (units per A tile)
   int pairs_per_split;  // 256-column tile pairs per unit
   int nstage;
+  int n_atiles;         // 128-row tiles of A (pair kernel: the second CTA of the last pair may have none)
   float* cand_d;        // [A rows padded][nsplit][TC_LISTS][TC_KS]; slot TC_K of a list = its bound
   int* cand_j;
 };
 
-template <bool TF32>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) {
+// PAIR: two CTAs of a cluster (one SM each) work on two A tiles against the SAME column pairs.  Each loads ONE B tile of
+// a pair (half the L2 -> shared-memory traffic per SM: with one CTA per unit every SM re-streams all of B and the
+// kernel paces on that), the leader's MMA thread issues 256 x 256 x 16 instructions for both (cta_group::2), and each
+// CTA's epilogue reads its own 128 rows x 256 columns from its own TMEM, exactly as in the single-CTA kernel.
+// Cross-CTA signalling: the leader's commits arrive on the stage-free and accumulator-ready barriers of both CTAs
+// (multicast); bulk copies can only signal a barrier of the CTA they land in, so the follower's idle MMA warp relays
+// "my half of stage s has landed" to the leader's stage barrier, and the follower's epilogue warps arrive on the
+// leader's accumulator-free barrier.
+template <bool TF32, bool PAIR>
+__device__ __forceinline__ void tc_candidates_body(const TcArgs& P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int a_tile = blockIdx.x / P.nsplit, split = blockIdx.x % P.nsplit;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0u;
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int split = unit % P.nsplit;
+  const int a_tile_raw = PAIR ? 2 * (unit / P.nsplit) + (int)rank : unit / P.nsplit;
+  const bool a_valid = a_tile_raw < P.n_atiles;
+  const int a_tile = a_valid ? a_tile_raw : P.n_atiles - 1;  // (an A tile to keep the pair's MMAs fed; nothing is written)
+  constexpr uint32_t STAGE_BYTES = PAIR ? TC_STAGE / 2 : TC_STAGE;
   const int nslab = P.nslab;
   const int nchunk = (nslab + 3) >> 2;
   const int npairs_all = (P.n_btiles + 1) >> 1;
@@ -267,32 +345,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
 
   unsigned char* sA = smem;
   unsigned char* sB = sA + (size_t)nslab * TC_SLAB;
-  float* nbs = reinterpret_cast<float*>(sB + (size_t)P.nstage * TC_STAGE);  // [2][256]
+  float* nbs = reinterpret_cast<float*>(sB + (size_t)P.nstage * STAGE_BYTES);  // [2][256]
   float* list_d = nbs + 512;                                               // [TC_K][epilogue threads]
   int* list_j = reinterpret_cast<int*>(list_d + TC_K * TC_EPI_THREADS);    // [TC_K][epilogue threads]
   uint64_t* bars = reinterpret_cast<uint64_t*>(list_j + TC_K * TC_EPI_THREADS);
-  // bars: [0, nstage) full, [nstage, 2 nstage) empty, then afull, tfull[2], tempty[2]
+  // bars: [0, nstage) full, [nstage, 2 nstage) empty, then afull, tfull[2], tempty[2], apeer (the follower's A tile)
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + P.nstage),
                  bar_afull = smem_u32(bars + 2 * P.nstage), bar_tfull = smem_u32(bars + 2 * P.nstage + 1),
-                 bar_tempty = smem_u32(bars + 2 * P.nstage + 3);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P.nstage + 5);
+                 bar_tempty = smem_u32(bars + 2 * P.nstage + 3), bar_apeer = smem_u32(bars + 2 * P.nstage + 5);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P.nstage + 6);
 
   if (warp == 1 && lane == 0) {
+    // (pair, leader) a stage is full when my own bytes have landed AND the follower has reported its half; an
+    // accumulator buffer is free when the epilogue warps of both CTAs are through with it
+    const uint32_t both = (PAIR && leader) ? 2u : 1u;
     for (int s = 0; s < P.nstage; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_full + 8 * s, both);
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_afull, 1);
     mbar_init(bar_tfull, 1);
     mbar_init(bar_tfull + 8, 1);
-    mbar_init(bar_tempty, TC_EPI_WARPS);
-    mbar_init(bar_tempty + 8, TC_EPI_WARPS);
+    mbar_init(bar_tempty, both * TC_EPI_WARPS);
+    mbar_init(bar_tempty + 8, both * TC_EPI_WARPS);
+    mbar_init(bar_apeer, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (PAIR) cluster_sync_all();  // the other CTA's barriers exist before anything arrives on them
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {  // (the same warp of BOTH CTAs issues the pair allocation)
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -316,11 +405,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
           mbar_wait(bar_empty + 8 * s, ph ^ 1u);
           const int ns = min(4, nslab - 4 * c);
           const uint32_t bytes = (uint32_t)ns * TC_SLAB;
-          mbar_expect_tx(bar_full + 8 * s, bytes * nh);
-          const uint32_t dst = smem_u32(sB) + (uint32_t)s * TC_STAGE;
-          const unsigned char* src = srcB + ((size_t)(2 * p) * nslab + (size_t)4 * c) * TC_SLAB;
-          bulk_g2s(dst, src, bytes, bar_full + 8 * s);
-          if (nh == 2) bulk_g2s(dst + 4 * TC_SLAB, src + (size_t)nslab * TC_SLAB, bytes, bar_full + 8 * s);
+          const uint32_t dst = smem_u32(sB) + (uint32_t)s * STAGE_BYTES;
+          if (PAIR) {
+            // my B tile of the pair: 2p + rank (the last pair of an odd tile count: the follower repeats tile 2p; its
+            // 128 columns are computed and ignored)
+            const int bt = min(2 * p + (int)rank, P.n_btiles - 1);
+            mbar_expect_tx(bar_full + 8 * s, bytes);
+            bulk_g2s(dst, srcB + ((size_t)bt * nslab + (size_t)4 * c) * TC_SLAB, bytes, bar_full + 8 * s);
+          } else {
+            mbar_expect_tx(bar_full + 8 * s, bytes * nh);
+            const unsigned char* src = srcB + ((size_t)(2 * p) * nslab + (size_t)4 * c) * TC_SLAB;
+            bulk_g2s(dst, src, bytes, bar_full + 8 * s);
+            if (nh == 2) bulk_g2s(dst + 4 * TC_SLAB, src + (size_t)nslab * TC_SLAB, bytes, bar_full + 8 * s);
+          }
           if (++s == P.nstage) {
             s = 0;
             ph ^= 1u;
@@ -332,45 +429,76 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
     // ===================== MMA issuer (one thread).  The loop must stay far below the tensor pipe's 64 cycles per
     // MMA, so descriptors are one 32-bit add away from a precomputed base (only the 14-bit start-address field
     // changes) and the ring position is a counter, not a division.
-    if (lane == 0) {
+    if (PAIR && !leader) {
+      // follower: no MMAs to issue - relay "my A tile / my half of stage s has landed" to the leader's barriers
+      // (one lane per ring stage: a remote arrive is a round trip through the cluster, and one thread relaying every
+      // stage in turn could not keep up with the MMAs)
+      if (lane == 0) {
+        mbar_wait(bar_afull, 0);
+        mbar_arrive_cluster(mapa_u32(bar_apeer, 0));
+      }
+      if (lane < P.nstage) {
+        const uint32_t mine = bar_full + 8 * lane, lead = mapa_u32(mine, 0);
+        const int uses = (p1 - p0) * nchunk;
+        uint32_t ph = 0;
+        for (int u = lane; u < uses; u += P.nstage) {
+          mbar_wait(mine, ph);
+          mbar_arrive_cluster(lead);
+          ph ^= 1u;
+        }
+      }
+    } else if (lane == 0) {
       mbar_wait(bar_afull, 0);
+      if (PAIR) mbar_wait_cluster(bar_apeer, 0);
       const uint64_t desc_hi = (uint64_t)(((128u >> 4) & 0x3FFFu) | (1u << 14)) << 32;  // SBO = 128 B, version 1
       const uint32_t lbo = (uint32_t)((TC_SLAB >> 4) & 0x3FFF) << 16;
       const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFFu) | lbo;
       const uint32_t b_lo0 = ((smem_u32(sB) >> 4) & 0x3FFFu) | lbo;
-      constexpr uint32_t SLAB16 = TC_SLAB >> 4, STAGE16 = TC_STAGE >> 4;
+      constexpr uint32_t SLAB16 = TC_SLAB >> 4, STAGE16 = STAGE_BYTES >> 4;
       const int last_nm = (nslab - 4 * (nchunk - 1)) >> 1;  // MMA steps (two K chunks each) of the last chunk: 1 or 2
       auto mma = [](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
-        if (TF32) umma_tf32(d, ad, bd, TC_IDESC_TF32, acc);
-        else umma_bf16(d, ad, bd, TC_IDESC, acc);
+        if (PAIR) {
+          if (TF32) umma2_tf32(d, ad, bd, TC_IDESC2_TF32, acc);
+          else umma2_bf16(d, ad, bd, TC_IDESC2, acc);
+        } else {
+          if (TF32) umma_tf32(d, ad, bd, TC_IDESC_TF32, acc);
+          else umma_bf16(d, ad, bd, TC_IDESC, acc);
+        }
+      };
+      auto commit = [](uint32_t bar) {
+        if (PAIR) umma2_commit(bar);
+        else umma_commit(bar);
       };
       int s = 0;
       uint32_t ph = 0;
       for (int p = p0; p < p1; ++p) {
         const int lp = p - p0, buf = lp & 1;
         const bool two = (P.n_btiles - 2 * p) >= 2;
-        mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((lp >> 1) & 1) ^ 1));
+        if (PAIR) mbar_wait_cluster(bar_tempty + 8 * buf, (uint32_t)(((lp >> 1) & 1) ^ 1));
+        else mbar_wait(bar_tempty + 8 * buf, (uint32_t)(((lp >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(buf * 256), d1 = d0 + 128;
         for (int c = 0; c < nchunk; ++c) {
-          mbar_wait(bar_full + 8 * s, ph);
+          if (PAIR) mbar_wait_cluster(bar_full + 8 * s, ph);
+          else mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + (uint32_t)c * (4 * SLAB16);
           const uint32_t b_lo = b_lo0 + (uint32_t)s * STAGE16;
           const uint32_t acc0 = c ? 1u : 0u;
+          // (pair: one instruction covers the 256 columns - 128 from each CTA's stage)
           mma(d0, desc_hi | a_lo, desc_hi | b_lo, acc0);
-          if (two) mma(d1, desc_hi | a_lo, desc_hi | (b_lo + 4 * SLAB16), acc0);
+          if (!PAIR && two) mma(d1, desc_hi | a_lo, desc_hi | (b_lo + 4 * SLAB16), acc0);
           if (c + 1 < nchunk || last_nm == 2) {
             mma(d0, desc_hi | (a_lo + 2 * SLAB16), desc_hi | (b_lo + 2 * SLAB16), 1u);
-            if (two) mma(d1, desc_hi | (a_lo + 2 * SLAB16), desc_hi | (b_lo + 6 * SLAB16), 1u);
+            if (!PAIR && two) mma(d1, desc_hi | (a_lo + 2 * SLAB16), desc_hi | (b_lo + 6 * SLAB16), 1u);
           }
-          umma_commit(bar_empty + 8 * s);  // frees the stage when these MMAs have read it
+          commit(bar_empty + 8 * s);  // frees the stage (in both CTAs) when these MMAs have read it
           if (++s == P.nstage) {
             s = 0;
             ph ^= 1u;
           }
         }
-        umma_commit(bar_tfull + 8 * buf);  // accumulators of this pair are complete
+        commit(bar_tfull + 8 * buf);  // accumulators of this pair are complete
       }
     }
   } else if (warp >= 4) {
@@ -403,14 +531,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
       const int lp = p - p0, buf = lp & 1;
       const int nh = min(2, P.n_btiles - 2 * p);
       float* nbuf = nbs + buf * 256;
-      nbuf[et] = nb_next;
+      if (et < 256) nbuf[et] = nb_next;
       nb_next = load_nb(p + 1);
       asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
       mbar_wait(bar_tfull + 8 * buf, (uint32_t)((lp >> 1) & 1));
       tc_fence_after();
-      if (hsel < nh) {
-        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + hsel * 128);
-        const float* nh_buf = nbuf + hsel * 128;
+      if (((hsel * TC_COLS) >> 7) < nh) {  // my columns belong to a B tile that exists
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + hsel * TC_COLS);
+        const float* nh_buf = nbuf + hsel * TC_COLS;
         float m1 = 3e38f, m2 = 3e38f, m3 = 3e38f;
         // sorted insertion of the 32 keys of one accumulator slab into (m1 <= m2 <= m3)
         auto consume = [&](const uint32_t (&v)[32], int c0) {
@@ -448,17 +576,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
         uint32_t va[32], vb[32];
         tmem_ld32(tbase, va);
         tmem_ld_wait();
-        tmem_ld32(tbase + 32u, vb);
-        consume(va, 0);
-        tmem_ld_wait();
-        tmem_ld32(tbase + 64u, va);
-        consume(vb, 32);
-        tmem_ld_wait();
-        tmem_ld32(tbase + 96u, vb);
-        consume(va, 64);
-        tmem_ld_wait();
-        consume(vb, 96);
-        const int jbase = p * 256 + hsel * 128;
+#pragma unroll
+        for (int sl = 0; sl < TC_COLS / 32; sl += 2) {
+          tmem_ld32(tbase + 32u * (sl + 1), vb);
+          consume(va, 32 * sl);
+          tmem_ld_wait();
+          if (sl + 2 < TC_COLS / 32) tmem_ld32(tbase + 32u * (sl + 2), va);
+          consume(vb, 32 * (sl + 1));
+          if (sl + 2 < TC_COLS / 32) tmem_ld_wait();
+        }
+        const int jbase = p * 256 + hsel * TC_COLS;
         const int j1 = (int)(__float_as_uint(m1) & 0x7Fu), j2 = (int)(__float_as_uint(m2) & 0x7Fu);
         m1 += na;
         m2 += na;
@@ -469,24 +596,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(TcArgs P) 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      if (lane == 0) {
+        if (PAIR && !leader) mbar_arrive_cluster(mapa_u32(bar_tempty + 8 * buf, 0));
+        else mbar_arrive(bar_tempty + 8 * buf);
+      }
     }
-    float* od = P.cand_d + (((size_t)row * P.nsplit + split) * TC_LISTS + hsel) * TC_KS;
-    int* oj = P.cand_j + (((size_t)row * P.nsplit + split) * TC_LISTS + hsel) * TC_KS;
+    if (a_valid) {
+      float* od = P.cand_d + (((size_t)row * P.nsplit + split) * TC_LISTS + hsel) * TC_KS;
+      int* oj = P.cand_j + (((size_t)row * P.nsplit + split) * TC_LISTS + hsel) * TC_KS;
 #pragma unroll
-    for (int i = 0; i < TC_K; ++i) {
-      od[i] = sd[i * TC_EPI_THREADS];
-      oj[i] = sj[i * TC_EPI_THREADS];
+      for (int i = 0; i < TC_K; ++i) {
+        od[i] = sd[i * TC_EPI_THREADS];
+        oj[i] = sj[i * TC_EPI_THREADS];
+      }
+      od[TC_K] = bound;
+      oj[TC_K] = -1;
     }
-    od[TC_K] = bound;
-    oj[TC_K] = -1;
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other may still signal it / write into it
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+}
+
+template <bool TF32>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_candidates_kernel(const __grid_constant__ TcArgs P) {
+  tc_candidates_body<TF32, false>(P);
+}
+template <bool TF32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_candidates_pair_kernel(const __grid_constant__ TcArgs P) {
+  tc_candidates_body<TF32, true>(P);
 }
 
 // ------------------------------------------------------------------------------------------ rescore
@@ -690,12 +834,15 @@ static int tc_run(Ctx* ctx, int slot_a, const float* a, int na, int lda, const f
   // unit should own as many columns as possible.  B is split (a) to give idle SMs work when there are fewer A
   // tiles than SMs and (b) into 2-4 parts when that fills the last wave of CTAs better (512 A tiles on 148 SMs:
   // 3.46 waves as whole units, 6.92 as halves), as long as a unit keeps >= 32 column pairs.
-  int nsplit = std::max(1, std::min(npairs, ctx->sm_count / std::max(n_at, 1)));
-  if (n_at >= ctx->sm_count) {
+  // CTA pairs: a unit is two A tiles on two SMs
+  const bool pair = ctx->tc_pair != 0 && n_at >= 2;
+  const int n_au = pair ? div_up(n_at, 2) : n_at, n_smu = pair ? ctx->sm_count / 2 : ctx->sm_count;
+  int nsplit = std::max(1, std::min(npairs, n_smu / std::max(n_au, 1)));
+  if (n_au >= n_smu) {
     double best_eff = 0.0;
     for (int cand = 1; cand <= 4; ++cand) {
       if (cand > 1 && npairs / cand < 32) break;
-      const double waves = (double)n_at * cand / ctx->sm_count;
+      const double waves = (double)n_au * cand / n_smu;
       const double eff = waves / std::ceil(waves);
       if (eff > best_eff + 0.02) {
         best_eff = eff;
@@ -710,9 +857,10 @@ static int tc_run(Ctx* ctx, int slot_a, const float* a, int na, int lda, const f
   const size_t fixed = a_bytes + TC_FIXED_SMEM;
   // signed arithmetic: a resident A tile beyond the budget must give nstage < 2, not a wrapped size_t
   const long long room = (long long)TC_SMEM_BUDGET - (long long)fixed;
-  const int nstage = room < 0 ? 0 : (int)std::min<long long>(8, room / (long long)TC_STAGE);
+  const long long stage_bytes = pair ? TC_STAGE / 2 : TC_STAGE;  // a CTA of a pair holds one B tile of a stage
+  const int nstage = room < 0 ? 0 : (int)std::min<long long>(pair ? 12 : 8, room / stage_bytes);
   if (nstage < 2) return ctx->fail(PFX_E_INVALID, "tensor-core matching: descriptor dimension too large for one A tile");
-  const size_t smem = std::max<size_t>(fixed + (size_t)nstage * TC_STAGE, 120 * 1024);
+  const size_t smem = std::max<size_t>(fixed + (size_t)nstage * stage_bytes, 120 * 1024);
   const int nlists = nsplit * TC_LISTS;
   const int ncand = nlists * TC_KS;
   PFX_CUDA(ctx->tc_cand_d.ensure((size_t)A.npad * ncand * sizeof(float)));
@@ -724,6 +872,8 @@ static int tc_run(Ctx* ctx, int slot_a, const float* a, int na, int lda, const f
   if (!ctx->smem_attr_match_tc) {
     PFX_CUDA(cudaFuncSetAttribute(tc_candidates_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     PFX_CUDA(cudaFuncSetAttribute(tc_candidates_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PFX_CUDA(cudaFuncSetAttribute(tc_candidates_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PFX_CUDA(cudaFuncSetAttribute(tc_candidates_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     ctx->smem_attr_match_tc = true;
   }
   TcArgs P;
@@ -736,9 +886,15 @@ static int tc_run(Ctx* ctx, int slot_a, const float* a, int na, int lda, const f
   P.nsplit = nsplit;
   P.pairs_per_split = pps;
   P.nstage = nstage;
+  P.n_atiles = n_at;
   P.cand_d = ctx->tc_cand_d.as<float>();
   P.cand_j = ctx->tc_cand_j.as<int>();
-  if (A.tf32)
+  if (pair) {
+    if (A.tf32)
+      PFX_LAUNCH(ctx, tc_candidates_pair_kernel<true>, 2 * n_au * nsplit, TC_THREADS, smem, P);
+    else
+      PFX_LAUNCH(ctx, tc_candidates_pair_kernel<false>, 2 * n_au * nsplit, TC_THREADS, smem, P);
+  } else if (A.tf32)
     PFX_LAUNCH(ctx, tc_candidates_kernel<true>, n_at * nsplit, TC_THREADS, smem, P);
   else
     PFX_LAUNCH(ctx, tc_candidates_kernel<false>, n_at * nsplit, TC_THREADS, smem, P);

@@ -580,6 +580,39 @@ def test_match_wide_descriptors(ctx, orc, dim, engine, tc_expected):
     assert np.array_equal(c["index_query"], q) and np.array_equal(c["index_match"], mm)
 
 
+@pytest.mark.parametrize("dim,na,nb", [(352, 700, 900), (352, 300, 130), (33, 1000, 1100), (125, 257, 513)])
+def test_match_tensor_core_cta_pairs(orc, monkeypatch, dim, na, nb):
+    """the cta_group::2 variant of the candidate kernel (opt-in: PFX_TC_PAIR=1 when the context is created): two A tiles
+    per cluster, each CTA loading one B tile of a column pair.  Odd tile counts on both sides (the follower of the last
+    pair has no A tile; the last column pair has one B tile) must give the bits of the exact scan."""
+    import pcl_feature_extraction_b200 as pfx
+    monkeypatch.setenv("PFX_TC_PAIR", "1")
+    c2 = pfx.Context(0)
+    monkeypatch.delenv("PFX_TC_PAIR")
+    try:
+        rng = np.random.default_rng(dim + na)
+        a = rng.uniform(0, 1, (na, dim)).astype(np.float32)
+        b = rng.uniform(0, 1, (nb, dim)).astype(np.float32)
+        m = min(na, nb) // 2
+        b[:m] = a[:m] + rng.normal(0, 0.01, (m, dim)).astype(np.float32)
+        c2.set_match_engine(1)
+        before = c2.match_info()
+        idx, d2 = c2.match_nn(a, b)
+        c = c2.match(a, b, reciprocal=True)
+        after = c2.match_info()
+    finally:
+        c2.close()
+    assert after["tc_passes"] > before["tc_passes"]
+    oidx, od2 = orc.match_nn(a, b)
+    assert np.array_equal(idx, oidx)
+    assert np.array_equal(d2.view(np.uint32), od2.view(np.uint32))
+    q, mm, dist = orc.match_reciprocal(a, b)
+    assert np.array_equal(c["index_query"], q) and np.array_equal(c["index_match"], mm)
+    # (with 130 random targets in 352-D a few rows hold genuine near-ties: 22 of 300 are redone by either kernel)
+    redone = after["redone_exact"] - before["redone_exact"]
+    assert redone <= 0.1 * (after["rows"] - before["rows"]) + 2, (redone, after["rows"] - before["rows"])
+
+
 def test_match_tensor_core_ties_nan_and_near_duplicates(ctx, orc):
     rng = np.random.default_rng(12)
     a = rng.integers(0, 3, (300, 33)).astype(np.float32)  # many exact ties -> certificate fails -> exact redo
