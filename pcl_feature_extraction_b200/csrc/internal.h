@@ -216,7 +216,7 @@ struct Ctx {
   // dense SHOT takes its radius neighbourhoods from the resident k-search rows when it can (shot_fused.cu);
   // PFX_SHOT_ROWS=0 in the environment keeps the stencil walk on a radius grid (A/B measurements)
   bool shot_from_rows = true;
-  int tc_pair = 0;  // tensor-core matcher on CTA pairs (cta_group::2): 0 off, 1 on (PFX_TC_PAIR)
+  int tc_pair = 1;  // tensor-core matcher on CTA pairs (cta_group::2): 1 on (default), 0 off (PFX_TC_PAIR=0)
   struct RowsStat {  // share of the k-search rows the last rows-based SHOT call could not close (asynchronous read-back)
     int* host = nullptr;
     cudaEvent_t ev = nullptr;

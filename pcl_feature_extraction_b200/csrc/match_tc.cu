@@ -207,29 +207,21 @@ tc_prep_kernel(const float* __restrict__ X, int n, int ld, int dim, int dpad, in
   if (threadIdx.x < 8) s_bad[threadIdx.x] = 0;
   __syncthreads();
   const float* row = X + (size_t)r * ld;
-  bool bad = false;
-  if (r < n) {
-    for (int c = w; c < nchunk; c += 8) {
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        const int k = c * EPC + part * EPT + e;
-        if (k < dim) bad = bad || !isfinite(row[k]);
-      }
-    }
-  }
-  if (bad) s_bad[ro] = 1;
-  __syncthreads();
-  const bool fin = r < n && !s_bad[ro];
+  const bool in = r < n;
   const size_t tile_base = (size_t)(r >> 7) * (size_t)nchunk * TC_SLAB;  // bytes
   const int rr = r & 127;
   const size_t row_off = (size_t)(rr >> 3) * 128 + (size_t)(rr & 7) * 16;
+  // ONE pass over the row: convert, store and look for non-finite values on the way; a row that holds one (rare) is
+  // overwritten with zeros afterwards.  (A separate finiteness pass read every row twice.)
+  bool bad = false;
   float s2 = 0.f, e2 = 0.f;
   for (int c = w; c < nchunk; c += 8) {
     float v[EPT], vr[EPT];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
       const int k = c * EPC + part * EPT + e;
-      v[e] = (fin && k < dim) ? row[k] : 0.f;
+      v[e] = (in && k < dim) ? row[k] : 0.f;
+      bad = bad || !isfinite(v[e]);
     }
     unsigned char* dst = Xt + tile_base + (size_t)c * TC_SLAB + row_off + (size_t)part * 4;
     if (TF32) {
@@ -252,6 +244,12 @@ tc_prep_kernel(const float* __restrict__ X, int n, int ld, int dim, int dpad, in
       const float dv = v[e] - vr[e];
       e2 = fmaf(dv, dv, e2);
     }
+  }
+  if (bad) s_bad[ro] = 1;
+  __syncthreads();
+  if (s_bad[ro]) {  // the whole row becomes zeros with an infinite norm (never a candidate)
+    for (int c = w; c < nchunk; c += 8)
+      *reinterpret_cast<uint32_t*>(Xt + tile_base + (size_t)c * TC_SLAB + row_off + (size_t)part * 4) = 0u;
   }
   // the four lanes of a row, then the eight warps in a fixed order
   s2 += __shfl_xor_sync(FULL, s2, 1);
@@ -644,7 +642,10 @@ tc_candidates_pair_kernel(const __grid_constant__ TcArgs P) {
 // 352 dependent additions - with a lane per candidate of its own row a warp ran that loop for two or three busy
 // lanes); the best (d2, j) key per row is kept with a shared-memory atomicMin.  (3) Lane 0 of each row's warp checks
 // the certificate.
-constexpr int RS_ROWS = 8, RS_MAXPAIRS = 512;
+#ifndef PFX_RS_ROWS
+#define PFX_RS_ROWS 8
+#endif
+constexpr int RS_ROWS = PFX_RS_ROWS, RS_MAXPAIRS = 64 * RS_ROWS;
 
 __device__ __forceinline__ float tc_exact_d2(const float* __restrict__ a, const float* __restrict__ b, int dim) {
   float acc = 0.f;
@@ -902,7 +903,7 @@ static int tc_run(Ctx* ctx, int slot_a, const float* a, int na, int lda, const f
     PFX_LAUNCH(ctx, tc_candidates_kernel<true>, n_at * nsplit, TC_THREADS, smem, P);
   else
     PFX_LAUNCH(ctx, tc_candidates_kernel<false>, n_at * nsplit, TC_THREADS, smem, P);
-  PFX_LAUNCH(ctx, tc_rescore_kernel, div_up(na, 8), 256, 0, a, na, lda, b, nb, ldb, dim, P.cand_d, P.cand_j, nlists,
+  PFX_LAUNCH(ctx, tc_rescore_kernel, div_up(na, RS_ROWS), RS_ROWS * 32, 0, a, na, lda, b, nb, ldb, dim, P.cand_d, P.cand_j, nlists,
              A.norm.as<float>(), A.err.as<float>(), B.maxima.as<unsigned>(), nn_idx, nn_d2, redo_list, redo_count);
   PFX_CUDA(cudaGetLastError());
   int redo = 0;

@@ -580,13 +580,15 @@ def test_match_wide_descriptors(ctx, orc, dim, engine, tc_expected):
     assert np.array_equal(c["index_query"], q) and np.array_equal(c["index_match"], mm)
 
 
+@pytest.mark.parametrize("pair", ["1", "0"])
 @pytest.mark.parametrize("dim,na,nb", [(352, 700, 900), (352, 300, 130), (33, 1000, 1100), (125, 257, 513)])
-def test_match_tensor_core_cta_pairs(orc, monkeypatch, dim, na, nb):
-    """the cta_group::2 variant of the candidate kernel (opt-in: PFX_TC_PAIR=1 when the context is created): two A tiles
-    per cluster, each CTA loading one B tile of a column pair.  Odd tile counts on both sides (the follower of the last
-    pair has no A tile; the last column pair has one B tile) must give the bits of the exact scan."""
+def test_match_tensor_core_cta_pairs(orc, monkeypatch, dim, na, nb, pair):
+    """the cta_group::2 variant of the candidate kernel (the default; PFX_TC_PAIR=0 when the context is created selects
+    the single-CTA kernel): two A tiles per cluster, each CTA loading one B tile of a column pair.  Odd tile counts on
+    both sides (the follower of the last pair has no A tile; the last column pair has one B tile) must give the bits
+    of the exact scan, from either kernel."""
     import pcl_feature_extraction_b200 as pfx
-    monkeypatch.setenv("PFX_TC_PAIR", "1")
+    monkeypatch.setenv("PFX_TC_PAIR", pair)
     c2 = pfx.Context(0)
     monkeypatch.delenv("PFX_TC_PAIR")
     try:
