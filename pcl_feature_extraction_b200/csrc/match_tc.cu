@@ -27,6 +27,9 @@
 
 namespace pfx {
 
+#ifndef PFX_TC_UNSORTED_LIST
+#define PFX_TC_UNSORTED_LIST 1
+#endif
 constexpr int TC_TILE = 128;              // rows per operand tile (= UMMA M, and N of one half tile)
 constexpr int TC_K = 8;                   // candidates kept per (row, column split)
 constexpr int TC_SLAB = TC_TILE * 16;     // bytes of one K-slab (8 bf16 of K for 128 rows)
@@ -521,6 +524,36 @@ __device__ __forceinline__ void tc_candidates_body(const TcArgs& P) {
       sj[i * TC_EPI_THREADS] = -1;
     }
     float worst = CUDART_INF_F;  // K-th smallest key offered so far
+#if PFX_TC_UNSORTED_LIST
+    // The list is kept UNSORTED with its largest entry tracked (value `worst`, slot `wpos`): an offer that beats the
+    // largest entry overwrites it and the largest of the eight is found again - a fixed, branch-free sequence.  With
+    // 32 rows per warp and two offers per column pair some lane inserts in every pair, so the sorted insertion (a
+    // data-dependent shift loop of dependent shared-memory loads and stores, behind a call) ran twice per pair for
+    // the whole warp and took a fifth of the epilogue's time.
+    int wpos = 0;
+    auto offer = [&](float d, int j) {
+      if (d < worst) {
+        sd[wpos * TC_EPI_THREADS] = d;
+        sj[wpos * TC_EPI_THREADS] = j;
+        float mx = sd[0];
+        int mp = 0;
+#pragma unroll
+        for (int i = 1; i < TC_K; ++i) {
+          const float v = sd[i * TC_EPI_THREADS];
+          if (v > mx) {
+            mx = v;
+            mp = i;
+          }
+        }
+        worst = mx;
+        wpos = mp;
+      }
+    };
+#else
+    auto offer = [&](float d, int j) {
+      if (d < worst) worst = tc_topk_insert(sd, sj, d, j);
+    };
+#endif
     float bound = CUDART_INF_F;  // lower bound of every key never offered
     // |b~|^2 of the pair's 256 columns: one value per epilogue thread, fetched one pair ahead so that the global
     // load's latency is hidden behind the previous pair's min/max network
@@ -593,8 +626,8 @@ __device__ __forceinline__ void tc_candidates_body(const TcArgs& P) {
         m2 += na;
         m3 += na;
         bound = fminf(bound, m3);
-        if (m1 < worst) worst = tc_topk_insert(sd, sj, m1, jbase + j1);
-        if (m2 < worst) worst = tc_topk_insert(sd, sj, m2, jbase + j2);
+        offer(m1, jbase + j1);
+        offer(m2, jbase + j2);
       }
       tc_fence_before();
       __syncwarp();
@@ -606,6 +639,18 @@ __device__ __forceinline__ void tc_candidates_body(const TcArgs& P) {
     if (a_valid) {
       float* od = P.cand_d + (((size_t)row * P.nsplit + split) * TC_LISTS + hsel) * TC_KS;
       int* oj = P.cand_j + (((size_t)row * P.nsplit + split) * TC_LISTS + hsel) * TC_KS;
+#if PFX_TC_UNSORTED_LIST
+      // the rescore reads slot K-1 as "the K-th entry of a full list": the largest entry goes there (an unfilled list
+      // keeps an infinite entry with index -1 in that slot, as the sorted list did)
+      {
+        const float dl = sd[(TC_K - 1) * TC_EPI_THREADS], dw = sd[wpos * TC_EPI_THREADS];
+        const int jl = sj[(TC_K - 1) * TC_EPI_THREADS], jw = sj[wpos * TC_EPI_THREADS];
+        sd[wpos * TC_EPI_THREADS] = dl;
+        sj[wpos * TC_EPI_THREADS] = jl;
+        sd[(TC_K - 1) * TC_EPI_THREADS] = dw;
+        sj[(TC_K - 1) * TC_EPI_THREADS] = jw;
+      }
+#endif
 #pragma unroll
       for (int i = 0; i < TC_K; ++i) {
         od[i] = sd[i * TC_EPI_THREADS];
