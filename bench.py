@@ -210,7 +210,7 @@ def matching_record(pfx, ctx, torch, dev, peaks, rows=65536, dim=352, reps=5):
         torch.cuda.synchronize()
         i1 = ctx.match_info()
         ms = e0.elapsed_time(e1) / reps
-        ctx.profile_begin("tc_candidates_kernel")
+        ctx.profile_begin("tc_candidates")
         ctx.match_nn_dev(a.data_ptr(), rows, b.data_ptr(), rows, dim, idx.data_ptr(), d2.data_ptr())
         prof = ctx.profile_end()
         cand_ms = sum(t for _, t in prof.values())
