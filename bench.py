@@ -3,15 +3,16 @@
 "FPFH+SHOT descriptors/sec, 1M-pt cloud").
 
 A step = one pass of the hot path over one synthetic 1M-point cloud (BASELINE config C4 widened with
-C5's SHOT stage): voxel-hash build -> kNN(32) -> normals -> SPFH -> FPFH33 -> radius grid -> SHOT LRF
--> SHOT352, i.e. 2 descriptors (one FPFH33 row + one SHOT352 row) per point.
+C5's SHOT stage): voxel-hash build -> kNN(32) -> normals -> SPFH -> FPFH33 -> SHOT LRF
+-> SHOT352 (neighbourhoods from the resident k-search rows), i.e. 2 descriptors (one FPFH33 row + one SHOT352 row) per point.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--side S]
 
 N > 1 is launched by torchrun (one rank per GPU, NCCL); clouds are sharded over ranks with no
 data-path collective (weak scaling).  `value` times the C-ABI with inputs resident in HBM and
 outputs left in HBM; `e2e` times the same calls with HOST buffers (H2D of the cloud and D2H of every
-descriptor inside the timed region).  `roofline` is measured live with CUDA events around the
+descriptor inside the timed region); `e2e_resident` describes a pair of host clouds, leaves the rows in HBM,
+matches them on the device and copies only the correspondences back (BASELINE config 5's shape).  `roofline` is measured live with CUDA events around the
 dominant kernel; `cpu_baseline` is the CPU oracle (a restatement of PCL: kind "port") on a bounded
 sample.  `--impl reference` times that CPU path alone (the reference itself - ROS + PCL - cannot be
 built here: DESIGN.md §3).
@@ -567,6 +568,54 @@ def main():
                "note": "C-ABI with pinned HOST buffers: cloud uploaded and every FPFH33 and SHOT352 row copied back inside the timed "
                        "region (asynchronous delivery on the copy stream, pfx_sync at the end; PCIe-bound: 1.65 GB per step)"}
 
+    # ---- e2e with the descriptors left in HBM (BASELINE config 5's shape: describe two clouds, match them): host
+    # clouds in, only the 1-NN indices / distances of the matched rows come back - what a caller pays when the rows
+    # feed the matcher instead of host code (the plain e2e above is bound by copying 1.5 GB of SHOT rows per cloud)
+    e2e_resident = None
+    if rank == 0 and not args.no_e2e and not args.no_extras:
+        try:
+            STEP = 64
+            m = n // STEP
+            d_f = [d_fpfh, torch.empty((n, 33), dtype=torch.float32, device=dev)]
+            d_s = [d_shot, torch.empty((n, 361), dtype=torch.float32, device=dev)]
+            nn_i = torch.empty(m, dtype=torch.int32, device=dev)
+            nn_d = torch.empty(m, dtype=torch.float32, device=dev)
+            h_i = [torch.empty(m, dtype=torch.int32).pin_memory() for _ in range(2)]
+            h_d = [torch.empty(m, dtype=torch.float32).pin_memory() for _ in range(2)]
+            HOSTM = pfx.capi.HOST
+
+            def pair_step():
+                for c in range(2):
+                    ctx._chk(ctx.lib.pfx_set_surface(ctx.h, pfx.capi._ptr(hosts[c]), n, 16, HOSTM))
+                    ctx.normals_dev(0.0, K_NN, None)
+                    ctx.fpfh_dev(0.0, K_NN, d_f[c].data_ptr())
+                    ctx.shot352_dev(SHOT_RADIUS, d_s[c].data_ptr())
+                for t, (rows, dim, stride) in enumerate(((d_f, 33, 132), (d_s, 352, 1444))):
+                    # every 64th descriptor of cloud 0 against every 64th of cloud 1, read in place
+                    ctx.match_nn_dev(rows[0].data_ptr(), m, rows[1].data_ptr(), m, dim, nn_i.data_ptr(), nn_d.data_ptr(),
+                                     stride_a=STEP * stride, stride_b=STEP * stride)
+                    h_i[t].copy_(nn_i, non_blocking=True)
+                    h_d[t].copy_(nn_d, non_blocking=True)
+                torch.cuda.synchronize()
+
+            for _ in range(3):
+                pair_step()
+            reps = 5
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                pair_step()
+            dtp = (time.perf_counter() - t0) / reps
+            e2e_resident = {"value": 4.0 * n / dtp, "unit": UNIT, "ms_per_cloud_pair": 1e3 * dtp,
+                            "h2d_bytes_per_pair": 2 * n * 16, "d2h_bytes_per_pair": 2 * m * 8,
+                            "workload": f"two {n}-point clouds from pinned host memory: dense normals + FPFH33 + SHOT352 each (rows left in HBM), "
+                                        f"then exact 1-NN of every {STEP}th FPFH33 and SHOT352 row of cloud 0 among those of cloud 1 "
+                                        f"({m} x {m}); indices and distances copied to the host; wall clock, synchronised per pair"}
+            del d_f, d_s
+        except Exception as e:
+            e2e_resident = {"error": str(e)}
+        ctx.set_queries(None)
+        torch.cuda.empty_cache()
+
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         # the dominant kernel may run as more than one launch per cloud (shot_fused_kernel: the pass over the k-search
@@ -637,7 +686,7 @@ def main():
                                    "(one context and stream each)"},
             "points_per_s": value / 2.0, "single_cloud_latency_ms": latency_ms, "ms_per_step_single_cloud": latency_ms,
             "matching": matching, "bundled": bundled, "slab": slab,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_resident": e2e_resident, "gpu_launches": int(lt.item()), "clocks": clocks,
             "host_binding": "GPU-local CPUs (NVML affinity)" if cpus_before else "none",
         }
         os.write(result_fd, (json.dumps(out) + "\n").encode())
