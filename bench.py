@@ -615,6 +615,7 @@ def main():
             e2e_resident = {"error": str(e)}
         ctx.set_queries(None)
         torch.cuda.empty_cache()
+    barrier()  # (the other ranks wait here for rank 0's extra record instead of tearing the process group down)
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
