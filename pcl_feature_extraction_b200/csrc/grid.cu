@@ -351,7 +351,7 @@ struct SortCtl {
 static size_t sort_ctl_bytes(int ntiles) { return sizeof(SortCtl) + (size_t)4 * ntiles * 256 * sizeof(unsigned); }
 
 __global__ void __launch_bounds__(RS_THREADS)
-rs_onesweep_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ vals, int n, int pass,
+rs_onesweep_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ vals, int n, int pass, int morton_keys,
                    SortCtl* __restrict__ ctl, unsigned* __restrict__ status /* [ntiles][256] of this pass */,
                    uint32_t* __restrict__ okeys, int* __restrict__ ovals) {
   __shared__ int wcnt[8][256];
@@ -362,6 +362,27 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ va
   __shared__ int s_tile;
   if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ctl->ticket[pass], 1u);
   for (int i = threadIdx.x; i < 8 * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
+  // A pass whose digit is the same for every key moves nothing: the tile is copied across and that is all.  So does
+  // the top pass of a voxel hash (morton_keys: 30-bit Morton keys, 0xffffffff for non-finite points) whose cells need
+  // fewer than 24 key bits (any grid of up to 256 cells per axis): the keys of the finite points share the digit 0,
+  // the invalid key is alone in digit 255, and the three passes before have already put the invalid keys last - as
+  // long as no valid key ends in 0xffffff, which the histogram of the third digit tells (digit 255 there belongs to
+  // the invalid keys alone).
+  bool ident;
+  {
+    const unsigned gh = ctl->ghist[pass][threadIdx.x];
+    ident = __syncthreads_or(gh == (unsigned)n) != 0;
+    if (!ident && pass == 3 && morton_keys)
+      ident = ctl->ghist[3][0] + ctl->ghist[3][255] == (unsigned)n && ctl->ghist[2][255] == ctl->ghist[3][255];
+  }
+  if (ident) {
+    const int t0 = blockIdx.x * RS_TILE;
+    for (int i = t0 + threadIdx.x; i < min(n, t0 + RS_TILE); i += RS_THREADS) {
+      okeys[i] = keys[i];
+      ovals[i] = vals[i];
+    }
+    return;
+  }
   __syncthreads();
   const int tile = s_tile;
   const int shift = pass * 8;
@@ -465,7 +486,7 @@ static int radix_sort_pairs(Ctx* ctx, Grid* g, int n, bool have_hist = false) {
   SortCtl* ctl = g->ghist.as<SortCtl>();
   unsigned* status = reinterpret_cast<unsigned*>(ctl + 1);
   for (int pass = 0; pass < 4; ++pass) {
-    PFX_LAUNCH(ctx, rs_onesweep_kernel, ntiles, RS_THREADS, 0, k0, v0, n, pass, ctl,
+    PFX_LAUNCH(ctx, rs_onesweep_kernel, ntiles, RS_THREADS, 0, k0, v0, n, pass, have_hist ? 1 : 0, ctl,
                status + (size_t)pass * ntiles * 256, k1, v1);
     std::swap(k0, k1);
     std::swap(v0, v1);
