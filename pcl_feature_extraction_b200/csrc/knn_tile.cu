@@ -98,6 +98,9 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
       S->gidx[t] = j;
       S->pts[t] = g.pts[j];
     }
+    // the tile is padded to a multiple of 32 candidates with points at infinity: their distances come out infinite
+    // by themselves, and the distance loop needs neither an index clamp nor a select per candidate
+    if (M + lane < ((M + 31) & ~31)) S->pts[M + lane] = make_float4(INF, 0.f, 0.f, 0.f);
     __syncwarp();
     int cx, cy, cz;
     {
@@ -116,10 +119,8 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
 #pragma unroll
         for (int r = 0; r < TR; ++r) {
           if ((r & 3) == 0 && r * 8 >= M) break;
-          int c = r * 8 + sl;
-          float4 p = S->pts[min(c, M - 1)];
-          float d = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
-          d2[r] = (c < M) ? d : INF;
+          const float4 p = S->pts[r * 8 + sl];
+          d2[r] = dist2_flann(q.x, q.y, q.z, p.x, p.y, p.z);
         }
         // ---- find tau with count(d2 <= tau) == k.  The first sweep counts at two thresholds around the density
         // estimate (0.8 / 1.25 tau0), which usually brackets rank k at once; interpolation narrows a wide bracket
