@@ -26,6 +26,14 @@ namespace pfx {
 constexpr int NCAP = 48;       // neighbours a query may have in the stencil variants
 constexpr int NCAP_ROWS = 32;  // ... and in the rows variant (k <= 32): a smaller table, more warps per SM
 constexpr int FS_WPB = 4;
+#ifndef PFX_SHOT_A_UNROLL
+#define PFX_SHOT_A_UNROLL 8
+#endif
+constexpr int SHOT_A_UNROLL = PFX_SHOT_A_UNROLL;  // rows of phase A (rows variant) in flight per warp
+#ifndef PFX_SHOT_BC_UNROLL
+#define PFX_SHOT_BC_UNROLL 1
+#endif
+constexpr int SHOT_BC_UNROLL = PFX_SHOT_BC_UNROLL;  // neighbours of the lane-per-query loops (scatter matrix, votes) in flight
 constexpr int NPAD = 33;  // row pitch of the neighbour table: [position][query lane], conflict-free both ways
 
 template <int CAP>
@@ -103,7 +111,7 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
         // k = 32: one slot per lane, two coalesced 128-byte loads per query
         const int* ri = rows_idx + (size_t)qbase * 32 + lane;
         const float* rd = rows_d2 + (size_t)qbase * 32 + lane;
-#pragma unroll 4
+#pragma unroll SHOT_A_UNROLL
         for (int t = 0; t < qend_a; ++t) {
           const int j = ri[t * 32];
           const float d2 = rd[t * 32];
@@ -193,6 +201,7 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
     {
       // scatter matrix from the compact list (uniform trip counts: no lanes idle on rejected candidates)
       const int n_list = (q_ok && !handoff) ? min(n_all, CAP) : 0;
+#pragma unroll SHOT_BC_UNROLL
       for (int c = 0; c < n_list; ++c) {
         const float4 p = g.pts[S->nbr[c][lane]];
         if (!(p.x == q.x && p.y == q.y && p.z == q.z)) {
@@ -226,6 +235,7 @@ shot_fused_kernel(GridDev g, const float4* __restrict__ queries, int nq, const f
     int votex = 1, votez = 1;
     if (good) {
       int px = 0, pz = 0;
+#pragma unroll SHOT_BC_UNROLL
       for (int c = 0; c < n_all; ++c) {
         const float4 p = g.pts[S->nbr[c][lane]];
         if (!(p.x == q.x && p.y == q.y && p.z == q.z)) {
