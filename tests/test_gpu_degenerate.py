@@ -179,3 +179,34 @@ def test_host_input_reuse_keeps_grids_and_normals(ctx, orc, clouds):
     assert ctx.reuse_info()["surface_uploads"] - i2["surface_uploads"] == 2
     ctx.set_reuse(True)
     ctx.set_queries(None)
+
+
+def test_long_strip_with_nan_points_beyond_256_cells_per_axis(ctx, orc):
+    """A 16 m long strip: the k-search grid has ~800 cells along x, so the Morton keys use more than 24 bits and the top
+    pass of the radix sort has real work to do (on compact clouds it only copies); non-finite points carry the invalid
+    key and must end up behind every finite one.  Sampled k-search rows and the points' normals against the oracle."""
+    from pcl_feature_extraction_b200.synth import sheet_cloud
+    full = sheet_cloud(side=1024, pitch=0.016, seed=7)           # 16.4 m x 16.4 m, generation order shuffled
+    pts = np.ascontiguousarray(full[full[:, 1] < 0.016 * 64])    # a strip 64 rows wide
+    assert 60000 < len(pts) < 70000
+    rng = np.random.default_rng(1)
+    bad = rng.choice(len(pts), 50, replace=False)
+    pts[bad[:25], 0] = np.nan
+    pts[bad[25:], 2] = np.inf
+    ctx.set_viewpoint(0, 0, 0)
+    ctx.set_surface(pts)
+    ctx.set_queries(None)
+    nr = ctx.normals(k=16)
+    info = ctx.grid_info()
+    assert max(info["dims"]) > 256, info
+    idx, d2 = ctx.knn(16)
+    rows = rng.choice(len(pts), 3000, replace=False)
+    rows = rows[np.isfinite(pts[rows]).all(1)]
+    finite = np.isfinite(pts).all(1)
+    oi, od = orc.knn(pts[finite], pts[rows], 16)
+    back = np.flatnonzero(finite)
+    assert np.array_equal(back[oi], idx[rows]) and np.array_equal(od, d2[rows])
+    assert np.isnan(nr[bad, 0]).all() and not np.isnan(nr[finite, 0]).any()
+    f = ctx.fpfh(k=16)
+    blocks = f[finite].reshape(-1, 3, 11).sum(2)
+    assert np.abs(blocks - 100).max() < 1e-2
