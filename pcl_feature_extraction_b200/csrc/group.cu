@@ -157,27 +157,36 @@ __global__ void slab_hist_kernel(const float4* __restrict__ pts, int n, int axis
   }
 }
 
-// flags[i] = does rank `peer` need point i?  peer's slab is [lo, hi); it needs [lo - halo, hi + halo).  Non-finite
-// points belong to slab 0 and are nobody's halo.
-__global__ void slab_need_kernel(const float4* __restrict__ pts, int n, int axis, float lo, float hi, float halo,
-                                 int peer_is_first, int* __restrict__ flags) {
+// All peers in one pass.  A point goes to every rank whose slab, widened by the halo, holds it (non-finite points: to
+// rank 0 only).  The order inside a peer's block does not matter - the receiver sorts by global id - so positions
+// come from one atomic per (warp, peer) instead of a stable compaction per peer (two scans and three launches for
+// each of the `world` peers, twice: for the counts and for the rows).
+struct SlabCuts {
+  float c[34];  // c[p] .. c[p + 1]: slab of rank p
+  int world;
+};
+template <bool SCATTER>
+__global__ void slab_route_kernel(const float4* __restrict__ pts, int n, int axis, SlabCuts cuts, float halo,
+                                  int* __restrict__ counters /* COUNT: totals per peer; SCATTER: running write positions */,
+                                  float4* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 p = pts[i];
-  int f;
-  if (!finite3(p.x, p.y, p.z)) {
-    f = peer_is_first;
-  } else {
-    const float c = coord_of(p, axis);
-    f = (c >= lo - halo && c < hi + halo) ? 1 : 0;
+  const int lane = threadIdx.x & 31;
+  const bool in = i < n;
+  const float4 p = in ? pts[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool fin = in && finite3(p.x, p.y, p.z);
+  const float c = coord_of(p, axis);
+  for (int peer = 0; peer < cuts.world; ++peer) {
+    const bool need = in && (fin ? (c >= cuts.c[peer] - halo && c < cuts.c[peer + 1] + halo) : peer == 0);
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (m == 0u) continue;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&counters[peer], __popc(m));
+    if (SCATTER) {
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (need) out[base + __popc(m & ((1u << lane) - 1u))] = p;
+    }
   }
-  flags[i] = f;
-}
-
-__global__ void slab_pack_kernel(const float4* __restrict__ pts, const int* __restrict__ flags, const int* __restrict__ pos,
-                                 int n, float4* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && flags[i]) out[pos[i]] = pts[i];
 }
 
 // sort keys of the received rows: the global id (unique), value = position in the receive buffer
@@ -432,27 +441,24 @@ extern "C" int pfx_slab_distribute(pfx_ctx* ctx, const void* part, size_t n_part
   PFX_CUDA(ctx->tmp2.ensure(std::max<size_t>(n, 1) * sizeof(int)));
   int* flags = ctx->tmp1.as<int>();
   int* pos = ctx->tmp2.as<int>();
-  // pass 1: counts per peer (device totals gathered in d_counts)
-  for (int p = 0; p < world && n > 0; ++p) {
-    PFX_LAUNCH(ctx, slab_need_kernel, div_up(n, 256), 256, 0, rows.as<float4>(), n, axis, cuts[p], cuts[p + 1], (float)halo,
-               p == 0 ? 1 : 0, flags);
-    PFX_TRY(scan_exclusive_i32(ctx, flags, pos, n, d_counts + p, ctx->scanbuf));
-  }
+  // pass 1: counts per peer
+  SlabCuts sc;
+  sc.world = world;
+  for (int p = 0; p <= world; ++p) sc.c[p] = cuts[p];
+  PFX_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)world * sizeof(int), st));
   if (n > 0) {
+    PFX_LAUNCH(ctx, slab_route_kernel<false>, div_up(n, 256), 256, 0, rows.as<float4>(), n, axis, sc, (float)halo, d_counts, nullptr);
     PFX_CUDA(cudaMemcpyAsync(send_count.data(), d_counts, (size_t)world * sizeof(int), cudaMemcpyDeviceToHost, st));
     PFX_CUDA(cudaStreamSynchronize(st));
-  } else {
-    PFX_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)world * sizeof(int), st));
   }
   for (int p = 0; p < world; ++p) send_off[p + 1] = send_off[p] + send_count[p];
   PFX_CUDA(pack.ensure(std::max<size_t>(send_off[world], 1) * sizeof(float4)));
-  // pass 2: the rows
-  for (int p = 0; p < world && n > 0; ++p) {
-    if (send_count[p] == 0) continue;
-    PFX_LAUNCH(ctx, slab_need_kernel, div_up(n, 256), 256, 0, rows.as<float4>(), n, axis, cuts[p], cuts[p + 1], (float)halo,
-               p == 0 ? 1 : 0, flags);
-    PFX_TRY(scan_exclusive_i32(ctx, flags, pos, n, nullptr, ctx->scanbuf));
-    PFX_LAUNCH(ctx, slab_pack_kernel, div_up(n, 256), 256, 0, rows.as<float4>(), flags, pos, n, pack.as<float4>() + send_off[p]);
+  // pass 2: the rows, each peer's block starting at its offset
+  if (n > 0) {
+    int* d_cursor = d_counts + 32;  // (d_counts has room for 64 ints before the matrix; world <= 32)
+    PFX_CUDA(cudaMemcpyAsync(d_cursor, send_off.data(), (size_t)world * sizeof(int), cudaMemcpyHostToDevice, st));
+    PFX_LAUNCH(ctx, slab_route_kernel<true>, div_up(n, 256), 256, 0, rows.as<float4>(), n, axis, sc, (float)halo, d_cursor,
+               pack.as<float4>());
   }
 
   // ---- count matrix: row r = what rank r sends to each rank
