@@ -3,8 +3,8 @@
 //
 //   pfx_slab_distribute   one cloud, held in arbitrary parts by the ranks, is cut into `world` slabs along its longest
 //                         axis (equal-count cuts from an all-reduced histogram) and every rank receives the points of
-//                         its slab plus a halo of the given width: a device-side pack per peer (stable stream
-//                         compaction), the count matrix by ncclAllGather, the payload by grouped ncclSend / ncclRecv
+//                         its slab plus a halo of the given width: one device-side routing pass for all peers
+//                         (an atomic per warp and peer), the count matrix by ncclAllGather, the payload by grouped ncclSend / ncclRecv
 //                         (NVLink P2P), then a sort by global id.  The surface of the context becomes the owned +
 //                         halo points in ascending global-id order (so that index tie-breaks resolve as on one
 //                         GPU); the unchanged dense stages run on it and pfx_slab_owned_rows lists the rows that
