@@ -446,11 +446,14 @@ extern "C" int pfx_slab_distribute(pfx_ctx* ctx, const void* part, size_t n_part
   sc.world = world;
   for (int p = 0; p <= world; ++p) sc.c[p] = cuts[p];
   PFX_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)world * sizeof(int), st));
-  if (n > 0) {
+  if (n > 0)
     PFX_LAUNCH(ctx, slab_route_kernel<false>, div_up(n, 256), 256, 0, rows.as<float4>(), n, axis, sc, (float)halo, d_counts, nullptr);
-    PFX_CUDA(cudaMemcpyAsync(send_count.data(), d_counts, (size_t)world * sizeof(int), cudaMemcpyDeviceToHost, st));
-    PFX_CUDA(cudaStreamSynchronize(st));
-  }
+  // ---- count matrix: row r = what rank r sends to each rank (my own row comes back with it: one host round trip)
+  std::vector<int> matrix((size_t)world * world, 0);
+  PFX_NCCL(api->AllGather(d_counts, d_matrix, (size_t)world, ncclInt32, G->comm, st));
+  PFX_CUDA(cudaMemcpyAsync(matrix.data(), d_matrix, matrix.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+  PFX_CUDA(cudaStreamSynchronize(st));
+  for (int p = 0; p < world; ++p) send_count[p] = matrix[(size_t)rank * world + p];
   for (int p = 0; p < world; ++p) send_off[p + 1] = send_off[p] + send_count[p];
   PFX_CUDA(pack.ensure(std::max<size_t>(send_off[world], 1) * sizeof(float4)));
   // pass 2: the rows, each peer's block starting at its offset
@@ -461,12 +464,6 @@ extern "C" int pfx_slab_distribute(pfx_ctx* ctx, const void* part, size_t n_part
                pack.as<float4>());
   }
 
-  // ---- count matrix: row r = what rank r sends to each rank
-  std::vector<int> matrix((size_t)world * world, 0);
-  PFX_CUDA(cudaMemcpyAsync(d_counts, send_count.data(), (size_t)world * sizeof(int), cudaMemcpyHostToDevice, st));
-  PFX_NCCL(api->AllGather(d_counts, d_matrix, (size_t)world, ncclInt32, G->comm, st));
-  PFX_CUDA(cudaMemcpyAsync(matrix.data(), d_matrix, matrix.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
-  PFX_CUDA(cudaStreamSynchronize(st));
   std::vector<int> recv_off(world + 1, 0);
   for (int p = 0; p < world; ++p) recv_off[p + 1] = recv_off[p] + matrix[(size_t)p * world + rank];
   const int n_local = recv_off[world];
