@@ -208,23 +208,29 @@ knn_tile_kernel(GridDev g, int k, int* __restrict__ out_idx, float* __restrict__
             __syncwarp();
             const int nb = want_x ? chi - clo : 0, need = k - clo;
             const float v0 = (sl < nb) ? xs[sl] : INF, v1 = (sl + 8 < nb) ? xs[sl + 8] : INF;
-            int r0 = 0, e0 = 0, r1 = 0, e1 = 0;
+            // strict ranks only: the value of rank need-1 (0-based) is the LARGEST value with fewer than `need` values
+            // below it; whether a run of equal values straddles rank k (the set then depends on the index tie-break,
+            // which only the generic kernel implements) is told by counting the copies of that one value afterwards
+            int r0 = 0, r1 = 0;
             const int nbmax = __reduce_max_sync(FULL, nb);
             for (int j = 0; j < nbmax; ++j) {
               const float x = (j < nb) ? xs[j] : INF;
-              r0 += (x < v0) ? 1 : 0; e0 += (x == v0) ? 1 : 0;
-              r1 += (x < v1) ? 1 : 0; e1 += (x == v1) ? 1 : 0;
+              r0 += (x < v0) ? 1 : 0;
+              r1 += (x < v1) ? 1 : 0;
             }
-            // the value of rank need-1 (0-based); a run of equal values across rank k leaves the set to the index
-            // tie-break, which only the generic kernel implements
-            float cand = INF;
-            int bad = 0;
-            if (v0 != INF && r0 < need && need <= r0 + e0) { cand = v0; bad = (r0 + e0 != need); }
-            if (v1 != INF && r1 < need && need <= r1 + e1) { cand = v1; bad = (r1 + e1 != need); }
-            cand = fminf(cand, __shfl_xor_sync(FULL, cand, 1));
-            cand = fminf(cand, __shfl_xor_sync(FULL, cand, 2));
-            cand = fminf(cand, __shfl_xor_sync(FULL, cand, 4));
+            const float NINF = -CUDART_INF_F;
+            float cand = NINF;
+            int rc = 0;
+            if (v0 != INF && r0 < need) { cand = v0; rc = r0; }
+            if (v1 != INF && r1 < need && v1 >= cand) { cand = v1; rc = r1; }   // (v1 >= v0 is not implied: slots are unordered)
+            float gmax = fmaxf(cand, __shfl_xor_sync(FULL, cand, 1));
+            gmax = fmaxf(gmax, __shfl_xor_sync(FULL, gmax, 2));
+            gmax = fmaxf(gmax, __shfl_xor_sync(FULL, gmax, 4));
+            const int copies = group_sum8(((v0 == gmax) ? 1 : 0) + ((v1 == gmax) ? 1 : 0));
+            // the lanes that hold the value know its strict rank
+            int bad = (cand == gmax && gmax != NINF && rc + copies != need) ? 1 : 0;
             bad = group_sum8(bad);
+            cand = (gmax == NINF) ? INF : gmax;
             if (want_x) {
               if (cand == INF || bad) fail = true;
               else { tau = cand; done = true; }
