@@ -537,6 +537,126 @@ fpfh_list_kernel(GridDev g, const float4* __restrict__ queries, int nq, const in
   }  // batch
 }
 
+// k = 32: FOUR queries per warp, EIGHT lanes per query - 32 list entries are exactly four per lane, and no lane idles
+// (the nine-lane layout above leaves 5 of 32 lanes and 4 of 36 list slots unused).  Lane c of a group owns words
+// 0..7 of the 36-byte count rows (bins 4c .. 4c+3); the ninth word holds bin 32 alone and is read by lane 0 of the
+// group with a second load.  Same fixed-point sum as fpfh_list_kernel (integer arithmetic: identical results).
+#ifndef PFX_FL8
+#define PFX_FL8 1
+#endif
+__device__ __forceinline__ unsigned group8_sum(unsigned v) {
+  v += __shfl_xor_sync(FULL, v, 1);
+  v += __shfl_xor_sync(FULL, v, 2);
+  v += __shfl_xor_sync(FULL, v, 4);
+  return v;
+}
+__device__ __forceinline__ float group8_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(FULL, v, 1));
+  v = fmaxf(v, __shfl_xor_sync(FULL, v, 2));
+  v = fmaxf(v, __shfl_xor_sync(FULL, v, 4));
+  return v;
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(FWPB * 32, PFX_FL_MINB)
+fpfh_list32_kernel(GridDev g, const float4* __restrict__ queries, int nq, const int* __restrict__ lists,
+                   const float* __restrict__ ld2, int wbits, const unsigned char* __restrict__ rows8,
+                   float* __restrict__ out, size_t stride) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int grp = lane >> 3, c8 = lane & 7;
+  const int n_valid = g.gp->n_valid;
+  const unsigned* rows32 = reinterpret_cast<const unsigned*>(rows8);
+  const int qwarp = (blockIdx.x * FWPB + wid) * (4 * FL_NB);
+  int pj[4];
+  float pd[4];
+  float4 pq;
+  auto prefetch = [&](int qn) {  // list entries c8 + 8 t and the point of query qn
+    const bool mem = qn < nq;
+    const int qsn = mem ? qn : 0;
+    pq = DENSE ? g.pts[qsn] : queries[qsn];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      pj[t] = mem ? lists[(size_t)qsn * 32 + c8 + 8 * t] : -1;
+      pd[t] = mem ? ld2[(size_t)qsn * 32 + c8 + 8 * t] : 0.f;
+    }
+  };
+  prefetch(qwarp + grp);
+  for (int batch = 0; batch < FL_NB; ++batch) {
+    const int qi = qwarp + batch * 4 + grp;
+    const bool member = qi < nq;
+    if (__all_sync(FULL, !member)) return;
+    const float4 q = pq;
+    const size_t row = DENSE ? (size_t)__float_as_int(q.w) : (size_t)(member ? qi : 0);
+    float* o = out + row * stride;
+    const bool ok = member && finite3(q.x, q.y, q.z) && (!DENSE || qi < n_valid);
+    int myj[4];
+    float myw[4];
+    int n_nb = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      myj[t] = ok ? pj[t] : -1;
+      myw[t] = 0.f;
+      // "minus the query point itself": dists == 0 skipped (weights enter through their 24-bit quantised ratios only)
+      if (myj[t] >= 0 && pd[t] != 0.f) myw[t] = __fdividef(1.0f, pd[t]);
+      n_nb += (myj[t] >= 0) ? 1 : 0;
+    }
+    if (batch + 1 < FL_NB) prefetch(qi + 4);
+    n_nb = (int)group8_sum((unsigned)n_nb);
+    const float wmax = group8_max(fmaxf(fmaxf(myw[0], myw[1]), fmaxf(myw[2], myw[3])));
+    const float inv = (wmax > 0.f) ? __fdividef(16777216.0f, wmax) : 0.f;
+    unsigned qv[4], wsum = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      qv[t] = (unsigned)__float2int_rn(myw[t] * inv);
+      wsum += qv[t];
+    }
+    wsum = group8_sum(wsum);
+    const int sh = max(0, (32 - __clz((int)wsum)) - wbits);
+    const unsigned half = (1u << sh) >> 1;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) qv[t] = (qv[t] + half) >> sh;
+    unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0, a32 = 0;
+#pragma unroll
+    for (int sidx = 0; sidx < 32; ++sidx) {
+      const int src = (lane & 24) | (sidx & 7), t = sidx >> 3;
+      const int j = __shfl_sync(FULL, myj[t], src);
+      const unsigned wi = __shfl_sync(FULL, qv[t], src);
+      const bool use = wi != 0u && member;
+      const unsigned cw = use ? rows32[(size_t)j * 9 + c8] : 0u;
+      a0 += __byte_perm(cw, 0u, 0x4440) * wi;  // one PRMT per zero-extended byte
+      a1 += __byte_perm(cw, 0u, 0x4441) * wi;
+      a2 += __byte_perm(cw, 0u, 0x4442) * wi;
+      a3 += __byte_perm(cw, 0u, 0x4443) * wi;
+      if (c8 == 0 && use) a32 += (rows32[(size_t)j * 9 + 8] & 255u) * wi;
+    }
+    const bool nan_row = !ok || n_nb == 0;  // PCL: NaN row, is_dense = false
+    // per-block sums (bins 0..10 | 11..21 | 22..32)
+    const unsigned v[4] = {a0, a1, a2, a3};
+    unsigned s0 = 0, s1 = 0, s2 = a32;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int bin = c8 * 4 + b;
+      if (bin < 11) s0 += v[b];
+      else if (bin < 22) s1 += v[b];
+      else s2 += v[b];
+    }
+    s0 = group8_sum(s0);
+    s1 = group8_sum(s1);
+    s2 = group8_sum(s2);
+    const float k0 = s0 ? __fdiv_rn(100.0f, (float)s0) : 0.f, k1 = s1 ? __fdiv_rn(100.0f, (float)s1) : 0.f,
+                k2 = s2 ? __fdiv_rn(100.0f, (float)s2) : 0.f;
+    const float nanv = __int_as_float(0x7fc00000);
+    if (member) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int bin = c8 * 4 + b;
+        o[bin] = nan_row ? nanv : __fmul_rn((float)v[b], bin < 11 ? k0 : (bin < 22 ? k1 : k2));
+      }
+      if (c8 == 0) o[32] = nan_row ? nanv : __fmul_rn((float)a32, k2);
+    }
+  }
+}
+
 __global__ void spfh_export_kernel(GridDev g, const float* __restrict__ spfh, const unsigned char* __restrict__ rows8,
                                    int n, int n_nb, float* __restrict__ out) {
   long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -601,7 +721,10 @@ int fpfh_compute(Ctx* ctx, Grid* g, double radius, int k, float* out_dev, size_t
       while ((1 << kb) <= std::max(k - 1, 1)) ++kb;
       const int wbits = 31 - kb;
       if (dense) {
-        if (k == 32)
+        if (k == 32 && PFX_FL8)
+          PFX_LAUNCH(ctx, fpfh_list32_kernel<true>, div_up(nq, FWPB * 4 * FL_NB), FWPB * 32, 0, g->view(), nullptr, nq,
+                     ctx->knn_idx.as<int>(), ctx->knn_d2.as<float>(), wbits, rows8.as<unsigned char>(), out_dev, stride_floats);
+        else if (k == 32)
           PFX_LAUNCH(ctx, (fpfh_list_kernel<true, true>), blocks, FWPB * 32, 0, g->view(), nullptr, nq, ctx->knn_idx.as<int>(),
                      ctx->knn_d2.as<float>(), k, wbits, rows8.as<unsigned char>(), out_dev, stride_floats);
         else
