@@ -48,6 +48,8 @@ ALG_BYTES = {
     "shot_fused_kernel": lambda nb: (52 + 8 * nb) + (1512 + 8 * nb),
     "knn_tile_kernel": lambda nb: (16 + 8 * nb) + (32 + 4 * nb),  # kNN sets + fused normals (S1 + S2)
     "fpfh_list_kernel": lambda nb: 264 + 8 * nb,
+    "fpfh_list32_kernel": lambda nb: 264 + 8 * nb,
+    "spfh_list32_kernel": lambda nb: 164 + 4 * nb,
 }
 
 
